@@ -1,0 +1,1128 @@
+// C ABI of the GBP hot path (include/gbp_cuda.h): handle, device layout
+// construction, program entry points and tensor (de)serialisation.
+//
+// What used to be Poplar graph construction -- tensors mapped onto IPU tiles and
+// vertices wired to tensor slices (ba/ba.cpp:45-371, 658-937) -- becomes: build
+// the edge-slot layout (gbp_layout.h), upload, and launch the kernels of
+// gbp_kernels.cuh on one stream.  There is no CPU path in this file.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/gbp_cuda.h"
+#include "gbp_kernels.cuh"
+
+void gbp_set_error(const std::string& s);  // host_error.cpp
+
+namespace {
+
+using gbp::DeviceGraph;
+
+#define GBP_CUDA_TRY(expr)                                                              \
+  do {                                                                                  \
+    cudaError_t err__ = (expr);                                                         \
+    if (err__ != cudaSuccess) {                                                         \
+      gbp_set_error(std::string(#expr) + ": " + cudaGetErrorString(err__));             \
+      return GBP_ERR_CUDA;                                                              \
+    }                                                                                   \
+  } while (0)
+
+template <class T>
+int dev_alloc(T** p, size_t n, bool zero = true) {
+  *p = nullptr;
+  if (n == 0) n = 1;
+  GBP_CUDA_TRY(cudaMalloc((void**)p, n * sizeof(T)));
+  if (zero) GBP_CUDA_TRY(cudaMemset(*p, 0, n * sizeof(T)));
+  return GBP_OK;
+}
+
+inline float u2f(uint32_t u) {
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
+inline uint32_t f2u(float f) {
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  return u;
+}
+inline float i2f(int32_t i) {
+  float f;
+  std::memcpy(&f, &i, 4);
+  return f;
+}
+inline int32_t f2i(float f) {
+  int32_t i;
+  std::memcpy(&i, &f, 4);
+  return i;
+}
+
+}  // namespace
+
+struct gbp_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  DeviceGraph g;
+  uint32_t C = 0, L = 0, E = 0, E_pad = 0, n_tiles = 0, SK = 1, SL = 1;
+  // host-side index maps (reference edge order <-> edge slots)
+  std::vector<uint32_t> cam_ids, lmk_ids, slot_c, slot_l, pos_of_orig, active_host;
+  uint32_t n_active = 0;
+  std::vector<float> mu_init;     // host copy of the streamed `mu` (empty = zeros)
+  std::vector<float> oldmu_init;  // host copy of the streamed `oldmu` (empty = zeros)
+  bool pending_shift = false;     // a PrepMessageVertex pass ran since the last belief update
+  int use_graph = 0;
+  // staging for READ_PROG
+  uint32_t* d_pos_of_orig = nullptr;
+  float* d_exp_lmk_eta = nullptr;
+  float* d_exp_lmk_lam = nullptr;
+  float* d_exp_damping = nullptr;
+  int32_t* d_exp_dcount = nullptr;
+  uint32_t* d_exp_robust = nullptr;
+  // metric
+  gbp::MetricPartial* d_metric_parts = nullptr;
+  gbp::DeviceStats* d_stats = nullptr;
+  size_t d_stats_cap = 0;
+  // timing
+  float last_ms = 0.f;
+  uint64_t kernels_launched = 0;
+  uint64_t last_kernels = 0;
+  std::vector<void*> allocs;
+};
+
+namespace {
+
+template <class T>
+int h_alloc(gbp_handle* h, T** p, size_t n, bool zero = true) {
+  int rc = dev_alloc(p, n, zero);
+  if (rc == GBP_OK) h->allocs.push_back((void*)*p);
+  return rc;
+}
+
+template <class T>
+int upload(T* dst, const T* src, size_t n, cudaStream_t s) {
+  if (n == 0) return GBP_OK;
+  GBP_CUDA_TRY(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, s));
+  return GBP_OK;
+}
+template <class T>
+int download(T* dst, const T* src, size_t n, cudaStream_t s) {
+  if (n == 0) return GBP_OK;
+  GBP_CUDA_TRY(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, s));
+  return GBP_OK;
+}
+
+inline uint32_t vars_grid(const gbp_handle* h) { return h->C + (h->L + GBP_TILE - 1) / GBP_TILE; }
+
+int launch_update_vars(gbp_handle* h) {
+  const int shift = h->pending_shift ? 1 : 0;
+  const uint32_t grid = vars_grid(h);
+  if (grid) {
+    gbp::k_update_vars<<<grid, GBP_TILE, 0, h->stream>>>(h->g, shift);
+    h->kernels_launched++;
+  }
+  h->pending_shift = false;
+  GBP_CUDA_TRY(cudaGetLastError());
+  return GBP_OK;
+}
+
+template <bool PREP, bool MSG>
+int launch_sweep(gbp_handle* h) {
+  if (h->n_tiles) {
+    gbp::k_sweep<PREP, MSG><<<h->n_tiles, GBP_TILE, 0, h->stream>>>(h->g);
+    h->kernels_launched++;
+  }
+  if (PREP) h->pending_shift = true;
+  GBP_CUDA_TRY(cudaGetLastError());
+  return GBP_OK;
+}
+
+int launch_metric(gbp_handle* h, gbp::DeviceStats* d_out) {
+  if (h->n_tiles) {
+    gbp::k_metric<<<h->n_tiles, GBP_TILE, 0, h->stream>>>(h->g, h->n_active, h->d_metric_parts);
+    h->kernels_launched++;
+  }
+  gbp::k_metric_finish<<<1, 256, 0, h->stream>>>(h->d_metric_parts, h->n_tiles, d_out);
+  h->kernels_launched++;
+  GBP_CUDA_TRY(cudaGetLastError());
+  return GBP_OK;
+}
+
+int ensure_stats(gbp_handle* h, size_t n) {
+  if (n <= h->d_stats_cap) return GBP_OK;
+  if (h->d_stats) cudaFree(h->d_stats);
+  h->d_stats = nullptr;
+  GBP_CUDA_TRY(cudaMalloc((void**)&h->d_stats, n * sizeof(gbp::DeviceStats)));
+  h->d_stats_cap = n;
+  return GBP_OK;
+}
+
+int set_device(const gbp_handle* h) {
+  GBP_CUDA_TRY(cudaSetDevice(h->device));
+  return GBP_OK;
+}
+
+// ---- host <-> device record conversion -----------------------------------------
+struct HostRecs {  // full host mirrors of the per-edge records, fetched on demand
+  std::vector<float4> fac, mcam, mlmk, recA, recB;
+};
+
+int fetch(gbp_handle* h, std::vector<float4>& v, const float4* d, size_t n) {
+  v.resize(n);
+  int rc = download(v.data(), d, n, h->stream);
+  if (rc) return rc;
+  GBP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return GBP_OK;
+}
+int push(gbp_handle* h, const std::vector<float4>& v, float4* d) {
+  int rc = upload(d, v.data(), v.size(), h->stream);
+  if (rc) return rc;
+  GBP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return GBP_OK;
+}
+
+inline float& quad_field(std::vector<float4>& v, size_t stride, size_t e, int field) {
+  float4& q = v[(size_t)(field / 4) * stride + e];
+  return (&q.x)[field % 4];
+}
+inline float& aos_field(std::vector<float4>& v, int quads, size_t e, int field) {
+  float4& q = v[e * quads + field / 4];
+  return (&q.x)[field % 4];
+}
+
+enum TensorId {
+  T_CAM_B_ETA, T_CAM_B_LAM, T_LMK_B_ETA, T_LMK_B_LAM, T_CAM_M_ETA, T_CAM_M_LAM, T_LMK_M_ETA, T_LMK_M_LAM,
+  T_F_ETA, T_F_LAM, T_DAMPING, T_DCOUNT, T_MU, T_OLDMU, T_DMU, T_ACTIVE, T_ROBUST, T_Z, T_VAR,
+  T_CAM_SCALING, T_LMK_SCALING, T_CAM_WFLAG, T_LMK_WFLAG, T_NONE
+};
+
+TensorId tensor_id(const std::string& n) {
+  if (n == "cam_beliefs_eta") return T_CAM_B_ETA;
+  if (n == "cam_beliefs_lambda") return T_CAM_B_LAM;
+  if (n == "lmk_beliefs_eta") return T_LMK_B_ETA;
+  if (n == "lmk_beliefs_lambda") return T_LMK_B_LAM;
+  // messages and previous messages share one buffer: a factor only ever reads
+  // its OWN previous messages, so they are updated in place (no Copy, ba.cpp:902-905)
+  if (n == "cam_messages_eta" || n == "pcam_messages_eta") return T_CAM_M_ETA;
+  if (n == "cam_messages_lambda" || n == "pcam_messages_lambda") return T_CAM_M_LAM;
+  if (n == "lmk_messages_eta" || n == "plmk_messages_eta") return T_LMK_M_ETA;
+  if (n == "lmk_messages_lambda" || n == "plmk_messages_lambda") return T_LMK_M_LAM;
+  if (n == "factor_potentials_eta") return T_F_ETA;
+  if (n == "factor_potentials_lambda") return T_F_LAM;
+  if (n == "damping") return T_DAMPING;
+  if (n == "damping_count") return T_DCOUNT;
+  if (n == "mu") return T_MU;
+  if (n == "oldmu") return T_OLDMU;
+  if (n == "dmu") return T_DMU;
+  if (n == "active_flag") return T_ACTIVE;
+  if (n == "robust_flag") return T_ROBUST;
+  if (n == "measurements") return T_Z;
+  if (n == "meas_variances") return T_VAR;
+  if (n == "cam_scaling") return T_CAM_SCALING;
+  if (n == "lmk_scaling") return T_LMK_SCALING;
+  if (n == "cam_weaken_flag") return T_CAM_WFLAG;
+  if (n == "lmk_weaken_flag") return T_LMK_WFLAG;
+  return T_NONE;
+}
+
+size_t tensor_elems(const gbp_handle* h, TensorId id) {
+  const size_t C = h->C, L = h->L, E = h->E, SK = h->SK, SL = h->SL;
+  switch (id) {
+    case T_CAM_B_ETA: return 6 * C;
+    case T_CAM_B_LAM: return 36 * C;
+    case T_LMK_B_ETA: return 3 * L;
+    case T_LMK_B_LAM: return 9 * L;
+    case T_CAM_M_ETA: return C * SK * 6;
+    case T_CAM_M_LAM: return C * SK * 36;
+    case T_LMK_M_ETA: return L * SL * 3;
+    case T_LMK_M_LAM: return L * SL * 9;
+    case T_F_ETA: return 9 * E;
+    case T_F_LAM: return 81 * E;
+    case T_MU: case T_OLDMU: return 9 * E;
+    case T_Z: return 2 * E;
+    case T_DAMPING: case T_DCOUNT: case T_DMU: case T_ACTIVE: case T_ROBUST: case T_VAR: return E;
+    case T_CAM_SCALING: case T_CAM_WFLAG: return C;
+    case T_LMK_SCALING: case T_LMK_WFLAG: return L;
+    default: return 0;
+  }
+}
+
+int recompute_means(gbp_handle* h) {
+  const uint32_t n = h->C + h->L;
+  if (n) {
+    gbp::k_means_from_beliefs<<<(n + 127) / 128, 128, 0, h->stream>>>(h->g);
+    h->kernels_launched++;
+  }
+  GBP_CUDA_TRY(cudaGetLastError());
+  return GBP_OK;
+}
+
+int import_edges(gbp_handle* h, const float* damping, const int32_t* dcount, const uint32_t* active,
+                 const uint32_t* robust, const float* dmu, int clear_muvalid) {
+  const uint32_t E = h->E;
+  if (!E) return GBP_OK;
+  float* d_damp = nullptr;
+  int32_t* d_dc = nullptr;
+  uint32_t *d_act = nullptr, *d_rob = nullptr;
+  float* d_dmu = nullptr;
+  int rc = GBP_OK;
+  auto stage = [&](auto** d, const auto* src) -> int {
+    if (!src) return GBP_OK;
+    int r = dev_alloc(d, (size_t)E, false);
+    if (r) return r;
+    return upload(*d, src, (size_t)E, h->stream);
+  };
+  if (!rc) rc = stage(&d_damp, damping);
+  if (!rc) rc = stage(&d_dc, dcount);
+  if (!rc) rc = stage(&d_act, active);
+  if (!rc) rc = stage(&d_rob, robust);
+  if (!rc) rc = stage(&d_dmu, dmu);
+  if (!rc) {
+    gbp::k_import_edges<<<(E + 255) / 256, 256, 0, h->stream>>>(h->g, h->d_pos_of_orig, d_damp, d_dc, d_act, d_rob,
+                                                                  d_dmu, clear_muvalid);
+    h->kernels_launched++;
+    if (cudaGetLastError() != cudaSuccess) rc = GBP_ERR_CUDA;
+  }
+  cudaStreamSynchronize(h->stream);
+  cudaFree(d_damp); cudaFree(d_dc); cudaFree(d_act); cudaFree(d_rob); cudaFree(d_dmu);
+  if (active) {
+    h->active_host.assign(active, active + E);
+    h->n_active = 0;
+    for (uint32_t e = 0; e < E; ++e) h->n_active += (active[e] == 1u) ? 1u : 0u;
+  }
+  return rc;
+}
+
+int upload_lmk_priors(gbp_handle* h, const float* eta, const float* lam) {
+  // partial update allowed: fetch current, patch, push
+  std::vector<float4> pr((size_t)h->L * 3);
+  int rc = download(pr.data(), h->g.lmk_prior, pr.size(), h->stream);
+  if (rc) return rc;
+  GBP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  for (size_t l = 0; l < h->L; ++l) {
+    float* r = &pr[l * 3].x;
+    if (eta) for (int i = 0; i < 3; ++i) r[i] = eta[l * 3 + i];
+    if (lam) for (int i = 0; i < 9; ++i) r[3 + i] = lam[l * 9 + i];
+  }
+  rc = upload(h->g.lmk_prior, pr.data(), pr.size(), h->stream);
+  if (rc) return rc;
+  GBP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return GBP_OK;
+}
+
+int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o) {
+  const uint32_t C = p->n_keyframes, L = p->n_points, E = p->n_edges;
+  h->C = C; h->L = L; h->E = E;
+  h->cam_ids.assign(p->cam_ids, p->cam_ids + E);
+  h->lmk_ids.assign(p->lmk_ids, p->lmk_ids + E);
+  // degree counts and slots in O(E) (the reference's are O(V*E) / O(E^2): ba.cpp:267-279,514-521)
+  std::vector<uint32_t> deg_c(C, 0), deg_l(L, 0);
+  h->slot_c.resize(E);
+  h->slot_l.resize(E);
+  for (uint32_t e = 0; e < E; ++e) {
+    if (h->cam_ids[e] >= C || h->lmk_ids[e] >= L) {
+      gbp_set_error("edge index out of range");
+      return GBP_ERR_ARG;
+    }
+    h->slot_c[e] = deg_c[h->cam_ids[e]]++;
+    h->slot_l[e] = deg_l[h->lmk_ids[e]]++;
+  }
+  h->SK = (C ? *std::max_element(deg_c.begin(), deg_c.end()) : 0) + 1;
+  h->SL = (L ? *std::max_element(deg_l.begin(), deg_l.end()) : 0) + 1;
+  // tiles: each camera's factors padded to a multiple of GBP_TILE
+  std::vector<uint32_t> cam_tile_begin(C + 1, 0);
+  for (uint32_t c = 0; c < C; ++c) cam_tile_begin[c + 1] = cam_tile_begin[c] + (deg_c[c] + GBP_TILE - 1) / GBP_TILE;
+  h->n_tiles = cam_tile_begin[C];
+  const uint64_t epad64 = (uint64_t)h->n_tiles * GBP_TILE;
+  if (epad64 >= 0xffffffffull) {
+    gbp_set_error("problem too large for 32-bit edge slots");
+    return GBP_ERR_ARG;
+  }
+  h->E_pad = (uint32_t)epad64;
+  const size_t EP = h->E_pad;
+  std::vector<uint32_t> tile_cam(h->n_tiles);
+  for (uint32_t c = 0; c < C; ++c)
+    for (uint32_t t = cam_tile_begin[c]; t < cam_tile_begin[c + 1]; ++t) tile_cam[t] = c;
+  h->pos_of_orig.resize(E);
+  std::vector<uint32_t> edge_orig(EP, 0xffffffffu);
+  for (uint32_t e = 0; e < E; ++e) {
+    const uint32_t pos = cam_tile_begin[h->cam_ids[e]] * GBP_TILE + h->slot_c[e];
+    h->pos_of_orig[e] = pos;
+    edge_orig[pos] = e;
+  }
+  std::vector<uint32_t> lmk_ptr(L + 1, 0), lmk_edges(E);
+  for (uint32_t l = 0; l < L; ++l) lmk_ptr[l + 1] = lmk_ptr[l] + deg_l[l];
+  for (uint32_t e = 0; e < E; ++e) lmk_edges[lmk_ptr[h->lmk_ids[e]] + h->slot_l[e]] = h->pos_of_orig[e];
+  // per-edge state records
+  std::vector<float4> recA(EP), recB(EP);
+  for (size_t s = 0; s < EP; ++s) {
+    recA[s] = make_float4(0.f, i2f(0), u2f(GBP_FLAG_PAD), 0.f);
+    recB[s] = make_float4(0.f, 0.f, 1.f, u2f(0));
+  }
+  h->active_host.assign(E, 1u);
+  if (p->active_flag) h->active_host.assign(p->active_flag, p->active_flag + E);
+  h->n_active = 0;
+  for (uint32_t e = 0; e < E; ++e) {
+    const size_t s = h->pos_of_orig[e];
+    const uint32_t act = (h->active_host[e] == 1u) ? 1u : 0u;
+    h->n_active += act;
+    recA[s] = make_float4(p->damping ? p->damping[e] : 0.f, i2f(p->damping_count ? p->damping_count[e] : -15),
+                          u2f(act ? GBP_FLAG_ACTIVE : 0u), 0.f);
+    recB[s] = make_float4(p->measurements[2 * (size_t)e], p->measurements[2 * (size_t)e + 1], p->meas_variances[e],
+                          u2f(h->lmk_ids[e]));
+  }
+  auto any_nonzero = [](const float* a, size_t n) {
+    if (!a) return false;
+    for (size_t i = 0; i < n; ++i)
+      if (a[i] != 0.f) return true;
+    return false;
+  };
+  if (any_nonzero(p->mu, (size_t)9 * E)) h->mu_init.assign(p->mu, p->mu + (size_t)9 * E);
+  if (any_nonzero(p->oldmu, (size_t)9 * E)) h->oldmu_init.assign(p->oldmu, p->oldmu + (size_t)9 * E);
+
+  // ---- device allocation (everything the reference relies on being zero IS zeroed, quirk Q4)
+  DeviceGraph& g = h->g;
+  std::memset(&g, 0, sizeof(g));
+  g.C = C; g.L = L; g.E = E; g.E_pad = h->E_pad; g.n_tiles = h->n_tiles;
+  g.K[0] = p->K[0]; g.K[1] = p->K[4]; g.K[2] = p->K[2]; g.K[3] = p->K[5];
+  g.hp.maxeta_damping = o->maxeta_damping;
+  g.hp.num_undamped_iters = o->num_undamped_iters;
+  g.hp.dmu_threshold = o->dmu_threshold;
+  g.hp.min_linear_iters = o->min_linear_iters;
+  g.hp.Nstds = o->Nstds;
+  int rc = GBP_OK;
+#define A_(ptr, n) if (!rc) rc = h_alloc(h, &(ptr), (size_t)(n))
+  A_(g.fac, GBP_FAC_QUADS * EP);
+  A_(g.mcam, GBP_MCAM_QUADS * EP);
+  A_(g.mlmk, GBP_MLMK_QUADS * EP);
+  A_(g.recA, EP);
+  A_(g.recB, EP);
+  A_(g.edge_orig, EP);
+  A_(g.tile_cam, h->n_tiles);
+  A_(g.cam_tile_begin, C + 1);
+  A_(g.cam_partial, (size_t)h->n_tiles * GBP_CAMPART);
+  A_(g.cam_b_eta, 6 * (size_t)C);
+  A_(g.cam_b_lam, 36 * (size_t)C);
+  A_(g.cam_mean, 6 * (size_t)C);
+  A_(g.cam_mean_prev, 6 * (size_t)C);
+  A_(g.cam_R, 9 * (size_t)C);
+  A_(g.cam_prior_eta, 6 * (size_t)C);
+  A_(g.cam_prior_lam, 36 * (size_t)C);
+  A_(g.cam_scaling, C);
+  A_(g.cam_wflag, C);
+  A_(g.lmk_b, GBP_LMKB_QUADS * (size_t)L);
+  A_(g.lmk_mean_prev, L);
+  A_(g.lmk_prior, 3 * (size_t)L);
+  A_(g.lmk_scaling, L);
+  A_(g.lmk_wflag, L);
+  A_(g.lmk_ptr, L + 1);
+  A_(g.lmk_edges, E);
+  A_(h->d_pos_of_orig, E);
+  A_(h->d_metric_parts, h->n_tiles);
+#undef A_
+  if (rc) return rc;
+  cudaStream_t s = h->stream;
+#define U_(dst, src, n) if (!rc) rc = upload(dst, src, (size_t)(n), s)
+  U_(g.recA, recA.data(), EP);
+  U_(g.recB, recB.data(), EP);
+  U_(g.edge_orig, edge_orig.data(), EP);
+  U_(g.tile_cam, tile_cam.data(), h->n_tiles);
+  U_(g.cam_tile_begin, cam_tile_begin.data(), C + 1);
+  U_(g.cam_prior_eta, p->cam_priors_eta, 6 * (size_t)C);
+  U_(g.cam_prior_lam, p->cam_priors_lambda, 36 * (size_t)C);
+  U_(g.cam_scaling, p->cam_scaling, C);
+  U_(g.cam_wflag, p->cam_weaken_flag, C);
+  U_(g.lmk_scaling, p->lmk_scaling, L);
+  U_(g.lmk_wflag, p->lmk_weaken_flag, L);
+  U_(g.lmk_ptr, lmk_ptr.data(), L + 1);
+  U_(g.lmk_edges, lmk_edges.data(), E);
+  U_(h->d_pos_of_orig, h->pos_of_orig.data(), E);
+  std::vector<float4> lpr((size_t)L * 3);
+  for (size_t l = 0; l < L; ++l) {
+    float* r = &lpr[l * 3].x;
+    for (int i = 0; i < 3; ++i) r[i] = p->lmk_priors_eta[l * 3 + i];
+    for (int i = 0; i < 9; ++i) r[3 + i] = p->lmk_priors_lambda[l * 9 + i];
+  }
+  U_(g.lmk_prior, lpr.data(), lpr.size());
+  std::vector<float> oldmu_t;
+  if (!h->oldmu_init.empty()) {
+    if (!rc) rc = h_alloc(h, &g.oldmu_edge, 9 * EP);
+    oldmu_t.assign(9 * EP, 0.f);
+    for (uint32_t e = 0; e < E; ++e)
+      for (int i = 0; i < 9; ++i) oldmu_t[(size_t)i * EP + h->pos_of_orig[e]] = h->oldmu_init[(size_t)9 * e + i];
+    U_(g.oldmu_edge, oldmu_t.data(), oldmu_t.size());
+  }
+#undef U_
+  if (rc) return rc;
+  GBP_CUDA_TRY(cudaStreamSynchronize(s));
+  // LINEARISE_PROG (ba/ba.cpp:890-893): beliefs <- priors, then linearise every factor
+  h->pending_shift = false;
+  rc = launch_update_vars(h);
+  if (rc) return rc;
+  if (h->n_tiles) {
+    gbp::k_relinearise_all<<<h->n_tiles, GBP_TILE, 0, s>>>(h->g);
+    h->kernels_launched++;
+  }
+  GBP_CUDA_TRY(cudaGetLastError());
+  GBP_CUDA_TRY(cudaStreamSynchronize(s));
+  return GBP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* gbp_cuda_version(void) { return "gbp-b200 0.1 (sm_100a)"; }
+
+void gbp_opts_default(gbp_opts* o) {
+  std::memset(o, 0, sizeof(*o));
+  o->device = 0;
+  o->maxeta_damping = 0.4f;
+  o->num_undamped_iters = 8;
+  o->dmu_threshold = 3e-3f;
+  o->min_linear_iters = 10;
+  o->Nstds = 2.5f;
+  o->use_cuda_graph = 1;
+}
+
+int gbp_cuda_init(const gbp_problem* p, const gbp_opts* o_in, gbp_handle** out) {
+  if (!p || !out) {
+    gbp_set_error("null argument");
+    return GBP_ERR_ARG;
+  }
+  if ((p->n_edges && (!p->cam_ids || !p->lmk_ids || !p->measurements || !p->meas_variances)) ||
+      (p->n_keyframes && (!p->cam_priors_eta || !p->cam_priors_lambda || !p->cam_scaling || !p->cam_weaken_flag)) ||
+      (p->n_points && (!p->lmk_priors_eta || !p->lmk_priors_lambda || !p->lmk_scaling || !p->lmk_weaken_flag))) {
+    gbp_set_error("gbp_problem has a null required array");
+    return GBP_ERR_ARG;
+  }
+  gbp_opts o;
+  if (o_in) o = *o_in; else gbp_opts_default(&o);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    gbp_set_error("no CUDA device available (the GBP hot path has no CPU fallback)");
+    return GBP_ERR_CUDA;
+  }
+  if (o.device < 0 || o.device >= ndev) {
+    gbp_set_error("device ordinal out of range");
+    return GBP_ERR_ARG;
+  }
+  gbp_handle* h = new gbp_handle();
+  h->device = o.device;
+  h->use_graph = o.use_cuda_graph;
+  int rc = set_device(h);
+  if (!rc && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) rc = GBP_ERR_CUDA;
+  if (!rc && cudaEventCreate(&h->ev0) != cudaSuccess) rc = GBP_ERR_CUDA;
+  if (!rc && cudaEventCreate(&h->ev1) != cudaSuccess) rc = GBP_ERR_CUDA;
+  if (!rc) rc = build(h, p, &o);
+  if (rc) {
+    if (rc == GBP_ERR_CUDA && !*gbp_cuda_last_error()) gbp_set_error("CUDA initialisation failed");
+    gbp_cuda_free(h);
+    return rc;
+  }
+  *out = h;
+  return GBP_OK;
+}
+
+int gbp_cuda_free(gbp_handle* h) {
+  if (!h) return GBP_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->d_stats) cudaFree(h->d_stats);
+  if (h->d_exp_lmk_eta) cudaFree(h->d_exp_lmk_eta);
+  if (h->d_exp_lmk_lam) cudaFree(h->d_exp_lmk_lam);
+  if (h->d_exp_damping) cudaFree(h->d_exp_damping);
+  if (h->d_exp_dcount) cudaFree(h->d_exp_dcount);
+  if (h->d_exp_robust) cudaFree(h->d_exp_robust);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return GBP_OK;
+}
+
+int gbp_cuda_dims(gbp_handle* h, uint32_t* C, uint32_t* L, uint32_t* E, uint32_t* mk, uint32_t* ml) {
+  if (!h) return GBP_ERR_ARG;
+  if (C) *C = h->C;
+  if (L) *L = h->L;
+  if (E) *E = h->E;
+  if (mk) *mk = h->SK - 1;
+  if (ml) *ml = h->SL - 1;
+  return GBP_OK;
+}
+
+void* gbp_cuda_stream(gbp_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+int gbp_cuda_synchronize(gbp_handle* h) {
+  if (!h) return GBP_ERR_ARG;
+  int rc = set_device(h);
+  if (rc) return rc;
+  GBP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return GBP_OK;
+}
+
+int gbp_cuda_weaken_priors(gbp_handle* h) {
+  if (!h) return GBP_ERR_ARG;
+  int rc = gbp_cuda_weaken_prior_vertices(h);
+  if (rc) return rc;
+  return launch_update_vars(h);
+}
+
+int gbp_cuda_weaken_prior_vertices(gbp_handle* h) {
+  if (!h) return GBP_ERR_ARG;
+  int rc = set_device(h);
+  if (rc) return rc;
+  const uint32_t n = h->C + h->L;
+  if (n) {
+    gbp::k_weaken<<<(n + 255) / 256, 256, 0, h->stream>>>(h->g);
+    h->kernels_launched++;
+  }
+  GBP_CUDA_TRY(cudaGetLastError());
+  return GBP_OK;
+}
+
+int gbp_cuda_iterate_async(gbp_handle* h, int n_sweeps) {
+  if (!h || n_sweeps < 0) return GBP_ERR_ARG;
+  int rc = set_device(h);
+  for (int i = 0; i < n_sweeps && !rc; ++i) {
+    rc = launch_sweep<true, true>(h);
+    if (!rc) rc = launch_update_vars(h);
+  }
+  return rc;
+}
+
+int gbp_cuda_iterate(gbp_handle* h, int n_sweeps, gbp_iter_stats* stats) {
+  if (!h || n_sweeps < 0) return GBP_ERR_ARG;
+  int rc = set_device(h);
+  if (rc) return rc;
+  if (stats) {
+    rc = ensure_stats(h, (size_t)n_sweeps);
+    if (rc) return rc;
+  }
+  const uint64_t k0 = h->kernels_launched;
+  GBP_CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+  for (int i = 0; i < n_sweeps && !rc; ++i) {
+    rc = launch_sweep<true, true>(h);
+    if (!rc) rc = launch_update_vars(h);
+    if (!rc && stats) rc = launch_metric(h, h->d_stats + i);
+  }
+  if (rc) return rc;
+  GBP_CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+  if (stats && n_sweeps)
+    GBP_CUDA_TRY(cudaMemcpyAsync(stats, h->d_stats, (size_t)n_sweeps * sizeof(gbp_iter_stats), cudaMemcpyDeviceToHost,
+                                 h->stream));
+  GBP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  GBP_CUDA_TRY(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+  h->last_kernels = h->kernels_launched - k0;
+  return GBP_OK;
+}
+
+int gbp_cuda_last_timing(gbp_handle* h, float* ms_total, uint64_t* kernels) {
+  if (!h) return GBP_ERR_ARG;
+  if (ms_total) *ms_total = h->last_ms;
+  if (kernels) *kernels = h->last_kernels;
+  return GBP_OK;
+}
+
+int gbp_cuda_eval(gbp_handle* h, gbp_iter_stats* out) {
+  if (!h || !out) return GBP_ERR_ARG;
+  int rc = set_device(h);
+  if (!rc) rc = ensure_stats(h, 1);
+  if (!rc) rc = launch_metric(h, h->d_stats);
+  if (rc) return rc;
+  GBP_CUDA_TRY(cudaMemcpyAsync(out, h->d_stats, sizeof(gbp_iter_stats), cudaMemcpyDeviceToHost, h->stream));
+  GBP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return GBP_OK;
+}
+
+int gbp_cuda_get_beliefs(gbp_handle* h, float* cam_eta, float* cam_lambda, float* lmk_eta, float* lmk_lambda,
+                         float* damping, int32_t* damping_count, uint32_t* robust_flag) {
+  if (!h) return GBP_ERR_ARG;
+  int rc = set_device(h);
+  if (rc) return rc;
+  cudaStream_t s = h->stream;
+  if (cam_eta) rc = download(cam_eta, h->g.cam_b_eta, 6 * (size_t)h->C, s);
+  if (!rc && cam_lambda) rc = download(cam_lambda, h->g.cam_b_lam, 36 * (size_t)h->C, s);
+  if (!rc && (lmk_eta || lmk_lambda) && h->L) {
+    if (!h->d_exp_lmk_eta) {
+      rc = dev_alloc(&h->d_exp_lmk_eta, 3 * (size_t)h->L, false);
+      if (!rc) rc = dev_alloc(&h->d_exp_lmk_lam, 9 * (size_t)h->L, false);
+    }
+    if (!rc) {
+      gbp::k_export_lmk_beliefs<<<(h->L + 255) / 256, 256, 0, s>>>(h->g, h->d_exp_lmk_eta, h->d_exp_lmk_lam);
+      h->kernels_launched++;
+      if (lmk_eta) rc = download(lmk_eta, h->d_exp_lmk_eta, 3 * (size_t)h->L, s);
+      if (!rc && lmk_lambda) rc = download(lmk_lambda, h->d_exp_lmk_lam, 9 * (size_t)h->L, s);
+    }
+  }
+  if (!rc && (damping || damping_count || robust_flag) && h->E) {
+    if (!h->d_exp_damping) {
+      rc = dev_alloc(&h->d_exp_damping, (size_t)h->E, false);
+      if (!rc) rc = dev_alloc(&h->d_exp_dcount, (size_t)h->E, false);
+      if (!rc) rc = dev_alloc(&h->d_exp_robust, (size_t)h->E, false);
+    }
+    if (!rc) {
+      gbp::k_export_edges<<<(h->E + 255) / 256, 256, 0, s>>>(h->g, h->d_pos_of_orig, h->d_exp_damping,
+                                                               h->d_exp_dcount, h->d_exp_robust);
+      h->kernels_launched++;
+      if (damping) rc = download(damping, h->d_exp_damping, (size_t)h->E, s);
+      if (!rc && damping_count) rc = download(damping_count, h->d_exp_dcount, (size_t)h->E, s);
+      if (!rc && robust_flag) rc = download(robust_flag, h->d_exp_robust, (size_t)h->E, s);
+    }
+  }
+  if (rc) return rc;
+  GBP_CUDA_TRY(cudaGetLastError());
+  GBP_CUDA_TRY(cudaStreamSynchronize(s));
+  return GBP_OK;
+}
+
+int gbp_cuda_get_priors(gbp_handle* h, float* cam_eta, float* cam_lambda, float* lmk_eta, float* lmk_lambda) {
+  if (!h) return GBP_ERR_ARG;
+  int rc = set_device(h);
+  if (rc) return rc;
+  cudaStream_t s = h->stream;
+  if (cam_eta) rc = download(cam_eta, h->g.cam_prior_eta, 6 * (size_t)h->C, s);
+  if (!rc && cam_lambda) rc = download(cam_lambda, h->g.cam_prior_lam, 36 * (size_t)h->C, s);
+  std::vector<float4> pr;
+  if (!rc && (lmk_eta || lmk_lambda)) {
+    pr.resize((size_t)h->L * 3);
+    rc = download(pr.data(), h->g.lmk_prior, pr.size(), s);
+  }
+  if (rc) return rc;
+  GBP_CUDA_TRY(cudaStreamSynchronize(s));
+  for (size_t l = 0; l < h->L && !pr.empty(); ++l) {
+    const float* r = &pr[l * 3].x;
+    if (lmk_eta) for (int i = 0; i < 3; ++i) lmk_eta[l * 3 + i] = r[i];
+    if (lmk_lambda) for (int i = 0; i < 9; ++i) lmk_lambda[l * 9 + i] = r[3 + i];
+  }
+  return GBP_OK;
+}
+
+int gbp_cuda_add_keyframe(gbp_handle* h, const int32_t* damping_count, const float* cam_prior_eta,
+                          const float* cam_prior_lambda, const float* lmk_prior_eta, const float* lmk_prior_lambda,
+                          const uint32_t* active_flag, const uint32_t* cam_weaken_flag,
+                          const uint32_t* lmk_weaken_flag) {
+  if (!h) return GBP_ERR_ARG;
+  int rc = set_device(h);
+  if (rc) return rc;
+  cudaStream_t s = h->stream;
+  if (cam_prior_eta) rc = upload(h->g.cam_prior_eta, cam_prior_eta, 6 * (size_t)h->C, s);
+  if (!rc && cam_prior_lambda) rc = upload(h->g.cam_prior_lam, cam_prior_lambda, 36 * (size_t)h->C, s);
+  if (!rc && (lmk_prior_eta || lmk_prior_lambda)) rc = upload_lmk_priors(h, lmk_prior_eta, lmk_prior_lambda);
+  if (!rc && cam_weaken_flag) rc = upload(h->g.cam_wflag, cam_weaken_flag, (size_t)h->C, s);
+  if (!rc && lmk_weaken_flag) rc = upload(h->g.lmk_wflag, lmk_weaken_flag, (size_t)h->L, s);
+  if (!rc && (damping_count || active_flag)) rc = import_edges(h, nullptr, damping_count, active_flag, nullptr, nullptr, 0);
+  if (!rc) rc = launch_update_vars(h);  // prog_ub at the end of NEW_KEYFRAME (slam.cpp:928)
+  if (rc) return rc;
+  GBP_CUDA_TRY(cudaStreamSynchronize(s));
+  return GBP_OK;
+}
+
+int gbp_cuda_relinearise_factors(gbp_handle* h) {
+  if (!h) return GBP_ERR_ARG;
+  int rc = set_device(h);
+  if (rc) return rc;
+  if (h->n_tiles) {
+    gbp::k_relinearise_all<<<h->n_tiles, GBP_TILE, 0, h->stream>>>(h->g);
+    h->kernels_launched++;
+  }
+  GBP_CUDA_TRY(cudaGetLastError());
+  return GBP_OK;
+}
+
+int gbp_cuda_prep_messages(gbp_handle* h) {
+  if (!h) return GBP_ERR_ARG;
+  int rc = set_device(h);
+  if (rc) return rc;
+  return launch_sweep<true, false>(h);
+}
+
+int gbp_cuda_compute_messages(gbp_handle* h) {
+  if (!h) return GBP_ERR_ARG;
+  int rc = set_device(h);
+  if (rc) return rc;
+  return launch_sweep<false, true>(h);
+}
+
+int gbp_cuda_update_beliefs(gbp_handle* h) {
+  if (!h) return GBP_ERR_ARG;
+  int rc = set_device(h);
+  if (rc) return rc;
+  return launch_update_vars(h);
+}
+
+int gbp_cuda_tensor_nbytes(gbp_handle* h, const char* name, size_t* nbytes) {
+  if (!h || !name || !nbytes) return GBP_ERR_ARG;
+  const TensorId id = tensor_id(name);
+  if (id == T_NONE) {
+    gbp_set_error(std::string("unknown tensor ") + name);
+    return GBP_ERR_NAME;
+  }
+  *nbytes = tensor_elems(h, id) * 4;
+  return GBP_OK;
+}
+
+int gbp_cuda_get_tensor(gbp_handle* h, const char* name, void* dst, size_t nbytes) {
+  if (!h || !name || !dst) return GBP_ERR_ARG;
+  const TensorId id = tensor_id(name);
+  if (id == T_NONE) {
+    gbp_set_error(std::string("unknown tensor ") + name);
+    return GBP_ERR_NAME;
+  }
+  if (nbytes != tensor_elems(h, id) * 4) {
+    gbp_set_error(std::string("size mismatch for tensor ") + name);
+    return GBP_ERR_SIZE;
+  }
+  int rc = set_device(h);
+  if (rc) return rc;
+  cudaStream_t s = h->stream;
+  float* out = (float*)dst;
+  uint32_t* outu = (uint32_t*)dst;
+  int32_t* outi = (int32_t*)dst;
+  const size_t C = h->C, L = h->L, E = h->E, EP = h->E_pad, SK = h->SK, SL = h->SL;
+  std::vector<float4> v;
+  switch (id) {
+    case T_CAM_B_ETA: rc = download(out, h->g.cam_b_eta, 6 * C, s); break;
+    case T_CAM_B_LAM: rc = download(out, h->g.cam_b_lam, 36 * C, s); break;
+    case T_CAM_SCALING: rc = download(out, h->g.cam_scaling, C, s); break;
+    case T_LMK_SCALING: rc = download(out, h->g.lmk_scaling, L, s); break;
+    case T_CAM_WFLAG: rc = download(outu, h->g.cam_wflag, C, s); break;
+    case T_LMK_WFLAG: rc = download(outu, h->g.lmk_wflag, L, s); break;
+    case T_LMK_B_ETA:
+    case T_LMK_B_LAM: {
+      rc = fetch(h, v, h->g.lmk_b, L * GBP_LMKB_QUADS);
+      if (rc) break;
+      for (size_t l = 0; l < L; ++l) {
+        const float* r = &v[l * GBP_LMKB_QUADS].x;
+        if (id == T_LMK_B_ETA) for (int i = 0; i < 3; ++i) out[l * 3 + i] = r[i];
+        else for (int i = 0; i < 9; ++i) out[l * 9 + i] = r[3 + i];
+      }
+      break;
+    }
+    case T_CAM_M_ETA:
+    case T_CAM_M_LAM: {
+      const int d = (id == T_CAM_M_ETA) ? 6 : 36;
+      std::memset(out, 0, nbytes);
+      std::vector<float> pr(d * C);
+      rc = download(pr.data(), id == T_CAM_M_ETA ? h->g.cam_prior_eta : h->g.cam_prior_lam, pr.size(), s);
+      if (!rc) rc = fetch(h, v, h->g.mcam, GBP_MCAM_QUADS * EP);
+      if (rc) break;
+      for (size_t c = 0; c < C; ++c) std::memcpy(out + c * SK * d, pr.data() + c * d, d * 4);
+      for (size_t e = 0; e < E; ++e) {
+        float* o = out + ((size_t)h->cam_ids[e] * SK + h->slot_c[e] + 1) * d;
+        const size_t pos = h->pos_of_orig[e];
+        if (id == T_CAM_M_ETA) {
+          for (int i = 0; i < 6; ++i) o[i] = quad_field(v, EP, pos, i);
+        } else {
+          for (int i = 0; i < 6; ++i)
+            for (int j = 0; j < 6; ++j) o[i * 6 + j] = quad_field(v, EP, pos, gbp_mcam_lam_field(i, j));
+        }
+      }
+      break;
+    }
+    case T_LMK_M_ETA:
+    case T_LMK_M_LAM: {
+      const int d = (id == T_LMK_M_ETA) ? 3 : 9;
+      const int off = (id == T_LMK_M_ETA) ? 0 : 3;
+      std::memset(out, 0, nbytes);
+      std::vector<float4> pr;
+      rc = fetch(h, pr, h->g.lmk_prior, L * 3);
+      if (!rc) rc = fetch(h, v, h->g.mlmk, GBP_MLMK_QUADS * EP);
+      if (rc) break;
+      for (size_t l = 0; l < L; ++l)
+        for (int i = 0; i < d; ++i) out[l * SL * d + i] = aos_field(pr, 3, l, off + i);
+      for (size_t e = 0; e < E; ++e) {
+        float* o = out + ((size_t)h->lmk_ids[e] * SL + h->slot_l[e] + 1) * d;
+        for (int i = 0; i < d; ++i) o[i] = aos_field(v, GBP_MLMK_QUADS, h->pos_of_orig[e], off + i);
+      }
+      break;
+    }
+    case T_F_ETA:
+    case T_F_LAM: {
+      rc = fetch(h, v, h->g.fac, GBP_FAC_QUADS * EP);
+      if (rc) break;
+      for (size_t e = 0; e < E; ++e) {
+        const size_t pos = h->pos_of_orig[e];
+        if (id == T_F_ETA) {
+          for (int i = 0; i < 9; ++i) out[e * 9 + i] = quad_field(v, EP, pos, GBP_FAC_ETA + i);
+        } else {  // block-packed [cc 36 | cl 18 | lc 18 | ll 9], ba/ba.cpp:93-96
+          float* o = out + e * 81;
+          for (int i = 0; i < 36; ++i) o[i] = quad_field(v, EP, pos, GBP_FAC_CC + i);
+          for (int i = 0; i < 18; ++i) o[36 + i] = quad_field(v, EP, pos, GBP_FAC_CL + i);
+          for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 6; ++j) o[54 + i * 6 + j] = quad_field(v, EP, pos, GBP_FAC_CL + j * 3 + i);
+          for (int i = 0; i < 9; ++i) o[72 + i] = quad_field(v, EP, pos, GBP_FAC_LL + i);
+        }
+      }
+      break;
+    }
+    case T_DAMPING: case T_DCOUNT: case T_DMU: case T_ACTIVE: case T_ROBUST: {
+      rc = fetch(h, v, h->g.recA, EP);
+      if (rc) break;
+      for (size_t e = 0; e < E; ++e) {
+        const float4 r = v[h->pos_of_orig[e]];
+        if (id == T_DAMPING) out[e] = r.x;
+        else if (id == T_DCOUNT) outi[e] = f2i(r.y);
+        else if (id == T_DMU) out[e] = r.w;
+        else if (id == T_ACTIVE) outu[e] = h->active_host[e];
+        else outu[e] = (f2u(r.z) & GBP_FLAG_ROBUST) ? 1u : 0u;
+      }
+      break;
+    }
+    case T_Z: case T_VAR: {
+      rc = fetch(h, v, h->g.recB, EP);
+      if (rc) break;
+      for (size_t e = 0; e < E; ++e) {
+        const float4 r = v[h->pos_of_orig[e]];
+        if (id == T_Z) { out[2 * e] = r.x; out[2 * e + 1] = r.y; }
+        else out[e] = r.z;
+      }
+      break;
+    }
+    case T_MU: case T_OLDMU: {
+      // mu == oldmu after a full sweep (Copy(mu,oldmu), ba.cpp:898).  For an edge
+      // whose prep has run, both equal the variable means that prep used.
+      std::vector<float> cm(6 * C);
+      std::vector<float4> lm, lb;
+      const bool pend = h->pending_shift;
+      rc = download(cm.data(), pend ? h->g.cam_mean : h->g.cam_mean_prev, cm.size(), s);
+      if (!rc) rc = fetch(h, v, h->g.recA, EP);
+      if (!rc && pend) rc = fetch(h, lb, h->g.lmk_b, L * GBP_LMKB_QUADS);
+      if (!rc && !pend) rc = fetch(h, lm, h->g.lmk_mean_prev, L);
+      if (rc) break;
+      const std::vector<float>& init = (id == T_MU) ? h->mu_init : h->oldmu_init;
+      for (size_t e = 0; e < E; ++e) {
+        float* o = out + e * 9;
+        if (f2u(v[h->pos_of_orig[e]].z) & GBP_FLAG_MUVALID) {
+          const size_t c = h->cam_ids[e], l = h->lmk_ids[e];
+          for (int i = 0; i < 6; ++i) o[i] = cm[c * 6 + i];
+          const float* m = pend ? &lb[l * GBP_LMKB_QUADS + 3].x : &lm[l].x;
+          for (int i = 0; i < 3; ++i) o[6 + i] = m[i];
+        } else {
+          for (int i = 0; i < 9; ++i) o[i] = init.empty() ? 0.f : init[e * 9 + i];
+        }
+      }
+      break;
+    }
+    default: return GBP_ERR_NAME;
+  }
+  if (rc) return rc;
+  GBP_CUDA_TRY(cudaStreamSynchronize(s));
+  return GBP_OK;
+}
+
+int gbp_cuda_set_tensor(gbp_handle* h, const char* name, const void* src, size_t nbytes) {
+  if (!h || !name || !src) return GBP_ERR_ARG;
+  const TensorId id = tensor_id(name);
+  if (id == T_NONE) {
+    gbp_set_error(std::string("unknown tensor ") + name);
+    return GBP_ERR_NAME;
+  }
+  if (nbytes != tensor_elems(h, id) * 4) {
+    gbp_set_error(std::string("size mismatch for tensor ") + name);
+    return GBP_ERR_SIZE;
+  }
+  int rc = set_device(h);
+  if (rc) return rc;
+  cudaStream_t s = h->stream;
+  const float* in = (const float*)src;
+  const uint32_t* inu = (const uint32_t*)src;
+  const int32_t* ini = (const int32_t*)src;
+  const size_t C = h->C, L = h->L, E = h->E, EP = h->E_pad, SK = h->SK, SL = h->SL;
+  std::vector<float4> v;
+  switch (id) {
+    case T_CAM_B_ETA: rc = upload(h->g.cam_b_eta, in, 6 * C, s); if (!rc) rc = recompute_means(h); break;
+    case T_CAM_B_LAM: rc = upload(h->g.cam_b_lam, in, 36 * C, s); if (!rc) rc = recompute_means(h); break;
+    case T_CAM_SCALING: rc = upload(h->g.cam_scaling, in, C, s); break;
+    case T_LMK_SCALING: rc = upload(h->g.lmk_scaling, in, L, s); break;
+    case T_CAM_WFLAG: rc = upload(h->g.cam_wflag, inu, C, s); break;
+    case T_LMK_WFLAG: rc = upload(h->g.lmk_wflag, inu, L, s); break;
+    case T_LMK_B_ETA:
+    case T_LMK_B_LAM: {
+      rc = fetch(h, v, h->g.lmk_b, L * GBP_LMKB_QUADS);
+      if (rc) break;
+      for (size_t l = 0; l < L; ++l) {
+        float* r = &v[l * GBP_LMKB_QUADS].x;
+        if (id == T_LMK_B_ETA) for (int i = 0; i < 3; ++i) r[i] = in[l * 3 + i];
+        else for (int i = 0; i < 9; ++i) r[3 + i] = in[l * 9 + i];
+      }
+      rc = push(h, v, h->g.lmk_b);
+      if (!rc) rc = recompute_means(h);
+      break;
+    }
+    case T_CAM_M_ETA:
+    case T_CAM_M_LAM: {
+      const int d = (id == T_CAM_M_ETA) ? 6 : 36;
+      std::vector<float> pr(d * C);
+      for (size_t c = 0; c < C; ++c) std::memcpy(pr.data() + c * d, in + c * SK * d, d * 4);
+      rc = upload(id == T_CAM_M_ETA ? h->g.cam_prior_eta : h->g.cam_prior_lam, pr.data(), pr.size(), s);
+      if (!rc) rc = fetch(h, v, h->g.mcam, GBP_MCAM_QUADS * EP);
+      if (rc) break;
+      for (size_t e = 0; e < E; ++e) {
+        const float* o = in + ((size_t)h->cam_ids[e] * SK + h->slot_c[e] + 1) * d;
+        const size_t pos = h->pos_of_orig[e];
+        if (id == T_CAM_M_ETA) {
+          for (int i = 0; i < 6; ++i) quad_field(v, EP, pos, i) = o[i];
+        } else {
+          for (int i = 0; i < 6; ++i)
+            for (int j = 0; j < 6; ++j) quad_field(v, EP, pos, gbp_mcam_lam_field(i, j)) = o[i * 6 + j];
+        }
+      }
+      rc = push(h, v, h->g.mcam);
+      if (!rc && h->n_tiles) {
+        gbp::k_cam_partials<<<h->n_tiles, GBP_TILE, 0, s>>>(h->g);
+        h->kernels_launched++;
+      }
+      break;
+    }
+    case T_LMK_M_ETA:
+    case T_LMK_M_LAM: {
+      const int d = (id == T_LMK_M_ETA) ? 3 : 9;
+      const int off = (id == T_LMK_M_ETA) ? 0 : 3;
+      std::vector<float4> pr;
+      rc = fetch(h, pr, h->g.lmk_prior, L * 3);
+      if (!rc) rc = fetch(h, v, h->g.mlmk, GBP_MLMK_QUADS * EP);
+      if (rc) break;
+      for (size_t l = 0; l < L; ++l)
+        for (int i = 0; i < d; ++i) aos_field(pr, 3, l, off + i) = in[l * SL * d + i];
+      for (size_t e = 0; e < E; ++e) {
+        const float* o = in + ((size_t)h->lmk_ids[e] * SL + h->slot_l[e] + 1) * d;
+        for (int i = 0; i < d; ++i) aos_field(v, GBP_MLMK_QUADS, h->pos_of_orig[e], off + i) = o[i];
+      }
+      rc = push(h, pr, h->g.lmk_prior);
+      if (!rc) rc = push(h, v, h->g.mlmk);
+      break;
+    }
+    case T_F_ETA:
+    case T_F_LAM: {
+      rc = fetch(h, v, h->g.fac, GBP_FAC_QUADS * EP);
+      if (rc) break;
+      for (size_t e = 0; e < E; ++e) {
+        const size_t pos = h->pos_of_orig[e];
+        if (id == T_F_ETA) {
+          for (int i = 0; i < 9; ++i) quad_field(v, EP, pos, GBP_FAC_ETA + i) = in[e * 9 + i];
+        } else {  // Lambda_lc (o[54..71]) is implied by Lambda_cl and not stored
+          const float* o = in + e * 81;
+          for (int i = 0; i < 36; ++i) quad_field(v, EP, pos, GBP_FAC_CC + i) = o[i];
+          for (int i = 0; i < 18; ++i) quad_field(v, EP, pos, GBP_FAC_CL + i) = o[36 + i];
+          for (int i = 0; i < 9; ++i) quad_field(v, EP, pos, GBP_FAC_LL + i) = o[72 + i];
+        }
+      }
+      rc = push(h, v, h->g.fac);
+      break;
+    }
+    case T_DAMPING: rc = import_edges(h, in, nullptr, nullptr, nullptr, nullptr, 0); break;
+    case T_DCOUNT: rc = import_edges(h, nullptr, ini, nullptr, nullptr, nullptr, 0); break;
+    case T_ACTIVE: rc = import_edges(h, nullptr, nullptr, inu, nullptr, nullptr, 0); break;
+    case T_ROBUST: rc = import_edges(h, nullptr, nullptr, nullptr, inu, nullptr, 0); break;
+    case T_DMU: rc = import_edges(h, nullptr, nullptr, nullptr, nullptr, in, 0); break;
+    case T_Z: case T_VAR: {
+      rc = fetch(h, v, h->g.recB, EP);
+      if (rc) break;
+      for (size_t e = 0; e < E; ++e) {
+        float4& r = v[h->pos_of_orig[e]];
+        if (id == T_Z) { r.x = in[2 * e]; r.y = in[2 * e + 1]; }
+        else r.z = in[e];
+      }
+      rc = push(h, v, h->g.recB);
+      break;
+    }
+    case T_MU:
+      // `mu` is pure output of PrepMessageVertex (overwritten before it is read);
+      // remember it only so that get_tensor echoes it for edges that never ran.
+      h->mu_init.assign(in, in + 9 * E);
+      break;
+    case T_OLDMU: {
+      // per-edge oldmu: stored verbatim and used by the next prep of every edge
+      h->oldmu_init.assign(in, in + 9 * E);
+      if (!h->g.oldmu_edge) rc = h_alloc(h, &h->g.oldmu_edge, 9 * EP);
+      if (rc) break;
+      std::vector<float> t(9 * EP, 0.f);
+      for (size_t e = 0; e < E; ++e)
+        for (int i = 0; i < 9; ++i) t[(size_t)i * EP + h->pos_of_orig[e]] = in[9 * e + i];
+      rc = upload(h->g.oldmu_edge, t.data(), t.size(), s);
+      if (!rc) GBP_CUDA_TRY(cudaStreamSynchronize(s));
+      if (!rc) rc = import_edges(h, nullptr, nullptr, nullptr, nullptr, nullptr, 1);
+      h->pending_shift = false;
+      break;
+    }
+    default: return GBP_ERR_NAME;
+  }
+  if (rc) return rc;
+  GBP_CUDA_TRY(cudaGetLastError());
+  GBP_CUDA_TRY(cudaStreamSynchronize(s));
+  return GBP_OK;
+}
+
+int gbp_cuda_plan_shard(const gbp_problem* p, uint32_t world, uint32_t rank, gbp_shard_plan* out) {
+  if (!p || !out || world == 0 || rank >= world) return GBP_ERR_ARG;
+  const uint32_t C = p->n_keyframes, L = p->n_points, E = p->n_edges;
+  std::vector<uint64_t> deg(C, 0);
+  for (uint32_t e = 0; e < E; ++e) {
+    if (p->cam_ids[e] >= C || p->lmk_ids[e] >= L) return GBP_ERR_ARG;
+    deg[p->cam_ids[e]]++;
+  }
+  // contiguous camera ranges balanced by edge count: rank r owns the cameras whose
+  // cumulative edge midpoint falls in [r, r+1) * E / world
+  std::vector<uint32_t> bounds(world + 1, C);
+  bounds[0] = 0;
+  uint64_t cum = 0;
+  uint32_t r = 1;
+  for (uint32_t c = 0; c < C && r < world; ++c) {
+    cum += deg[c];
+    while (r < world && cum * world >= (uint64_t)r * E && cum > 0) bounds[r++] = c + 1;
+  }
+  for (uint32_t i = 1; i <= world; ++i) bounds[i] = std::max(bounds[i], bounds[i - 1]);
+  bounds[world] = C;
+  std::vector<uint32_t> cam_rank(C, 0);
+  for (uint32_t i = 0; i < world; ++i)
+    for (uint32_t c = bounds[i]; c < bounds[i + 1]; ++c) cam_rank[c] = i;
+  uint32_t n_local_edges = 0, n_local_points = 0, n_boundary = 0;
+  std::vector<uint8_t> touched(L, 0);
+  // edges are not required to be camera-sorted: count distinct ranks per landmark
+  // with a per-landmark bitmask for world <= 64, else a conservative two-value check
+  std::vector<uint64_t> mask(L, 0);
+  for (uint32_t e = 0; e < E; ++e) {
+    const uint32_t cr = cam_rank[p->cam_ids[e]];
+    mask[p->lmk_ids[e]] |= (1ull << (cr & 63));
+    if (cr == rank) {
+      n_local_edges++;
+      touched[p->lmk_ids[e]] = 1;
+    }
+  }
+  for (uint32_t l = 0; l < L; ++l) {
+    n_local_points += touched[l];
+    if (mask[l] & (mask[l] - 1)) n_boundary++;
+  }
+  out->world = world;
+  out->rank = rank;
+  out->cam_begin = bounds[rank];
+  out->cam_end = bounds[rank + 1];
+  out->n_local_edges = n_local_edges;
+  out->n_local_points = n_local_points;
+  out->n_boundary_points = n_boundary;
+  out->reserved = 0;
+  return GBP_OK;
+}
+
+int gbp_cuda_nccl_unique_id(void* id128) {
+  (void)id128;
+  gbp_set_error("multi-GPU exchange is not built into this version of the library");
+  return GBP_ERR_COMM;
+}
+
+int gbp_cuda_init_shard(const gbp_problem* p, const gbp_opts* o, uint32_t world, uint32_t rank,
+                        const void* nccl_unique_id, gbp_handle** out) {
+  (void)nccl_unique_id;
+  if (world == 1 && rank == 0) return gbp_cuda_init(p, o, out);
+  gbp_set_error("multi-GPU exchange is not built into this version of the library");
+  return GBP_ERR_COMM;
+}
+
+}  // extern "C"

@@ -1,0 +1,664 @@
+// CUDA kernels of the GBP sweep (sm_100a, fp32 SIMT; tensor cores are
+// deliberately unused: the work is ~2.5 kflop of tiny 3x3/6x6 solves per 0.7 KB
+// of streamed state, i.e. HBM-bound -- see DESIGN.md).
+//
+//   k_sweep<PREP,MSG>   one thread per factor, one tile (= one camera) per block.
+//                       PREP = PrepMessageVertex        gbp_codelets.cpp:241-378
+//                       MSG  = the four message vertices gbp_codelets.cpp:411-709
+//                              + on-chip reduction of the camera-bound messages
+//   k_update_vars       belief update (prog_ub, ba/ba.cpp:104-139) fused with the
+//                       per-variable mean (inf2mean hoisted out of PrepMessageVertex,
+//                       which recomputes it once per adjacent edge, :264-265)
+//   k_relinearise_all   RelineariseFactorVertex          gbp_codelets.cpp:38-171
+//   k_weaken            WeakenPriorVertex                gbp_codelets.cpp:184-196
+//   k_metric/_finish    eval_reprojection_error          ba/util.cpp:74-144
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gbp_layout.h"
+#include "gbp_math.cuh"
+
+namespace gbp {
+
+struct DeviceGraph {
+  // sizes
+  uint32_t C, L, E, E_pad, n_tiles;
+  // per-edge-slot records (quad-SoA, see gbp_layout.h)
+  float4* fac;        // [18][E_pad]
+  float4* mcam;       // [11][E_pad]
+  float4* mlmk;       // [E_pad][3]
+  float4* recA;       // [E_pad] {damping, damping_count, flags, dmu}
+  float4* recB;       // [E_pad] {z.x, z.y, var, landmark id}
+  float* oldmu_edge;  // [9][E_pad] or nullptr (= zeros); read only while !MUVALID
+  uint32_t* edge_orig;  // [E_pad] original edge id, 0xffffffff for padding
+  // tiles
+  uint32_t* tile_cam;        // [n_tiles]
+  uint32_t* cam_tile_begin;  // [C+1]
+  float* cam_partial;        // [n_tiles][42]
+  // cameras
+  float* cam_b_eta;      // [C][6]
+  float* cam_b_lam;      // [C][36]
+  float* cam_mean;       // [C][6]
+  float* cam_mean_prev;  // [C][6]
+  float* cam_R;          // [C][9] so3exp(mean[3:6]) for the metric
+  float* cam_prior_eta;  // [C][6]
+  float* cam_prior_lam;  // [C][36]
+  float* cam_scaling;    // [C]
+  uint32_t* cam_wflag;   // [C]
+  // landmarks
+  float4* lmk_b;          // [L][4] {eta3, lam9, mean3, pad}
+  float4* lmk_mean_prev;  // [L]
+  float4* lmk_prior;      // [L][3] {eta3, lam9}
+  float* lmk_scaling;     // [L]
+  uint32_t* lmk_wflag;    // [L]
+  uint32_t* lmk_ptr;      // [L+1] CSC over edge slots, in original edge order
+  uint32_t* lmk_edges;    // [E]
+  float K[4];             // fx fy cx cy
+  Hyper hp;
+};
+
+GBP_DEV float4 ldg4(const float4* p) { return __ldg(p); }
+
+template <int N>
+GBP_DEV void load_quads(const float4* base, size_t stride, size_t e, float (&out)[N * 4]) {
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    const float4 v = base[(size_t)q * stride + e];
+    out[q * 4 + 0] = v.x;
+    out[q * 4 + 1] = v.y;
+    out[q * 4 + 2] = v.z;
+    out[q * 4 + 3] = v.w;
+  }
+}
+
+template <int N>
+GBP_DEV void store_quads(float4* base, size_t stride, size_t e, const float (&in)[N * 4]) {
+#pragma unroll
+  for (int q = 0; q < N; ++q)
+    base[(size_t)q * stride + e] = make_float4(in[q * 4], in[q * 4 + 1], in[q * 4 + 2], in[q * 4 + 3]);
+}
+
+// (Re)linearisation of one factor (gbp_codelets.cpp:285-373 / :53-168): rare and
+// register hungry, so it is kept out of line of the streaming path.  Arguments
+// are passed by value so the kernel parameter block never has its address taken.
+__device__ __noinline__ uint32_t relinearise_in_place(float4* fac, size_t E_pad, size_t e, float4 K4, float Nstds,
+                                                      float z0, float z1, float var, float c0, float c1, float c2,
+                                                      float c3, float c4, float c5, float l0, float l1, float l2,
+                                                      bool zero_first) {
+  float f[GBP_FAC_QUADS * 4];
+  if (zero_first) {
+#pragma unroll
+    for (int i = 0; i < GBP_FAC_QUADS * 4; ++i) f[i] = 0.f;
+  } else {
+    load_quads<GBP_FAC_QUADS>(fac, E_pad, e, f);  // quirk Q1: accumulate onto the old blocks
+  }
+  const float K[4] = {K4.x, K4.y, K4.z, K4.w};
+  const float x_kf[6] = {c0, c1, c2, c3, c4, c5};
+  const float x_l[3] = {l0, l1, l2};
+  float(&eta)[9] = *reinterpret_cast<float(*)[9]>(f + GBP_FAC_ETA);
+  float(&ll)[9] = *reinterpret_cast<float(*)[9]>(f + GBP_FAC_LL);
+  float(&cl)[18] = *reinterpret_cast<float(*)[18]>(f + GBP_FAC_CL);
+  float(&cc)[36] = *reinterpret_cast<float(*)[36]>(f + GBP_FAC_CC);
+  const uint32_t robust = linearise_accumulate(z0, z1, var, K, x_kf, x_l, Nstds, eta, ll, cl, cc);
+  store_quads<GBP_FAC_QUADS>(fac, E_pad, e, f);
+  return robust;
+}
+
+#define GBP_RED_STRIDE (GBP_TILE + 1)
+
+template <bool PREP, bool MSG>
+__global__ void __launch_bounds__(GBP_TILE, 3) k_sweep(const DeviceGraph g) {
+  __shared__ float s_cam[54];  // belief eta 6 | belief lambda 36 | mean 6 | previous mean 6
+  __shared__ float s_red[MSG ? GBP_CAMPART * GBP_RED_STRIDE : 1];
+  __shared__ float s_part[MSG ? GBP_CAMPART * 3 : 1];
+
+  const uint32_t tile = blockIdx.x;
+  const uint32_t tid = threadIdx.x;
+  const uint32_t c = g.tile_cam[tile];
+  const size_t e = (size_t)tile * GBP_TILE + tid;
+  if (tid < 6) s_cam[tid] = g.cam_b_eta[c * 6 + tid];
+  else if (tid < 42) s_cam[tid] = g.cam_b_lam[c * 36 + (tid - 6)];
+  else if (tid < 48) s_cam[tid] = g.cam_mean[c * 6 + (tid - 42)];
+  else if (tid < 54) s_cam[tid] = g.cam_mean_prev[c * 6 + (tid - 48)];
+
+  float4 ra = g.recA[e];
+  float damping = ra.x;
+  int dcount = __float_as_int(ra.y);
+  uint32_t flags = __float_as_uint(ra.z);
+  float dmu = ra.w;
+  const bool active = (flags & GBP_FLAG_ACTIVE) != 0;
+  __syncthreads();
+
+  if (active) {
+    const float4 rb = ldg4(g.recB + e);
+    const uint32_t l = __float_as_uint(rb.w);
+    float lb[16];
+    {
+      const float4* p = g.lmk_b + (size_t)l * GBP_LMKB_QUADS;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 v = p[q];
+        lb[q * 4] = v.x; lb[q * 4 + 1] = v.y; lb[q * 4 + 2] = v.z; lb[q * 4 + 3] = v.w;
+      }
+    }
+    // lb: eta 0..2 | lambda 3..11 | mean 12..14
+
+    if (PREP) {
+      if (dcount == 0) damping = g.hp.maxeta_damping;  // gbp_codelets.cpp:245-248
+      dcount += 1;
+      float x_kf[6], x_l[3], old[9];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) x_kf[i] = s_cam[42 + i];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) x_l[i] = lb[12 + i];
+      if (flags & GBP_FLAG_MUVALID) {
+        const float4 mp = g.lmk_mean_prev[l];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) old[i] = s_cam[48 + i];
+        old[6] = mp.x; old[7] = mp.y; old[8] = mp.z;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) old[i] = g.oldmu_edge ? g.oldmu_edge[(size_t)i * g.E_pad + e] : 0.f;
+      }
+      float acc = 0.f;  // gbp_codelets.cpp:268-277
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const float d = fs(old[i], x_kf[i]);
+        acc = fa(acc, fm(d, d));
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const float d = fs(old[6 + i], x_l[i]);
+        acc = fa(acc, fm(d, d));
+      }
+      dmu = __fsqrt_rn(acc);
+      flags |= GBP_FLAG_MUVALID;
+      if (dmu < g.hp.dmu_threshold && dcount > g.hp.min_linear_iters - g.hp.num_undamped_iters) {
+        damping = 0.0f;  // gbp_codelets.cpp:280-283
+        dcount = -g.hp.num_undamped_iters;
+        const uint32_t robust = relinearise_in_place(g.fac, g.E_pad, e, make_float4(g.K[0], g.K[1], g.K[2], g.K[3]), g.hp.Nstds,
+                                                     rb.x, rb.y, rb.z, x_kf[0], x_kf[1], x_kf[2], x_kf[3], x_kf[4], x_kf[5],
+                                                     x_l[0], x_l[1], x_l[2], false);
+        flags = (flags & ~GBP_FLAG_ROBUST) | (robust ? GBP_FLAG_ROBUST : 0u);
+      }
+    }
+
+    if (MSG) {
+      float f[GBP_FAC_QUADS * 4];
+      load_quads<GBP_FAC_QUADS>(g.fac, g.E_pad, e, f);
+      float pc[GBP_MCAM_READ_QUADS * 4];  // previous f->cam message: eta 0..5, lower lambda 6..26
+      load_quads<GBP_MCAM_READ_QUADS>(g.mcam, g.E_pad, e, pc);
+      float pl[12];  // previous f->lmk message: eta 0..2, lambda 3..11
+      {
+        const float4* p = g.mlmk + e * GBP_MLMK_QUADS;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const float4 v = p[q];
+          pl[q * 4] = v.x; pl[q * 4 + 1] = v.y; pl[q * 4 + 2] = v.z; pl[q * 4 + 3] = v.w;
+        }
+      }
+      const float* eta = f + GBP_FAC_ETA;
+      const float* ll = f + GBP_FAC_LL;
+      const float* cl = f + GBP_FAC_CL;
+      const float* cc = f + GBP_FAC_CC;
+      const float omd = fs(1.0f, damping);
+
+      // ---- message to the landmark (gbp_codelets.cpp:536-552, 691-699) ----
+      float nl[12];
+      {
+        float Ld[21];
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+          for (int j = 0; j <= i; ++j)
+            Ld[lt(i, j)] = fs(fa(cc[i * 6 + j], s_cam[6 + i * 6 + j]), pc[GBP_MCAM_LOWER + lt(i, j)]);
+        float Ai[36];
+        inv6(Ld, Ai);
+        float P[18];  // Lambda_lc * inv  (3x6), Lambda_lc(i,k) = Lambda_cl(k,i)
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 6; ++j) {
+            float acc = fm(cl[i], Ai[j]);
+#pragma unroll
+            for (int k = 1; k < 6; ++k) acc = fa(acc, fm(cl[k * 3 + i], Ai[k * 6 + j]));
+            P[i * 6 + j] = acc;
+          }
+        float ed[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) ed[i] = fs(fa(eta[i], s_cam[i]), pc[i]);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          float acc = fm(P[i * 6], ed[0]);
+#pragma unroll
+          for (int k = 1; k < 6; ++k) acc = fa(acc, fm(P[i * 6 + k], ed[k]));
+          const float h = fs(eta[6 + i], acc);
+          nl[i] = fa(fm(h, omd), fm(pl[i], damping));
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            float acc = fm(P[i * 6], cl[j]);
+#pragma unroll
+            for (int k = 1; k < 6; ++k) acc = fa(acc, fm(P[i * 6 + k], cl[k * 3 + j]));
+            nl[3 + i * 3 + j] = fs(ll[i * 3 + j], acc);
+          }
+      }
+
+      // ---- message to the camera (gbp_codelets.cpp:446-462, 619-627) ----
+      float nc[GBP_MCAM_QUADS * 4];
+      {
+        float Ld[9], Li[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Ld[i] = fs(fa(ll[i], lb[3 + i]), pl[3 + i]);
+        inv3(Ld, Li);
+        float P[18];  // Lambda_cl * inv (6x3)
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+            P[i * 3 + j] = fa(fa(fm(cl[i * 3], Li[j]), fm(cl[i * 3 + 1], Li[3 + j])), fm(cl[i * 3 + 2], Li[6 + j]));
+        float ed[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) ed[i] = fs(fa(eta[6 + i], lb[i]), pl[i]);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const float acc = fa(fa(fm(P[i * 3], ed[0]), fm(P[i * 3 + 1], ed[1])), fm(P[i * 3 + 2], ed[2]));
+          const float h = fs(eta[i], acc);
+          const float v = fa(fm(h, omd), fm(pc[i], damping));
+          nc[i] = v;
+          s_red[i * GBP_RED_STRIDE + tid] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+          for (int j = 0; j < 6; ++j) {
+            const float acc = fa(fa(fm(P[i * 3], cl[j * 3]), fm(P[i * 3 + 1], cl[j * 3 + 1])), fm(P[i * 3 + 2], cl[j * 3 + 2]));
+            const float v = fs(cc[i * 6 + j], acc);
+            nc[(i >= j) ? (GBP_MCAM_LOWER + lt(i, j)) : (GBP_MCAM_UPPER + (5 * i - i * (i - 1) / 2) + (j - i - 1))] = v;
+            s_red[(6 + i * 6 + j) * GBP_RED_STRIDE + tid] = v;
+          }
+        nc[27] = 0.f;
+        nc[43] = 0.f;
+      }
+      store_quads<GBP_MCAM_QUADS>(g.mcam, g.E_pad, e, nc);
+      {
+        float4* p = g.mlmk + e * GBP_MLMK_QUADS;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) p[q] = make_float4(nl[q * 4], nl[q * 4 + 1], nl[q * 4 + 2], nl[q * 4 + 3]);
+      }
+      flags |= GBP_FLAG_HASMSG;
+    }
+    g.recA[e] = make_float4(damping, __int_as_float(dcount), __uint_as_float(flags), dmu);
+  } else if (MSG) {
+    // inactive (or padding) slot: its messages are zero (gbp_codelets.cpp:464-468 etc.)
+#pragma unroll
+    for (int k = 0; k < GBP_CAMPART; ++k) s_red[k * GBP_RED_STRIDE + tid] = 0.f;
+    if (flags & GBP_FLAG_HASMSG) {
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < GBP_MCAM_QUADS; ++q) g.mcam[(size_t)q * g.E_pad + e] = z4;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) g.mlmk[e * GBP_MLMK_QUADS + q] = z4;
+      flags &= ~GBP_FLAG_HASMSG;
+      g.recA[e] = make_float4(damping, __int_as_float(dcount), __uint_as_float(flags), dmu);
+    }
+  }
+
+  if (MSG) {
+    // deterministic on-chip sum of the tile's 128 camera-bound messages:
+    // 42 values x 3 contiguous parts, then the 3 parts in order.
+    __syncthreads();
+    if (tid < GBP_CAMPART * 3) {
+      const int k = tid / 3, part = tid % 3;
+      const int b = part * 43, en = (b + 43 < GBP_TILE) ? b + 43 : GBP_TILE;
+      const float* row = s_red + k * GBP_RED_STRIDE;
+      float acc = row[b];
+      for (int i = b + 1; i < en; ++i) acc = fa(acc, row[i]);
+      s_part[tid] = acc;
+    }
+    __syncthreads();
+    if (tid < GBP_CAMPART)
+      g.cam_partial[(size_t)tile * GBP_CAMPART + tid] = fa(fa(s_part[tid * 3], s_part[tid * 3 + 1]), s_part[tid * 3 + 2]);
+  }
+}
+
+// Recompute the per-tile camera partial sums from the stored messages (used
+// after set_tensor on the camera message tensors).
+__global__ void __launch_bounds__(GBP_TILE) k_cam_partials(const DeviceGraph g) {
+  __shared__ float s_red[GBP_CAMPART * GBP_RED_STRIDE];
+  __shared__ float s_part[GBP_CAMPART * 3];
+  const uint32_t tile = blockIdx.x, tid = threadIdx.x;
+  const size_t e = (size_t)tile * GBP_TILE + tid;
+  float m[GBP_MCAM_QUADS * 4];
+  load_quads<GBP_MCAM_QUADS>(g.mcam, g.E_pad, e, m);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) s_red[i * GBP_RED_STRIDE + tid] = m[i];
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+      s_red[(6 + i * 6 + j) * GBP_RED_STRIDE + tid] =
+          m[(i >= j) ? (GBP_MCAM_LOWER + lt(i, j)) : (GBP_MCAM_UPPER + (5 * i - i * (i - 1) / 2) + (j - i - 1))];
+  __syncthreads();
+  if (tid < GBP_CAMPART * 3) {
+    const int k = tid / 3, part = tid % 3;
+    const int b = part * 43, en = (b + 43 < GBP_TILE) ? b + 43 : GBP_TILE;
+    const float* row = s_red + k * GBP_RED_STRIDE;
+    float acc = row[b];
+    for (int i = b + 1; i < en; ++i) acc = fa(acc, row[i]);
+    s_part[tid] = acc;
+  }
+  __syncthreads();
+  if (tid < GBP_CAMPART)
+    g.cam_partial[(size_t)tile * GBP_CAMPART + tid] = fa(fa(s_part[tid * 3], s_part[tid * 3 + 1]), s_part[tid * 3 + 2]);
+}
+
+// Belief update + per-variable mean.  Blocks [0,C) own one camera each; the
+// remaining blocks own GBP_TILE landmarks each.  shift != 0: the mean that the
+// last PrepMessageVertex pass used becomes the "old mu" (Copy(mu, oldmu),
+// ba/ba.cpp:898) before the new mean is stored.
+__global__ void __launch_bounds__(GBP_TILE) k_update_vars(const DeviceGraph g, const int shift) {
+  const uint32_t tid = threadIdx.x;
+  if (blockIdx.x < g.C) {
+    __shared__ float s_b[GBP_CAMPART];
+    const uint32_t c = blockIdx.x;
+    if (tid < GBP_CAMPART) {
+      float acc = (tid < 6) ? g.cam_prior_eta[c * 6 + tid] : g.cam_prior_lam[c * 36 + (tid - 6)];
+      const uint32_t t0 = g.cam_tile_begin[c], t1 = g.cam_tile_begin[c + 1];
+      for (uint32_t t = t0; t < t1; ++t) acc = fa(acc, g.cam_partial[(size_t)t * GBP_CAMPART + tid]);
+      s_b[tid] = acc;
+      if (tid < 6) g.cam_b_eta[c * 6 + tid] = acc;
+      else g.cam_b_lam[c * 36 + (tid - 6)] = acc;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      float eta[6], lamL[21], mean[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) eta[i] = s_b[i];
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) lamL[lt(i, j)] = s_b[6 + i * 6 + j];
+      inf2mean6(eta, lamL, mean);
+      const float w[3] = {mean[3], mean[4], mean[5]};
+      float R[9];
+      so3exp(w, R);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        if (shift) g.cam_mean_prev[c * 6 + i] = g.cam_mean[c * 6 + i];
+        g.cam_mean[c * 6 + i] = mean[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 9; ++i) g.cam_R[c * 9 + i] = R[i];
+    }
+  } else {
+    const uint32_t l = (blockIdx.x - g.C) * GBP_TILE + tid;
+    if (l >= g.L) return;
+    float b[12];
+    {
+      const float4* p = g.lmk_prior + (size_t)l * 3;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const float4 v = p[q];
+        b[q * 4] = v.x; b[q * 4 + 1] = v.y; b[q * 4 + 2] = v.z; b[q * 4 + 3] = v.w;
+      }
+    }
+    const uint32_t k0 = g.lmk_ptr[l], k1 = g.lmk_ptr[l + 1];
+    for (uint32_t k = k0; k < k1; ++k) {  // slot order = original edge order
+      const float4* p = g.mlmk + (size_t)g.lmk_edges[k] * GBP_MLMK_QUADS;
+      const float4 v0 = p[0], v1 = p[1], v2 = p[2];
+      b[0] = fa(b[0], v0.x); b[1] = fa(b[1], v0.y); b[2] = fa(b[2], v0.z); b[3] = fa(b[3], v0.w);
+      b[4] = fa(b[4], v1.x); b[5] = fa(b[5], v1.y); b[6] = fa(b[6], v1.z); b[7] = fa(b[7], v1.w);
+      b[8] = fa(b[8], v2.x); b[9] = fa(b[9], v2.y); b[10] = fa(b[10], v2.z); b[11] = fa(b[11], v2.w);
+    }
+    const float eta[3] = {b[0], b[1], b[2]};
+    float lam[9], mean[3];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) lam[i] = b[3 + i];
+    inf2mean3(eta, lam, mean);
+    float4* o = g.lmk_b + (size_t)l * GBP_LMKB_QUADS;
+    if (shift) {
+      const float4 oldq = o[3];
+      g.lmk_mean_prev[l] = make_float4(oldq.x, oldq.y, oldq.z, 0.f);
+    }
+    o[0] = make_float4(b[0], b[1], b[2], b[3]);
+    o[1] = make_float4(b[4], b[5], b[6], b[7]);
+    o[2] = make_float4(b[8], b[9], b[10], b[11]);
+    o[3] = make_float4(mean[0], mean[1], mean[2], 0.f);
+  }
+}
+
+// RelineariseFactorVertex on every factor, active or not (ba/ba.cpp:68-97).
+__global__ void __launch_bounds__(GBP_TILE) k_relinearise_all(const DeviceGraph g) {
+  const uint32_t tile = blockIdx.x, tid = threadIdx.x;
+  const size_t e = (size_t)tile * GBP_TILE + tid;
+  float4 ra = g.recA[e];
+  uint32_t flags = __float_as_uint(ra.z);
+  if (flags & GBP_FLAG_PAD) return;
+  const uint32_t c = g.tile_cam[tile];
+  const float4 rb = g.recB[e];
+  const uint32_t l = __float_as_uint(rb.w);
+  float x_kf[6], x_l[3];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) x_kf[i] = g.cam_mean[c * 6 + i];
+  const float4 m = g.lmk_b[(size_t)l * GBP_LMKB_QUADS + 3];
+  x_l[0] = m.x; x_l[1] = m.y; x_l[2] = m.z;
+  const uint32_t robust = relinearise_in_place(g.fac, g.E_pad, e, make_float4(g.K[0], g.K[1], g.K[2], g.K[3]), g.hp.Nstds,
+                                                   rb.x, rb.y, rb.z, x_kf[0], x_kf[1], x_kf[2], x_kf[3], x_kf[4], x_kf[5],
+                                                   x_l[0], x_l[1], x_l[2], true);
+  flags = (flags & ~GBP_FLAG_ROBUST) | (robust ? GBP_FLAG_ROBUST : 0u);
+  ra.z = __uint_as_float(flags);
+  g.recA[e] = ra;
+}
+
+// WeakenPriorVertex on every variable (ba/ba.cpp:165-182).
+__global__ void k_weaken(const DeviceGraph g) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < g.C) {
+    const uint32_t fl = g.cam_wflag[i];
+    if (fl >= 1 && fl <= 5) {  // quirk Q5
+      g.cam_wflag[i] = fl - 1;
+      const float s = g.cam_scaling[i];
+      for (int k = 0; k < 6; ++k) g.cam_prior_eta[i * 6 + k] = fm(g.cam_prior_eta[i * 6 + k], s);
+      for (int k = 0; k < 36; ++k) g.cam_prior_lam[i * 36 + k] = fm(g.cam_prior_lam[i * 36 + k], s);
+    }
+  } else if (i < g.C + g.L) {
+    const uint32_t l = i - g.C;
+    const uint32_t fl = g.lmk_wflag[l];
+    if (fl >= 1 && fl <= 5) {
+      g.lmk_wflag[l] = fl - 1;
+      const float s = g.lmk_scaling[l];
+      float4* p = g.lmk_prior + (size_t)l * 3;
+      for (int q = 0; q < 3; ++q) {
+        float4 v = p[q];
+        v.x = fm(v.x, s); v.y = fm(v.y, s); v.z = fm(v.z, s); v.w = fm(v.w, s);
+        p[q] = v;
+      }
+    }
+  }
+}
+
+// ---- metric (ba/util.cpp:74-144) ------------------------------------------------
+struct MetricPartial {
+  float sum_norm, sum_sq;
+  uint32_t n_relins, n_robust, n_active, pad;
+};
+
+__global__ void __launch_bounds__(GBP_TILE) k_metric(const DeviceGraph g, const uint32_t n_active_total,
+                                                    MetricPartial* __restrict__ out) {
+  __shared__ float s_cam[15];  // mean 6 | R 9
+  __shared__ float s_f[2][GBP_TILE / 32];
+  __shared__ uint32_t s_u[3][GBP_TILE / 32];
+  const uint32_t tile = blockIdx.x, tid = threadIdx.x;
+  const uint32_t c = g.tile_cam[tile];
+  const size_t e = (size_t)tile * GBP_TILE + tid;
+  if (tid < 6) s_cam[tid] = g.cam_mean[c * 6 + tid];
+  else if (tid < 15) s_cam[tid] = g.cam_R[c * 9 + (tid - 6)];
+  __syncthreads();
+  const float4 ra = g.recA[e];
+  const uint32_t flags = __float_as_uint(ra.z);
+  float nrm = 0.f, sq = 0.f;
+  uint32_t relin = 0, robust = 0, act = 0;
+  if (!(flags & GBP_FLAG_PAD)) {
+    robust = (flags & GBP_FLAG_ROBUST) ? 1u : 0u;
+    relin = (__float_as_int(ra.y) == -g.hp.num_undamped_iters) ? 1u : 0u;
+    act = (flags & GBP_FLAG_ACTIVE) ? 1u : 0u;
+    // quirk Q7: the reference evaluates edges [0, n_active) of the ORIGINAL order
+    if (g.edge_orig[e] < n_active_total) {
+      const float4 rb = g.recB[e];
+      const float4 m = g.lmk_b[(size_t)__float_as_uint(rb.w) * GBP_LMKB_QUADS + 3];
+      float y[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+        y[i] = s_cam[6 + i * 3] * m.x + s_cam[6 + i * 3 + 1] * m.y + s_cam[6 + i * 3 + 2] * m.z + s_cam[i];
+      const float u = g.K[0] * y[0] / y[2] + g.K[2];
+      const float v = g.K[1] * y[1] / y[2] + g.K[3];
+      const float r0 = rb.x - u, r1 = rb.y - v;
+      const float s = r0 * r0 + r1 * r1;
+      nrm = sqrtf(s);
+      sq = 0.5f * s;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    nrm += __shfl_down_sync(0xffffffffu, nrm, o);
+    sq += __shfl_down_sync(0xffffffffu, sq, o);
+    relin += __shfl_down_sync(0xffffffffu, relin, o);
+    robust += __shfl_down_sync(0xffffffffu, robust, o);
+    act += __shfl_down_sync(0xffffffffu, act, o);
+  }
+  const int w = tid >> 5;
+  if ((tid & 31) == 0) {
+    s_f[0][w] = nrm; s_f[1][w] = sq;
+    s_u[0][w] = relin; s_u[1][w] = robust; s_u[2][w] = act;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    MetricPartial p = {0.f, 0.f, 0u, 0u, 0u, 0u};
+    for (int i = 0; i < GBP_TILE / 32; ++i) {
+      p.sum_norm += s_f[0][i]; p.sum_sq += s_f[1][i];
+      p.n_relins += s_u[0][i]; p.n_robust += s_u[1][i]; p.n_active += s_u[2][i];
+    }
+    out[tile] = p;
+  }
+}
+
+struct DeviceStats {  // == gbp_iter_stats
+  float reproj_mean, cost;
+  uint32_t n_relins, n_robust, n_active, reserved;
+};
+
+// One block: fixed-order reduction of the per-tile partials in double.
+__global__ void __launch_bounds__(256) k_metric_finish(const MetricPartial* __restrict__ parts, const uint32_t n_tiles,
+                                                      DeviceStats* __restrict__ out) {
+  __shared__ double s_d[2][256];
+  __shared__ uint32_t s_u[3][256];
+  const uint32_t tid = threadIdx.x;
+  double a = 0.0, b = 0.0;
+  uint32_t r = 0, ro = 0, ac = 0;
+  for (uint32_t t = tid; t < n_tiles; t += 256) {
+    const MetricPartial p = parts[t];
+    a += (double)p.sum_norm; b += (double)p.sum_sq;
+    r += p.n_relins; ro += p.n_robust; ac += p.n_active;
+  }
+  s_d[0][tid] = a; s_d[1][tid] = b; s_u[0][tid] = r; s_u[1][tid] = ro; s_u[2][tid] = ac;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) {
+      s_d[0][tid] += s_d[0][tid + o]; s_d[1][tid] += s_d[1][tid + o];
+      s_u[0][tid] += s_u[0][tid + o]; s_u[1][tid] += s_u[1][tid + o]; s_u[2][tid] += s_u[2][tid + o];
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    DeviceStats s;
+    s.n_active = s_u[2][0];
+    s.reproj_mean = (float)(s_d[0][0] / (double)s.n_active);
+    s.cost = (float)s_d[1][0];
+    s.n_relins = s_u[0][0];
+    s.n_robust = s_u[1][0];
+    s.reserved = 0;
+    *out = s;
+  }
+}
+
+// READ_PROG helpers: gather per-edge scalars back into the reference's edge order
+// and unpack the landmark belief records.
+__global__ void k_export_edges(const DeviceGraph g, const uint32_t* __restrict__ pos_of_orig,
+                               float* __restrict__ damping, int32_t* __restrict__ dcount,
+                               uint32_t* __restrict__ robust) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.E) return;
+  const float4 ra = g.recA[pos_of_orig[i]];
+  damping[i] = ra.x;
+  dcount[i] = __float_as_int(ra.y);
+  robust[i] = (__float_as_uint(ra.z) & GBP_FLAG_ROBUST) ? 1u : 0u;
+}
+
+__global__ void k_export_lmk_beliefs(const DeviceGraph g, float* __restrict__ eta, float* __restrict__ lam) {
+  const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= g.L) return;
+  const float4* p = g.lmk_b + (size_t)l * GBP_LMKB_QUADS;
+  const float4 a = p[0], b = p[1], c = p[2];
+  eta[l * 3] = a.x; eta[l * 3 + 1] = a.y; eta[l * 3 + 2] = a.z;
+  float* o = lam + (size_t)l * 9;
+  o[0] = a.w; o[1] = b.x; o[2] = b.y; o[3] = b.z; o[4] = b.w; o[5] = c.x; o[6] = c.y; o[7] = c.z; o[8] = c.w;
+}
+
+// NEW_KEYFRAME / set_tensor helper: scatter per-edge scalars given in the
+// reference's edge order into the edge-slot records (null pointer = keep).
+__global__ void k_import_edges(const DeviceGraph g, const uint32_t* __restrict__ pos_of_orig,
+                               const float* __restrict__ damping, const int32_t* __restrict__ dcount,
+                               const uint32_t* __restrict__ active, const uint32_t* __restrict__ robust,
+                               const float* __restrict__ dmu, const int clear_muvalid) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.E) return;
+  const uint32_t p = pos_of_orig[i];
+  float4 ra = g.recA[p];
+  uint32_t flags = __float_as_uint(ra.z);
+  if (damping) ra.x = damping[i];
+  if (dcount) ra.y = __int_as_float(dcount[i]);
+  if (active) flags = (flags & ~GBP_FLAG_ACTIVE) | ((active[i] == 1u) ? GBP_FLAG_ACTIVE : 0u);
+  if (robust) flags = (flags & ~GBP_FLAG_ROBUST) | (robust[i] ? GBP_FLAG_ROBUST : 0u);
+  if (clear_muvalid) flags &= ~GBP_FLAG_MUVALID;
+  if (dmu) ra.w = dmu[i];
+  ra.z = __uint_as_float(flags);
+  g.recA[p] = ra;
+}
+
+// set_tensor on a belief tensor: recompute the per-variable means (and camera
+// rotations) from the stored beliefs without re-summing the messages.
+__global__ void k_means_from_beliefs(const DeviceGraph g) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < g.C) {
+    float eta[6], lamL[21], mean[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) eta[k] = g.cam_b_eta[i * 6 + k];
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int j = 0; j <= r; ++j) lamL[lt(r, j)] = g.cam_b_lam[i * 36 + r * 6 + j];
+    inf2mean6(eta, lamL, mean);
+    const float w[3] = {mean[3], mean[4], mean[5]};
+    float R[9];
+    so3exp(w, R);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) g.cam_mean[i * 6 + k] = mean[k];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) g.cam_R[i * 9 + k] = R[k];
+  } else if (i < g.C + g.L) {
+    const uint32_t l = i - g.C;
+    float4* o = g.lmk_b + (size_t)l * GBP_LMKB_QUADS;
+    const float4 a = o[0], b = o[1], c = o[2];
+    const float eta[3] = {a.x, a.y, a.z};
+    const float lam[9] = {a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+    float mean[3];
+    inf2mean3(eta, lam, mean);
+    o[3] = make_float4(mean[0], mean[1], mean[2], 0.f);
+  }
+}
+
+}  // namespace gbp

@@ -1,0 +1,214 @@
+"""GBPEngine: Python mirror of the reference's engine/program interface.
+
+The reference host loop drives its device with `engine.run(PROG)` over seven
+programs (ba/ba.cpp:925-934, ba/slam.cpp:937-948).  Each method below is the
+call a maintainer would make instead, forwarding to the C ABI of
+include/gbp_cuda.h:
+
+    WRITE_PROG + LINEARISE_PROG -> GBPEngine(problem)        (gbp_cuda_init)
+    GBP_PROG                    -> engine.iterate(n)         (gbp_cuda_iterate)
+    WEAKEN_PRIORS               -> engine.weaken_priors()
+    READ_PROG                   -> engine.get_beliefs()
+    READ_PRIORS                 -> engine.get_priors()
+    NEW_KEYFRAME                -> engine.add_keyframe(...)
+
+The class is generic over (library, symbol prefix) only so that the test-suite
+can drive the CPU oracle through the very same code; the product always binds
+libgbp_cuda.so / "gbp_cuda_" and raises if that library is missing.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import GbpIterStats, GbpOpts
+
+_F32 = np.float32
+_TENSOR_DTYPES = {
+    "damping_count": np.int32, "active_flag": np.uint32, "robust_flag": np.uint32,
+    "cam_weaken_flag": np.uint32, "lmk_weaken_flag": np.uint32,
+}
+TENSOR_NAMES = [
+    "cam_beliefs_eta", "cam_beliefs_lambda", "lmk_beliefs_eta", "lmk_beliefs_lambda",
+    "cam_messages_eta", "cam_messages_lambda", "lmk_messages_eta", "lmk_messages_lambda",
+    "pcam_messages_eta", "pcam_messages_lambda", "plmk_messages_eta", "plmk_messages_lambda",
+    "factor_potentials_eta", "factor_potentials_lambda", "damping", "damping_count", "mu", "oldmu", "dmu",
+    "active_flag", "robust_flag", "measurements", "meas_variances", "cam_scaling", "lmk_scaling",
+    "cam_weaken_flag", "lmk_weaken_flag",
+]
+
+
+def default_opts(**kw):
+    """gbp_opts with the hyper-parameters of ba/gbp_codelets.cpp:11-16."""
+    o = GbpOpts()
+    o.device = 0
+    o.maxeta_damping = 0.4
+    o.num_undamped_iters = 8
+    o.dmu_threshold = 3e-3
+    o.min_linear_iters = 10
+    o.Nstds = 2.5
+    o.use_cuda_graph = 1
+    for k, v in kw.items():
+        if not hasattr(o, k):
+            raise TypeError(f"unknown option {k}")
+        setattr(o, k, v)
+    return o
+
+
+def stats_to_dict(s):
+    return {"reproj_mean": s.reproj_mean, "cost": s.cost, "n_relins": s.n_relins, "n_robust": s.n_robust,
+            "n_active": s.n_active}
+
+
+class GBPEngine:
+    def __init__(self, problem, opts=None, lib=None, prefix="gbp_cuda_", keepalive=None):
+        if lib is None:
+            lib = _capi.load_library()
+        self._lib = lib
+        self._prefix = prefix
+        self._f = _capi.bind_engine(lib, prefix)
+        self._keepalive = keepalive
+        self.opts = opts if opts is not None else default_opts()
+        self._h = C.c_void_p()
+        self._check(self._f["init"](C.byref(problem), C.byref(self.opts), C.byref(self._h)))
+        c, l, e, mk, ml = (C.c_uint32() for _ in range(5))
+        self._check(self._f["dims"](self._h, c, l, e, mk, ml))
+        self.n_keyframes, self.n_points, self.n_edges = c.value, l.value, e.value
+        self.max_nkfedges, self.max_nlmkedges = mk.value, ml.value
+
+    # -- plumbing ---------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            msg = ""
+            try:
+                fn = getattr(self._lib, self._prefix + "last_error")
+                fn.restype = C.c_char_p
+                msg = fn().decode()
+            except AttributeError:
+                pass
+            raise RuntimeError(f"{self._prefix}* failed with code {rc}: {msg}")
+
+    @property
+    def handle(self):
+        return self._h
+
+    def close(self):
+        if self._h:
+            self._f["free"](self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- programs ---------------------------------------------------------
+    def weaken_priors(self):
+        self._check(self._f["weaken_priors"](self._h))
+
+    def iterate(self, n_sweeps=1, stats=False):
+        if stats:
+            arr = (GbpIterStats * n_sweeps)()
+            self._check(self._f["iterate"](self._h, n_sweeps, arr))
+            return [stats_to_dict(s) for s in arr]
+        self._check(self._f["iterate"](self._h, n_sweeps, None))
+        return None
+
+    def eval(self):
+        s = GbpIterStats()
+        self._check(self._f["eval"](self._h, C.byref(s)))
+        return stats_to_dict(s)
+
+    def get_beliefs(self):
+        Cn, Ln, En = self.n_keyframes, self.n_points, self.n_edges
+        out = {
+            "cam_beliefs_eta": np.empty(6 * Cn, _F32), "cam_beliefs_lambda": np.empty(36 * Cn, _F32),
+            "lmk_beliefs_eta": np.empty(3 * Ln, _F32), "lmk_beliefs_lambda": np.empty(9 * Ln, _F32),
+            "damping": np.empty(En, _F32), "damping_count": np.empty(En, np.int32),
+            "robust_flag": np.empty(En, np.uint32),
+        }
+        f = lambda k: out[k].ctypes.data_as(_capi.c_f32p)
+        self._check(self._f["get_beliefs"](self._h, f("cam_beliefs_eta"), f("cam_beliefs_lambda"),
+                                           f("lmk_beliefs_eta"), f("lmk_beliefs_lambda"), f("damping"),
+                                           out["damping_count"].ctypes.data_as(_capi.c_i32p),
+                                           out["robust_flag"].ctypes.data_as(_capi.c_u32p)))
+        return out
+
+    def get_priors(self):
+        Cn, Ln = self.n_keyframes, self.n_points
+        out = {"cam_priors_eta": np.empty(6 * Cn, _F32), "cam_priors_lambda": np.empty(36 * Cn, _F32),
+               "lmk_priors_eta": np.empty(3 * Ln, _F32), "lmk_priors_lambda": np.empty(9 * Ln, _F32)}
+        f = lambda k: out[k].ctypes.data_as(_capi.c_f32p)
+        self._check(self._f["get_priors"](self._h, f("cam_priors_eta"), f("cam_priors_lambda"),
+                                          f("lmk_priors_eta"), f("lmk_priors_lambda")))
+        return out
+
+    def add_keyframe(self, damping_count, cam_prior_eta, cam_prior_lambda, lmk_prior_eta, lmk_prior_lambda,
+                     active_flag, cam_weaken_flag, lmk_weaken_flag):
+        def p(a, dt, ct):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dtype=dt)
+            keep.append(a)
+            return a.ctypes.data_as(ct)
+        keep = []
+        self._check(self._f["add_keyframe"](
+            self._h, p(damping_count, np.int32, _capi.c_i32p), p(cam_prior_eta, _F32, _capi.c_f32p),
+            p(cam_prior_lambda, _F32, _capi.c_f32p), p(lmk_prior_eta, _F32, _capi.c_f32p),
+            p(lmk_prior_lambda, _F32, _capi.c_f32p), p(active_flag, np.uint32, _capi.c_u32p),
+            p(cam_weaken_flag, np.uint32, _capi.c_u32p), p(lmk_weaken_flag, np.uint32, _capi.c_u32p)))
+
+    # -- codelet-level entry points (Execute(cs_*)) -------------------------
+    def relinearise_factors(self):
+        self._check(self._f["relinearise_factors"](self._h))
+
+    def prep_messages(self):
+        self._check(self._f["prep_messages"](self._h))
+
+    def compute_messages(self):
+        self._check(self._f["compute_messages"](self._h))
+
+    def update_beliefs(self):
+        self._check(self._f["update_beliefs"](self._h))
+
+    def weaken_prior_vertices(self):
+        self._check(self._f["weaken_prior_vertices"](self._h))
+
+    # -- tensors by reference name ------------------------------------------
+    def tensor_nbytes(self, name):
+        n = C.c_size_t()
+        self._check(self._f["tensor_nbytes"](self._h, name.encode(), C.byref(n)))
+        return n.value
+
+    def get_tensor(self, name):
+        n = self.tensor_nbytes(name)
+        dt = _TENSOR_DTYPES.get(name, _F32)
+        out = np.empty(n // 4, dtype=dt)
+        self._check(self._f["get_tensor"](self._h, name.encode(), out.ctypes.data_as(C.c_void_p), n))
+        return out
+
+    def set_tensor(self, name, arr):
+        dt = _TENSOR_DTYPES.get(name, _F32)
+        a = np.ascontiguousarray(arr, dtype=dt).reshape(-1)
+        self._check(self._f["set_tensor"](self._h, name.encode(), a.ctypes.data_as(C.c_void_p), a.nbytes))
+
+    def snapshot(self, names=None):
+        return {n: self.get_tensor(n) for n in (names or TENSOR_NAMES)}
+
+    def restore(self, snap):
+        for n, a in snap.items():
+            self.set_tensor(n, a)
+
+    # -- CUDA-only conveniences -----------------------------------------------
+    def last_timing(self):
+        ms = C.c_float()
+        k = C.c_uint64()
+        self._check(self._lib.gbp_cuda_last_timing(self._h, C.byref(ms), C.byref(k)))
+        return ms.value, k.value
+
+    def iterate_async(self, n_sweeps):
+        self._check(self._lib.gbp_cuda_iterate_async(self._h, n_sweeps))
+
+    def synchronize(self):
+        self._check(self._lib.gbp_cuda_synchronize(self._h))

@@ -1,0 +1,211 @@
+/*
+ * gbp_cuda.h -- C ABI of the B200-native GBP bundle-adjustment hot path.
+ *
+ * This is the drop-in boundary for the Poplar graph/engine layer of
+ * joeaortiz/gbp-poplar (reference paths below are relative to the reference
+ * tree).  The reference host loop talks to its device through
+ *   - numbered programs run with engine.run(id)        ba/ba.cpp:925-934, ba/slam.cpp:937-948
+ *   - named FIFOs bound to caller-owned host buffers   ba/ba.cpp:940-976
+ * Every entry point below replaces one of those programs / stream groups.
+ * All pointers are caller-owned HOST memory in the reference's own (AoS,
+ * padded) layouts; the library owns every device buffer.  No torch / C++
+ * types cross this boundary.
+ *
+ * Return value: 0 = GBP_OK, negative = error (text via gbp_cuda_last_error()).
+ * A handle is not thread-safe; distinct handles are independent.
+ * There is NO CPU fallback: without a CUDA device every compute entry point
+ * fails with GBP_ERR_CUDA.
+ */
+#ifndef GBP_CUDA_H_
+#define GBP_CUDA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GBP_OK 0
+#define GBP_ERR_ARG (-1)      /* bad argument / inconsistent problem        */
+#define GBP_ERR_CUDA (-2)     /* CUDA runtime error or no device            */
+#define GBP_ERR_NAME (-3)     /* unknown tensor name                        */
+#define GBP_ERR_SIZE (-4)     /* nbytes does not match the tensor           */
+#define GBP_ERR_IO (-5)       /* file could not be opened / parsed          */
+#define GBP_ERR_COMM (-6)     /* multi-GPU exchange not initialised/failed  */
+
+/* Fixed sizes of the reference's factor graph (ba/ba.cpp:576-578). */
+#define GBP_CAM_DOFS 6
+#define GBP_LMK_DOFS 3
+#define GBP_FACTOR_DOFS 9
+
+/*
+ * One bundle-adjustment problem exactly as the reference's host code hands it
+ * to WRITE_PROG (ba/ba.cpp:868-886, stream bindings ba/ba.cpp:940-961).
+ * Arrays marked "may be NULL" default to what ba.cpp streams (zeros).
+ */
+typedef struct gbp_problem {
+  uint32_t n_keyframes;               /* C  */
+  uint32_t n_points;                  /* L  */
+  uint32_t n_edges;                   /* E  */
+  const uint32_t* cam_ids;            /* [E]   measurements_camIDs  ba/ba.cpp:505 */
+  const uint32_t* lmk_ids;            /* [E]   measurements_lIDs    ba/ba.cpp:506 */
+  const float* measurements;          /* [2E]  ba/ba.cpp:504 */
+  const float* meas_variances;        /* [E]   ba/ba.cpp:503 */
+  float K[9];                         /* shared 3x3 intrinsics, row-major; the reference
+                                         replicates it per edge (ba/ba.cpp:494-501) */
+  const float* cam_priors_eta;        /* [6C]  slot 0 of cam_messages_eta   ba/ba.cpp:880 */
+  const float* cam_priors_lambda;     /* [36C] slot 0 of cam_messages_lambda ba/ba.cpp:881 */
+  const float* lmk_priors_eta;        /* [3L]  ba/ba.cpp:882 */
+  const float* lmk_priors_lambda;     /* [9L]  ba/ba.cpp:883 */
+  const float* cam_scaling;           /* [C]   ba/ba.cpp:561-568 */
+  const float* lmk_scaling;           /* [L]   ba/ba.cpp:569-572 */
+  const uint32_t* cam_weaken_flag;    /* [C]   ba/ba.cpp:589 */
+  const uint32_t* lmk_weaken_flag;    /* [L]   ba/ba.cpp:590 */
+  const uint32_t* active_flag;        /* [E]   ba/ba.cpp:588; may be NULL = all 1 */
+  const float* damping;               /* [E]   ba/ba.cpp:580; may be NULL = 0 */
+  const int32_t* damping_count;       /* [E]   ba/ba.cpp:581; may be NULL = -15 */
+  const float* mu;                    /* [9E]  ba/ba.cpp:582; may be NULL = 0 */
+  const float* oldmu;                 /* [9E]  ba/ba.cpp:583; may be NULL = 0 */
+} gbp_problem;
+
+/* Hyper-parameters = the file-scope globals of ba/gbp_codelets.cpp:11-16. */
+typedef struct gbp_opts {
+  int device;                 /* CUDA device ordinal (default 0)                       */
+  float maxeta_damping;       /* 0.4   gbp_codelets.cpp:11 */
+  int num_undamped_iters;     /* 8     gbp_codelets.cpp:12 */
+  float dmu_threshold;        /* 3e-3  gbp_codelets.cpp:13 */
+  int min_linear_iters;       /* 10    gbp_codelets.cpp:14 */
+  float Nstds;                /* 2.5   gbp_codelets.cpp:16 */
+  int use_cuda_graph;         /* 1 = replay sweeps through a CUDA graph (default 1)     */
+  int reserved[7];
+} gbp_opts;
+
+/* Per-sweep metrics = what the reference's host computes after READ_PROG
+ * (ba/ba.cpp:1011-1028, ba/util.cpp:74-144), evaluated on the device. */
+typedef struct gbp_iter_stats {
+  float reproj_mean;          /* mean |z - h(mu)| over active edges   util.cpp:126,143 */
+  float cost;                 /* sum 0.5*|r|^2, un-robustified         util.cpp:127     */
+  uint32_t n_relins;          /* #edges with damping_count == -num_undamped_iters  ba.cpp:1016-1020 */
+  uint32_t n_robust;          /* sum of robust_flag over all edges     ba.cpp:1013-1015 */
+  uint32_t n_active;          /* #active edges                          util.cpp:95-97   */
+  uint32_t reserved;
+} gbp_iter_stats;
+
+typedef struct gbp_handle gbp_handle;
+
+/* Sharding description for the multi-GPU path (one process per GPU).  The
+ * exchange itself is performed by the caller-provided callbacks or by NCCL
+ * (gbp_cuda_attach_nccl). rank r owns cameras [cam_begin, cam_end). */
+typedef struct gbp_shard_plan {
+  uint32_t world;             /* number of ranks                                   */
+  uint32_t rank;              /* this rank                                         */
+  uint32_t cam_begin;         /* first camera owned by this rank                   */
+  uint32_t cam_end;           /* one past the last owned camera                    */
+  uint32_t n_local_edges;     /* edges whose camera is owned here                  */
+  uint32_t n_local_points;    /* landmarks touched by local edges                  */
+  uint32_t n_boundary_points; /* landmarks observed from >1 rank (global count)    */
+  uint32_t reserved;
+} gbp_shard_plan;
+
+const char* gbp_cuda_last_error(void);
+const char* gbp_cuda_version(void);
+void gbp_opts_default(gbp_opts* o);
+
+/* Graph build + WRITE_PROG + LINEARISE_PROG (ba/ba.cpp:659-986): uploads the
+ * problem, zero-fills all non-prior message slots (the reference relies on
+ * zeroed device memory, ba/ba.cpp:868-886), sums the priors into the beliefs
+ * and linearises every factor (RelineariseFactorVertex, no active check). */
+int gbp_cuda_init(const gbp_problem* p, const gbp_opts* o, gbp_handle** out);
+
+/* Engine teardown. */
+int gbp_cuda_free(gbp_handle* h);
+
+/* WEAKEN_PRIORS (ba/ba.cpp:863-865): WeakenPriorVertex on every variable,
+ * then the belief update. */
+int gbp_cuda_weaken_priors(gbp_handle* h);
+
+/* GBP_PROG x n_sweeps (ba/ba.cpp:895-905).  If stats != NULL it must hold
+ * n_sweeps entries; entry i is evaluated on the beliefs after sweep i. */
+int gbp_cuda_iterate(gbp_handle* h, int n_sweeps, gbp_iter_stats* stats);
+
+/* Metrics of the current beliefs (what the host prints as "Initial
+ * Reprojection error", ba/ba.cpp:992-996). */
+int gbp_cuda_eval(gbp_handle* h, gbp_iter_stats* out);
+
+/* READ_PROG (ba/ba.cpp:908-916). Any pointer may be NULL to skip it. */
+int gbp_cuda_get_beliefs(gbp_handle* h, float* cam_eta, float* cam_lambda, float* lmk_eta,
+                         float* lmk_lambda, float* damping, int32_t* damping_count,
+                         uint32_t* robust_flag);
+
+/* READ_PRIORS (ba/slam.cpp:913-917): slot 0 of the four message tensors. */
+int gbp_cuda_get_priors(gbp_handle* h, float* cam_eta, float* cam_lambda, float* lmk_eta,
+                        float* lmk_lambda);
+
+/* NEW_KEYFRAME (ba/slam.cpp:919-928) including the trailing belief update.
+ * Streams damping_count, the four prior tensors, active_flag and both weaken
+ * flag tensors; `damping` itself is not re-streamed (as in the reference). */
+int gbp_cuda_add_keyframe(gbp_handle* h, const int32_t* damping_count, const float* cam_prior_eta,
+                          const float* cam_prior_lambda, const float* lmk_prior_eta,
+                          const float* lmk_prior_lambda, const uint32_t* active_flag,
+                          const uint32_t* cam_weaken_flag, const uint32_t* lmk_weaken_flag);
+
+/* Codelet-level entry points = Execute(cs_*) of one compute set on the
+ * handle's state (used by the parity tests).
+ *   relinearise_factors      cs_relinearise         ba/ba.cpp:68-97   gbp_codelets.cpp:20-172
+ *   prep_messages            cs_compmess_prep       ba/ba.cpp:234,249 gbp_codelets.cpp:215-379
+ *   compute_messages         Copy(mu,oldmu) + cs_computemessages + the four
+ *                            Copy(messages,pmessages) that always follow it in
+ *                            GBP_PROG (ba/ba.cpp:898-905); the copies are pure
+ *                            double-buffer bookkeeping and commute with update_beliefs
+ *   update_beliefs           prog_ub                ba/ba.cpp:104-139
+ *   weaken_prior_vertices    cs_weaken_prior        ba/ba.cpp:144-185 (no belief update) */
+int gbp_cuda_relinearise_factors(gbp_handle* h);
+int gbp_cuda_prep_messages(gbp_handle* h);
+int gbp_cuda_compute_messages(gbp_handle* h);
+int gbp_cuda_update_beliefs(gbp_handle* h);
+int gbp_cuda_weaken_prior_vertices(gbp_handle* h);
+
+/* Snapshot / restore of any device tensor by its reference name, in the
+ * reference's padded layout (ba/ba.cpp:665-687,759-775):
+ *   cam_beliefs_eta[6C] cam_beliefs_lambda[36C] lmk_beliefs_eta[3L] lmk_beliefs_lambda[9L]
+ *   cam_messages_eta[C*SK*6] cam_messages_lambda[C*SK*36] lmk_messages_eta[L*SL*3]
+ *   lmk_messages_lambda[L*SL*9] and the p* previous-message twins
+ *   factor_potentials_eta[9E] factor_potentials_lambda[81E]
+ *   damping[E] damping_count[E] mu[9E] oldmu[9E] dmu[E] active_flag[E] robust_flag[E]
+ *   measurements[2E] meas_variances[E] cam_scaling[C] lmk_scaling[L]
+ *   cam_weaken_flag[C] lmk_weaken_flag[L]
+ * with SK = max_nkfedges+1, SL = max_nlmkedges+1 (slot 0 = prior). */
+int gbp_cuda_tensor_nbytes(gbp_handle* h, const char* name, size_t* nbytes);
+int gbp_cuda_get_tensor(gbp_handle* h, const char* name, void* dst, size_t nbytes);
+int gbp_cuda_set_tensor(gbp_handle* h, const char* name, const void* src, size_t nbytes);
+
+/* Graph shape as the reference derives it (ba/ba.cpp:514-521,594-595). */
+int gbp_cuda_dims(gbp_handle* h, uint32_t* n_keyframes, uint32_t* n_points, uint32_t* n_edges,
+                  uint32_t* max_nkfedges, uint32_t* max_nlmkedges);
+
+/* Device timing of the last gbp_cuda_iterate call (CUDA events on the
+ * handle's stream): total milliseconds and number of kernels launched. */
+int gbp_cuda_last_timing(gbp_handle* h, float* ms_total, uint64_t* kernels_launched);
+
+/* ---- asynchronous / resident use (bench, multi-GPU) ------------------- */
+/* Enqueue n sweeps on the handle's stream without synchronising. */
+int gbp_cuda_iterate_async(gbp_handle* h, int n_sweeps);
+int gbp_cuda_synchronize(gbp_handle* h);
+/* The cudaStream_t the handle launches on (as void*), for event timing. */
+void* gbp_cuda_stream(gbp_handle* h);
+
+/* ---- multi-GPU: camera-range sharding with boundary-landmark exchange --- */
+/* Pure host: contiguous camera ranges balanced by edge count. */
+int gbp_cuda_plan_shard(const gbp_problem* p, uint32_t world, uint32_t rank, gbp_shard_plan* out);
+/* Build the handle for this rank's shard of `p` (p is the GLOBAL problem).
+ * nccl_unique_id: 128 bytes from gbp_cuda_nccl_unique_id on rank 0, broadcast
+ * by the caller's plumbing (torch.distributed). */
+int gbp_cuda_nccl_unique_id(void* id128);
+int gbp_cuda_init_shard(const gbp_problem* p, const gbp_opts* o, uint32_t world, uint32_t rank,
+                        const void* nccl_unique_id, gbp_handle** out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GBP_CUDA_H_ */
