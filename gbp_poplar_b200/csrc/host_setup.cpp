@@ -589,45 +589,44 @@ int gbp_synth_generate(uint32_t C, uint32_t L, double obs_per_point, uint32_t se
   std::vector<uint32_t> deg(C, 0);
   const int W = 40;
   std::vector<int> cand(2 * W + 1);
+  std::vector<Obs> mine;
   for (uint32_t l = 0; l < L; ++l) {
     const uint32_t a = (uint32_t)(((uint64_t)l * C) / L);  // anchor camera, spread evenly
-    const double u = 20 + 600 * rng.uni(), v = 20 + 440 * rng.uni(), d = 0.5 + 4.5 * rng.uni();
-    const double yc[3] = {d * (u - cx) / fx, d * (v - cy) / fy, d};
-    const double* R = &Rgt[(size_t)9 * a];
-    const double* x = &cam_gt[(size_t)6 * a];
     double* p = &pts_gt[(size_t)3 * l];
-    const double dd[3] = {yc[0] - x[0], yc[1] - x[1], yc[2] - x[2]};
-    for (int i = 0; i < 3; ++i) p[i] = R[i] * dd[0] + R[3 + i] * dd[1] + R[6 + i] * dd[2];
-    int k = rng.poisson(obs_per_point);
-    k = std::max(2, std::min(k, (int)(2 * obs_per_point)));
-    for (int i = 0; i <= 2 * W; ++i) cand[i] = i - W;
-    for (int i = 2 * W; i > 0; --i) std::swap(cand[i], cand[rng.next() % (uint64_t)(i + 1)]);
-    // the anchor always observes the landmark; then random nearby cameras
-    int found = 0;
-    for (int ci = -1; ci <= 2 * W && found < k; ++ci) {
-      const int off = (ci < 0) ? 0 : cand[ci];
-      if (ci >= 0 && off == 0) continue;
-      const long cc = (long)a + off;
-      if (cc < 0 || cc >= (long)C) continue;
-      const double* Rc = &Rgt[(size_t)9 * cc];
-      const double* xc = &cam_gt[(size_t)6 * cc];
-      double y[3];
-      for (int i = 0; i < 3; ++i) y[i] = Rc[i * 3] * p[0] + Rc[i * 3 + 1] * p[1] + Rc[i * 3 + 2] * p[2] + xc[i];
-      if (y[2] < 0.3) continue;
-      const double pu = fx * y[0] / y[2] + cx, pv = fy * y[1] / y[2] + cy;
-      if (pu < 19 || pu > 620 || pv < 19 || pv > 460) continue;
-      obs.push_back({(uint32_t)cc, l, pu + rng.normal(), pv + rng.normal()});
-      deg[cc]++;
-      ++found;
+    // re-draw the landmark until at least two cameras see it inside the image
+    for (int attempt = 0; attempt < 200; ++attempt) {
+      const double u = 20 + 600 * rng.uni(), v = 20 + 440 * rng.uni(), d = 0.5 + 4.5 * rng.uni();
+      const double yc[3] = {d * (u - cx) / fx, d * (v - cy) / fy, d};
+      const double* R = &Rgt[(size_t)9 * a];
+      const double* x = &cam_gt[(size_t)6 * a];
+      const double dd[3] = {yc[0] - x[0], yc[1] - x[1], yc[2] - x[2]};
+      for (int i = 0; i < 3; ++i) p[i] = R[i] * dd[0] + R[3 + i] * dd[1] + R[6 + i] * dd[2];
+      int k = rng.poisson(obs_per_point);
+      k = std::max(2, std::min(k, (int)(2 * obs_per_point)));
+      for (int i = 0; i <= 2 * W; ++i) cand[i] = i - W;
+      for (int i = 2 * W; i > 0; --i) std::swap(cand[i], cand[rng.next() % (uint64_t)(i + 1)]);
+      mine.clear();
+      // the anchor is tried first; then random nearby cameras
+      for (int ci = -1; ci <= 2 * W && (int)mine.size() < k; ++ci) {
+        const int off = (ci < 0) ? 0 : cand[ci];
+        if (ci >= 0 && off == 0) continue;
+        const long cc = (long)a + off;
+        if (cc < 0 || cc >= (long)C) continue;
+        const double* Rc = &Rgt[(size_t)9 * cc];
+        const double* xc = &cam_gt[(size_t)6 * cc];
+        double y[3];
+        for (int i = 0; i < 3; ++i) y[i] = Rc[i * 3] * p[0] + Rc[i * 3 + 1] * p[1] + Rc[i * 3 + 2] * p[2] + xc[i];
+        if (y[2] < 0.3) continue;
+        const double pu = fx * y[0] / y[2] + cx, pv = fy * y[1] / y[2] + cy;
+        if (pu < 22 || pu > 618 || pv < 22 || pv > 458) continue;
+        const double nu = std::max(-2.5, std::min(2.5, rng.normal())), nv = std::max(-2.5, std::min(2.5, rng.normal()));
+        mine.push_back({(uint32_t)cc, l, pu + nu, pv + nv});
+      }
+      if (mine.size() >= 2) break;
     }
-    if (found < 2) {  // degenerate near the trajectory ends: force the neighbour of the anchor
-      const uint32_t cc = (a + 1 < C) ? a + 1 : a - 1;
-      const double* Rc = &Rgt[(size_t)9 * cc];
-      const double* xc = &cam_gt[(size_t)6 * cc];
-      double y[3];
-      for (int i = 0; i < 3; ++i) y[i] = Rc[i * 3] * p[0] + Rc[i * 3 + 1] * p[1] + Rc[i * 3 + 2] * p[2] + xc[i];
-      obs.push_back({cc, l, fx * y[0] / y[2] + cx + rng.normal(), fy * y[1] / y[2] + cy + rng.normal()});
-      deg[cc]++;
+    for (const Obs& ob : mine) {
+      obs.push_back(ob);
+      deg[ob.c]++;
     }
   }
   // counting sort by camera (stable in landmark order)

@@ -21,10 +21,17 @@ def _check(rc, lib):
         raise RuntimeError(f"gbp error {rc}: {lib.gbp_cuda_last_error().decode()}")
 
 
-def _view(ptr, n, dtype):
+class _OwnedArray(np.ndarray):
+    """ndarray view into library-owned memory that keeps its owner alive."""
+    _owner = None
+
+
+def _view(ptr, n, dtype, owner=None):
     if n == 0:
         return np.zeros(0, dtype=dtype)
-    return np.ctypeslib.as_array(ptr, shape=(n,)).view(dtype)
+    a = np.ctypeslib.as_array(ptr, shape=(n,)).view(dtype).view(_OwnedArray)
+    a._owner = owner
+    return a
 
 
 class BALProblem:
@@ -76,23 +83,23 @@ class BALProblem:
 
     @property
     def camera_index(self):
-        return _view(self._lib.gbp_bal_camera_index(self._h), self.n_edges, np.uint32)
+        return _view(self._lib.gbp_bal_camera_index(self._h), self.n_edges, np.uint32, self)
 
     @property
     def point_index(self):
-        return _view(self._lib.gbp_bal_point_index(self._h), self.n_edges, np.uint32)
+        return _view(self._lib.gbp_bal_point_index(self._h), self.n_edges, np.uint32, self)
 
     @property
     def observations(self):
-        return _view(self._lib.gbp_bal_observations(self._h), 2 * self.n_edges, np.float64)
+        return _view(self._lib.gbp_bal_observations(self._h), 2 * self.n_edges, np.float64, self)
 
     @property
     def parameters(self):
-        return _view(self._lib.gbp_bal_parameters(self._h), 6 * self.n_keyframes + 3 * self.n_points, np.float64)
+        return _view(self._lib.gbp_bal_parameters(self._h), 6 * self.n_keyframes + 3 * self.n_points, np.float64, self)
 
     @property
     def intrinsics(self):
-        return _view(self._lib.gbp_bal_intrinsics(self._h), 4, np.float64)
+        return _view(self._lib.gbp_bal_intrinsics(self._h), 4, np.float64, self)
 
     def close(self):
         if self._h:
@@ -148,7 +155,7 @@ class Setup:
             "damping_count": (E_, np.int32), "mu": (9 * E_, np.float32), "oldmu": (9 * E_, np.float32),
         }
         n, dt = sizes[field]
-        return _view(getattr(p, field), n, dt)
+        return _view(getattr(p, field), n, dt, self)
 
     @property
     def K(self):

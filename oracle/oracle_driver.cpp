@@ -26,6 +26,29 @@
 
 #include "../include/gbp_cuda.h"
 
+// Transcendentals: both oracle builds bind sinf/cosf (the only libm calls of
+// the hot path besides sqrt, bafuncs.cpp:39-40) to the definitions below --
+// the double-precision result rounded once, i.e. a correctly rounded libm --
+// instead of glibc's <1-ulp-but-not-correctly-rounded sinf/cosf.  The CUDA
+// path evaluates them the same way, which makes CPU and GPU trajectories
+// comparable bit for bit.  (Linked with -Wl,-Bsymbolic, oracle/Makefile.)
+extern "C" {
+__attribute__((noinline)) float sinf(float x) {
+  volatile double d = std::sin((double)x);
+  return (float)d;
+}
+__attribute__((noinline)) float cosf(float x) {
+  volatile double d = std::cos((double)x);
+  return (float)d;
+}
+// gcc fuses sinf(x)+cosf(x) into one sincosf call
+__attribute__((noinline)) void sincosf(float x, float* s, float* c) {
+  volatile double ds = std::sin((double)x), dc = std::cos((double)x);
+  *s = (float)ds;
+  *c = (float)dc;
+}
+}
+
 #ifdef GBP_ORACLE_USE_REFERENCE
 #include "ref_backend.hpp"
 namespace be = gbp_ref_backend;
@@ -47,6 +70,7 @@ struct Oracle {
   float K[9];
   Hyper hp;
   int nthreads = 1;
+  int reduce_order = 0;  // 0 = serial slot order; 1 = the CUDA path's tile order (see update_beliefs)
   // variable-side tensors (ba/ba.cpp:665-687)
   std::vector<float> cam_b_eta, cam_b_lam, lmk_b_eta, lmk_b_lam;
   std::vector<float> cam_scaling, lmk_scaling;
@@ -67,18 +91,54 @@ inline size_t cml(const Oracle& o, uint32_t c, uint32_t slot) { return ((size_t)
 inline size_t lme(const Oracle& o, uint32_t l, uint32_t slot) { return ((size_t)o.SL * l + slot) * 3; }
 inline size_t lml(const Oracle& o, uint32_t l, uint32_t slot) { return ((size_t)o.SL * l + slot) * 9; }
 
-// prog_ub: belief = sum over slots, serial slot order, fp32 (ba/ba.cpp:104-139).
+// prog_ub: belief = sum over slots, fp32 (ba/ba.cpp:104-139).  popops::reduce does
+// not specify its summation order; two realisations are provided:
+//   reduce_order 0: serial slot order  ((prior + m1) + m2) + ...
+//   reduce_order 1: the order of the CUDA path -- camera messages are summed per
+//     tile of 128 consecutive slots (three contiguous parts of 43/43/42 summed
+//     serially, then (p0+p1)+p2), and the tiles are added to the prior in order.
+//     Landmarks are serial in both modes.
+float cam_tile_sum(const Oracle& o, const std::vector<float>& m, uint32_t c, uint32_t d, uint32_t dim,
+                   uint32_t tile) {
+  float part[3];
+  for (int p = 0; p < 3; ++p) {
+    const uint32_t b = p * 43, en = std::min<uint32_t>(b + 43, 128);
+    float acc = 0.f;
+    bool first = true;
+    for (uint32_t i = b; i < en; ++i) {
+      const uint32_t slot = tile * 128 + i + 1;  // slot 0 is the prior
+      const float v = (slot < o.SK) ? m[((size_t)o.SK * c + slot) * dim + d] : 0.f;
+      acc = first ? v : acc + v;
+      first = false;
+    }
+    part[p] = acc;
+  }
+  return (part[0] + part[1]) + part[2];
+}
+
 void update_beliefs(Oracle& o) {
+  const uint32_t n_tiles_max = (o.SK - 1 + 127) / 128;
 #pragma omp parallel for schedule(static) num_threads(o.nthreads)
   for (int64_t c = 0; c < (int64_t)o.C; ++c) {
+    // number of tiles of this camera = ceil(deg/128); slots beyond deg are zero anyway
     for (int d = 0; d < 6; ++d) {
       float s = 0.f;
-      for (uint32_t k = 0; k < o.SK; ++k) s += o.cam_m_eta[cme(o, c, k) + d];
+      if (o.reduce_order == 0) {
+        for (uint32_t k = 0; k < o.SK; ++k) s += o.cam_m_eta[cme(o, c, k) + d];
+      } else {
+        s = o.cam_m_eta[cme(o, c, 0) + d];
+        for (uint32_t t = 0; t < n_tiles_max; ++t) s += cam_tile_sum(o, o.cam_m_eta, c, d, 6, t);
+      }
       o.cam_b_eta[c * 6 + d] = s;
     }
     for (int d = 0; d < 36; ++d) {
       float s = 0.f;
-      for (uint32_t k = 0; k < o.SK; ++k) s += o.cam_m_lam[cml(o, c, k) + d];
+      if (o.reduce_order == 0) {
+        for (uint32_t k = 0; k < o.SK; ++k) s += o.cam_m_lam[cml(o, c, k) + d];
+      } else {
+        s = o.cam_m_lam[cml(o, c, 0) + d];
+        for (uint32_t t = 0; t < n_tiles_max; ++t) s += cam_tile_sum(o, o.cam_m_lam, c, d, 36, t);
+      }
       o.cam_b_lam[c * 36 + d] = s;
     }
   }
@@ -314,6 +374,12 @@ int gbp_oracle_max_threads(void) {
 #else
   return 1;
 #endif
+}
+
+int gbp_oracle_set_reduce_order(void* h, int mode) {
+  if (!h || mode < 0 || mode > 1) return GBP_ERR_ARG;
+  ((Oracle*)h)->reduce_order = mode;
+  return GBP_OK;
 }
 
 int gbp_oracle_set_threads(void* h, int n) {

@@ -37,6 +37,7 @@ def load(kind="port"):
         lib.gbp_oracle_kind.restype = C.c_char_p
         lib.gbp_oracle_last_error.restype = C.c_char_p
         lib.gbp_oracle_set_threads.argtypes = [C.c_void_p, C.c_int]
+        lib.gbp_oracle_set_reduce_order.argtypes = [C.c_void_p, C.c_int]
         lib.gbp_oracle_commit_messages.argtypes = [C.c_void_p]
         lib.gbp_oracle_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         f32p = C.POINTER(C.c_float)
@@ -58,6 +59,10 @@ class OracleEngine(GBPEngine):
         n = threads if threads is not None else lib.gbp_oracle_max_threads()
         lib.gbp_oracle_set_threads(self._h, int(n))
         self.threads = int(n)
+
+    def set_reduce_order(self, mode):
+        """0 = serial slot order (default), 1 = the CUDA path's tile order (bit-comparable)."""
+        self._check(self._lib.gbp_oracle_set_reduce_order(self._h, int(mode)))
 
     def commit_messages(self):
         self._check(self._lib.gbp_oracle_commit_messages(self._h))
