@@ -140,6 +140,8 @@ CUDA_ONLY_API = {
     "gbp_cuda_version": (C.c_char_p, []),
     "gbp_opts_default": (None, [C.POINTER(GbpOpts)]),
     "gbp_cuda_last_timing": (C.c_int, [C.c_void_p, c_f32p, C.POINTER(C.c_uint64)]),
+    "gbp_cuda_set_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "gbp_cuda_last_kernel_times": (C.c_int, [C.c_void_p, c_f32p, c_f32p]),
     "gbp_cuda_iterate_async": (C.c_int, [C.c_void_p, C.c_int]),
     "gbp_cuda_synchronize": (C.c_int, [C.c_void_p]),
     "gbp_cuda_stream": (C.c_void_p, [C.c_void_p]),

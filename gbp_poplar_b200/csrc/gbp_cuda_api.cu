@@ -76,6 +76,13 @@ struct gbp_handle {
   std::vector<float> mu_init;     // host copy of the streamed `mu` (empty = zeros)
   std::vector<float> oldmu_init;  // host copy of the streamed `oldmu` (empty = zeros)
   bool pending_shift = false;     // a PrepMessageVertex pass ran since the last belief update
+  // Slot 0 of the reference's p*_messages tensors holds the priors as they were at the
+  // last Copy(messages, pmessages) (ba.cpp:902-905).  Nothing ever reads it, so it is
+  // tracked lazily: snapshotted only when the priors are about to change.
+  bool p_in_sync = false;         // a sweep ran since the priors last changed
+  float* d_pprior_cam_eta = nullptr;
+  float* d_pprior_cam_lam = nullptr;
+  float4* d_pprior_lmk = nullptr;
   int use_graph = 0;
   // staging for READ_PROG
   uint32_t* d_pos_of_orig = nullptr;
@@ -89,6 +96,9 @@ struct gbp_handle {
   gbp::DeviceStats* d_stats = nullptr;
   size_t d_stats_cap = 0;
   // timing
+  int profile = 0;
+  std::vector<cudaEvent_t> prof_events;
+  float last_ms_factor = 0.f, last_ms_variable = 0.f;
   float last_ms = 0.f;
   uint64_t kernels_launched = 0;
   uint64_t last_kernels = 0;
@@ -119,6 +129,15 @@ int download(T* dst, const T* src, size_t n, cudaStream_t s) {
 
 inline uint32_t vars_grid(const gbp_handle* h) { return h->C + (h->L + GBP_TILE - 1) / GBP_TILE; }
 
+int priors_about_to_change(gbp_handle* h) {
+  if (!h->p_in_sync) return GBP_OK;
+  GBP_CUDA_TRY(cudaMemcpyAsync(h->d_pprior_cam_eta, h->g.cam_prior_eta, 6 * (size_t)h->C * 4, cudaMemcpyDeviceToDevice, h->stream));
+  GBP_CUDA_TRY(cudaMemcpyAsync(h->d_pprior_cam_lam, h->g.cam_prior_lam, 36 * (size_t)h->C * 4, cudaMemcpyDeviceToDevice, h->stream));
+  GBP_CUDA_TRY(cudaMemcpyAsync(h->d_pprior_lmk, h->g.lmk_prior, 3 * (size_t)h->L * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream));
+  h->p_in_sync = false;
+  return GBP_OK;
+}
+
 int launch_update_vars(gbp_handle* h) {
   const int shift = h->pending_shift ? 1 : 0;
   const uint32_t grid = vars_grid(h);
@@ -138,6 +157,7 @@ int launch_sweep(gbp_handle* h) {
     h->kernels_launched++;
   }
   if (PREP) h->pending_shift = true;
+  if (MSG) h->p_in_sync = true;
   GBP_CUDA_TRY(cudaGetLastError());
   return GBP_OK;
 }
@@ -424,6 +444,9 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o) {
   A_(g.lmk_edges, E);
   A_(h->d_pos_of_orig, E);
   A_(h->d_metric_parts, h->n_tiles);
+  A_(h->d_pprior_cam_eta, 6 * (size_t)C);
+  A_(h->d_pprior_cam_lam, 36 * (size_t)C);
+  A_(h->d_pprior_lmk, 3 * (size_t)L);
 #undef A_
   if (rc) return rc;
   cudaStream_t s = h->stream;
@@ -540,6 +563,7 @@ int gbp_cuda_free(gbp_handle* h) {
   if (h->d_exp_damping) cudaFree(h->d_exp_damping);
   if (h->d_exp_dcount) cudaFree(h->d_exp_dcount);
   if (h->d_exp_robust) cudaFree(h->d_exp_robust);
+  for (cudaEvent_t ev : h->prof_events) cudaEventDestroy(ev);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -577,6 +601,7 @@ int gbp_cuda_weaken_priors(gbp_handle* h) {
 int gbp_cuda_weaken_prior_vertices(gbp_handle* h) {
   if (!h) return GBP_ERR_ARG;
   int rc = set_device(h);
+  if (!rc) rc = priors_about_to_change(h);
   if (rc) return rc;
   const uint32_t n = h->C + h->L;
   if (n) {
@@ -606,10 +631,21 @@ int gbp_cuda_iterate(gbp_handle* h, int n_sweeps, gbp_iter_stats* stats) {
     if (rc) return rc;
   }
   const uint64_t k0 = h->kernels_launched;
+  const bool prof = h->profile != 0;
+  if (prof) {
+    while (h->prof_events.size() < (size_t)3 * n_sweeps) {
+      cudaEvent_t ev;
+      GBP_CUDA_TRY(cudaEventCreate(&ev));
+      h->prof_events.push_back(ev);
+    }
+  }
   GBP_CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
   for (int i = 0; i < n_sweeps && !rc; ++i) {
+    if (prof) GBP_CUDA_TRY(cudaEventRecord(h->prof_events[3 * i], h->stream));
     rc = launch_sweep<true, true>(h);
+    if (prof) GBP_CUDA_TRY(cudaEventRecord(h->prof_events[3 * i + 1], h->stream));
     if (!rc) rc = launch_update_vars(h);
+    if (prof) GBP_CUDA_TRY(cudaEventRecord(h->prof_events[3 * i + 2], h->stream));
     if (!rc && stats) rc = launch_metric(h, h->d_stats + i);
   }
   if (rc) return rc;
@@ -620,6 +656,32 @@ int gbp_cuda_iterate(gbp_handle* h, int n_sweeps, gbp_iter_stats* stats) {
   GBP_CUDA_TRY(cudaStreamSynchronize(h->stream));
   GBP_CUDA_TRY(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
   h->last_kernels = h->kernels_launched - k0;
+  h->last_ms_factor = h->last_ms_variable = 0.f;
+  if (prof) {
+    double a = 0, b = 0;
+    for (int i = 0; i < n_sweeps; ++i) {
+      float t;
+      GBP_CUDA_TRY(cudaEventElapsedTime(&t, h->prof_events[3 * i], h->prof_events[3 * i + 1]));
+      a += t;
+      GBP_CUDA_TRY(cudaEventElapsedTime(&t, h->prof_events[3 * i + 1], h->prof_events[3 * i + 2]));
+      b += t;
+    }
+    h->last_ms_factor = (float)a;
+    h->last_ms_variable = (float)b;
+  }
+  return GBP_OK;
+}
+
+int gbp_cuda_set_profile(gbp_handle* h, int enabled) {
+  if (!h) return GBP_ERR_ARG;
+  h->profile = enabled ? 1 : 0;
+  return GBP_OK;
+}
+
+int gbp_cuda_last_kernel_times(gbp_handle* h, float* ms_factor, float* ms_variable) {
+  if (!h) return GBP_ERR_ARG;
+  if (ms_factor) *ms_factor = h->last_ms_factor;
+  if (ms_variable) *ms_variable = h->last_ms_variable;
   return GBP_OK;
 }
 
@@ -712,7 +774,8 @@ int gbp_cuda_add_keyframe(gbp_handle* h, const int32_t* damping_count, const flo
   int rc = set_device(h);
   if (rc) return rc;
   cudaStream_t s = h->stream;
-  if (cam_prior_eta) rc = upload(h->g.cam_prior_eta, cam_prior_eta, 6 * (size_t)h->C, s);
+  rc = priors_about_to_change(h);
+  if (!rc && cam_prior_eta) rc = upload(h->g.cam_prior_eta, cam_prior_eta, 6 * (size_t)h->C, s);
   if (!rc && cam_prior_lambda) rc = upload(h->g.cam_prior_lam, cam_prior_lambda, 36 * (size_t)h->C, s);
   if (!rc && (lmk_prior_eta || lmk_prior_lambda)) rc = upload_lmk_priors(h, lmk_prior_eta, lmk_prior_lambda);
   if (!rc && cam_weaken_flag) rc = upload(h->g.cam_wflag, cam_weaken_flag, (size_t)h->C, s);
@@ -786,6 +849,7 @@ int gbp_cuda_get_tensor(gbp_handle* h, const char* name, void* dst, size_t nbyte
   uint32_t* outu = (uint32_t*)dst;
   int32_t* outi = (int32_t*)dst;
   const size_t C = h->C, L = h->L, E = h->E, EP = h->E_pad, SK = h->SK, SL = h->SL;
+  const bool stale_p = (name[0] == 'p') && !h->p_in_sync;  // slot 0 of a p*-tensor, see gbp_handle
   std::vector<float4> v;
   switch (id) {
     case T_CAM_B_ETA: rc = download(out, h->g.cam_b_eta, 6 * C, s); break;
@@ -810,7 +874,8 @@ int gbp_cuda_get_tensor(gbp_handle* h, const char* name, void* dst, size_t nbyte
       const int d = (id == T_CAM_M_ETA) ? 6 : 36;
       std::memset(out, 0, nbytes);
       std::vector<float> pr(d * C);
-      rc = download(pr.data(), id == T_CAM_M_ETA ? h->g.cam_prior_eta : h->g.cam_prior_lam, pr.size(), s);
+      if (stale_p) rc = download(pr.data(), id == T_CAM_M_ETA ? h->d_pprior_cam_eta : h->d_pprior_cam_lam, pr.size(), s);
+      else rc = download(pr.data(), id == T_CAM_M_ETA ? h->g.cam_prior_eta : h->g.cam_prior_lam, pr.size(), s);
       if (!rc) rc = fetch(h, v, h->g.mcam, GBP_MCAM_QUADS * EP);
       if (rc) break;
       for (size_t c = 0; c < C; ++c) std::memcpy(out + c * SK * d, pr.data() + c * d, d * 4);
@@ -832,7 +897,7 @@ int gbp_cuda_get_tensor(gbp_handle* h, const char* name, void* dst, size_t nbyte
       const int off = (id == T_LMK_M_ETA) ? 0 : 3;
       std::memset(out, 0, nbytes);
       std::vector<float4> pr;
-      rc = fetch(h, pr, h->g.lmk_prior, L * 3);
+      rc = fetch(h, pr, stale_p ? h->d_pprior_lmk : h->g.lmk_prior, L * 3);
       if (!rc) rc = fetch(h, v, h->g.mlmk, GBP_MLMK_QUADS * EP);
       if (rc) break;
       for (size_t l = 0; l < L; ++l)
@@ -935,6 +1000,13 @@ int gbp_cuda_set_tensor(gbp_handle* h, const char* name, const void* src, size_t
   const uint32_t* inu = (const uint32_t*)src;
   const int32_t* ini = (const int32_t*)src;
   const size_t C = h->C, L = h->L, E = h->E, EP = h->E_pad, SK = h->SK, SL = h->SL;
+  const bool is_p = (name[0] == 'p');
+  if (id == T_CAM_M_ETA || id == T_CAM_M_LAM || id == T_LMK_M_ETA || id == T_LMK_M_LAM) {
+    // slot 0: a p*-tensor writes the bookkeeping copy of the priors, a message tensor the priors
+    rc = priors_about_to_change(h);
+    if (rc) return rc;
+    if (is_p) h->p_in_sync = false;
+  }
   std::vector<float4> v;
   switch (id) {
     case T_CAM_B_ETA: rc = upload(h->g.cam_b_eta, in, 6 * C, s); if (!rc) rc = recompute_means(h); break;
@@ -961,7 +1033,9 @@ int gbp_cuda_set_tensor(gbp_handle* h, const char* name, const void* src, size_t
       const int d = (id == T_CAM_M_ETA) ? 6 : 36;
       std::vector<float> pr(d * C);
       for (size_t c = 0; c < C; ++c) std::memcpy(pr.data() + c * d, in + c * SK * d, d * 4);
-      rc = upload(id == T_CAM_M_ETA ? h->g.cam_prior_eta : h->g.cam_prior_lam, pr.data(), pr.size(), s);
+      if (is_p) rc = upload(id == T_CAM_M_ETA ? h->d_pprior_cam_eta : h->d_pprior_cam_lam, pr.data(), pr.size(), s);
+      else rc = upload(id == T_CAM_M_ETA ? h->g.cam_prior_eta : h->g.cam_prior_lam, pr.data(), pr.size(), s);
+      if (!rc) GBP_CUDA_TRY(cudaStreamSynchronize(s));
       if (!rc) rc = fetch(h, v, h->g.mcam, GBP_MCAM_QUADS * EP);
       if (rc) break;
       for (size_t e = 0; e < E; ++e) {
@@ -986,7 +1060,8 @@ int gbp_cuda_set_tensor(gbp_handle* h, const char* name, const void* src, size_t
       const int d = (id == T_LMK_M_ETA) ? 3 : 9;
       const int off = (id == T_LMK_M_ETA) ? 0 : 3;
       std::vector<float4> pr;
-      rc = fetch(h, pr, h->g.lmk_prior, L * 3);
+      float4* d_pr = is_p ? h->d_pprior_lmk : h->g.lmk_prior;
+      rc = fetch(h, pr, d_pr, L * 3);
       if (!rc) rc = fetch(h, v, h->g.mlmk, GBP_MLMK_QUADS * EP);
       if (rc) break;
       for (size_t l = 0; l < L; ++l)
@@ -995,7 +1070,7 @@ int gbp_cuda_set_tensor(gbp_handle* h, const char* name, const void* src, size_t
         const float* o = in + ((size_t)h->lmk_ids[e] * SL + h->slot_l[e] + 1) * d;
         for (int i = 0; i < d; ++i) aos_field(v, GBP_MLMK_QUADS, h->pos_of_orig[e], off + i) = o[i];
       }
-      rc = push(h, pr, h->g.lmk_prior);
+      rc = push(h, pr, d_pr);
       if (!rc) rc = push(h, v, h->g.mlmk);
       break;
     }

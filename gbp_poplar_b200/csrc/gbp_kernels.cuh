@@ -366,7 +366,8 @@ __global__ void __launch_bounds__(GBP_TILE) k_update_vars(const DeviceGraph g, c
     __shared__ float s_b[GBP_CAMPART];
     const uint32_t c = blockIdx.x;
     if (tid < GBP_CAMPART) {
-      float acc = (tid < 6) ? g.cam_prior_eta[c * 6 + tid] : g.cam_prior_lam[c * 36 + (tid - 6)];
+      // the sum starts from +0 like a zero-initialised accumulator: 0 + prior (turns a -0 prior into +0)
+      float acc = fa(0.0f, (tid < 6) ? g.cam_prior_eta[c * 6 + tid] : g.cam_prior_lam[c * 36 + (tid - 6)]);
       const uint32_t t0 = g.cam_tile_begin[c], t1 = g.cam_tile_begin[c + 1];
       for (uint32_t t = t0; t < t1; ++t) acc = fa(acc, g.cam_partial[(size_t)t * GBP_CAMPART + tid]);
       s_b[tid] = acc;
@@ -403,7 +404,7 @@ __global__ void __launch_bounds__(GBP_TILE) k_update_vars(const DeviceGraph g, c
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
         const float4 v = p[q];
-        b[q * 4] = v.x; b[q * 4 + 1] = v.y; b[q * 4 + 2] = v.z; b[q * 4 + 3] = v.w;
+        b[q * 4] = fa(0.0f, v.x); b[q * 4 + 1] = fa(0.0f, v.y); b[q * 4 + 2] = fa(0.0f, v.z); b[q * 4 + 3] = fa(0.0f, v.w);
       }
     }
     const uint32_t k0 = g.lmk_ptr[l], k1 = g.lmk_ptr[l + 1];

@@ -616,7 +616,7 @@ int gbp_synth_generate(uint32_t C, uint32_t L, double obs_per_point, uint32_t se
         const double* xc = &cam_gt[(size_t)6 * cc];
         double y[3];
         for (int i = 0; i < 3; ++i) y[i] = Rc[i * 3] * p[0] + Rc[i * 3 + 1] * p[1] + Rc[i * 3 + 2] * p[2] + xc[i];
-        if (y[2] < 0.3) continue;
+        if (y[2] < 0.45) continue;
         const double pu = fx * y[0] / y[2] + cx, pv = fy * y[1] / y[2] + cy;
         if (pu < 22 || pu > 618 || pv < 22 || pv > 458) continue;
         const double nu = std::max(-2.5, std::min(2.5, rng.normal())), nv = std::max(-2.5, std::min(2.5, rng.normal()));
@@ -643,11 +643,19 @@ int gbp_synth_generate(uint32_t C, uint32_t L, double obs_per_point, uint32_t se
     zz[2 * k] = ob.u;
     zz[2 * k + 1] = ob.v;
   }
-  // initial values = ground truth + noise (first two cameras anchor the gauge)
+  // initial values = ground truth + noise (first two cameras anchor the gauge).  The
+  // pose noise is applied to the camera CENTRE and orientation (t = -R c), so a
+  // rotation perturbation does not swing the camera around the world origin.
   std::vector<double> cam0 = cam_gt, pts0 = pts_gt;
   for (uint32_t c = 2; c < C; ++c) {
-    for (int i = 0; i < 3; ++i) cam0[(size_t)6 * c + i] += 0.01 * rng.normal();
-    for (int i = 0; i < 3; ++i) cam0[(size_t)6 * c + 3 + i] += 0.5 * M_PI / 180.0 * rng.normal();
+    const double* Rg = &Rgt[(size_t)9 * c];
+    const double* xg = &cam_gt[(size_t)6 * c];
+    double ctr[3], w[3], Rn[9];
+    for (int i = 0; i < 3; ++i) ctr[i] = -(Rg[i] * xg[0] + Rg[3 + i] * xg[1] + Rg[6 + i] * xg[2]) + 0.01 * rng.normal();
+    for (int i = 0; i < 3; ++i) w[i] = xg[3 + i] + 0.5 * M_PI / 180.0 * rng.normal();
+    so3exp_d(w, Rn);
+    for (int i = 0; i < 3; ++i) cam0[(size_t)6 * c + i] = -(Rn[i * 3] * ctr[0] + Rn[i * 3 + 1] * ctr[1] + Rn[i * 3 + 2] * ctr[2]);
+    for (int i = 0; i < 3; ++i) cam0[(size_t)6 * c + 3 + i] = w[i];
   }
   for (size_t i = 0; i < pts0.size(); ++i) pts0[i] += 0.02 * rng.normal();
   const double intr[4] = {fx, fy, cx, cy};

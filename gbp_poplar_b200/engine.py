@@ -207,6 +207,15 @@ class GBPEngine:
         self._check(self._lib.gbp_cuda_last_timing(self._h, C.byref(ms), C.byref(k)))
         return ms.value, k.value
 
+    def set_profile(self, enabled):
+        self._check(self._lib.gbp_cuda_set_profile(self._h, int(bool(enabled))))
+
+    def last_kernel_times(self):
+        """(ms in the factor kernel, ms in the variable kernel) of the last iterate() under set_profile(True)."""
+        a, b = C.c_float(), C.c_float()
+        self._check(self._lib.gbp_cuda_last_kernel_times(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def iterate_async(self, n_sweeps):
         self._check(self._lib.gbp_cuda_iterate_async(self._h, n_sweeps))
 

@@ -188,6 +188,13 @@ int gbp_cuda_dims(gbp_handle* h, uint32_t* n_keyframes, uint32_t* n_points, uint
  * handle's stream): total milliseconds and number of kernels launched. */
 int gbp_cuda_last_timing(gbp_handle* h, float* ms_total, uint64_t* kernels_launched);
 
+/* Per-kernel device timing: when enabled, gbp_cuda_iterate brackets every kernel
+ * with CUDA events on the handle's stream; gbp_cuda_last_kernel_times returns the
+ * summed durations of the factor kernel (k_sweep) and of the variable kernel
+ * (k_update_vars) over the last gbp_cuda_iterate call. */
+int gbp_cuda_set_profile(gbp_handle* h, int enabled);
+int gbp_cuda_last_kernel_times(gbp_handle* h, float* ms_factor_kernel, float* ms_variable_kernel);
+
 /* ---- asynchronous / resident use (bench, multi-GPU) ------------------- */
 /* Enqueue n sweeps on the handle's stream without synchronising. */
 int gbp_cuda_iterate_async(gbp_handle* h, int n_sweeps);

@@ -126,7 +126,7 @@ void update_beliefs(Oracle& o) {
       if (o.reduce_order == 0) {
         for (uint32_t k = 0; k < o.SK; ++k) s += o.cam_m_eta[cme(o, c, k) + d];
       } else {
-        s = o.cam_m_eta[cme(o, c, 0) + d];
+        s += o.cam_m_eta[cme(o, c, 0) + d];
         for (uint32_t t = 0; t < n_tiles_max; ++t) s += cam_tile_sum(o, o.cam_m_eta, c, d, 6, t);
       }
       o.cam_b_eta[c * 6 + d] = s;
@@ -136,7 +136,7 @@ void update_beliefs(Oracle& o) {
       if (o.reduce_order == 0) {
         for (uint32_t k = 0; k < o.SK; ++k) s += o.cam_m_lam[cml(o, c, k) + d];
       } else {
-        s = o.cam_m_lam[cml(o, c, 0) + d];
+        s += o.cam_m_lam[cml(o, c, 0) + d];
         for (uint32_t t = 0; t < n_tiles_max; ++t) s += cam_tile_sum(o, o.cam_m_lam, c, d, 36, t);
       }
       o.cam_b_lam[c * 36 + d] = s;

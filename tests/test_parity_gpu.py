@@ -156,16 +156,29 @@ def test_slam_schedule_bit_exact():
         assert (a["n_active"], a["n_robust"], a["n_relins"]) == (b["n_active"], b["n_robust"], b["n_relins"])
 
 
-def test_plateau_reprojection_error_within_one_percent():
-    """Config 1: fixed 1500 sweeps on fr1xyz; final mean reprojection error within 1 % (serial-order oracle)."""
-    st, ora, gpu = make_pair("fr1xyz", order=0)
+def test_config1_1500_sweeps_final_error():
+    """Config 1: fixed 1500 sweeps on fr1xyz (`./ba` default).
+
+    Against the oracle run with the same belief-summation order the whole trajectory is
+    bit-identical, so the final mean reprojection error agrees to the metric's own rounding
+    (<< 1 %).  The reference leaves that order open (popops::reduce), and GBP is chaotic at
+    rounding level: the oracle's two orders sit 1.5 % apart on the final plateau (1.445 vs
+    1.424 px) and hundreds of sweeps apart on the way there, which bounds what any
+    order-agnostic comparison can assert."""
+    st, ora, gpu = make_pair("fr1xyz", order=1)
+    ser = oracle_lib.OracleEngine(st.problem, kind=KIND)  # serial order
     for it in range(1500):
-        common.ba_schedule_step(ora, it)
-        common.ba_schedule_step(gpu, it)
+        for e in (ora, gpu, ser):
+            common.ba_schedule_step(e, it)
         if it in (499, 999, 1499):
+            assert_bit_identical(gpu, ora, f"sweep {it}", ["cam_beliefs_eta", "cam_beliefs_lambda", "lmk_beliefs_eta",
+                                                            "lmk_beliefs_lambda", "damping_count", "robust_flag"])
             a, b = gpu.eval(), ora.eval()
             assert a["reproj_mean"] == pytest.approx(b["reproj_mean"], rel=0.01), it
-    assert gpu.eval()["reproj_mean"] < 1.6  # SURVEY 8c: 1.43 px plateau
+    a, b, c = gpu.eval(), ora.eval(), ser.eval()
+    assert a["reproj_mean"] == pytest.approx(b["reproj_mean"], rel=1e-3)
+    assert a["reproj_mean"] < 1.5 and c["reproj_mean"] < 1.5      # SURVEY 8c: ~1.43 px plateau
+    assert a["reproj_mean"] == pytest.approx(c["reproj_mean"], rel=0.03)
 
 
 def test_device_metric_matches_oracle_metric():
@@ -226,7 +239,6 @@ def test_empty_graph():
                                  np.array([0, 0, 0, 0.01, 0.02, 0.03, 0.1, 0, 0, 0.01, 0.02, 0.03]), np.array([0.0, 0, 2, 1, 0, 2]))
     st = Setup(bal)
     gpu = GBPEngine(st.problem)
-    gpu.weaken_priors()
     gpu.iterate(3)
     b = gpu.get_beliefs()
     assert b["damping"].size == 0 and np.all(np.isfinite(b["cam_beliefs_eta"]))
