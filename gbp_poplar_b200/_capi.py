@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgbp_cuda.so")
+# GBP_CUDA_LIB selects an alternative build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("GBP_CUDA_LIB") or os.path.join(_HERE, "libgbp_cuda.so")
 
 c_f32p = C.POINTER(C.c_float)
 c_f64p = C.POINTER(C.c_double)

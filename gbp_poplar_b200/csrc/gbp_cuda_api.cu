@@ -153,7 +153,7 @@ int launch_update_vars(gbp_handle* h) {
 template <bool PREP, bool MSG>
 int launch_sweep(gbp_handle* h) {
   if (h->n_tiles) {
-    gbp::k_sweep<PREP, MSG><<<h->n_tiles, GBP_TILE, 0, h->stream>>>(h->g);
+    gbp::k_sweep<PREP, MSG><<<h->n_tiles, GBP_TILE, MSG ? GBP_SWEEP_SMEM : GBP_WARPS * GBP_SCAM * 4, h->stream>>>(h->g);
     h->kernels_launched++;
   }
   if (PREP) h->pending_shift = true;
@@ -366,8 +366,13 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o) {
   h->E_pad = (uint32_t)epad64;
   const size_t EP = h->E_pad;
   std::vector<uint32_t> tile_cam(h->n_tiles);
+  std::vector<uint2> tile_info(h->n_tiles);
   for (uint32_t c = 0; c < C; ++c)
-    for (uint32_t t = cam_tile_begin[c]; t < cam_tile_begin[c + 1]; ++t) tile_cam[t] = c;
+    for (uint32_t t = cam_tile_begin[c]; t < cam_tile_begin[c + 1]; ++t) {
+      tile_cam[t] = c;
+      const uint32_t first = (t - cam_tile_begin[c]) * GBP_TILE;
+      tile_info[t] = make_uint2(c, std::min<uint32_t>(GBP_TILE, deg_c[c] - first));
+    }
   h->pos_of_orig.resize(E);
   std::vector<uint32_t> edge_orig(EP, 0xffffffffu);
   for (uint32_t e = 0; e < E; ++e) {
@@ -424,8 +429,10 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o) {
   A_(g.recB, EP);
   A_(g.edge_orig, EP);
   A_(g.tile_cam, h->n_tiles);
+  A_(g.tile_info, h->n_tiles);
+  A_(g.cam_rec, 16 * (size_t)C);
   A_(g.cam_tile_begin, C + 1);
-  A_(g.cam_partial, (size_t)h->n_tiles * GBP_CAMPART);
+  A_(g.cam_partial, (size_t)h->n_tiles * GBP_WARPS * GBP_CAMPART);
   A_(g.cam_b_eta, 6 * (size_t)C);
   A_(g.cam_b_lam, 36 * (size_t)C);
   A_(g.cam_mean, 6 * (size_t)C);
@@ -455,6 +462,7 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o) {
   U_(g.recB, recB.data(), EP);
   U_(g.edge_orig, edge_orig.data(), EP);
   U_(g.tile_cam, tile_cam.data(), h->n_tiles);
+  U_(g.tile_info, tile_info.data(), h->n_tiles);
   U_(g.cam_tile_begin, cam_tile_begin.data(), C + 1);
   U_(g.cam_prior_eta, p->cam_priors_eta, 6 * (size_t)C);
   U_(g.cam_prior_lam, p->cam_priors_lambda, 36 * (size_t)C);
@@ -483,6 +491,8 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o) {
 #undef U_
   if (rc) return rc;
   GBP_CUDA_TRY(cudaStreamSynchronize(s));
+  GBP_CUDA_TRY(cudaFuncSetAttribute(gbp::k_sweep<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GBP_SWEEP_SMEM));
+  GBP_CUDA_TRY(cudaFuncSetAttribute(gbp::k_sweep<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GBP_SWEEP_SMEM));
   // LINEARISE_PROG (ba/ba.cpp:890-893): beliefs <- priors, then linearise every factor
   h->pending_shift = false;
   rc = launch_update_vars(h);

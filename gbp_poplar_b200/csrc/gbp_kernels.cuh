@@ -19,6 +19,10 @@
 #include "gbp_layout.h"
 #include "gbp_math.cuh"
 
+#ifndef GBP_MIN_BLOCKS
+#define GBP_MIN_BLOCKS 3  // resident blocks per SM the factor kernel is compiled for (58 KB of stage each)
+#endif
+
 namespace gbp {
 
 struct DeviceGraph {
@@ -34,14 +38,16 @@ struct DeviceGraph {
   uint32_t* edge_orig;  // [E_pad] original edge id, 0xffffffff for padding
   // tiles
   uint32_t* tile_cam;        // [n_tiles]
+  uint2* tile_info;          // [n_tiles] {camera, number of real factors in the tile}
   uint32_t* cam_tile_begin;  // [C+1]
-  float* cam_partial;        // [n_tiles][42]
+  float* cam_partial;        // [n_tiles * 4 warps][42]
   // cameras
   float* cam_b_eta;      // [C][6]
   float* cam_b_lam;      // [C][36]
   float* cam_mean;       // [C][6]
   float* cam_mean_prev;  // [C][6]
   float* cam_R;          // [C][9] so3exp(mean[3:6]) for the metric
+  float4* cam_rec;       // [C][16] packed {belief eta 6 | belief lambda 36 | mean 6 | previous mean 6 | pad}: what k_sweep stages
   float* cam_prior_eta;  // [C][6]
   float* cam_prior_lam;  // [C][36]
   float* cam_scaling;    // [C]
@@ -59,6 +65,52 @@ struct DeviceGraph {
 };
 
 GBP_DEV float4 ldg4(const float4* p) { return __ldg(p); }
+
+// ---- L2 residency control --------------------------------------------------------
+// Per sweep the factor kernel streams ~0.6 KB per factor that is touched exactly once
+// (factor potentials, camera-bound messages) and ~0.1 KB per factor that is touched
+// again within microseconds (landmark-bound messages: written here, gathered by the
+// belief kernel, read back by the next sweep; the small per-edge state records).  On
+// B200 the second class fits the 126 MB L2 for graphs of a few million factors, so it
+// is tagged evict_last while the streams are tagged evict_first.
+#ifndef GBP_L2_HINTS
+#define GBP_L2_HINTS 0  // (measured: no gain on B200, kept for experiments) bitmask: 1 keep landmark messages, 2 keep edge-state records, 4 stream loads, 8 stream stores
+#endif
+GBP_DEV uint64_t l2_policy_stream() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p));
+  return p;
+}
+GBP_DEV uint64_t l2_policy_keep() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(p));
+  return p;
+}
+template <int EN>
+GBP_DEV float4 ld4_hint(const float4* ptr, uint64_t pol) {
+  if (!EN) return *ptr;
+#if GBP_L2_HINTS
+  float4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;\n"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr), "l"(pol) : "memory");
+  return v;
+#else
+  return *ptr;
+#endif
+}
+template <int EN>
+GBP_DEV void st4_hint(float4* ptr, const float4 v, uint64_t pol) {
+  if (!EN) {
+    *ptr = v;
+    return;
+  }
+#if GBP_L2_HINTS
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;\n"
+               ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+#else
+  *ptr = v;
+#endif
+}
 
 template <int N>
 GBP_DEV void load_quads(const float4* base, size_t stride, size_t e, float (&out)[N * 4]) {
@@ -105,116 +157,240 @@ __device__ __noinline__ uint32_t relinearise_in_place(float4* fac, size_t E_pad,
   return robust;
 }
 
-#define GBP_RED_STRIDE (GBP_TILE + 1)
+// ---- k_sweep ---------------------------------------------------------------------
+// One thread per factor; every WARP is autonomous (no block-wide barrier): it
+//   1. issues cp.async (LDGSTS, L1-bypassing) copies of its 32 factors' records
+//      (factor potential 18 quads, previous camera message 7, previous landmark
+//      message 3) into its private shared-memory stage, so the whole 14 KB per
+//      warp is in flight before any arithmetic and without tying up registers;
+//   2. meanwhile gathers the landmark beliefs (L2-resident, 64 B each) and runs
+//      PrepMessageVertex on the hoisted per-variable means;
+//   3. computes both messages from the staged data, stores them in place;
+//   4. sums the 32 camera-bound messages in lane order (serial fp32 adds, so the
+//      result is defined independently of the hardware) through the same shared
+//      memory and writes one partial per warp.
+#define GBP_WARPS (GBP_TILE / 32)
+#ifndef GBP_STAGE_LMK
+#define GBP_STAGE_LMK 0  // 1: the previous landmark message goes through the stage too; 0: plain loads
+#endif
+#define GBP_STAGE_QUADS (GBP_FAC_QUADS + GBP_MCAM_READ_QUADS + (GBP_STAGE_LMK ? GBP_MLMK_QUADS : 0))  // 28 or 25
+#define GBP_STAGE_MCAM GBP_FAC_QUADS
+#define GBP_STAGE_MLMK (GBP_FAC_QUADS + GBP_MCAM_READ_QUADS)
+#define GBP_SCAM 56  // per-warp copy of: belief eta 6 | belief lambda 36 | mean 6 | previous mean 6
+#define GBP_RED_STRIDE 33
+#define GBP_SWEEP_SMEM (GBP_WARPS * GBP_STAGE_QUADS * 32 * 16 + GBP_WARPS * GBP_SCAM * 4)
+
+GBP_DEV void cp_async16(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+template <int EN>
+GBP_DEV void cp_async16_hint(void* smem, const void* gmem, uint64_t pol) {
+  if (!EN) {
+    cp_async16(smem, gmem);
+    return;
+  }
+#if GBP_L2_HINTS
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "l"(pol) : "memory");
+#else
+  cp_async16(smem, gmem);
+#endif
+}
+// L2 prefetch of one contiguous run (bytes % 16 == 0): the records of the tile that
+// will be processed `GBP_PREFETCH_TILES` blocks from now are pulled DRAM->L2 while this
+// block computes, so that its cp.async stage fill sees L2 latency instead of HBM latency.
+GBP_DEV void bulk_prefetch_l2(const void* gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gmem), "r"(bytes) : "memory");
+}
+#ifndef GBP_PREFETCH_TILES
+#define GBP_PREFETCH_TILES 148
+#endif
+
+GBP_DEV void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;\n" ::: "memory");
+}
+
+template <int Q0, int N>
+GBP_DEV void stage_read(const float4* stage, uint32_t lane, float (&out)[N * 4]) {
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    const float4 v = stage[(Q0 + q) * 32 + lane];
+    out[q * 4] = v.x; out[q * 4 + 1] = v.y; out[q * 4 + 2] = v.z; out[q * 4 + 3] = v.w;
+  }
+}
+
+// lane-ordered sum of the 42 camera-message values of the warp's 32 factors
+GBP_DEV void warp_cam_reduce(float* red, uint32_t lane, float* __restrict__ out42) {
+  {
+    const float* row = red + lane * GBP_RED_STRIDE;
+    float acc = row[0];
+#pragma unroll 8
+    for (int i = 1; i < 32; ++i) acc = fa(acc, row[i]);
+    out42[lane] = acc;
+  }
+  if (lane < GBP_CAMPART - 32) {
+    const float* row = red + (32 + lane) * GBP_RED_STRIDE;
+    float acc = row[0];
+#pragma unroll 8
+    for (int i = 1; i < 32; ++i) acc = fa(acc, row[i]);
+    out42[32 + lane] = acc;
+  }
+}
 
 template <bool PREP, bool MSG>
-__global__ void __launch_bounds__(GBP_TILE, 3) k_sweep(const DeviceGraph g) {
-  __shared__ float s_cam[54];  // belief eta 6 | belief lambda 36 | mean 6 | previous mean 6
-  __shared__ float s_red[MSG ? GBP_CAMPART * GBP_RED_STRIDE : 1];
-  __shared__ float s_part[MSG ? GBP_CAMPART * 3 : 1];
-
+__global__ void __launch_bounds__(GBP_TILE, GBP_MIN_BLOCKS) k_sweep(const DeviceGraph g) {
+  extern __shared__ float4 smem4[];
   const uint32_t tile = blockIdx.x;
   const uint32_t tid = threadIdx.x;
-  const uint32_t c = g.tile_cam[tile];
+  const uint32_t warp = tid >> 5, lane = tid & 31;
+  float4* stage = smem4 + warp * (GBP_STAGE_QUADS * 32);
+  float* s_cam = reinterpret_cast<float*>(smem4 + (MSG ? GBP_WARPS * GBP_STAGE_QUADS * 32 : 0)) + warp * GBP_SCAM;
   const size_t e = (size_t)tile * GBP_TILE + tid;
-  if (tid < 6) s_cam[tid] = g.cam_b_eta[c * 6 + tid];
-  else if (tid < 42) s_cam[tid] = g.cam_b_lam[c * 36 + (tid - 6)];
-  else if (tid < 48) s_cam[tid] = g.cam_mean[c * 6 + (tid - 42)];
-  else if (tid < 54) s_cam[tid] = g.cam_mean_prev[c * 6 + (tid - 48)];
-
-  float4 ra = g.recA[e];
+  // critical path first: the per-edge state carries the landmark id the belief gather
+  // depends on (reading it for a padding slot is harmless)
+  const uint64_t pol_keep = l2_policy_keep(), pol_stream = l2_policy_stream();
+  float4 ra = ld4_hint<(GBP_L2_HINTS & 2)>(g.recA + e, pol_keep);
+  const float4 rb = ld4_hint<(GBP_L2_HINTS & 2)>(g.recB + e, pol_keep);
+  const uint2 ti = __ldg(g.tile_info + tile);
+  const uint32_t c = ti.x;
+  const bool valid = tid < ti.y;  // padding slots hold no factor
+  if (GBP_PREFETCH_TILES > 0 && MSG && warp == 0 && lane < 2) {
+    const uint32_t pt = tile + GBP_PREFETCH_TILES;
+    if (pt < g.n_tiles) bulk_prefetch_l2((lane ? g.recB : g.recA) + (size_t)pt * GBP_TILE, GBP_TILE * 16);
+  }
+  // the camera's packed belief/mean record goes through the stage as well (224 B per warp)
+  if (lane < GBP_SCAM / 4) cp_async16(s_cam + lane * 4, g.cam_rec + (size_t)c * 16 + lane);
+  if (MSG && valid) {
+#pragma unroll
+    for (int q = 0; q < GBP_FAC_QUADS; ++q)
+      cp_async16_hint<(GBP_L2_HINTS & 4)>(stage + q * 32 + lane, g.fac + (size_t)q * g.E_pad + e, pol_stream);
+#pragma unroll
+    for (int q = 0; q < GBP_MCAM_READ_QUADS; ++q)
+      cp_async16_hint<(GBP_L2_HINTS & 4)>(stage + (GBP_STAGE_MCAM + q) * 32 + lane, g.mcam + (size_t)q * g.E_pad + e, pol_stream);
+    if (GBP_STAGE_LMK) {
+#pragma unroll
+      for (int q = 0; q < GBP_MLMK_QUADS; ++q)
+        cp_async16(stage + (GBP_STAGE_MLMK + q) * 32 + lane, g.mlmk + e * GBP_MLMK_QUADS + q);
+    }
+  }
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  float pl[12];  // previous f->lmk message: eta 0..2, lambda 3..11
+  if (MSG && !GBP_STAGE_LMK && valid) {
+    const float4* p = g.mlmk + e * GBP_MLMK_QUADS;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const float4 v = ld4_hint<(GBP_L2_HINTS & 1)>(p + q, pol_keep);
+      pl[q * 4] = v.x; pl[q * 4 + 1] = v.y; pl[q * 4 + 2] = v.z; pl[q * 4 + 3] = v.w;
+    }
+  }
   float damping = ra.x;
   int dcount = __float_as_int(ra.y);
   uint32_t flags = __float_as_uint(ra.z);
   float dmu = ra.w;
-  const bool active = (flags & GBP_FLAG_ACTIVE) != 0;
-  __syncthreads();
-
+  const bool active = valid && (flags & GBP_FLAG_ACTIVE) != 0;
+  const uint32_t l = __float_as_uint(rb.w);
+  float lb[16];  // landmark belief: eta 0..2 | lambda 3..11 | mean 12..14
   if (active) {
-    const float4 rb = ldg4(g.recB + e);
-    const uint32_t l = __float_as_uint(rb.w);
-    float lb[16];
-    {
-      const float4* p = g.lmk_b + (size_t)l * GBP_LMKB_QUADS;
+    const float4* p = g.lmk_b + (size_t)l * GBP_LMKB_QUADS;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 v = p[q];
-        lb[q * 4] = v.x; lb[q * 4 + 1] = v.y; lb[q * 4 + 2] = v.z; lb[q * 4 + 3] = v.w;
+    for (int q = 0; q < 4; ++q) {
+      const float4 v = p[q];
+      lb[q * 4] = v.x; lb[q * 4 + 1] = v.y; lb[q * 4 + 2] = v.z; lb[q * 4 + 3] = v.w;
+    }
+  }
+  // everything staged so far (camera record + this warp's factor records) has landed
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  __syncwarp();
+
+  if (PREP && active) {
+    if (dcount == 0) damping = g.hp.maxeta_damping;  // gbp_codelets.cpp:245-248
+    dcount += 1;
+    float x_kf[6], x_l[3], old[9];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) x_kf[i] = s_cam[42 + i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) x_l[i] = lb[12 + i];
+    if (flags & GBP_FLAG_MUVALID) {
+      const float4 mp = g.lmk_mean_prev[l];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) old[i] = s_cam[48 + i];
+      old[6] = mp.x; old[7] = mp.y; old[8] = mp.z;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) old[i] = g.oldmu_edge ? g.oldmu_edge[(size_t)i * g.E_pad + e] : 0.f;
+    }
+    float acc = 0.f;  // gbp_codelets.cpp:268-277
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const float d = fs(old[i], x_kf[i]);
+      acc = fa(acc, fm(d, d));
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const float d = fs(old[6 + i], x_l[i]);
+      acc = fa(acc, fm(d, d));
+    }
+    dmu = __fsqrt_rn(acc);
+    flags |= GBP_FLAG_MUVALID;
+    if (dmu < g.hp.dmu_threshold && dcount > g.hp.min_linear_iters - g.hp.num_undamped_iters) {
+      damping = 0.0f;  // gbp_codelets.cpp:280-283
+      dcount = -g.hp.num_undamped_iters;
+      const uint32_t robust = relinearise_in_place(g.fac, g.E_pad, e, make_float4(g.K[0], g.K[1], g.K[2], g.K[3]), g.hp.Nstds,
+                                                   rb.x, rb.y, rb.z, x_kf[0], x_kf[1], x_kf[2], x_kf[3], x_kf[4], x_kf[5],
+                                                   x_l[0], x_l[1], x_l[2], false);
+      flags = (flags & ~GBP_FLAG_ROBUST) | (robust ? GBP_FLAG_ROBUST : 0u);
+      if (MSG) {  // re-stage the relinearised potential (plain loads: ordered after this thread's stores)
+#pragma unroll
+        for (int q = 0; q < GBP_FAC_QUADS; ++q) stage[q * 32 + lane] = g.fac[(size_t)q * g.E_pad + e];
       }
     }
-    // lb: eta 0..2 | lambda 3..11 | mean 12..14
+  }
 
-    if (PREP) {
-      if (dcount == 0) damping = g.hp.maxeta_damping;  // gbp_codelets.cpp:245-248
-      dcount += 1;
-      float x_kf[6], x_l[3], old[9];
+  float nc[GBP_MCAM_QUADS * 4];  // new f->cam message record
+  if (MSG) {
+#ifdef GBP_EXPERIMENT_NOCOMPUTE
+    if (active) {
+      float t[100];
+      stage_read<0, 25>(stage, lane, t);
 #pragma unroll
-      for (int i = 0; i < 6; ++i) x_kf[i] = s_cam[42 + i];
+      for (int k = 0; k < 44; ++k) nc[k] = t[k] + t[k + 50] * lb[k % 16];
+      float nl[12];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) x_l[i] = lb[12 + i];
-      if (flags & GBP_FLAG_MUVALID) {
-        const float4 mp = g.lmk_mean_prev[l];
+      for (int k = 0; k < 12; ++k) nl[k] = pl[k] + t[44 + k % 6];
+      float4* p = g.mlmk + e * GBP_MLMK_QUADS;
 #pragma unroll
-        for (int i = 0; i < 6; ++i) old[i] = s_cam[48 + i];
-        old[6] = mp.x; old[7] = mp.y; old[8] = mp.z;
-      } else {
-#pragma unroll
-        for (int i = 0; i < 9; ++i) old[i] = g.oldmu_edge ? g.oldmu_edge[(size_t)i * g.E_pad + e] : 0.f;
-      }
-      float acc = 0.f;  // gbp_codelets.cpp:268-277
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const float d = fs(old[i], x_kf[i]);
-        acc = fa(acc, fm(d, d));
-      }
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const float d = fs(old[6 + i], x_l[i]);
-        acc = fa(acc, fm(d, d));
-      }
-      dmu = __fsqrt_rn(acc);
-      flags |= GBP_FLAG_MUVALID;
-      if (dmu < g.hp.dmu_threshold && dcount > g.hp.min_linear_iters - g.hp.num_undamped_iters) {
-        damping = 0.0f;  // gbp_codelets.cpp:280-283
-        dcount = -g.hp.num_undamped_iters;
-        const uint32_t robust = relinearise_in_place(g.fac, g.E_pad, e, make_float4(g.K[0], g.K[1], g.K[2], g.K[3]), g.hp.Nstds,
-                                                     rb.x, rb.y, rb.z, x_kf[0], x_kf[1], x_kf[2], x_kf[3], x_kf[4], x_kf[5],
-                                                     x_l[0], x_l[1], x_l[2], false);
-        flags = (flags & ~GBP_FLAG_ROBUST) | (robust ? GBP_FLAG_ROBUST : 0u);
-      }
-    }
-
-    if (MSG) {
-      float f[GBP_FAC_QUADS * 4];
-      load_quads<GBP_FAC_QUADS>(g.fac, g.E_pad, e, f);
-      float pc[GBP_MCAM_READ_QUADS * 4];  // previous f->cam message: eta 0..5, lower lambda 6..26
-      load_quads<GBP_MCAM_READ_QUADS>(g.mcam, g.E_pad, e, pc);
-      float pl[12];  // previous f->lmk message: eta 0..2, lambda 3..11
-      {
-        const float4* p = g.mlmk + e * GBP_MLMK_QUADS;
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          const float4 v = p[q];
-          pl[q * 4] = v.x; pl[q * 4 + 1] = v.y; pl[q * 4 + 2] = v.z; pl[q * 4 + 3] = v.w;
-        }
-      }
-      const float* eta = f + GBP_FAC_ETA;
-      const float* ll = f + GBP_FAC_LL;
-      const float* cl = f + GBP_FAC_CL;
-      const float* cc = f + GBP_FAC_CC;
+      for (int q = 0; q < 3; ++q) p[q] = make_float4(nl[q * 4], nl[q * 4 + 1], nl[q * 4 + 2], nl[q * 4 + 3]);
+      store_quads<GBP_MCAM_QUADS>(g.mcam, g.E_pad, e, nc);
+    } else if (false) {
+#else
+    if (active) {
+#endif
       const float omd = fs(1.0f, damping);
+      float head[36];  // eta 0..8 | ll 9..17 | cl 18..35
+      stage_read<0, 9>(stage, lane, head);
+      const float* eta = head + GBP_FAC_ETA;
+      const float* ll = head + GBP_FAC_LL;
+      const float* cl = head + GBP_FAC_CL;
+      if (GBP_STAGE_LMK) stage_read<GBP_STAGE_MLMK, 3>(stage, lane, pl);
+      float pc_eta[8];  // previous f->cam eta 0..5 (+2 lower-lambda entries)
+      stage_read<GBP_STAGE_MCAM, 2>(stage, lane, pc_eta);
 
       // ---- message to the landmark (gbp_codelets.cpp:536-552, 691-699) ----
       float nl[12];
       {
-        float Ld[21];
-#pragma unroll
-        for (int i = 0; i < 6; ++i)
-#pragma unroll
-          for (int j = 0; j <= i; ++j)
-            Ld[lt(i, j)] = fs(fa(cc[i * 6 + j], s_cam[6 + i * 6 + j]), pc[GBP_MCAM_LOWER + lt(i, j)]);
         float Ai[36];
-        inv6(Ld, Ai);
+        {
+          float cc[36], pc[28], Ld[21];
+          stage_read<9, 9>(stage, lane, cc);
+          stage_read<GBP_STAGE_MCAM, 7>(stage, lane, pc);
+#pragma unroll
+          for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j)
+              Ld[lt(i, j)] = fs(fa(cc[i * 6 + j], s_cam[6 + i * 6 + j]), pc[GBP_MCAM_LOWER + lt(i, j)]);
+          inv6(Ld, Ai);
+        }
         float P[18];  // Lambda_lc * inv  (3x6), Lambda_lc(i,k) = Lambda_cl(k,i)
 #pragma unroll
         for (int i = 0; i < 3; ++i)
@@ -227,7 +403,7 @@ __global__ void __launch_bounds__(GBP_TILE, 3) k_sweep(const DeviceGraph g) {
           }
         float ed[6];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) ed[i] = fs(fa(eta[i], s_cam[i]), pc[i]);
+        for (int i = 0; i < 6; ++i) ed[i] = fs(fa(eta[i], s_cam[i]), pc_eta[i]);
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
           float acc = fm(P[i * 6], ed[0]);
@@ -246,9 +422,14 @@ __global__ void __launch_bounds__(GBP_TILE, 3) k_sweep(const DeviceGraph g) {
             nl[3 + i * 3 + j] = fs(ll[i * 3 + j], acc);
           }
       }
+      {
+        float4* p = g.mlmk + e * GBP_MLMK_QUADS;
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+          st4_hint<(GBP_L2_HINTS & 1)>(p + q, make_float4(nl[q * 4], nl[q * 4 + 1], nl[q * 4 + 2], nl[q * 4 + 3]), pol_keep);
+      }
 
       // ---- message to the camera (gbp_codelets.cpp:446-462, 619-627) ----
-      float nc[GBP_MCAM_QUADS * 4];
       {
         float Ld[9], Li[9];
 #pragma unroll
@@ -267,93 +448,79 @@ __global__ void __launch_bounds__(GBP_TILE, 3) k_sweep(const DeviceGraph g) {
         for (int i = 0; i < 6; ++i) {
           const float acc = fa(fa(fm(P[i * 3], ed[0]), fm(P[i * 3 + 1], ed[1])), fm(P[i * 3 + 2], ed[2]));
           const float h = fs(eta[i], acc);
-          const float v = fa(fm(h, omd), fm(pc[i], damping));
-          nc[i] = v;
-          s_red[i * GBP_RED_STRIDE + tid] = v;
+          nc[i] = fa(fm(h, omd), fm(pc_eta[i], damping));
         }
+        float cc[36];
+        stage_read<9, 9>(stage, lane, cc);
 #pragma unroll
         for (int i = 0; i < 6; ++i)
 #pragma unroll
           for (int j = 0; j < 6; ++j) {
             const float acc = fa(fa(fm(P[i * 3], cl[j * 3]), fm(P[i * 3 + 1], cl[j * 3 + 1])), fm(P[i * 3 + 2], cl[j * 3 + 2]));
-            const float v = fs(cc[i * 6 + j], acc);
-            nc[(i >= j) ? (GBP_MCAM_LOWER + lt(i, j)) : (GBP_MCAM_UPPER + (5 * i - i * (i - 1) / 2) + (j - i - 1))] = v;
-            s_red[(6 + i * 6 + j) * GBP_RED_STRIDE + tid] = v;
+            nc[(i >= j) ? (GBP_MCAM_LOWER + lt(i, j)) : (GBP_MCAM_UPPER + (5 * i - i * (i - 1) / 2) + (j - i - 1))] =
+                fs(cc[i * 6 + j], acc);
           }
         nc[27] = 0.f;
         nc[43] = 0.f;
       }
-      store_quads<GBP_MCAM_QUADS>(g.mcam, g.E_pad, e, nc);
-      {
-        float4* p = g.mlmk + e * GBP_MLMK_QUADS;
 #pragma unroll
-        for (int q = 0; q < 3; ++q) p[q] = make_float4(nl[q * 4], nl[q * 4 + 1], nl[q * 4 + 2], nl[q * 4 + 3]);
-      }
+      for (int q = 0; q < GBP_MCAM_QUADS; ++q)
+        st4_hint<(GBP_L2_HINTS & 8)>(g.mcam + (size_t)q * g.E_pad + e, make_float4(nc[q * 4], nc[q * 4 + 1], nc[q * 4 + 2], nc[q * 4 + 3]), pol_stream);
       flags |= GBP_FLAG_HASMSG;
-    }
-    g.recA[e] = make_float4(damping, __int_as_float(dcount), __uint_as_float(flags), dmu);
-  } else if (MSG) {
-    // inactive (or padding) slot: its messages are zero (gbp_codelets.cpp:464-468 etc.)
+    } else {
+      // inactive (or padding) slot: its messages are zero (gbp_codelets.cpp:464-468 etc.)
 #pragma unroll
-    for (int k = 0; k < GBP_CAMPART; ++k) s_red[k * GBP_RED_STRIDE + tid] = 0.f;
-    if (flags & GBP_FLAG_HASMSG) {
-      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < GBP_MCAM_QUADS * 4; ++k) nc[k] = 0.f;
+      if (valid && (flags & GBP_FLAG_HASMSG)) {
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int q = 0; q < GBP_MCAM_QUADS; ++q) g.mcam[(size_t)q * g.E_pad + e] = z4;
+        for (int q = 0; q < GBP_MCAM_QUADS; ++q) g.mcam[(size_t)q * g.E_pad + e] = z4;
 #pragma unroll
-      for (int q = 0; q < 3; ++q) g.mlmk[e * GBP_MLMK_QUADS + q] = z4;
-      flags &= ~GBP_FLAG_HASMSG;
-      g.recA[e] = make_float4(damping, __int_as_float(dcount), __uint_as_float(flags), dmu);
+        for (int q = 0; q < 3; ++q) g.mlmk[e * GBP_MLMK_QUADS + q] = z4;
+        flags &= ~GBP_FLAG_HASMSG;
+      }
     }
   }
+  if (valid && (active || MSG))
+    st4_hint<(GBP_L2_HINTS & 2)>(g.recA + e, make_float4(damping, __int_as_float(dcount), __uint_as_float(flags), dmu), pol_keep);
 
   if (MSG) {
-    // deterministic on-chip sum of the tile's 128 camera-bound messages:
-    // 42 values x 3 contiguous parts, then the 3 parts in order.
-    __syncthreads();
-    if (tid < GBP_CAMPART * 3) {
-      const int k = tid / 3, part = tid % 3;
-      const int b = part * 43, en = (b + 43 < GBP_TILE) ? b + 43 : GBP_TILE;
-      const float* row = s_red + k * GBP_RED_STRIDE;
-      float acc = row[b];
-      for (int i = b + 1; i < en; ++i) acc = fa(acc, row[i]);
-      s_part[tid] = acc;
-    }
-    __syncthreads();
-    if (tid < GBP_CAMPART)
-      g.cam_partial[(size_t)tile * GBP_CAMPART + tid] = fa(fa(s_part[tid * 3], s_part[tid * 3 + 1]), s_part[tid * 3 + 2]);
+    // lane-ordered reduction through the warp's own (now consumed) stage
+    float* red = reinterpret_cast<float*>(stage);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 6; ++i) red[i * GBP_RED_STRIDE + lane] = nc[i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = 0; j < 6; ++j)
+        red[(6 + i * 6 + j) * GBP_RED_STRIDE + lane] =
+            nc[(i >= j) ? (GBP_MCAM_LOWER + lt(i, j)) : (GBP_MCAM_UPPER + (5 * i - i * (i - 1) / 2) + (j - i - 1))];
+    __syncwarp();
+    warp_cam_reduce(red, lane, g.cam_partial + ((size_t)tile * GBP_WARPS + warp) * GBP_CAMPART);
   }
 }
 
-// Recompute the per-tile camera partial sums from the stored messages (used
+// Recompute the per-warp camera partial sums from the stored messages (used
 // after set_tensor on the camera message tensors).
 __global__ void __launch_bounds__(GBP_TILE) k_cam_partials(const DeviceGraph g) {
-  __shared__ float s_red[GBP_CAMPART * GBP_RED_STRIDE];
-  __shared__ float s_part[GBP_CAMPART * 3];
+  __shared__ float s_red[GBP_WARPS][GBP_CAMPART * GBP_RED_STRIDE];
   const uint32_t tile = blockIdx.x, tid = threadIdx.x;
+  const uint32_t warp = tid >> 5, lane = tid & 31;
   const size_t e = (size_t)tile * GBP_TILE + tid;
   float m[GBP_MCAM_QUADS * 4];
   load_quads<GBP_MCAM_QUADS>(g.mcam, g.E_pad, e, m);
+  float* red = s_red[warp];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) s_red[i * GBP_RED_STRIDE + tid] = m[i];
+  for (int i = 0; i < 6; ++i) red[i * GBP_RED_STRIDE + lane] = m[i];
 #pragma unroll
   for (int i = 0; i < 6; ++i)
 #pragma unroll
     for (int j = 0; j < 6; ++j)
-      s_red[(6 + i * 6 + j) * GBP_RED_STRIDE + tid] =
+      red[(6 + i * 6 + j) * GBP_RED_STRIDE + lane] =
           m[(i >= j) ? (GBP_MCAM_LOWER + lt(i, j)) : (GBP_MCAM_UPPER + (5 * i - i * (i - 1) / 2) + (j - i - 1))];
-  __syncthreads();
-  if (tid < GBP_CAMPART * 3) {
-    const int k = tid / 3, part = tid % 3;
-    const int b = part * 43, en = (b + 43 < GBP_TILE) ? b + 43 : GBP_TILE;
-    const float* row = s_red + k * GBP_RED_STRIDE;
-    float acc = row[b];
-    for (int i = b + 1; i < en; ++i) acc = fa(acc, row[i]);
-    s_part[tid] = acc;
-  }
-  __syncthreads();
-  if (tid < GBP_CAMPART)
-    g.cam_partial[(size_t)tile * GBP_CAMPART + tid] = fa(fa(s_part[tid * 3], s_part[tid * 3 + 1]), s_part[tid * 3 + 2]);
+  __syncwarp();
+  warp_cam_reduce(red, lane, g.cam_partial + ((size_t)tile * GBP_WARPS + warp) * GBP_CAMPART);
 }
 
 // Belief update + per-variable mean.  Blocks [0,C) own one camera each; the
@@ -362,14 +529,24 @@ __global__ void __launch_bounds__(GBP_TILE) k_cam_partials(const DeviceGraph g) 
 // ba/ba.cpp:898) before the new mean is stored.
 __global__ void __launch_bounds__(GBP_TILE) k_update_vars(const DeviceGraph g, const int shift) {
   const uint32_t tid = threadIdx.x;
-  if (blockIdx.x < g.C) {
+  // landmark blocks come first so that the (latency-bound, mostly idle) camera blocks
+  // overlap with their tail instead of occupying the first wave
+  const uint32_t nb_lmk = (g.L + GBP_TILE - 1) / GBP_TILE;
+  if (blockIdx.x >= nb_lmk) {
     __shared__ float s_b[GBP_CAMPART];
-    const uint32_t c = blockIdx.x;
+    const uint32_t c = blockIdx.x - nb_lmk;
     if (tid < GBP_CAMPART) {
       // the sum starts from +0 like a zero-initialised accumulator: 0 + prior (turns a -0 prior into +0)
       float acc = fa(0.0f, (tid < 6) ? g.cam_prior_eta[c * 6 + tid] : g.cam_prior_lam[c * 36 + (tid - 6)]);
       const uint32_t t0 = g.cam_tile_begin[c], t1 = g.cam_tile_begin[c + 1];
-      for (uint32_t t = t0; t < t1; ++t) acc = fa(acc, g.cam_partial[(size_t)t * GBP_CAMPART + tid]);
+      // four partials (= one tile) are fetched together; the additions stay in order
+      for (uint32_t t = t0 * GBP_WARPS; t < t1 * GBP_WARPS; t += GBP_WARPS) {
+        float v[GBP_WARPS];
+#pragma unroll
+        for (int u = 0; u < GBP_WARPS; ++u) v[u] = g.cam_partial[(size_t)(t + u) * GBP_CAMPART + tid];
+#pragma unroll
+        for (int u = 0; u < GBP_WARPS; ++u) acc = fa(acc, v[u]);
+      }
       s_b[tid] = acc;
       if (tid < 6) g.cam_b_eta[c * 6 + tid] = acc;
       else g.cam_b_lam[c * 36 + (tid - 6)] = acc;
@@ -387,17 +564,23 @@ __global__ void __launch_bounds__(GBP_TILE) k_update_vars(const DeviceGraph g, c
       const float w[3] = {mean[3], mean[4], mean[5]};
       float R[9];
       so3exp(w, R);
+      float* rec = reinterpret_cast<float*>(g.cam_rec + (size_t)c * 16);
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
-        if (shift) g.cam_mean_prev[c * 6 + i] = g.cam_mean[c * 6 + i];
+        const float prev = shift ? g.cam_mean[c * 6 + i] : g.cam_mean_prev[c * 6 + i];
+        g.cam_mean_prev[c * 6 + i] = prev;
         g.cam_mean[c * 6 + i] = mean[i];
+        rec[42 + i] = mean[i];
+        rec[48 + i] = prev;
       }
 #pragma unroll
       for (int i = 0; i < 9; ++i) g.cam_R[c * 9 + i] = R[i];
     }
+    if (tid < GBP_CAMPART) reinterpret_cast<float*>(g.cam_rec + (size_t)c * 16)[tid] = s_b[tid];
   } else {
-    const uint32_t l = (blockIdx.x - g.C) * GBP_TILE + tid;
+    const uint32_t l = blockIdx.x * GBP_TILE + tid;
     if (l >= g.L) return;
+    const uint64_t pol_keep = l2_policy_keep();
     float b[12];
     {
       const float4* p = g.lmk_prior + (size_t)l * 3;
@@ -408,12 +591,28 @@ __global__ void __launch_bounds__(GBP_TILE) k_update_vars(const DeviceGraph g, c
       }
     }
     const uint32_t k0 = g.lmk_ptr[l], k1 = g.lmk_ptr[l + 1];
-    for (uint32_t k = k0; k < k1; ++k) {  // slot order = original edge order
-      const float4* p = g.mlmk + (size_t)g.lmk_edges[k] * GBP_MLMK_QUADS;
-      const float4 v0 = p[0], v1 = p[1], v2 = p[2];
-      b[0] = fa(b[0], v0.x); b[1] = fa(b[1], v0.y); b[2] = fa(b[2], v0.z); b[3] = fa(b[3], v0.w);
-      b[4] = fa(b[4], v1.x); b[5] = fa(b[5], v1.y); b[6] = fa(b[6], v1.z); b[7] = fa(b[7], v1.w);
-      b[8] = fa(b[8], v2.x); b[9] = fa(b[9], v2.y); b[10] = fa(b[10], v2.z); b[11] = fa(b[11], v2.w);
+    // slot order = original edge order.  The gathers of four slots are issued together
+    // (independent loads), the additions stay strictly in slot order.
+    for (uint32_t k = k0; k < k1; k += 4) {
+      uint32_t idx[4];
+      float4 v[4][3];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) idx[u] = (k + u < k1) ? __ldg(g.lmk_edges + k + u) : 0xffffffffu;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (idx[u] != 0xffffffffu) {
+          const float4* p = g.mlmk + (size_t)idx[u] * GBP_MLMK_QUADS;
+          v[u][0] = ld4_hint<(GBP_L2_HINTS & 1)>(p, pol_keep); v[u][1] = ld4_hint<(GBP_L2_HINTS & 1)>(p + 1, pol_keep); v[u][2] = ld4_hint<(GBP_L2_HINTS & 1)>(p + 2, pol_keep);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (idx[u] != 0xffffffffu) {
+          b[0] = fa(b[0], v[u][0].x); b[1] = fa(b[1], v[u][0].y); b[2] = fa(b[2], v[u][0].z); b[3] = fa(b[3], v[u][0].w);
+          b[4] = fa(b[4], v[u][1].x); b[5] = fa(b[5], v[u][1].y); b[6] = fa(b[6], v[u][1].z); b[7] = fa(b[7], v[u][1].w);
+          b[8] = fa(b[8], v[u][2].x); b[9] = fa(b[9], v[u][2].y); b[10] = fa(b[10], v[u][2].z); b[11] = fa(b[11], v[u][2].w);
+        }
+      }
     }
     const float eta[3] = {b[0], b[1], b[2]};
     float lam[9], mean[3];
@@ -646,8 +845,16 @@ __global__ void k_means_from_beliefs(const DeviceGraph g) {
     const float w[3] = {mean[3], mean[4], mean[5]};
     float R[9];
     so3exp(w, R);
+    float* rec = reinterpret_cast<float*>(g.cam_rec + (size_t)i * 16);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) g.cam_mean[i * 6 + k] = mean[k];
+    for (int k = 0; k < 6; ++k) {
+      g.cam_mean[i * 6 + k] = mean[k];
+      rec[k] = eta[k];
+      rec[42 + k] = mean[k];
+      rec[48 + k] = g.cam_mean_prev[i * 6 + k];
+    }
+#pragma unroll
+    for (int k = 0; k < 36; ++k) rec[6 + k] = g.cam_b_lam[i * 36 + k];
 #pragma unroll
     for (int k = 0; k < 9; ++k) g.cam_R[i * 9 + k] = R[k];
   } else if (i < g.C + g.L) {

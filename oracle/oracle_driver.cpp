@@ -94,40 +94,33 @@ inline size_t lml(const Oracle& o, uint32_t l, uint32_t slot) { return ((size_t)
 // prog_ub: belief = sum over slots, fp32 (ba/ba.cpp:104-139).  popops::reduce does
 // not specify its summation order; two realisations are provided:
 //   reduce_order 0: serial slot order  ((prior + m1) + m2) + ...
-//   reduce_order 1: the order of the CUDA path -- camera messages are summed per
-//     tile of 128 consecutive slots (three contiguous parts of 43/43/42 summed
-//     serially, then (p0+p1)+p2), and the tiles are added to the prior in order.
+//   reduce_order 1: the order of the CUDA path -- camera messages are summed serially
+//     inside chunks of 32 consecutive slots (one warp's factors), and the chunk sums
+//     are added to the prior in order (chunks are counted in whole 128-slot tiles).
 //     Landmarks are serial in both modes.
-float cam_tile_sum(const Oracle& o, const std::vector<float>& m, uint32_t c, uint32_t d, uint32_t dim,
-                   uint32_t tile) {
-  float part[3];
-  for (int p = 0; p < 3; ++p) {
-    const uint32_t b = p * 43, en = std::min<uint32_t>(b + 43, 128);
-    float acc = 0.f;
-    bool first = true;
-    for (uint32_t i = b; i < en; ++i) {
-      const uint32_t slot = tile * 128 + i + 1;  // slot 0 is the prior
-      const float v = (slot < o.SK) ? m[((size_t)o.SK * c + slot) * dim + d] : 0.f;
-      acc = first ? v : acc + v;
-      first = false;
-    }
-    part[p] = acc;
+float cam_chunk_sum(const Oracle& o, const std::vector<float>& m, uint32_t c, uint32_t d, uint32_t dim,
+                    uint32_t chunk) {
+  float acc = 0.f;
+  for (uint32_t i = 0; i < 32; ++i) {
+    const uint32_t slot = chunk * 32 + i + 1;  // slot 0 is the prior
+    const float v = (slot < o.SK) ? m[((size_t)o.SK * c + slot) * dim + d] : 0.f;
+    acc = (i == 0) ? v : acc + v;
   }
-  return (part[0] + part[1]) + part[2];
+  return acc;
 }
 
 void update_beliefs(Oracle& o) {
-  const uint32_t n_tiles_max = (o.SK - 1 + 127) / 128;
+  const uint32_t n_chunks = ((o.SK - 1 + 127) / 128) * 4;
 #pragma omp parallel for schedule(static) num_threads(o.nthreads)
   for (int64_t c = 0; c < (int64_t)o.C; ++c) {
-    // number of tiles of this camera = ceil(deg/128); slots beyond deg are zero anyway
+    // slots beyond the camera's degree are zero, so summing max-degree many chunks is exact
     for (int d = 0; d < 6; ++d) {
       float s = 0.f;
       if (o.reduce_order == 0) {
         for (uint32_t k = 0; k < o.SK; ++k) s += o.cam_m_eta[cme(o, c, k) + d];
       } else {
         s += o.cam_m_eta[cme(o, c, 0) + d];
-        for (uint32_t t = 0; t < n_tiles_max; ++t) s += cam_tile_sum(o, o.cam_m_eta, c, d, 6, t);
+        for (uint32_t t = 0; t < n_chunks; ++t) s += cam_chunk_sum(o, o.cam_m_eta, c, d, 6, t);
       }
       o.cam_b_eta[c * 6 + d] = s;
     }
@@ -137,7 +130,7 @@ void update_beliefs(Oracle& o) {
         for (uint32_t k = 0; k < o.SK; ++k) s += o.cam_m_lam[cml(o, c, k) + d];
       } else {
         s += o.cam_m_lam[cml(o, c, 0) + d];
-        for (uint32_t t = 0; t < n_tiles_max; ++t) s += cam_tile_sum(o, o.cam_m_lam, c, d, 36, t);
+        for (uint32_t t = 0; t < n_chunks; ++t) s += cam_chunk_sum(o, o.cam_m_lam, c, d, 36, t);
       }
       o.cam_b_lam[c * 36 + d] = s;
     }
