@@ -7,7 +7,10 @@
 A "step" is ONE GBP sweep (GBP_PROG, ba/ba.cpp:895-905: prep -> messages -> belief
 update) over the whole factor graph.  Workload at N=1 = BASELINE.json configs[3]:
 synthetic BAL-format problem, 1k cameras / 100k landmarks / ~1M reprojection factors
-(generated in-process, seed 1234; no dataset is read).  `value` = factor-message
+(generated in-process, seed 1234; no dataset is read).  At N>1 the SAME generator makes
+ONE graph N times as large (N k cameras / N x 100k landmarks / ~N M factors -- N=8 is the
+scale of configs[4]) which is partitioned by camera range over the N GPUs, one process
+per GPU, with the per-sweep boundary-landmark exchange over NVLink (weak scaling).  `value` = factor-message
 updates per second (= factors x sweeps / s, one update = both directed messages of one
 factor), device-timed with CUDA events on the library's stream, state resident in HBM.
 `e2e` = the same metric for a whole `ba`-style job through the C ABI with host buffers:
@@ -127,7 +130,7 @@ def cpu_baseline_run(setup, n_sweeps, budget_s, warmup=1):
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    bal, setup = build_problem()
+    bal, setup = build_problem(scale=max(args.gpus, 1))   # the graph our arm runs at this N
     E = setup.problem.n_edges
     warm = min(args.warmup, 3)
     base, done, ms = cpu_baseline_run(setup, args.steps, budget_s=120.0, warmup=warm)
@@ -137,7 +140,8 @@ def run_reference_arm(args, rank, world):
         "n_gpus": args.gpus, "steps": done, "warmup": warm, "ms_per_step": ms / max(done, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "sweeps_per_sec": 1e3 * done / ms,
-        "config": {"workload": "synthetic BAL 1k cameras / 100k landmarks / ~1M factors (configs[3])",
+        "config": {"workload": "synthetic BAL 1k cameras / 100k landmarks / ~1M factors per GPU (configs[3]); at N>1 "
+                               "one N-times larger graph (N=8 ~ configs[4])",
                    "cameras": bal.n_keyframes, "landmarks": bal.n_points, "factors": E,
                    "note": "reference codelets (gbp_codelets.cpp) on host cores; Poplar IPUModel is not installable"},
         "cpu_baseline": base,
@@ -174,12 +178,20 @@ def main():
 
     from gbp_poplar_b200 import GBPEngine, default_opts
 
-    bal, setup = build_problem()
+    bal, setup = build_problem(scale=world)          # ONE graph, `world` times config-4 size
     E, Cn, Ln = setup.problem.n_edges, setup.problem.n_keyframes, setup.problem.n_points
+
+    def make_engine():
+        if world > 1:
+            return GBPEngine.sharded(setup.problem, opts)
+        return GBPEngine(setup.problem, opts)
+
     opts = default_opts(device=local_rank)
     t_init0 = time.time()
-    eng = GBPEngine(setup.problem, opts)
+    eng = make_engine()
     init_s = time.time() - t_init0
+    E_loc, C_loc, L_loc = eng.n_edges, eng.n_keyframes, eng.n_points   # this rank's shard (== global at N=1)
+    n_boundary = eng.shard.n_boundary_points if eng.shard else 0
     ba_preroll(eng)
 
     sampler = ClockSampler(local_rank)
@@ -200,7 +212,7 @@ def main():
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    value = E * world * args.steps / (ms / 1e3)
+    value = E * args.steps / (ms / 1e3)              # whole-job: all factors of the one graph
 
     # ---- per-kernel durations (CUDA events around every launch) for the roofline
     eng.set_profile(True)
@@ -213,7 +225,7 @@ def main():
     sampler.join(timeout=2)
 
     peak, peak_src = read_peaks()
-    algo_bytes_factor_kernel = ALGO_BYTES_PER_FACTOR * E
+    algo_bytes_factor_kernel = ALGO_BYTES_PER_FACTOR * E_loc   # one launch = this rank's factors
     t_factor = ms_factor / args.steps / 1e3
     achieved = algo_bytes_factor_kernel / t_factor / 1e9
     roofline = {
@@ -229,7 +241,7 @@ def main():
     if os.path.exists(traffic_file):
         with open(traffic_file) as f:
             tr = json.load(f)
-        if tr.get("factors") == E:
+        if tr.get("factors") == E_loc:
             roofline["traffic"] = tr.get("dram_bytes_per_launch")
 
     # ---- e2e: a whole ba-style job through the C ABI with host buffers (rank-local problem)
@@ -237,7 +249,7 @@ def main():
     if rank == 0 or world > 1:
         barrier()
         t0 = time.time()
-        eng2 = GBPEngine(setup.problem, opts)          # H2D of the whole problem + LINEARISE_PROG
+        eng2 = make_engine()                           # H2D of the (rank's part of the) problem + LINEARISE_PROG
         last = None
         for it in range(args.steps):
             if (it + 1) % 2 == 0 and it < 10:
@@ -245,13 +257,17 @@ def main():
             last = eng2.iterate(1, stats=True)[0]      # D2H of the per-sweep metric
         beliefs = eng2.get_beliefs()                   # READ_PROG: D2H beliefs + damping state
         wall = time.time() - t0
-        h2d = 4 * (2 * E + 2 * E + E + 42 * Cn + 12 * Ln + Cn + Ln + Cn + Ln + E + E + E)
+        h2d = 4 * (2 * E_loc + 2 * E_loc + E_loc + 42 * C_loc + 12 * L_loc + C_loc + L_loc + C_loc + L_loc + 3 * E_loc)
         d2h = 24 * args.steps + sum(v.nbytes for v in beliefs.values())
+        if world > 1:
+            t = torch.tensor([float(h2d), float(d2h)], device="cuda")
+            dist.all_reduce(t)
+            h2d, d2h = float(t[0].item()), float(t[1].item())
         if world > 1:
             t = torch.tensor([wall], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             wall = float(t.item())
-        e2e = {"value": E * world * args.steps / wall, "unit": "factor-updates/s",
+        e2e = {"value": E * args.steps / wall, "unit": "factor-updates/s",
                "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
                "wall_s": wall, "final_reproj_px": last["reproj_mean"] if last else None,
                "what": "gbp_cuda_init + K x gbp_cuda_iterate(1, stats) + gbp_cuda_get_beliefs, host clock"}
@@ -267,9 +283,13 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "sweeps_per_sec": args.steps / (ms / 1e3) * 1.0,
-            "config": {"workload": "synthetic BAL 1k cameras / 100k landmarks / ~1M factors per GPU (configs[3])",
-                       "cameras": Cn, "landmarks": Ln, "factors": E, "per_gpu": True,
-                       "parallelism": "replicas" if world > 1 else "single",
+            "config": {"workload": "synthetic BAL 1k cameras / 100k landmarks / ~1M factors per GPU (configs[3]); at N>1 "
+                                   "one N-times larger graph partitioned by camera range (N=8 ~ configs[4])",
+                       "cameras": Cn, "landmarks": Ln, "factors": E, "per_gpu": False,
+                       "parallelism": f"camera-range shards x{world}, NCCL all-gather of boundary-landmark partials "
+                                      f"per sweep ({n_boundary} boundary landmarks, {48 * n_boundary} B per rank)"
+                       if world > 1 else "single",
+                       "rank0_shard": {"cameras": C_loc, "landmarks": L_loc, "factors": E_loc},
                        "cache": "per-sweep working set ~0.75 GB >> 126 MB L2 (no flush needed)",
                        "preroll": f"{BA_PREROLL} sweeps of the ba.cpp schedule incl. prior weakening, untimed",
                        "init_s": init_s},

@@ -150,6 +150,19 @@ CUDA_ONLY_API = {
     "gbp_cuda_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "gbp_cuda_init_shard": (C.c_int, [C.POINTER(GbpProblem), C.POINTER(GbpOpts), C.c_uint32, C.c_uint32,
                                       C.c_void_p, C.POINTER(C.c_void_p)]),
+    "gbp_cuda_shard_info": (C.c_void_p, [C.c_void_p]),
+    # pure host: the rank-local sub-problem of a camera-range partition
+    "gbp_shard_build": (C.c_int, [C.POINTER(GbpProblem), C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "gbp_shard_free": (None, [C.c_void_p]),
+    "gbp_shard_problem": (C.POINTER(GbpProblem), [C.c_void_p]),
+    "gbp_shard_get_plan": (C.POINTER(GbpShardPlan), [C.c_void_p]),
+    "gbp_shard_lmk_global": (c_u32p, [C.c_void_p]),
+    "gbp_shard_edge_global": (c_u32p, [C.c_void_p]),
+    "gbp_shard_n_boundary_local": (C.c_uint32, [C.c_void_p]),
+    "gbp_shard_boundary_local": (c_u32p, [C.c_void_p]),
+    "gbp_shard_boundary_slot": (c_u32p, [C.c_void_p]),
+    "gbp_shard_n_active_global": (C.c_uint32, [C.c_void_p]),
+    "gbp_shard_cam_bounds": (c_u32p, [C.c_void_p]),
 }
 
 HOST_API = {

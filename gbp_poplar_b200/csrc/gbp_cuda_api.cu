@@ -16,6 +16,7 @@
 
 #include "../../include/gbp_cuda.h"
 #include "gbp_kernels.cuh"
+#include "nccl_dyn.h"
 
 void gbp_set_error(const std::string& s);  // host_error.cpp
 
@@ -103,6 +104,15 @@ struct gbp_handle {
   uint64_t kernels_launched = 0;
   uint64_t last_kernels = 0;
   std::vector<void*> allocs;
+  // multi-GPU shard (null / 0 on a single-GPU handle)
+  gbp_shard* shard = nullptr;
+  uint32_t world = 1, rank = 0;
+  ncclComm_t comm = nullptr;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_send = nullptr, ev_recv = nullptr;
+  double* d_metric_raw = nullptr;   // [8]         this rank's metric sums
+  double* d_metric_all = nullptr;   // [world][8]  all-gathered
+  uint64_t exchanges = 0;
 };
 
 namespace {
@@ -138,12 +148,45 @@ int priors_about_to_change(gbp_handle* h) {
   return GBP_OK;
 }
 
+#define GBP_NCCL_TRY(expr)                                                                         \
+  do {                                                                                             \
+    ncclResult_t r__ = (expr);                                                                     \
+    if (r__ != ncclSuccess) {                                                                      \
+      gbp_set_error(std::string(#expr) + ": " + gbp::nccl_api().GetErrorString(r__));              \
+      return GBP_ERR_COMM;                                                                         \
+    }                                                                                              \
+  } while (0)
+
+// prog_ub (ba/ba.cpp:104-139).  On a shard the boundary landmarks go first: their partial
+// sums are all-gathered on the communication stream while the main stream updates the
+// interior landmarks and the cameras; k_boundary_finish then waits for the gather.
 int launch_update_vars(gbp_handle* h) {
   const int shift = h->pending_shift ? 1 : 0;
   const uint32_t grid = vars_grid(h);
+  const bool exchange = h->shard && h->g.n_bnd_global > 0;
+  const uint32_t bgrid = (h->g.n_bnd_local + GBP_TILE - 1) / GBP_TILE;
+  if (exchange) {
+    if (bgrid) {
+      gbp::k_boundary_partial<<<bgrid, GBP_TILE, 0, h->stream>>>(h->g);
+      h->kernels_launched++;
+    }
+    GBP_CUDA_TRY(cudaEventRecord(h->ev_send, h->stream));
+    GBP_CUDA_TRY(cudaStreamWaitEvent(h->comm_stream, h->ev_send, 0));
+    GBP_NCCL_TRY(gbp::nccl_api().AllGather(h->g.bnd_send, (void*)h->g.bnd_recv, (size_t)h->g.n_bnd_global * 12, ncclFloat,
+                                           h->comm, h->comm_stream));
+    GBP_CUDA_TRY(cudaEventRecord(h->ev_recv, h->comm_stream));
+    h->exchanges++;
+  }
   if (grid) {
     gbp::k_update_vars<<<grid, GBP_TILE, 0, h->stream>>>(h->g, shift);
     h->kernels_launched++;
+  }
+  if (exchange) {
+    GBP_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_recv, 0));
+    if (bgrid) {
+      gbp::k_boundary_finish<<<bgrid, GBP_TILE, 0, h->stream>>>(h->g, shift);
+      h->kernels_launched++;
+    }
   }
   h->pending_shift = false;
   GBP_CUDA_TRY(cudaGetLastError());
@@ -167,8 +210,17 @@ int launch_metric(gbp_handle* h, gbp::DeviceStats* d_out) {
     gbp::k_metric<<<h->n_tiles, GBP_TILE, 0, h->stream>>>(h->g, h->n_active, h->d_metric_parts);
     h->kernels_launched++;
   }
-  gbp::k_metric_finish<<<1, 256, 0, h->stream>>>(h->d_metric_parts, h->n_tiles, d_out);
+  gbp::k_metric_finish<<<1, 256, 0, h->stream>>>(h->d_metric_parts, h->n_tiles, d_out, h->shard ? h->d_metric_raw : nullptr);
   h->kernels_launched++;
+  if (h->shard) {  // every rank reports the metric of the WHOLE graph
+    GBP_CUDA_TRY(cudaEventRecord(h->ev_send, h->stream));
+    GBP_CUDA_TRY(cudaStreamWaitEvent(h->comm_stream, h->ev_send, 0));
+    GBP_NCCL_TRY(gbp::nccl_api().AllGather(h->d_metric_raw, h->d_metric_all, 8, ncclDouble, h->comm, h->comm_stream));
+    GBP_CUDA_TRY(cudaEventRecord(h->ev_recv, h->comm_stream));
+    GBP_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_recv, 0));
+    gbp::k_metric_combine<<<1, 32, 0, h->stream>>>(h->d_metric_all, h->world, d_out);
+    h->kernels_launched++;
+  }
   GBP_CUDA_TRY(cudaGetLastError());
   return GBP_OK;
 }
@@ -312,8 +364,10 @@ int import_edges(gbp_handle* h, const float* damping, const int32_t* dcount, con
   cudaFree(d_damp); cudaFree(d_dc); cudaFree(d_act); cudaFree(d_rob); cudaFree(d_dmu);
   if (active) {
     h->active_host.assign(active, active + E);
-    h->n_active = 0;
-    for (uint32_t e = 0; e < E; ++e) h->n_active += (active[e] == 1u) ? 1u : 0u;
+    if (!h->shard) {  // a shard keeps the active-edge count of the whole graph
+      h->n_active = 0;
+      for (uint32_t e = 0; e < E; ++e) h->n_active += (active[e] == 1u) ? 1u : 0u;
+    }
   }
   return rc;
 }
@@ -335,7 +389,7 @@ int upload_lmk_priors(gbp_handle* h, const float* eta, const float* lam) {
   return GBP_OK;
 }
 
-int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o) {
+int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t* edge_global = nullptr) {
   const uint32_t C = p->n_keyframes, L = p->n_points, E = p->n_edges;
   h->C = C; h->L = L; h->E = E;
   h->cam_ids.assign(p->cam_ids, p->cam_ids + E);
@@ -378,7 +432,7 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o) {
   for (uint32_t e = 0; e < E; ++e) {
     const uint32_t pos = cam_tile_begin[h->cam_ids[e]] * GBP_TILE + h->slot_c[e];
     h->pos_of_orig[e] = pos;
-    edge_orig[pos] = e;
+    edge_orig[pos] = edge_global ? edge_global[e] : e;  // quirk Q7 compares GLOBAL edge ids
   }
   std::vector<uint32_t> lmk_ptr(L + 1, 0), lmk_edges(E);
   for (uint32_t l = 0; l < L; ++l) lmk_ptr[l + 1] = lmk_ptr[l] + deg_l[l];
@@ -401,6 +455,7 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o) {
     recB[s] = make_float4(p->measurements[2 * (size_t)e], p->measurements[2 * (size_t)e + 1], p->meas_variances[e],
                           u2f(h->lmk_ids[e]));
   }
+  if (h->shard) h->n_active = gbp_shard_n_active_global(h->shard);
   auto any_nonzero = [](const float* a, size_t n) {
     if (!a) return false;
     for (size_t i = 0; i < n; ++i)
@@ -454,6 +509,24 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o) {
   A_(h->d_pprior_cam_eta, 6 * (size_t)C);
   A_(h->d_pprior_cam_lam, 36 * (size_t)C);
   A_(h->d_pprior_lmk, 3 * (size_t)L);
+  std::vector<uint32_t> lmk_bslot;
+  if (h->shard) {
+    const uint32_t nbl = gbp_shard_n_boundary_local(h->shard);
+    g.n_bnd_local = nbl;
+    g.n_bnd_global = gbp_shard_get_plan(h->shard)->n_boundary_points;
+    g.world = h->world;
+    lmk_bslot.assign(L, 0xffffffffu);
+    for (uint32_t k = 0; k < nbl; ++k) lmk_bslot[gbp_shard_boundary_local(h->shard)[k]] = gbp_shard_boundary_slot(h->shard)[k];
+    float4* recv = nullptr;
+    A_(g.lmk_bslot, L);
+    A_(g.bnd_local, nbl);
+    A_(g.bnd_slot, nbl);
+    A_(g.bnd_send, 3 * (size_t)g.n_bnd_global);
+    A_(recv, 3 * (size_t)g.n_bnd_global * h->world);
+    g.bnd_recv = recv;
+    A_(h->d_metric_raw, 8);
+    A_(h->d_metric_all, 8 * (size_t)h->world);
+  }
 #undef A_
   if (rc) return rc;
   cudaStream_t s = h->stream;
@@ -473,6 +546,11 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o) {
   U_(g.lmk_ptr, lmk_ptr.data(), L + 1);
   U_(g.lmk_edges, lmk_edges.data(), E);
   U_(h->d_pos_of_orig, h->pos_of_orig.data(), E);
+  if (h->shard) {
+    U_(g.lmk_bslot, lmk_bslot.data(), L);
+    U_(g.bnd_local, gbp_shard_boundary_local(h->shard), g.n_bnd_local);
+    U_(g.bnd_slot, gbp_shard_boundary_slot(h->shard), g.n_bnd_local);
+  }
   std::vector<float4> lpr((size_t)L * 3);
   for (size_t l = 0; l < L; ++l) {
     float* r = &lpr[l * 3].x;
@@ -574,6 +652,12 @@ int gbp_cuda_free(gbp_handle* h) {
   if (h->d_exp_dcount) cudaFree(h->d_exp_dcount);
   if (h->d_exp_robust) cudaFree(h->d_exp_robust);
   for (cudaEvent_t ev : h->prof_events) cudaEventDestroy(ev);
+  if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
+  if (h->comm) gbp::nccl_api().CommDestroy(h->comm);
+  if (h->ev_send) cudaEventDestroy(h->ev_send);
+  if (h->ev_recv) cudaEventDestroy(h->ev_recv);
+  if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+  if (h->shard) gbp_shard_free(h->shard);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -781,6 +865,10 @@ int gbp_cuda_add_keyframe(gbp_handle* h, const int32_t* damping_count, const flo
                           const uint32_t* active_flag, const uint32_t* cam_weaken_flag,
                           const uint32_t* lmk_weaken_flag) {
   if (!h) return GBP_ERR_ARG;
+  if (h->shard) {
+    gbp_set_error("add_keyframe (incremental SLAM) is single-GPU only");
+    return GBP_ERR_ARG;
+  }
   int rc = set_device(h);
   if (rc) return rc;
   cudaStream_t s = h->stream;
@@ -1145,69 +1233,79 @@ int gbp_cuda_set_tensor(gbp_handle* h, const char* name, const void* src, size_t
   return GBP_OK;
 }
 
-int gbp_cuda_plan_shard(const gbp_problem* p, uint32_t world, uint32_t rank, gbp_shard_plan* out) {
-  if (!p || !out || world == 0 || rank >= world) return GBP_ERR_ARG;
-  const uint32_t C = p->n_keyframes, L = p->n_points, E = p->n_edges;
-  std::vector<uint64_t> deg(C, 0);
-  for (uint32_t e = 0; e < E; ++e) {
-    if (p->cam_ids[e] >= C || p->lmk_ids[e] >= L) return GBP_ERR_ARG;
-    deg[p->cam_ids[e]]++;
+int gbp_cuda_nccl_unique_id(void* id128) {
+  if (!id128) return GBP_ERR_ARG;
+  gbp::NcclApi& nc = gbp::nccl_api();
+  if (!nc.load()) {
+    gbp_set_error(nc.error);
+    return GBP_ERR_COMM;
   }
-  // contiguous camera ranges balanced by edge count: rank r owns the cameras whose
-  // cumulative edge midpoint falls in [r, r+1) * E / world
-  std::vector<uint32_t> bounds(world + 1, C);
-  bounds[0] = 0;
-  uint64_t cum = 0;
-  uint32_t r = 1;
-  for (uint32_t c = 0; c < C && r < world; ++c) {
-    cum += deg[c];
-    while (r < world && cum * world >= (uint64_t)r * E && cum > 0) bounds[r++] = c + 1;
-  }
-  for (uint32_t i = 1; i <= world; ++i) bounds[i] = std::max(bounds[i], bounds[i - 1]);
-  bounds[world] = C;
-  std::vector<uint32_t> cam_rank(C, 0);
-  for (uint32_t i = 0; i < world; ++i)
-    for (uint32_t c = bounds[i]; c < bounds[i + 1]; ++c) cam_rank[c] = i;
-  uint32_t n_local_edges = 0, n_local_points = 0, n_boundary = 0;
-  std::vector<uint8_t> touched(L, 0);
-  // edges are not required to be camera-sorted: count distinct ranks per landmark
-  // with a per-landmark bitmask for world <= 64, else a conservative two-value check
-  std::vector<uint64_t> mask(L, 0);
-  for (uint32_t e = 0; e < E; ++e) {
-    const uint32_t cr = cam_rank[p->cam_ids[e]];
-    mask[p->lmk_ids[e]] |= (1ull << (cr & 63));
-    if (cr == rank) {
-      n_local_edges++;
-      touched[p->lmk_ids[e]] = 1;
-    }
-  }
-  for (uint32_t l = 0; l < L; ++l) {
-    n_local_points += touched[l];
-    if (mask[l] & (mask[l] - 1)) n_boundary++;
-  }
-  out->world = world;
-  out->rank = rank;
-  out->cam_begin = bounds[rank];
-  out->cam_end = bounds[rank + 1];
-  out->n_local_edges = n_local_edges;
-  out->n_local_points = n_local_points;
-  out->n_boundary_points = n_boundary;
-  out->reserved = 0;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  GBP_NCCL_TRY(nc.GetUniqueId(&id));
+  std::memcpy(id128, &id, sizeof(id));
   return GBP_OK;
 }
 
-int gbp_cuda_nccl_unique_id(void* id128) {
-  (void)id128;
-  gbp_set_error("multi-GPU exchange is not built into this version of the library");
-  return GBP_ERR_COMM;
+int gbp_cuda_init_shard(const gbp_problem* p, const gbp_opts* o_in, uint32_t world, uint32_t rank,
+                        const void* nccl_unique_id, gbp_handle** out) {
+  if (world == 1 && rank == 0) return gbp_cuda_init(p, o_in, out);
+  if (!p || !out || world == 0 || rank >= world || !nccl_unique_id) {
+    gbp_set_error("bad gbp_cuda_init_shard arguments");
+    return GBP_ERR_ARG;
+  }
+  gbp_opts o;
+  if (o_in) o = *o_in; else gbp_opts_default(&o);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    gbp_set_error("no CUDA device available (the GBP hot path has no CPU fallback)");
+    return GBP_ERR_CUDA;
+  }
+  if (o.device < 0 || o.device >= ndev) {
+    gbp_set_error("device ordinal out of range");
+    return GBP_ERR_ARG;
+  }
+  gbp::NcclApi& nc = gbp::nccl_api();
+  if (!nc.load()) {
+    gbp_set_error(nc.error);
+    return GBP_ERR_COMM;
+  }
+  gbp_shard* sh = nullptr;
+  int rc = gbp_shard_build(p, world, rank, &sh);
+  if (rc) return rc;
+  gbp_handle* h = new gbp_handle();
+  h->device = o.device;
+  h->use_graph = o.use_cuda_graph;
+  h->shard = sh;
+  h->world = world;
+  h->rank = rank;
+  rc = set_device(h);
+  if (!rc && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) rc = GBP_ERR_CUDA;
+  if (!rc && cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking) != cudaSuccess) rc = GBP_ERR_CUDA;
+  if (!rc && cudaEventCreate(&h->ev0) != cudaSuccess) rc = GBP_ERR_CUDA;
+  if (!rc && cudaEventCreate(&h->ev1) != cudaSuccess) rc = GBP_ERR_CUDA;
+  if (!rc && cudaEventCreateWithFlags(&h->ev_send, cudaEventDisableTiming) != cudaSuccess) rc = GBP_ERR_CUDA;
+  if (!rc && cudaEventCreateWithFlags(&h->ev_recv, cudaEventDisableTiming) != cudaSuccess) rc = GBP_ERR_CUDA;
+  if (!rc) {
+    ncclUniqueId id;
+    std::memcpy(&id, nccl_unique_id, sizeof(id));
+    ncclResult_t r = nc.CommInitRank(&h->comm, (int)world, id, (int)rank);
+    if (r != ncclSuccess) {
+      gbp_set_error(std::string("ncclCommInitRank: ") + nc.GetErrorString(r));
+      h->comm = nullptr;
+      rc = GBP_ERR_COMM;
+    }
+  }
+  if (!rc) rc = build(h, gbp_shard_problem(sh), &o, gbp_shard_edge_global(sh));
+  if (rc) {
+    if (rc == GBP_ERR_CUDA && !*gbp_cuda_last_error()) gbp_set_error("CUDA initialisation failed");
+    gbp_cuda_free(h);
+    return rc;
+  }
+  *out = h;
+  return GBP_OK;
 }
 
-int gbp_cuda_init_shard(const gbp_problem* p, const gbp_opts* o, uint32_t world, uint32_t rank,
-                        const void* nccl_unique_id, gbp_handle** out) {
-  (void)nccl_unique_id;
-  if (world == 1 && rank == 0) return gbp_cuda_init(p, o, out);
-  gbp_set_error("multi-GPU exchange is not built into this version of the library");
-  return GBP_ERR_COMM;
-}
+const gbp_shard* gbp_cuda_shard_info(gbp_handle* h) { return h ? h->shard : nullptr; }
 
 }  // extern "C"

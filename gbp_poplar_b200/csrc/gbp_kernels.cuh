@@ -60,6 +60,14 @@ struct DeviceGraph {
   uint32_t* lmk_wflag;    // [L]
   uint32_t* lmk_ptr;      // [L+1] CSC over edge slots, in original edge order
   uint32_t* lmk_edges;    // [E]
+  // multi-GPU shard (all null / 0 on a single-GPU handle): boundary landmarks = landmarks
+  // that other ranks observe too; their beliefs are formed from all-gathered partials
+  uint32_t* lmk_bslot;    // [L] position in the global boundary list, 0xffffffff = interior
+  uint32_t* bnd_local;    // [n_bnd_local] local landmark id
+  uint32_t* bnd_slot;     // [n_bnd_local] position in the global boundary list
+  float4* bnd_send;       // [n_bnd_global][3]  this rank's partial sums (zero where it has no factor)
+  const float4* bnd_recv; // [world][n_bnd_global][3]  all ranks' partial sums
+  uint32_t n_bnd_local, n_bnd_global, world;
   float K[4];             // fx fy cx cy
   Hyper hp;
 };
@@ -523,6 +531,64 @@ __global__ void __launch_bounds__(GBP_TILE) k_cam_partials(const DeviceGraph g) 
   warp_cam_reduce(red, lane, g.cam_partial + ((size_t)tile * GBP_WARPS + warp) * GBP_CAMPART);
 }
 
+// b += the factor->landmark messages of landmark l, strictly in slot order (= original
+// edge order, the reference's message slots 1..deg).  The gathers of four slots are
+// issued together (independent loads); the additions stay in order.
+GBP_DEV void lmk_accumulate(const DeviceGraph& g, const uint32_t l, float (&b)[12]) {
+  const uint64_t pol_keep = l2_policy_keep();
+  const uint32_t k0 = g.lmk_ptr[l], k1 = g.lmk_ptr[l + 1];
+  for (uint32_t k = k0; k < k1; k += 4) {
+    uint32_t idx[4];
+    float4 v[4][3];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) idx[u] = (k + u < k1) ? __ldg(g.lmk_edges + k + u) : 0xffffffffu;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (idx[u] != 0xffffffffu) {
+        const float4* p = g.mlmk + (size_t)idx[u] * GBP_MLMK_QUADS;
+        v[u][0] = ld4_hint<(GBP_L2_HINTS & 1)>(p, pol_keep); v[u][1] = ld4_hint<(GBP_L2_HINTS & 1)>(p + 1, pol_keep); v[u][2] = ld4_hint<(GBP_L2_HINTS & 1)>(p + 2, pol_keep);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (idx[u] != 0xffffffffu) {
+        b[0] = fa(b[0], v[u][0].x); b[1] = fa(b[1], v[u][0].y); b[2] = fa(b[2], v[u][0].z); b[3] = fa(b[3], v[u][0].w);
+        b[4] = fa(b[4], v[u][1].x); b[5] = fa(b[5], v[u][1].y); b[6] = fa(b[6], v[u][1].z); b[7] = fa(b[7], v[u][1].w);
+        b[8] = fa(b[8], v[u][2].x); b[9] = fa(b[9], v[u][2].y); b[10] = fa(b[10], v[u][2].z); b[11] = fa(b[11], v[u][2].w);
+      }
+    }
+  }
+}
+
+// belief record of one landmark: [eta 3 | Lambda 9 | mean 3 | pad]; shift != 0 keeps the
+// mean the last PrepMessageVertex pass used as the "old mu" (Copy(mu, oldmu), ba/ba.cpp:898)
+GBP_DEV void lmk_store_belief(const DeviceGraph& g, const uint32_t l, const float (&b)[12], const int shift) {
+  const float eta[3] = {b[0], b[1], b[2]};
+  float lam[9], mean[3];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) lam[i] = b[3 + i];
+  inf2mean3(eta, lam, mean);
+  float4* o = g.lmk_b + (size_t)l * GBP_LMKB_QUADS;
+  if (shift) {
+    const float4 oldq = o[3];
+    g.lmk_mean_prev[l] = make_float4(oldq.x, oldq.y, oldq.z, 0.f);
+  }
+  o[0] = make_float4(b[0], b[1], b[2], b[3]);
+  o[1] = make_float4(b[4], b[5], b[6], b[7]);
+  o[2] = make_float4(b[8], b[9], b[10], b[11]);
+  o[3] = make_float4(mean[0], mean[1], mean[2], 0.f);
+}
+
+GBP_DEV void lmk_load_prior(const DeviceGraph& g, const uint32_t l, float (&b)[12]) {
+  // the sum starts from +0 like a zero-initialised accumulator: 0 + prior (turns a -0 prior into +0)
+  const float4* p = g.lmk_prior + (size_t)l * 3;
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const float4 v = p[q];
+    b[q * 4] = fa(0.0f, v.x); b[q * 4 + 1] = fa(0.0f, v.y); b[q * 4 + 2] = fa(0.0f, v.z); b[q * 4 + 3] = fa(0.0f, v.w);
+  }
+}
+
 // Belief update + per-variable mean.  Blocks [0,C) own one camera each; the
 // remaining blocks own GBP_TILE landmarks each.  shift != 0: the mean that the
 // last PrepMessageVertex pass used becomes the "old mu" (Copy(mu, oldmu),
@@ -580,55 +646,50 @@ __global__ void __launch_bounds__(GBP_TILE) k_update_vars(const DeviceGraph g, c
   } else {
     const uint32_t l = blockIdx.x * GBP_TILE + tid;
     if (l >= g.L) return;
-    const uint64_t pol_keep = l2_policy_keep();
+    // boundary landmarks of a multi-GPU shard are finished by k_boundary_finish
+    if (g.lmk_bslot && g.lmk_bslot[l] != 0xffffffffu) return;
     float b[12];
-    {
-      const float4* p = g.lmk_prior + (size_t)l * 3;
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const float4 v = p[q];
-        b[q * 4] = fa(0.0f, v.x); b[q * 4 + 1] = fa(0.0f, v.y); b[q * 4 + 2] = fa(0.0f, v.z); b[q * 4 + 3] = fa(0.0f, v.w);
-      }
-    }
-    const uint32_t k0 = g.lmk_ptr[l], k1 = g.lmk_ptr[l + 1];
-    // slot order = original edge order.  The gathers of four slots are issued together
-    // (independent loads), the additions stay strictly in slot order.
-    for (uint32_t k = k0; k < k1; k += 4) {
-      uint32_t idx[4];
-      float4 v[4][3];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) idx[u] = (k + u < k1) ? __ldg(g.lmk_edges + k + u) : 0xffffffffu;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (idx[u] != 0xffffffffu) {
-          const float4* p = g.mlmk + (size_t)idx[u] * GBP_MLMK_QUADS;
-          v[u][0] = ld4_hint<(GBP_L2_HINTS & 1)>(p, pol_keep); v[u][1] = ld4_hint<(GBP_L2_HINTS & 1)>(p + 1, pol_keep); v[u][2] = ld4_hint<(GBP_L2_HINTS & 1)>(p + 2, pol_keep);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (idx[u] != 0xffffffffu) {
-          b[0] = fa(b[0], v[u][0].x); b[1] = fa(b[1], v[u][0].y); b[2] = fa(b[2], v[u][0].z); b[3] = fa(b[3], v[u][0].w);
-          b[4] = fa(b[4], v[u][1].x); b[5] = fa(b[5], v[u][1].y); b[6] = fa(b[6], v[u][1].z); b[7] = fa(b[7], v[u][1].w);
-          b[8] = fa(b[8], v[u][2].x); b[9] = fa(b[9], v[u][2].y); b[10] = fa(b[10], v[u][2].z); b[11] = fa(b[11], v[u][2].w);
-        }
-      }
-    }
-    const float eta[3] = {b[0], b[1], b[2]};
-    float lam[9], mean[3];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) lam[i] = b[3 + i];
-    inf2mean3(eta, lam, mean);
-    float4* o = g.lmk_b + (size_t)l * GBP_LMKB_QUADS;
-    if (shift) {
-      const float4 oldq = o[3];
-      g.lmk_mean_prev[l] = make_float4(oldq.x, oldq.y, oldq.z, 0.f);
-    }
-    o[0] = make_float4(b[0], b[1], b[2], b[3]);
-    o[1] = make_float4(b[4], b[5], b[6], b[7]);
-    o[2] = make_float4(b[8], b[9], b[10], b[11]);
-    o[3] = make_float4(mean[0], mean[1], mean[2], 0.f);
+    lmk_load_prior(g, l, b);
+    lmk_accumulate(g, l, b);
+    lmk_store_belief(g, l, b, shift);
   }
+}
+
+// ---- multi-GPU boundary landmarks -------------------------------------
+// k_boundary_partial: this rank's partial sum (local factor->landmark messages in slot
+// order, starting from +0) of every boundary landmark it touches, written to its slot of
+// the exchange buffer.  k_boundary_finish, after the all-gather: belief = (0 + prior) +
+// partial[rank 0] + partial[rank 1] + ... -- the same operations on every rank, so all
+// replicas of a boundary landmark stay bit-identical.
+__global__ void __launch_bounds__(GBP_TILE) k_boundary_partial(const DeviceGraph g) {
+  const uint32_t k = blockIdx.x * GBP_TILE + threadIdx.x;
+  if (k >= g.n_bnd_local) return;
+  const uint32_t l = g.bnd_local[k];
+  float b[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) b[i] = 0.f;
+  lmk_accumulate(g, l, b);
+  float4* o = g.bnd_send + (size_t)g.bnd_slot[k] * 3;
+  o[0] = make_float4(b[0], b[1], b[2], b[3]);
+  o[1] = make_float4(b[4], b[5], b[6], b[7]);
+  o[2] = make_float4(b[8], b[9], b[10], b[11]);
+}
+
+__global__ void __launch_bounds__(GBP_TILE) k_boundary_finish(const DeviceGraph g, const int shift) {
+  const uint32_t k = blockIdx.x * GBP_TILE + threadIdx.x;
+  if (k >= g.n_bnd_local) return;
+  const uint32_t l = g.bnd_local[k];
+  const size_t slot = g.bnd_slot[k];
+  float b[12];
+  lmk_load_prior(g, l, b);
+  for (uint32_t r = 0; r < g.world; ++r) {
+    const float4* p = g.bnd_recv + ((size_t)r * g.n_bnd_global + slot) * 3;
+    const float4 v0 = p[0], v1 = p[1], v2 = p[2];
+    b[0] = fa(b[0], v0.x); b[1] = fa(b[1], v0.y); b[2] = fa(b[2], v0.z); b[3] = fa(b[3], v0.w);
+    b[4] = fa(b[4], v1.x); b[5] = fa(b[5], v1.y); b[6] = fa(b[6], v1.z); b[7] = fa(b[7], v1.w);
+    b[8] = fa(b[8], v2.x); b[9] = fa(b[9], v2.y); b[10] = fa(b[10], v2.z); b[11] = fa(b[11], v2.w);
+  }
+  lmk_store_belief(g, l, b, shift);
 }
 
 // RelineariseFactorVertex on every factor, active or not (ba/ba.cpp:68-97).
@@ -752,8 +813,9 @@ struct DeviceStats {  // == gbp_iter_stats
 };
 
 // One block: fixed-order reduction of the per-tile partials in double.
+// raw != nullptr (multi-GPU): the five sums are written as doubles for k_metric_combine instead.
 __global__ void __launch_bounds__(256) k_metric_finish(const MetricPartial* __restrict__ parts, const uint32_t n_tiles,
-                                                      DeviceStats* __restrict__ out) {
+                                                      DeviceStats* __restrict__ out, double* __restrict__ raw) {
   __shared__ double s_d[2][256];
   __shared__ uint32_t s_u[3][256];
   const uint32_t tid = threadIdx.x;
@@ -773,7 +835,11 @@ __global__ void __launch_bounds__(256) k_metric_finish(const MetricPartial* __re
     }
     __syncthreads();
   }
-  if (tid == 0) {
+  if (tid == 0 && raw) {
+    raw[0] = s_d[0][0]; raw[1] = s_d[1][0];
+    raw[2] = (double)s_u[0][0]; raw[3] = (double)s_u[1][0]; raw[4] = (double)s_u[2][0];
+    raw[5] = raw[6] = raw[7] = 0.0;
+  } else if (tid == 0) {
     DeviceStats s;
     s.n_active = s_u[2][0];
     s.reproj_mean = (float)(s_d[0][0] / (double)s.n_active);
@@ -783,6 +849,22 @@ __global__ void __launch_bounds__(256) k_metric_finish(const MetricPartial* __re
     s.reserved = 0;
     *out = s;
   }
+}
+
+// multi-GPU: sum the all-gathered per-rank metric sums [world][8] in rank order
+__global__ void k_metric_combine(const double* __restrict__ all, const uint32_t world, DeviceStats* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double a[5] = {0, 0, 0, 0, 0};
+  for (uint32_t r = 0; r < world; ++r)
+    for (int i = 0; i < 5; ++i) a[i] += all[r * 8 + i];
+  DeviceStats s;
+  s.n_active = (uint32_t)a[4];
+  s.reproj_mean = (float)(a[0] / a[4]);
+  s.cost = (float)a[1];
+  s.n_relins = (uint32_t)a[2];
+  s.n_robust = (uint32_t)a[3];
+  s.reserved = 0;
+  *out = s;
 }
 
 // READ_PROG helpers: gather per-edge scalars back into the reference's edge order

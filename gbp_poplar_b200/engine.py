@@ -61,7 +61,10 @@ def stats_to_dict(s):
 
 
 class GBPEngine:
-    def __init__(self, problem, opts=None, lib=None, prefix="gbp_cuda_", keepalive=None):
+    def __init__(self, problem, opts=None, lib=None, prefix="gbp_cuda_", keepalive=None, shard=None):
+        """shard = (world, rank, nccl_unique_id bytes): this rank's part of the GLOBAL `problem`
+        (gbp_cuda_init_shard); every program then includes the boundary-landmark exchange and is
+        collective over the ranks.  See GBPEngine.sharded()."""
         if lib is None:
             lib = _capi.load_library()
         self._lib = lib
@@ -70,11 +73,41 @@ class GBPEngine:
         self._keepalive = keepalive
         self.opts = opts if opts is not None else default_opts()
         self._h = C.c_void_p()
-        self._check(self._f["init"](C.byref(problem), C.byref(self.opts), C.byref(self._h)))
+        self.shard = None
+        if shard is None:
+            self._check(self._f["init"](C.byref(problem), C.byref(self.opts), C.byref(self._h)))
+        else:
+            world, rank, uid = shard
+            buf = C.create_string_buffer(bytes(uid), 128)
+            self._check(lib.gbp_cuda_init_shard(C.byref(problem), C.byref(self.opts), world, rank, buf,
+                                                C.byref(self._h)))
+            if world > 1:
+                from .host import Shard
+                self.shard = Shard(None, world, rank, owner=self, handle=C.c_void_p(lib.gbp_cuda_shard_info(self._h)))
         c, l, e, mk, ml = (C.c_uint32() for _ in range(5))
         self._check(self._f["dims"](self._h, c, l, e, mk, ml))
         self.n_keyframes, self.n_points, self.n_edges = c.value, l.value, e.value
         self.max_nkfedges, self.max_nlmkedges = mk.value, ml.value
+
+    @classmethod
+    def sharded(cls, problem, opts=None, group=None):
+        """One rank of a multi-GPU run under torch.distributed (one process per GPU): rank 0 creates
+        the NCCL unique id, torch.distributed broadcasts it, every rank builds its shard."""
+        import torch
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if world == 1:
+            return cls(problem, opts)
+        lib = _capi.load_library()
+        uid = C.create_string_buffer(128)
+        if rank == 0:
+            rc = lib.gbp_cuda_nccl_unique_id(uid)
+            if rc != 0:
+                raise RuntimeError(f"gbp_cuda_nccl_unique_id failed: {lib.gbp_cuda_last_error().decode()}")
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else "cpu"
+        t = torch.frombuffer(bytearray(uid.raw), dtype=torch.uint8).to(dev)
+        dist.broadcast(t, src=0, group=group)
+        return cls(problem, opts, shard=(world, rank, bytes(t.cpu().numpy().tobytes())))
 
     # -- plumbing ---------------------------------------------------------
     def _check(self, rc):

@@ -196,6 +196,66 @@ class Setup:
             pass
 
 
+class Shard:
+    """Rank-local sub-problem of a camera-range partition (gbp_shard_build, include/gbp_cuda.h).
+
+    Replaces the reference's placement of variables and factors on the tiles of several
+    IPUs (ba/ba.cpp:617-631,717-753,795-834).  Pure host code; `owner` keeps the global
+    problem's arrays alive."""
+
+    def __init__(self, problem, world, rank, owner=None, handle=None):
+        self._lib = _capi.load_library()
+        self._owner = owner
+        self._owned = handle is None
+        if handle is None:
+            h = C.c_void_p()
+            _check(self._lib.gbp_shard_build(C.byref(problem), world, rank, C.byref(h)), self._lib)
+            handle = h
+        self._h = handle
+        pl = self._lib.gbp_shard_get_plan(self._h).contents
+        self.world, self.rank = pl.world, pl.rank
+        self.cam_begin, self.cam_end = pl.cam_begin, pl.cam_end
+        self.n_local_edges, self.n_local_points = pl.n_local_edges, pl.n_local_points
+        self.n_boundary_points = pl.n_boundary_points
+        self.n_boundary_local = self._lib.gbp_shard_n_boundary_local(self._h)
+        self.n_active_global = self._lib.gbp_shard_n_active_global(self._h)
+
+    @property
+    def problem(self):
+        return self._lib.gbp_shard_problem(self._h).contents
+
+    @property
+    def lmk_global(self):
+        return _view(self._lib.gbp_shard_lmk_global(self._h), self.n_local_points, np.uint32, self)
+
+    @property
+    def edge_global(self):
+        return _view(self._lib.gbp_shard_edge_global(self._h), self.n_local_edges, np.uint32, self)
+
+    @property
+    def boundary_local(self):
+        return _view(self._lib.gbp_shard_boundary_local(self._h), self.n_boundary_local, np.uint32, self)
+
+    @property
+    def boundary_slot(self):
+        return _view(self._lib.gbp_shard_boundary_slot(self._h), self.n_boundary_local, np.uint32, self)
+
+    @property
+    def cam_bounds(self):
+        return _view(self._lib.gbp_shard_cam_bounds(self._h), self.world + 1, np.uint32, self)
+
+    def close(self):
+        if self._h and self._owned:
+            self._lib.gbp_shard_free(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def problem_from_arrays(arrays, K):
     """Build a gbp_problem struct from a dict of numpy arrays (kept alive by the caller)."""
     p = GbpProblem()

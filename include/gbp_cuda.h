@@ -203,14 +203,53 @@ int gbp_cuda_synchronize(gbp_handle* h);
 void* gbp_cuda_stream(gbp_handle* h);
 
 /* ---- multi-GPU: camera-range sharding with boundary-landmark exchange --- */
-/* Pure host: contiguous camera ranges balanced by edge count. */
+/* The reference scales by spreading variables and factors over the tiles of
+ * 2^k IPUs (--ipus, ba/ba.cpp:617-631,717-753,795-834) and lets Poplar compile
+ * the exchange.  Here: one process per GPU; rank r owns a contiguous camera
+ * range (balanced by edge count), every factor of those cameras and a replica
+ * of every landmark they observe.  Landmarks observed from more than one rank
+ * are "boundary" landmarks; per sweep each rank contributes the partial sum of
+ * its own factor->landmark messages (12 floats) for them, the partials are
+ * all-gathered over NVLink (NCCL) and every rank forms
+ *     belief = prior + partial[rank 0] + partial[rank 1] + ...
+ * in rank order, so all replicas hold identical bits. */
+
+/* Pure host: the camera range and counts of rank `rank`. */
 int gbp_cuda_plan_shard(const gbp_problem* p, uint32_t world, uint32_t rank, gbp_shard_plan* out);
-/* Build the handle for this rank's shard of `p` (p is the GLOBAL problem).
- * nccl_unique_id: 128 bytes from gbp_cuda_nccl_unique_id on rank 0, broadcast
- * by the caller's plumbing (torch.distributed). */
+
+/* Pure host: the rank-local sub-problem of a GLOBAL problem.  Local cameras are
+ * [cam_begin, cam_end) renumbered from 0; local landmarks are the landmarks the
+ * local edges touch, in ascending global id; local edges keep their global order. */
+typedef struct gbp_shard gbp_shard;
+int gbp_shard_build(const gbp_problem* p, uint32_t world, uint32_t rank, gbp_shard** out);
+void gbp_shard_free(gbp_shard* s);
+const gbp_problem* gbp_shard_problem(const gbp_shard* s);    /* local ids, arrays owned by s */
+const gbp_shard_plan* gbp_shard_get_plan(const gbp_shard* s);
+const uint32_t* gbp_shard_lmk_global(const gbp_shard* s);    /* [n_local_points] global landmark id */
+const uint32_t* gbp_shard_edge_global(const gbp_shard* s);   /* [n_local_edges]  global edge id     */
+/* The boundary landmarks this rank touches: local landmark id and position in
+ * the global boundary list (ascending global id, identical on every rank). */
+uint32_t gbp_shard_n_boundary_local(const gbp_shard* s);
+const uint32_t* gbp_shard_boundary_local(const gbp_shard* s);
+const uint32_t* gbp_shard_boundary_slot(const gbp_shard* s);
+/* Number of active edges of the GLOBAL problem (quirk Q7: the metric covers global edges [0, n_active)). */
+uint32_t gbp_shard_n_active_global(const gbp_shard* s);
+/* camera-range bounds of all ranks: [world+1] */
+const uint32_t* gbp_shard_cam_bounds(const gbp_shard* s);
+
+/* 128-byte NCCL unique id (rank 0 creates it, the caller's plumbing -- e.g.
+ * torch.distributed -- broadcasts it). */
 int gbp_cuda_nccl_unique_id(void* id128);
+/* Build the handle for this rank's shard of the GLOBAL problem `p` and join the
+ * NCCL communicator.  Afterwards every entry point works on the LOCAL shard
+ * (sizes via gbp_cuda_dims, index maps via gbp_cuda_shard_info); iterate /
+ * weaken_priors / update_beliefs include the boundary exchange and are
+ * collective: every rank must make the same sequence of calls.  add_keyframe
+ * is single-GPU only. */
 int gbp_cuda_init_shard(const gbp_problem* p, const gbp_opts* o, uint32_t world, uint32_t rank,
                         const void* nccl_unique_id, gbp_handle** out);
+/* The shard a handle was built from (NULL for a single-GPU handle). */
+const gbp_shard* gbp_cuda_shard_info(gbp_handle* h);
 
 #ifdef __cplusplus
 }

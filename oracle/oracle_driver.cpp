@@ -70,7 +70,10 @@ struct Oracle {
   float K[9];
   Hyper hp;
   int nthreads = 1;
-  int reduce_order = 0;  // 0 = serial slot order; 1 = the CUDA path's tile order (see update_beliefs)
+  int reduce_order = 0;  // 0 = serial slot order; 1 = the CUDA path's tile order; 2 = its multi-GPU order (see update_beliefs)
+  uint32_t shard_world = 1;
+  std::vector<uint16_t> slot_rank;     // [L*SL] rank owning the camera of each landmark message slot (0xffff = none)
+  std::vector<uint8_t> lmk_boundary;   // [L] observed from more than one rank
   // variable-side tensors (ba/ba.cpp:665-687)
   std::vector<float> cam_b_eta, cam_b_lam, lmk_b_eta, lmk_b_lam;
   std::vector<float> cam_scaling, lmk_scaling;
@@ -98,6 +101,10 @@ inline size_t lml(const Oracle& o, uint32_t l, uint32_t slot) { return ((size_t)
 //     inside chunks of 32 consecutive slots (one warp's factors), and the chunk sums
 //     are added to the prior in order (chunks are counted in whole 128-slot tiles).
 //     Landmarks are serial in both modes.
+//   reduce_order 2: order 1 for cameras; a landmark observed from more than one rank of a
+//     camera-range partition (gbp_oracle_set_shard_bounds) is summed the way the multi-GPU
+//     path does: per-rank partial sums (serial, starting from +0), then
+//     (0 + prior) + partial[0] + partial[1] + ...; all other landmarks stay serial.
 float cam_chunk_sum(const Oracle& o, const std::vector<float>& m, uint32_t c, uint32_t d, uint32_t dim,
                     uint32_t chunk) {
   float acc = 0.f;
@@ -137,6 +144,25 @@ void update_beliefs(Oracle& o) {
   }
 #pragma omp parallel for schedule(static) num_threads(o.nthreads)
   for (int64_t l = 0; l < (int64_t)o.L; ++l) {
+    if (o.reduce_order == 2 && o.lmk_boundary[l]) {
+      const uint16_t* sr = &o.slot_rank[(size_t)l * o.SL];
+      for (int d = 0; d < 12; ++d) {
+        const bool is_eta = d < 3;
+        const std::vector<float>& m = is_eta ? o.lmk_m_eta : o.lmk_m_lam;
+        const size_t base = is_eta ? lme(o, l, 0) + d : lml(o, l, 0) + (d - 3);
+        const size_t dim = is_eta ? 3 : 9;
+        float s = 0.f;
+        s += m[base];
+        for (uint32_t r = 0; r < o.shard_world; ++r) {
+          float part = 0.f;
+          for (uint32_t k = 1; k < o.SL; ++k)
+            if (sr[k] == r) part += m[base + (size_t)k * dim];
+          s += part;
+        }
+        if (is_eta) o.lmk_b_eta[l * 3 + d] = s; else o.lmk_b_lam[l * 9 + (d - 3)] = s;
+      }
+      continue;
+    }
     for (int d = 0; d < 3; ++d) {
       float s = 0.f;
       for (uint32_t k = 0; k < o.SL; ++k) s += o.lmk_m_eta[lme(o, l, k) + d];
@@ -372,6 +398,26 @@ int gbp_oracle_max_threads(void) {
 int gbp_oracle_set_reduce_order(void* h, int mode) {
   if (!h || mode < 0 || mode > 1) return GBP_ERR_ARG;
   ((Oracle*)h)->reduce_order = mode;
+  return GBP_OK;
+}
+
+// Camera-range partition of the multi-GPU path: bounds[world+1]; selects reduce_order 2.
+int gbp_oracle_set_shard_bounds(void* h, const uint32_t* bounds, uint32_t world) {
+  if (!h || !bounds || world == 0) return GBP_ERR_ARG;
+  Oracle& o = *(Oracle*)h;
+  o.shard_world = world;
+  o.slot_rank.assign((size_t)o.L * o.SL, 0xffff);
+  o.lmk_boundary.assign(o.L, 0);
+  std::vector<uint16_t> first(o.L, 0xffff);
+  for (uint32_t e = 0; e < o.E; ++e) {
+    uint32_t r = 0;
+    while (r + 1 < world && o.cam_ids[e] >= bounds[r + 1]) ++r;
+    const uint32_t l = o.lmk_ids[e];
+    o.slot_rank[(size_t)l * o.SL + o.slot_l[e] + 1] = (uint16_t)r;
+    if (first[l] == 0xffff) first[l] = (uint16_t)r;
+    else if (first[l] != r) o.lmk_boundary[l] = 1;
+  }
+  o.reduce_order = 2;
   return GBP_OK;
 }
 

@@ -38,6 +38,7 @@ def load(kind="port"):
         lib.gbp_oracle_last_error.restype = C.c_char_p
         lib.gbp_oracle_set_threads.argtypes = [C.c_void_p, C.c_int]
         lib.gbp_oracle_set_reduce_order.argtypes = [C.c_void_p, C.c_int]
+        lib.gbp_oracle_set_shard_bounds.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.c_uint32]
         lib.gbp_oracle_commit_messages.argtypes = [C.c_void_p]
         lib.gbp_oracle_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         f32p = C.POINTER(C.c_float)
@@ -63,6 +64,11 @@ class OracleEngine(GBPEngine):
     def set_reduce_order(self, mode):
         """0 = serial slot order (default), 1 = the CUDA path's tile order (bit-comparable)."""
         self._check(self._lib.gbp_oracle_set_reduce_order(self._h, int(mode)))
+
+    def set_shard_bounds(self, bounds):
+        """Belief summation order of the multi-GPU path for the camera-range partition `bounds` [world+1]."""
+        b = np.ascontiguousarray(bounds, dtype=np.uint32)
+        self._check(self._lib.gbp_oracle_set_shard_bounds(self._h, b.ctypes.data_as(C.POINTER(C.c_uint32)), b.size - 1))
 
     def commit_messages(self):
         self._check(self._lib.gbp_oracle_commit_messages(self._h))

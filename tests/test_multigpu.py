@@ -1,0 +1,52 @@
+"""Multi-GPU product path (gbp_cuda_init_shard + in-library NCCL exchange), one process per GPU,
+against the single-process oracle summing beliefs in the multi-GPU order: bit-identical."""
+import numpy as np
+import pytest
+
+import common
+import oracle_lib
+import shard_worker
+from test_sharding_cpu import KIND, check_against_global, run_ranks
+
+pytestmark = pytest.mark.gpu
+
+
+def _n_gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs at least 2 GPUs")
+@pytest.mark.parametrize("spec,n", [("seq:fr1xyz", 40), ("synth:64:6000:9:11", 30)])
+def test_two_gpus_bit_identical_to_oracle_in_sharded_order(tmp_path, spec, n):
+    world = 2
+    ranks = run_ranks("nccl", world, spec, n, tmp_path)
+    st = shard_worker.make_problem(spec)
+    ora = oracle_lib.OracleEngine(st.problem, kind=KIND)
+    ora.set_shard_bounds(ranks[0]["cam_bounds"])
+    stats = []
+    for it in range(n):
+        common.ba_schedule_step(ora, it)
+        stats.append(ora.eval())
+    assert int(ranks[0]["n_boundary_points"][0]) > 0
+    check_against_global(ranks, ora, st, exact=True)
+    # every rank reports the metric of the WHOLE graph, identical on all ranks
+    assert np.array_equal(ranks[0]["stats"], ranks[1]["stats"])
+    for it in (0, n // 2, n - 1):
+        s, o = ranks[0]["stats"][it], stats[it]
+        assert s[0] == pytest.approx(o["reproj_mean"], rel=0.01)
+        assert (int(s[2]), int(s[3]), int(s[4])) == (o["n_relins"], o["n_robust"], o["n_active"])
+
+
+@pytest.mark.skipif(_n_gpus() < 4, reason="needs at least 4 GPUs")
+def test_four_gpus_bit_identical_to_oracle_in_sharded_order(tmp_path):
+    spec, n = "synth:96:9000:9:5", 24
+    ranks = run_ranks("nccl", 4, spec, n, tmp_path)
+    st = shard_worker.make_problem(spec)
+    ora = oracle_lib.OracleEngine(st.problem, kind=KIND)
+    ora.set_shard_bounds(ranks[0]["cam_bounds"])
+    common.run_ba(ora, n)
+    check_against_global(ranks, ora, st, exact=True)
