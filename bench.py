@@ -250,11 +250,13 @@ def main():
         barrier()
         t0 = time.time()
         eng2 = make_engine()                           # H2D of the (rank's part of the) problem + LINEARISE_PROG
+        t_init = time.time() - t0
         last = None
         for it in range(args.steps):
             if (it + 1) % 2 == 0 and it < 10:
                 eng2.weaken_priors()
             last = eng2.iterate(1, stats=True)[0]      # D2H of the per-sweep metric
+        t_loop = time.time() - t0 - t_init
         beliefs = eng2.get_beliefs()                   # READ_PROG: D2H beliefs + damping state
         wall = time.time() - t0
         h2d = 4 * (2 * E_loc + 2 * E_loc + E_loc + 42 * C_loc + 12 * L_loc + C_loc + L_loc + C_loc + L_loc + 3 * E_loc)
@@ -269,7 +271,7 @@ def main():
             wall = float(t.item())
         e2e = {"value": E * args.steps / wall, "unit": "factor-updates/s",
                "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
-               "wall_s": wall, "final_reproj_px": last["reproj_mean"] if last else None,
+               "wall_s": wall, "init_s": t_init, "loop_s": t_loop, "read_s": wall - t_init - t_loop, "final_reproj_px": last["reproj_mean"] if last else None,
                "what": "gbp_cuda_init + K x gbp_cuda_iterate(1, stats) + gbp_cuda_get_beliefs, host clock"}
         eng2.close()
 

@@ -148,6 +148,20 @@ int priors_about_to_change(gbp_handle* h) {
   return GBP_OK;
 }
 
+// NCCL communicators are cached per unique id for the life of the process: building one
+// costs ~1 s, and a host program that solves several problems in a row (or the SLAM-style
+// re-initialisation of an engine) should pay it once.  Handles only borrow them.
+struct CommEntry {
+  unsigned char id[128];
+  uint32_t world, rank;
+  int device;
+  ncclComm_t comm;
+};
+std::vector<CommEntry>& comm_cache() {
+  static std::vector<CommEntry> cache;
+  return cache;
+}
+
 #define GBP_NCCL_TRY(expr)                                                                         \
   do {                                                                                             \
     ncclResult_t r__ = (expr);                                                                     \
@@ -652,8 +666,7 @@ int gbp_cuda_free(gbp_handle* h) {
   if (h->d_exp_dcount) cudaFree(h->d_exp_dcount);
   if (h->d_exp_robust) cudaFree(h->d_exp_robust);
   for (cudaEvent_t ev : h->prof_events) cudaEventDestroy(ev);
-  if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
-  if (h->comm) gbp::nccl_api().CommDestroy(h->comm);
+  if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);  // the communicator itself stays cached
   if (h->ev_send) cudaEventDestroy(h->ev_send);
   if (h->ev_recv) cudaEventDestroy(h->ev_recv);
   if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
@@ -1287,6 +1300,11 @@ int gbp_cuda_init_shard(const gbp_problem* p, const gbp_opts* o_in, uint32_t wor
   if (!rc && cudaEventCreateWithFlags(&h->ev_send, cudaEventDisableTiming) != cudaSuccess) rc = GBP_ERR_CUDA;
   if (!rc && cudaEventCreateWithFlags(&h->ev_recv, cudaEventDisableTiming) != cudaSuccess) rc = GBP_ERR_CUDA;
   if (!rc) {
+    for (const CommEntry& ce : comm_cache())
+      if (ce.world == world && ce.rank == rank && ce.device == o.device && std::memcmp(ce.id, nccl_unique_id, 128) == 0)
+        h->comm = ce.comm;
+  }
+  if (!rc && !h->comm) {
     ncclUniqueId id;
     std::memcpy(&id, nccl_unique_id, sizeof(id));
     ncclResult_t r = nc.CommInitRank(&h->comm, (int)world, id, (int)rank);
@@ -1294,6 +1312,11 @@ int gbp_cuda_init_shard(const gbp_problem* p, const gbp_opts* o_in, uint32_t wor
       gbp_set_error(std::string("ncclCommInitRank: ") + nc.GetErrorString(r));
       h->comm = nullptr;
       rc = GBP_ERR_COMM;
+    } else {
+      CommEntry ce;
+      std::memcpy(ce.id, nccl_unique_id, 128);
+      ce.world = world; ce.rank = rank; ce.device = o.device; ce.comm = h->comm;
+      comm_cache().push_back(ce);
     }
   }
   if (!rc) rc = build(h, gbp_shard_problem(sh), &o, gbp_shard_edge_global(sh));

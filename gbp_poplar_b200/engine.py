@@ -61,6 +61,8 @@ def stats_to_dict(s):
 
 
 class GBPEngine:
+    _uid_cache = {}
+
     def __init__(self, problem, opts=None, lib=None, prefix="gbp_cuda_", keepalive=None, shard=None):
         """shard = (world, rank, nccl_unique_id bytes): this rank's part of the GLOBAL `problem`
         (gbp_cuda_init_shard); every program then includes the boundary-landmark exchange and is
@@ -99,6 +101,9 @@ class GBPEngine:
         if world == 1:
             return cls(problem, opts)
         lib = _capi.load_library()
+        key = (id(group), world, rank)
+        if key in cls._uid_cache:  # same ranks again: the library reuses the communicator of this id
+            return cls(problem, opts, shard=(world, rank, cls._uid_cache[key]))
         uid = C.create_string_buffer(128)
         if rank == 0:
             rc = lib.gbp_cuda_nccl_unique_id(uid)
@@ -107,7 +112,8 @@ class GBPEngine:
         dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else "cpu"
         t = torch.frombuffer(bytearray(uid.raw), dtype=torch.uint8).to(dev)
         dist.broadcast(t, src=0, group=group)
-        return cls(problem, opts, shard=(world, rank, bytes(t.cpu().numpy().tobytes())))
+        cls._uid_cache[key] = bytes(t.cpu().numpy().tobytes())
+        return cls(problem, opts, shard=(world, rank, cls._uid_cache[key]))
 
     # -- plumbing ---------------------------------------------------------
     def _check(self, rc):
