@@ -56,7 +56,8 @@ class GbpOpts(C.Structure):
         ("min_linear_iters", C.c_int),
         ("Nstds", C.c_float),
         ("use_cuda_graph", C.c_int),
-        ("reserved", C.c_int * 7),
+        ("store_full_messages", C.c_int),
+        ("reserved", C.c_int * 6),
     ]
 
 

@@ -72,7 +72,7 @@ struct gbp_handle {
   DeviceGraph g;
   uint32_t C = 0, L = 0, E = 0, E_pad = 0, n_tiles = 0, SK = 1, SL = 1;
   // host-side index maps (reference edge order <-> edge slots)
-  std::vector<uint32_t> cam_ids, lmk_ids, slot_c, slot_l, pos_of_orig, active_host;
+  std::vector<uint32_t> cam_ids, lmk_ids, slot_c, slot_l, pos_of_orig, active_host, lmk_ptr;
   uint32_t n_active = 0;
   std::vector<float> mu_init;     // host copy of the streamed `mu` (empty = zeros)
   std::vector<float> oldmu_init;  // host copy of the streamed `oldmu` (empty = zeros)
@@ -85,6 +85,7 @@ struct gbp_handle {
   float* d_pprior_cam_lam = nullptr;
   float4* d_pprior_lmk = nullptr;
   int use_graph = 0;
+  int num_sms = 148;
   // staging for READ_PROG
   uint32_t* d_pos_of_orig = nullptr;
   float* d_exp_lmk_eta = nullptr;
@@ -137,7 +138,7 @@ int download(T* dst, const T* src, size_t n, cudaStream_t s) {
   return GBP_OK;
 }
 
-inline uint32_t vars_grid(const gbp_handle* h) { return h->C + (h->L + GBP_TILE - 1) / GBP_TILE; }
+inline uint32_t lmks_grid(const gbp_handle* h) { return (h->L + GBP_LMK_PER_BLOCK - 1) / GBP_LMK_PER_BLOCK; }
 
 int priors_about_to_change(gbp_handle* h) {
   if (!h->p_in_sync) return GBP_OK;
@@ -176,7 +177,7 @@ std::vector<CommEntry>& comm_cache() {
 // interior landmarks and the cameras; k_boundary_finish then waits for the gather.
 int launch_update_vars(gbp_handle* h) {
   const int shift = h->pending_shift ? 1 : 0;
-  const uint32_t grid = vars_grid(h);
+  const uint32_t grid = lmks_grid(h);
   const bool exchange = h->shard && h->g.n_bnd_global > 0;
   const uint32_t bgrid = (h->g.n_bnd_local + GBP_TILE - 1) / GBP_TILE;
   if (exchange) {
@@ -191,8 +192,8 @@ int launch_update_vars(gbp_handle* h) {
     GBP_CUDA_TRY(cudaEventRecord(h->ev_recv, h->comm_stream));
     h->exchanges++;
   }
-  if (grid) {
-    gbp::k_update_vars<<<grid, GBP_TILE, 0, h->stream>>>(h->g, shift);
+  if (grid + h->C) {
+    gbp::k_update_vars<<<grid + h->C, GBP_TILE, 0, h->stream>>>(h->g, shift);
     h->kernels_launched++;
   }
   if (exchange) {
@@ -210,7 +211,10 @@ int launch_update_vars(gbp_handle* h) {
 template <bool PREP, bool MSG>
 int launch_sweep(gbp_handle* h) {
   if (h->n_tiles) {
-    gbp::k_sweep<PREP, MSG><<<h->n_tiles, GBP_TILE, MSG ? GBP_SWEEP_SMEM : GBP_WARPS * GBP_SCAM * 4, h->stream>>>(h->g);
+    // persistent: one block per SM (fewer when the graph has fewer warp-tiles than that)
+    const uint32_t n_wt = h->E_pad / 32;
+    const uint32_t grid = std::min<uint32_t>((uint32_t)h->num_sms, n_wt);
+    gbp::k_sweep<PREP, MSG><<<grid, GBP_SW_WARPS * 32, GBP_SWEEP_SMEM, h->stream>>>(h->g);
     h->kernels_launched++;
   }
   if (PREP) h->pending_shift = true;
@@ -422,40 +426,42 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   }
   h->SK = (C ? *std::max_element(deg_c.begin(), deg_c.end()) : 0) + 1;
   h->SL = (L ? *std::max_element(deg_l.begin(), deg_l.end()) : 0) + 1;
-  // tiles: each camera's factors padded to a multiple of GBP_TILE
-  std::vector<uint32_t> cam_tile_begin(C + 1, 0);
-  for (uint32_t c = 0; c < C; ++c) cam_tile_begin[c + 1] = cam_tile_begin[c] + (deg_c[c] + GBP_TILE - 1) / GBP_TILE;
-  h->n_tiles = cam_tile_begin[C];
-  const uint64_t epad64 = (uint64_t)h->n_tiles * GBP_TILE;
+  // warp-tiles: each camera's factors are padded to a multiple of 32 edge slots (one thread per
+  // factor, one camera per warp); the slot count is rounded up to whole GBP_TILE blocks for the
+  // helper kernels (trailing warp-tiles hold no factor)
+  std::vector<uint32_t> cam_wt_begin(C + 1, 0);
+  for (uint32_t c = 0; c < C; ++c) cam_wt_begin[c + 1] = cam_wt_begin[c] + (deg_c[c] + 31) / 32;
+  const uint64_t n_wt64 = ((uint64_t)cam_wt_begin[C] + GBP_WARPS - 1) / GBP_WARPS * GBP_WARPS;
+  const uint64_t epad64 = n_wt64 * 32;
   if (epad64 >= 0xffffffffull) {
     gbp_set_error("problem too large for 32-bit edge slots");
     return GBP_ERR_ARG;
   }
   h->E_pad = (uint32_t)epad64;
+  h->n_tiles = h->E_pad / GBP_TILE;
+  const uint32_t n_wt = h->E_pad / 32;
   const size_t EP = h->E_pad;
-  std::vector<uint32_t> tile_cam(h->n_tiles);
-  std::vector<uint2> tile_info(h->n_tiles);
+  std::vector<uint2> wt_info(n_wt, make_uint2(0u, 0u));
   for (uint32_t c = 0; c < C; ++c)
-    for (uint32_t t = cam_tile_begin[c]; t < cam_tile_begin[c + 1]; ++t) {
-      tile_cam[t] = c;
-      const uint32_t first = (t - cam_tile_begin[c]) * GBP_TILE;
-      tile_info[t] = make_uint2(c, std::min<uint32_t>(GBP_TILE, deg_c[c] - first));
-    }
+    for (uint32_t t = cam_wt_begin[c]; t < cam_wt_begin[c + 1]; ++t)
+      wt_info[t] = make_uint2(c, std::min<uint32_t>(32u, deg_c[c] - (t - cam_wt_begin[c]) * 32));
   h->pos_of_orig.resize(E);
   std::vector<uint32_t> edge_orig(EP, 0xffffffffu);
   for (uint32_t e = 0; e < E; ++e) {
-    const uint32_t pos = cam_tile_begin[h->cam_ids[e]] * GBP_TILE + h->slot_c[e];
+    const uint32_t pos = cam_wt_begin[h->cam_ids[e]] * 32 + h->slot_c[e];
     h->pos_of_orig[e] = pos;
     edge_orig[pos] = edge_global ? edge_global[e] : e;  // quirk Q7 compares GLOBAL edge ids
   }
-  std::vector<uint32_t> lmk_ptr(L + 1, 0), lmk_edges(E);
+  // landmark-bound messages live in LANDMARK order: message of edge e at lmk_ptr[l] + slot_l(e)
+  std::vector<uint32_t>& lmk_ptr = h->lmk_ptr;
+  lmk_ptr.assign(L + 1, 0);
   for (uint32_t l = 0; l < L; ++l) lmk_ptr[l + 1] = lmk_ptr[l] + deg_l[l];
-  for (uint32_t e = 0; e < E; ++e) lmk_edges[lmk_ptr[h->lmk_ids[e]] + h->slot_l[e]] = h->pos_of_orig[e];
+  std::vector<float> var(EP, 1.f);
   // per-edge state records
   std::vector<float4> recA(EP), recB(EP);
   for (size_t s = 0; s < EP; ++s) {
     recA[s] = make_float4(0.f, i2f(0), u2f(GBP_FLAG_PAD), 0.f);
-    recB[s] = make_float4(0.f, 0.f, 1.f, u2f(0));
+    recB[s] = make_float4(0.f, 0.f, u2f(0), u2f(0));
   }
   h->active_host.assign(E, 1u);
   if (p->active_flag) h->active_host.assign(p->active_flag, p->active_flag + E);
@@ -466,8 +472,9 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
     h->n_active += act;
     recA[s] = make_float4(p->damping ? p->damping[e] : 0.f, i2f(p->damping_count ? p->damping_count[e] : -15),
                           u2f(act ? GBP_FLAG_ACTIVE : 0u), 0.f);
-    recB[s] = make_float4(p->measurements[2 * (size_t)e], p->measurements[2 * (size_t)e + 1], p->meas_variances[e],
-                          u2f(h->lmk_ids[e]));
+    recB[s] = make_float4(p->measurements[2 * (size_t)e], p->measurements[2 * (size_t)e + 1], u2f(h->lmk_ids[e]),
+                          u2f(lmk_ptr[h->lmk_ids[e]] + h->slot_l[e]));
+    var[s] = p->meas_variances[e];
   }
   if (h->shard) h->n_active = gbp_shard_n_active_global(h->shard);
   auto any_nonzero = [](const float* a, size_t n) {
@@ -482,7 +489,7 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   // ---- device allocation (everything the reference relies on being zero IS zeroed, quirk Q4)
   DeviceGraph& g = h->g;
   std::memset(&g, 0, sizeof(g));
-  g.C = C; g.L = L; g.E = E; g.E_pad = h->E_pad; g.n_tiles = h->n_tiles;
+  g.C = C; g.L = L; g.E = E; g.E_pad = h->E_pad;
   g.K[0] = p->K[0]; g.K[1] = p->K[4]; g.K[2] = p->K[2]; g.K[3] = p->K[5];
   g.hp.maxeta_damping = o->maxeta_damping;
   g.hp.num_undamped_iters = o->num_undamped_iters;
@@ -493,15 +500,16 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
 #define A_(ptr, n) if (!rc) rc = h_alloc(h, &(ptr), (size_t)(n))
   A_(g.fac, GBP_FAC_QUADS * EP);
   A_(g.mcam, GBP_MCAM_QUADS * EP);
-  A_(g.mlmk, GBP_MLMK_QUADS * EP);
+  if (o->store_full_messages) A_(g.mcam_up, 4 * EP);
+  A_(g.mlmk, GBP_MLMK_QUADS * (size_t)E);
+  A_(g.var, EP);
   A_(g.recA, EP);
   A_(g.recB, EP);
   A_(g.edge_orig, EP);
-  A_(g.tile_cam, h->n_tiles);
-  A_(g.tile_info, h->n_tiles);
+  A_(g.wt_info, n_wt);
   A_(g.cam_rec, 16 * (size_t)C);
-  A_(g.cam_tile_begin, C + 1);
-  A_(g.cam_partial, (size_t)h->n_tiles * GBP_WARPS * GBP_CAMPART);
+  A_(g.cam_wt_begin, C + 1);
+  A_(g.cam_partial, (size_t)n_wt * GBP_CAMPART);
   A_(g.cam_b_eta, 6 * (size_t)C);
   A_(g.cam_b_lam, 36 * (size_t)C);
   A_(g.cam_mean, 6 * (size_t)C);
@@ -517,7 +525,6 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   A_(g.lmk_scaling, L);
   A_(g.lmk_wflag, L);
   A_(g.lmk_ptr, L + 1);
-  A_(g.lmk_edges, E);
   A_(h->d_pos_of_orig, E);
   A_(h->d_metric_parts, h->n_tiles);
   A_(h->d_pprior_cam_eta, 6 * (size_t)C);
@@ -548,9 +555,8 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   U_(g.recA, recA.data(), EP);
   U_(g.recB, recB.data(), EP);
   U_(g.edge_orig, edge_orig.data(), EP);
-  U_(g.tile_cam, tile_cam.data(), h->n_tiles);
-  U_(g.tile_info, tile_info.data(), h->n_tiles);
-  U_(g.cam_tile_begin, cam_tile_begin.data(), C + 1);
+  U_(g.wt_info, wt_info.data(), n_wt);
+  U_(g.cam_wt_begin, cam_wt_begin.data(), C + 1);
   U_(g.cam_prior_eta, p->cam_priors_eta, 6 * (size_t)C);
   U_(g.cam_prior_lam, p->cam_priors_lambda, 36 * (size_t)C);
   U_(g.cam_scaling, p->cam_scaling, C);
@@ -558,7 +564,7 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   U_(g.lmk_scaling, p->lmk_scaling, L);
   U_(g.lmk_wflag, p->lmk_weaken_flag, L);
   U_(g.lmk_ptr, lmk_ptr.data(), L + 1);
-  U_(g.lmk_edges, lmk_edges.data(), E);
+  U_(g.var, var.data(), EP);
   U_(h->d_pos_of_orig, h->pos_of_orig.data(), E);
   if (h->shard) {
     U_(g.lmk_bslot, lmk_bslot.data(), L);
@@ -585,6 +591,8 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   GBP_CUDA_TRY(cudaStreamSynchronize(s));
   GBP_CUDA_TRY(cudaFuncSetAttribute(gbp::k_sweep<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GBP_SWEEP_SMEM));
   GBP_CUDA_TRY(cudaFuncSetAttribute(gbp::k_sweep<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GBP_SWEEP_SMEM));
+  GBP_CUDA_TRY(cudaFuncSetAttribute(gbp::k_sweep<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GBP_SWEEP_SMEM));
+  GBP_CUDA_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
   // LINEARISE_PROG (ba/ba.cpp:890-893): beliefs <- priors, then linearise every factor
   h->pending_shift = false;
   rc = launch_update_vars(h);
@@ -644,6 +652,7 @@ int gbp_cuda_init(const gbp_problem* p, const gbp_opts* o_in, gbp_handle** out) 
   if (!rc && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) rc = GBP_ERR_CUDA;
   if (!rc && cudaEventCreate(&h->ev0) != cudaSuccess) rc = GBP_ERR_CUDA;
   if (!rc && cudaEventCreate(&h->ev1) != cudaSuccess) rc = GBP_ERR_CUDA;
+
   if (!rc) rc = build(h, p, &o);
   if (rc) {
     if (rc == GBP_ERR_CUDA && !*gbp_cuda_last_error()) gbp_set_error("CUDA initialisation failed");
@@ -988,6 +997,8 @@ int gbp_cuda_get_tensor(gbp_handle* h, const char* name, void* dst, size_t nbyte
       if (stale_p) rc = download(pr.data(), id == T_CAM_M_ETA ? h->d_pprior_cam_eta : h->d_pprior_cam_lam, pr.size(), s);
       else rc = download(pr.data(), id == T_CAM_M_ETA ? h->g.cam_prior_eta : h->g.cam_prior_lam, pr.size(), s);
       if (!rc) rc = fetch(h, v, h->g.mcam, GBP_MCAM_QUADS * EP);
+      std::vector<float4> vu;
+      if (!rc && h->g.mcam_up && id == T_CAM_M_LAM) rc = fetch(h, vu, h->g.mcam_up, 4 * EP);
       if (rc) break;
       for (size_t c = 0; c < C; ++c) std::memcpy(out + c * SK * d, pr.data() + c * d, d * 4);
       for (size_t e = 0; e < E; ++e) {
@@ -997,7 +1008,9 @@ int gbp_cuda_get_tensor(gbp_handle* h, const char* name, void* dst, size_t nbyte
           for (int i = 0; i < 6; ++i) o[i] = quad_field(v, EP, pos, i);
         } else {
           for (int i = 0; i < 6; ++i)
-            for (int j = 0; j < 6; ++j) o[i * 6 + j] = quad_field(v, EP, pos, gbp_mcam_lam_field(i, j));
+            for (int j = 0; j < 6; ++j)
+              o[i * 6 + j] = (j > i && !vu.empty()) ? quad_field(vu, EP, pos, gbp_upper(i, j))
+                                                    : quad_field(v, EP, pos, gbp_mcam_lam_field(i, j));
         }
       }
       break;
@@ -1009,13 +1022,14 @@ int gbp_cuda_get_tensor(gbp_handle* h, const char* name, void* dst, size_t nbyte
       std::memset(out, 0, nbytes);
       std::vector<float4> pr;
       rc = fetch(h, pr, stale_p ? h->d_pprior_lmk : h->g.lmk_prior, L * 3);
-      if (!rc) rc = fetch(h, v, h->g.mlmk, GBP_MLMK_QUADS * EP);
+      if (!rc) rc = fetch(h, v, h->g.mlmk, GBP_MLMK_QUADS * E);
       if (rc) break;
       for (size_t l = 0; l < L; ++l)
         for (int i = 0; i < d; ++i) out[l * SL * d + i] = aos_field(pr, 3, l, off + i);
       for (size_t e = 0; e < E; ++e) {
         float* o = out + ((size_t)h->lmk_ids[e] * SL + h->slot_l[e] + 1) * d;
-        for (int i = 0; i < d; ++i) o[i] = aos_field(v, GBP_MLMK_QUADS, h->pos_of_orig[e], off + i);
+        const size_t k = (size_t)h->lmk_ptr[h->lmk_ids[e]] + h->slot_l[e];
+        for (int i = 0; i < d; ++i) o[i] = aos_field(v, GBP_MLMK_QUADS, k, off + i);
       }
       break;
     }
@@ -1029,11 +1043,13 @@ int gbp_cuda_get_tensor(gbp_handle* h, const char* name, void* dst, size_t nbyte
           for (int i = 0; i < 9; ++i) out[e * 9 + i] = quad_field(v, EP, pos, GBP_FAC_ETA + i);
         } else {  // block-packed [cc 36 | cl 18 | lc 18 | ll 9], ba/ba.cpp:93-96
           float* o = out + e * 81;
-          for (int i = 0; i < 36; ++i) o[i] = quad_field(v, EP, pos, GBP_FAC_CC + i);
+          for (int i = 0; i < 6; ++i)
+            for (int j = 0; j < 6; ++j) o[i * 6 + j] = quad_field(v, EP, pos, GBP_FAC_CC + gbp_sym(i, j));
           for (int i = 0; i < 18; ++i) o[36 + i] = quad_field(v, EP, pos, GBP_FAC_CL + i);
           for (int i = 0; i < 3; ++i)
             for (int j = 0; j < 6; ++j) o[54 + i * 6 + j] = quad_field(v, EP, pos, GBP_FAC_CL + j * 3 + i);
-          for (int i = 0; i < 9; ++i) o[72 + i] = quad_field(v, EP, pos, GBP_FAC_LL + i);
+          for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) o[72 + i * 3 + j] = quad_field(v, EP, pos, GBP_FAC_LL + gbp_sym(i, j));
         }
       }
       break;
@@ -1051,14 +1067,20 @@ int gbp_cuda_get_tensor(gbp_handle* h, const char* name, void* dst, size_t nbyte
       }
       break;
     }
-    case T_Z: case T_VAR: {
+    case T_Z: {
       rc = fetch(h, v, h->g.recB, EP);
       if (rc) break;
       for (size_t e = 0; e < E; ++e) {
         const float4 r = v[h->pos_of_orig[e]];
-        if (id == T_Z) { out[2 * e] = r.x; out[2 * e + 1] = r.y; }
-        else out[e] = r.z;
+        out[2 * e] = r.x; out[2 * e + 1] = r.y;
       }
+      break;
+    }
+    case T_VAR: {
+      std::vector<float> vv(EP);
+      rc = download(vv.data(), h->g.var, EP, s);
+      if (!rc) GBP_CUDA_TRY(cudaStreamSynchronize(s));
+      for (size_t e = 0; e < E && !rc; ++e) out[e] = vv[h->pos_of_orig[e]];
       break;
     }
     case T_MU: case T_OLDMU: {
@@ -1148,6 +1170,8 @@ int gbp_cuda_set_tensor(gbp_handle* h, const char* name, const void* src, size_t
       else rc = upload(id == T_CAM_M_ETA ? h->g.cam_prior_eta : h->g.cam_prior_lam, pr.data(), pr.size(), s);
       if (!rc) GBP_CUDA_TRY(cudaStreamSynchronize(s));
       if (!rc) rc = fetch(h, v, h->g.mcam, GBP_MCAM_QUADS * EP);
+      std::vector<float4> vu;
+      if (!rc && h->g.mcam_up && id == T_CAM_M_LAM) rc = fetch(h, vu, h->g.mcam_up, 4 * EP);
       if (rc) break;
       for (size_t e = 0; e < E; ++e) {
         const float* o = in + ((size_t)h->cam_ids[e] * SK + h->slot_c[e] + 1) * d;
@@ -1155,11 +1179,15 @@ int gbp_cuda_set_tensor(gbp_handle* h, const char* name, const void* src, size_t
         if (id == T_CAM_M_ETA) {
           for (int i = 0; i < 6; ++i) quad_field(v, EP, pos, i) = o[i];
         } else {
-          for (int i = 0; i < 6; ++i)
-            for (int j = 0; j < 6; ++j) quad_field(v, EP, pos, gbp_mcam_lam_field(i, j)) = o[i * 6 + j];
+          for (int i = 0; i < 6; ++i)  // the lower triangle is what the algorithm reads (gbp_layout.h)
+            for (int j = 0; j <= i; ++j) quad_field(v, EP, pos, gbp_mcam_lam_field(i, j)) = o[i * 6 + j];
+          if (!vu.empty())
+            for (int i = 0; i < 6; ++i)
+              for (int j = i + 1; j < 6; ++j) quad_field(vu, EP, pos, gbp_upper(i, j)) = o[i * 6 + j];
         }
       }
       rc = push(h, v, h->g.mcam);
+      if (!rc && !vu.empty()) rc = push(h, vu, h->g.mcam_up);
       if (!rc && h->n_tiles) {
         gbp::k_cam_partials<<<h->n_tiles, GBP_TILE, 0, s>>>(h->g);
         h->kernels_launched++;
@@ -1173,13 +1201,14 @@ int gbp_cuda_set_tensor(gbp_handle* h, const char* name, const void* src, size_t
       std::vector<float4> pr;
       float4* d_pr = is_p ? h->d_pprior_lmk : h->g.lmk_prior;
       rc = fetch(h, pr, d_pr, L * 3);
-      if (!rc) rc = fetch(h, v, h->g.mlmk, GBP_MLMK_QUADS * EP);
+      if (!rc) rc = fetch(h, v, h->g.mlmk, GBP_MLMK_QUADS * E);
       if (rc) break;
       for (size_t l = 0; l < L; ++l)
         for (int i = 0; i < d; ++i) aos_field(pr, 3, l, off + i) = in[l * SL * d + i];
       for (size_t e = 0; e < E; ++e) {
         const float* o = in + ((size_t)h->lmk_ids[e] * SL + h->slot_l[e] + 1) * d;
-        for (int i = 0; i < d; ++i) aos_field(v, GBP_MLMK_QUADS, h->pos_of_orig[e], off + i) = o[i];
+        const size_t k = (size_t)h->lmk_ptr[h->lmk_ids[e]] + h->slot_l[e];
+        for (int i = 0; i < d; ++i) aos_field(v, GBP_MLMK_QUADS, k, off + i) = o[i];
       }
       rc = push(h, pr, d_pr);
       if (!rc) rc = push(h, v, h->g.mlmk);
@@ -1193,11 +1222,13 @@ int gbp_cuda_set_tensor(gbp_handle* h, const char* name, const void* src, size_t
         const size_t pos = h->pos_of_orig[e];
         if (id == T_F_ETA) {
           for (int i = 0; i < 9; ++i) quad_field(v, EP, pos, GBP_FAC_ETA + i) = in[e * 9 + i];
-        } else {  // Lambda_lc (o[54..71]) is implied by Lambda_cl and not stored
-          const float* o = in + e * 81;
-          for (int i = 0; i < 36; ++i) quad_field(v, EP, pos, GBP_FAC_CC + i) = o[i];
+        } else {  // Lambda_lc (o[54..71]) is implied by Lambda_cl; Lambda_cc / Lambda_ll are symmetric
+          const float* o = in + e * 81;     // (gbp_layout.h): their lower triangles are stored
+          for (int i = 0; i < 6; ++i)
+            for (int j = 0; j <= i; ++j) quad_field(v, EP, pos, GBP_FAC_CC + gbp_lt(i, j)) = o[i * 6 + j];
           for (int i = 0; i < 18; ++i) quad_field(v, EP, pos, GBP_FAC_CL + i) = o[36 + i];
-          for (int i = 0; i < 9; ++i) quad_field(v, EP, pos, GBP_FAC_LL + i) = o[72 + i];
+          for (int i = 0; i < 3; ++i)
+            for (int j = 0; j <= i; ++j) quad_field(v, EP, pos, GBP_FAC_LL + gbp_lt(i, j)) = o[72 + i * 3 + j];
         }
       }
       rc = push(h, v, h->g.fac);
@@ -1208,15 +1239,21 @@ int gbp_cuda_set_tensor(gbp_handle* h, const char* name, const void* src, size_t
     case T_ACTIVE: rc = import_edges(h, nullptr, nullptr, inu, nullptr, nullptr, 0); break;
     case T_ROBUST: rc = import_edges(h, nullptr, nullptr, nullptr, inu, nullptr, 0); break;
     case T_DMU: rc = import_edges(h, nullptr, nullptr, nullptr, nullptr, in, 0); break;
-    case T_Z: case T_VAR: {
+    case T_Z: {
       rc = fetch(h, v, h->g.recB, EP);
       if (rc) break;
       for (size_t e = 0; e < E; ++e) {
         float4& r = v[h->pos_of_orig[e]];
-        if (id == T_Z) { r.x = in[2 * e]; r.y = in[2 * e + 1]; }
-        else r.z = in[e];
+        r.x = in[2 * e]; r.y = in[2 * e + 1];
       }
       rc = push(h, v, h->g.recB);
+      break;
+    }
+    case T_VAR: {
+      std::vector<float> vv(EP, 1.f);
+      for (size_t e = 0; e < E; ++e) vv[h->pos_of_orig[e]] = in[e];
+      rc = upload(h->g.var, vv.data(), EP, s);
+      if (!rc) GBP_CUDA_TRY(cudaStreamSynchronize(s));
       break;
     }
     case T_MU:
@@ -1297,6 +1334,7 @@ int gbp_cuda_init_shard(const gbp_problem* p, const gbp_opts* o_in, uint32_t wor
   if (!rc && cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking) != cudaSuccess) rc = GBP_ERR_CUDA;
   if (!rc && cudaEventCreate(&h->ev0) != cudaSuccess) rc = GBP_ERR_CUDA;
   if (!rc && cudaEventCreate(&h->ev1) != cudaSuccess) rc = GBP_ERR_CUDA;
+
   if (!rc && cudaEventCreateWithFlags(&h->ev_send, cudaEventDisableTiming) != cudaSuccess) rc = GBP_ERR_CUDA;
   if (!rc && cudaEventCreateWithFlags(&h->ev_recv, cudaEventDisableTiming) != cudaSuccess) rc = GBP_ERR_CUDA;
   if (!rc) {

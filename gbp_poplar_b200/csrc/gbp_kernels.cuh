@@ -2,11 +2,11 @@
 // deliberately unused: the work is ~2.5 kflop of tiny 3x3/6x6 solves per 0.7 KB
 // of streamed state, i.e. HBM-bound -- see DESIGN.md).
 //
-//   k_sweep<PREP,MSG>   one thread per factor, one tile (= one camera) per block.
+//   k_sweep<PREP,MSG>   one thread per factor, persistent software-pipelined warps.
 //                       PREP = PrepMessageVertex        gbp_codelets.cpp:241-378
 //                       MSG  = the four message vertices gbp_codelets.cpp:411-709
 //                              + on-chip reduction of the camera-bound messages
-//   k_update_vars       belief update (prog_ub, ba/ba.cpp:104-139) fused with the
+//   k_update_cams/_lmks belief update (prog_ub, ba/ba.cpp:104-139) fused with the
 //                       per-variable mean (inf2mean hoisted out of PrepMessageVertex,
 //                       which recomputes it once per adjacent edge, :264-265)
 //   k_relinearise_all   RelineariseFactorVertex          gbp_codelets.cpp:38-171
@@ -19,28 +19,25 @@
 #include "gbp_layout.h"
 #include "gbp_math.cuh"
 
-#ifndef GBP_MIN_BLOCKS
-#define GBP_MIN_BLOCKS 3  // resident blocks per SM the factor kernel is compiled for (58 KB of stage each)
-#endif
-
 namespace gbp {
 
 struct DeviceGraph {
   // sizes
-  uint32_t C, L, E, E_pad, n_tiles;
+  uint32_t C, L, E, E_pad;  // E_pad: edge slots (multiple of GBP_TILE)
   // per-edge-slot records (quad-SoA, see gbp_layout.h)
   float4* fac;        // [18][E_pad]
-  float4* mcam;       // [11][E_pad]
-  float4* mlmk;       // [E_pad][3]
+  float4* mcam;       // [7][E_pad]
+  float4* mcam_up;    // [4][E_pad] strict upper triangle of the camera message Lambda, or nullptr (gbp_opts.store_full_messages)
+  float4* mlmk;       // [E][3] factor->landmark messages in LANDMARK order (see gbp_layout.h)
   float4* recA;       // [E_pad] {damping, damping_count, flags, dmu}
-  float4* recB;       // [E_pad] {z.x, z.y, var, landmark id}
+  float4* recB;       // [E_pad] {z.x, z.y, landmark id, position of the landmark message}
+  float* var;         // [E_pad] meas_variances (only read when a factor relinearises)
   float* oldmu_edge;  // [9][E_pad] or nullptr (= zeros); read only while !MUVALID
   uint32_t* edge_orig;  // [E_pad] original edge id, 0xffffffff for padding
   // tiles
-  uint32_t* tile_cam;        // [n_tiles]
-  uint2* tile_info;          // [n_tiles] {camera, number of real factors in the tile}
-  uint32_t* cam_tile_begin;  // [C+1]
-  float* cam_partial;        // [n_tiles * 4 warps][42]
+  uint2* wt_info;            // [E_pad/32] per warp-tile {camera, number of real factors (0..32)}
+  uint32_t* cam_wt_begin;    // [C+1] first warp-tile of every camera
+  float* cam_partial;        // [E_pad/32][42] per-warp-tile sums of the camera-bound messages
   // cameras
   float* cam_b_eta;      // [C][6]
   float* cam_b_lam;      // [C][36]
@@ -58,8 +55,7 @@ struct DeviceGraph {
   float4* lmk_prior;      // [L][3] {eta3, lam9}
   float* lmk_scaling;     // [L]
   uint32_t* lmk_wflag;    // [L]
-  uint32_t* lmk_ptr;      // [L+1] CSC over edge slots, in original edge order
-  uint32_t* lmk_edges;    // [E]
+  uint32_t* lmk_ptr;      // [L+1] first message of every landmark in mlmk (messages in original edge order)
   // multi-GPU shard (all null / 0 on a single-GPU handle): boundary landmarks = landmarks
   // that other ranks observe too; their beliefs are formed from all-gathered partials
   uint32_t* lmk_bslot;    // [L] position in the global boundary list, 0xffffffff = interior
@@ -139,84 +135,127 @@ GBP_DEV void store_quads(float4* base, size_t stride, size_t e, const float (&in
     base[(size_t)q * stride + e] = make_float4(in[q * 4], in[q * 4 + 1], in[q * 4 + 2], in[q * 4 + 3]);
 }
 
-// (Re)linearisation of one factor (gbp_codelets.cpp:285-373 / :53-168): rare and
-// register hungry, so it is kept out of line of the streaming path.  Arguments
-// are passed by value so the kernel parameter block never has its address taken.
-__device__ __noinline__ uint32_t relinearise_in_place(float4* fac, size_t E_pad, size_t e, float4 K4, float Nstds,
-                                                      float z0, float z1, float var, float c0, float c1, float c2,
-                                                      float c3, float c4, float c5, float l0, float l1, float l2,
-                                                      bool zero_first) {
-  float f[GBP_FAC_QUADS * 4];
-  if (zero_first) {
+// ---- factor record (un)packing ---------------------------------------------------
+// Registers hold a factor potential un-packed as f[72] = [eta 9 | ll 9 | cl 18 | cc 36]
+// (what linearise_accumulate works on); memory holds the 14-quad packed record of
+// gbp_layout.h (lower triangles of the symmetric ll / cc blocks).
+#define GBP_F_ETA 0
+#define GBP_F_LL 9
+#define GBP_F_CL 18
+#define GBP_F_CC 36
+GBP_DEV void fac_unpack(const float (&r)[GBP_FAC_QUADS * 4], float (&f)[72]) {
 #pragma unroll
-    for (int i = 0; i < GBP_FAC_QUADS * 4; ++i) f[i] = 0.f;
+  for (int i = 0; i < 9; ++i) f[GBP_F_ETA + i] = r[GBP_FAC_ETA + i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) f[GBP_F_LL + i * 3 + j] = r[GBP_FAC_LL + gbp_sym(i, j)];
+#pragma unroll
+  for (int i = 0; i < 18; ++i) f[GBP_F_CL + i] = r[GBP_FAC_CL + i];
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) f[GBP_F_CC + i * 6 + j] = r[GBP_FAC_CC + gbp_sym(i, j)];
+}
+GBP_DEV void fac_pack(const float (&f)[72], float (&r)[GBP_FAC_QUADS * 4]) {
+#pragma unroll
+  for (int i = 0; i < 9; ++i) r[GBP_FAC_ETA + i] = f[GBP_F_ETA + i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j <= i; ++j) r[GBP_FAC_LL + gbp_lt(i, j)] = f[GBP_F_LL + i * 3 + j];
+#pragma unroll
+  for (int i = 0; i < 18; ++i) r[GBP_FAC_CL + i] = f[GBP_F_CL + i];
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j <= i; ++j) r[GBP_FAC_CC + gbp_lt(i, j)] = f[GBP_F_CC + i * 6 + j];
+  r[54] = 0.f;
+  r[55] = 0.f;
+}
+
+// (Re)linearisation of one factor (gbp_codelets.cpp:285-373 / :53-168): rare and
+// register hungry, so it is kept out of line of the streaming path.  `src` is where the
+// current packed record is read from (quad q at src[q * src_stride]; nullptr = start from
+// zero, RelineariseFactorVertex), the new record goes to global memory and, when `stage`
+// is given, into the caller's shared-memory stage slot as well.  Arguments are passed by
+// value so the kernel parameter block never has its address taken.
+__device__ __noinline__ uint32_t relinearise_record(const float4* src, size_t src_stride, float4* dst, size_t dst_stride,
+                                                    float4* stage, float4 K4, float Nstds, float z0, float z1, float var,
+                                                    float c0, float c1, float c2, float c3, float c4, float c5, float l0,
+                                                    float l1, float l2) {
+  float f[72];
+  if (src) {  // quirk Q1: accumulate onto the old blocks
+    float r[GBP_FAC_QUADS * 4];
+#pragma unroll
+    for (int q = 0; q < GBP_FAC_QUADS; ++q) {
+      const float4 v = src[(size_t)q * src_stride];
+      r[q * 4] = v.x; r[q * 4 + 1] = v.y; r[q * 4 + 2] = v.z; r[q * 4 + 3] = v.w;
+    }
+    fac_unpack(r, f);
   } else {
-    load_quads<GBP_FAC_QUADS>(fac, E_pad, e, f);  // quirk Q1: accumulate onto the old blocks
+#pragma unroll
+    for (int i = 0; i < 72; ++i) f[i] = 0.f;
   }
   const float K[4] = {K4.x, K4.y, K4.z, K4.w};
   const float x_kf[6] = {c0, c1, c2, c3, c4, c5};
   const float x_l[3] = {l0, l1, l2};
-  float(&eta)[9] = *reinterpret_cast<float(*)[9]>(f + GBP_FAC_ETA);
-  float(&ll)[9] = *reinterpret_cast<float(*)[9]>(f + GBP_FAC_LL);
-  float(&cl)[18] = *reinterpret_cast<float(*)[18]>(f + GBP_FAC_CL);
-  float(&cc)[36] = *reinterpret_cast<float(*)[36]>(f + GBP_FAC_CC);
+  float(&eta)[9] = *reinterpret_cast<float(*)[9]>(f + GBP_F_ETA);
+  float(&ll)[9] = *reinterpret_cast<float(*)[9]>(f + GBP_F_LL);
+  float(&cl)[18] = *reinterpret_cast<float(*)[18]>(f + GBP_F_CL);
+  float(&cc)[36] = *reinterpret_cast<float(*)[36]>(f + GBP_F_CC);
   const uint32_t robust = linearise_accumulate(z0, z1, var, K, x_kf, x_l, Nstds, eta, ll, cl, cc);
-  store_quads<GBP_FAC_QUADS>(fac, E_pad, e, f);
+  float r[GBP_FAC_QUADS * 4];
+  fac_pack(f, r);
+#pragma unroll
+  for (int q = 0; q < GBP_FAC_QUADS; ++q) {
+    const float4 v = make_float4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
+    dst[(size_t)q * dst_stride] = v;
+    if (stage) stage[q * 32] = v;
+  }
   return robust;
 }
 
 // ---- k_sweep ---------------------------------------------------------------------
-// One thread per factor; every WARP is autonomous (no block-wide barrier): it
-//   1. issues cp.async (LDGSTS, L1-bypassing) copies of its 32 factors' records
-//      (factor potential 18 quads, previous camera message 7, previous landmark
-//      message 3) into its private shared-memory stage, so the whole 14 KB per
-//      warp is in flight before any arithmetic and without tying up registers;
-//   2. meanwhile gathers the landmark beliefs (L2-resident, 64 B each) and runs
-//      PrepMessageVertex on the hoisted per-variable means;
-//   3. computes both messages from the staged data, stores them in place;
-//   4. sums the 32 camera-bound messages in lane order (serial fp32 adds, so the
-//      result is defined independently of the hardware) through the same shared
-//      memory and writes one partial per warp.
-#define GBP_WARPS (GBP_TILE / 32)
-#ifndef GBP_STAGE_LMK
-#define GBP_STAGE_LMK 0  // 1: the previous landmark message goes through the stage too; 0: plain loads
+// Persistent, software-pipelined: one block of GBP_SW_WARPS warps per SM; every WARP is
+// autonomous (no block-wide barrier) and walks over warp-tiles (32 consecutive edge slots
+// = 32 factors of one camera, one thread per factor) with a double-buffered
+// shared-memory stage:
+//   top of iteration t   issue the cp.async (LDGSTS, L1-bypassing) copies of warp-tile
+//                        t+1 -- 26 quads per factor: potential 14, previous camera
+//                        message 7, previous landmark message 3, the two edge-state
+//                        records -- plus its camera record; start the register loads of
+//                        the landmark beliefs of t+1 (their landmark ids were fetched
+//                        during t-1); fetch tile info / landmark ids of t+2;
+//                        wait for the copies of t (issued one iteration ago);
+//   body                 PrepMessageVertex on the hoisted per-variable means, both
+//                        messages from the staged data, stores straight from registers;
+//   end                  lane-ordered sum of the 32 camera-bound messages through the
+//                        consumed stage (serial fp32 adds: the result is defined
+//                        independently of the hardware), one 42-float partial per warp.
+// So every DRAM byte a warp needs is requested a whole tile of arithmetic (~4 us) before
+// it is used and the SM never sits in a load phase.
+#ifndef GBP_SW_WARPS
+#define GBP_SW_WARPS 8   // warps per block (one block per SM)
 #endif
-#define GBP_STAGE_QUADS (GBP_FAC_QUADS + GBP_MCAM_READ_QUADS + (GBP_STAGE_LMK ? GBP_MLMK_QUADS : 0))  // 28 or 25
-#define GBP_STAGE_MCAM GBP_FAC_QUADS
-#define GBP_STAGE_MLMK (GBP_FAC_QUADS + GBP_MCAM_READ_QUADS)
+#ifndef GBP_NBUF
+#define GBP_NBUF 2       // 2: double-buffered stage (DRAM latency hidden by the pipeline);
+#endif                   // 1: single stage refilled from L2 after an L2 prefetch one tile ahead (more warps fit)
+#define GBP_WARPS (GBP_TILE / 32)  // warp-tiles per 128-slot tile
+#define GBP_SQ 26  // quads per factor in a stage
+#define GBP_SQ_FAC 0
+#define GBP_SQ_MCAM GBP_FAC_QUADS                      // 14
+#define GBP_SQ_MLMK (GBP_FAC_QUADS + GBP_MCAM_QUADS)   // 21
+#define GBP_SQ_RECA (GBP_SQ_MLMK + GBP_MLMK_QUADS)     // 24
+#define GBP_SQ_RECB (GBP_SQ_RECA + 1)                  // 25
+#define GBP_STAGE_QUADS (GBP_SQ * 32)
 #define GBP_SCAM 56  // per-warp copy of: belief eta 6 | belief lambda 36 | mean 6 | previous mean 6
 #define GBP_RED_STRIDE 33
-#define GBP_SWEEP_SMEM (GBP_WARPS * GBP_STAGE_QUADS * 32 * 16 + GBP_WARPS * GBP_SCAM * 4)
+#define GBP_SWEEP_SMEM (GBP_SW_WARPS * GBP_NBUF * (GBP_STAGE_QUADS * 16 + GBP_SCAM * 4))
 
 GBP_DEV void cp_async16(void* smem, const void* gmem) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
-}
-template <int EN>
-GBP_DEV void cp_async16_hint(void* smem, const void* gmem, uint64_t pol) {
-  if (!EN) {
-    cp_async16(smem, gmem);
-    return;
-  }
-#if GBP_L2_HINTS
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "l"(pol) : "memory");
-#else
-  cp_async16(smem, gmem);
-#endif
-}
-// L2 prefetch of one contiguous run (bytes % 16 == 0): the records of the tile that
-// will be processed `GBP_PREFETCH_TILES` blocks from now are pulled DRAM->L2 while this
-// block computes, so that its cp.async stage fill sees L2 latency instead of HBM latency.
-GBP_DEV void bulk_prefetch_l2(const void* gmem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gmem), "r"(bytes) : "memory");
-}
-#ifndef GBP_PREFETCH_TILES
-#define GBP_PREFETCH_TILES 148
-#endif
-
-GBP_DEV void cp_async_commit_wait_all() {
-  asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;\n" ::: "memory");
 }
 
 template <int Q0, int N>
@@ -226,6 +265,33 @@ GBP_DEV void stage_read(const float4* stage, uint32_t lane, float (&out)[N * 4])
     const float4 v = stage[(Q0 + q) * 32 + lane];
     out[q * 4] = v.x; out[q * 4 + 1] = v.y; out[q * 4 + 2] = v.z; out[q * 4 + 3] = v.w;
   }
+}
+
+// all per-factor records of warp-tile wt (+ the camera record) -> shared memory, asynchronously
+GBP_DEV void issue_stage(const DeviceGraph& g, float4* stage, float* s_cam, const uint32_t wt, const uint32_t cam,
+                         const uint32_t lpos, const uint32_t lane) {
+  const size_t e = (size_t)wt * 32 + lane;
+  cp_async16(stage + GBP_SQ_RECA * 32 + lane, g.recA + e);
+  cp_async16(stage + GBP_SQ_RECB * 32 + lane, g.recB + e);
+  if (lane < GBP_SCAM / 4) cp_async16(s_cam + lane * 4, g.cam_rec + (size_t)cam * 16 + lane);
+#pragma unroll
+  for (int q = 0; q < GBP_MLMK_QUADS; ++q) cp_async16(stage + (GBP_SQ_MLMK + q) * 32 + lane, g.mlmk + (size_t)lpos * GBP_MLMK_QUADS + q);
+#pragma unroll
+  for (int q = 0; q < GBP_MCAM_QUADS; ++q) cp_async16(stage + (GBP_SQ_MCAM + q) * 32 + lane, g.mcam + (size_t)q * g.E_pad + e);
+#pragma unroll
+  for (int q = 0; q < GBP_FAC_QUADS; ++q) cp_async16(stage + (GBP_SQ_FAC + q) * 32 + lane, g.fac + (size_t)q * g.E_pad + e);
+}
+
+// landmark record of one factor: belief eta 0..2 | lambda 3..11 | mean 12..14 | - | previous mean 16..18 | -
+GBP_DEV void load_lmk_belief(const DeviceGraph& g, const uint32_t l, float (&lb)[20]) {
+  const float4* p = g.lmk_b + (size_t)l * GBP_LMKB_QUADS;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 v = p[q];
+    lb[q * 4] = v.x; lb[q * 4 + 1] = v.y; lb[q * 4 + 2] = v.z; lb[q * 4 + 3] = v.w;
+  }
+  const float4 mp = g.lmk_mean_prev[l];
+  lb[16] = mp.x; lb[17] = mp.y; lb[18] = mp.z; lb[19] = mp.w;
 }
 
 // lane-ordered sum of the 42 camera-message values of the warp's 32 factors
@@ -246,70 +312,21 @@ GBP_DEV void warp_cam_reduce(float* red, uint32_t lane, float* __restrict__ out4
   }
 }
 
+// One warp-tile: prep + messages of 32 factors from the landed stage.
+// lb: landmark record of this lane's factor (load_lmk_belief).
 template <bool PREP, bool MSG>
-__global__ void __launch_bounds__(GBP_TILE, GBP_MIN_BLOCKS) k_sweep(const DeviceGraph g) {
-  extern __shared__ float4 smem4[];
-  const uint32_t tile = blockIdx.x;
-  const uint32_t tid = threadIdx.x;
-  const uint32_t warp = tid >> 5, lane = tid & 31;
-  float4* stage = smem4 + warp * (GBP_STAGE_QUADS * 32);
-  float* s_cam = reinterpret_cast<float*>(smem4 + (MSG ? GBP_WARPS * GBP_STAGE_QUADS * 32 : 0)) + warp * GBP_SCAM;
-  const size_t e = (size_t)tile * GBP_TILE + tid;
-  // critical path first: the per-edge state carries the landmark id the belief gather
-  // depends on (reading it for a padding slot is harmless)
-  const uint64_t pol_keep = l2_policy_keep(), pol_stream = l2_policy_stream();
-  float4 ra = ld4_hint<(GBP_L2_HINTS & 2)>(g.recA + e, pol_keep);
-  const float4 rb = ld4_hint<(GBP_L2_HINTS & 2)>(g.recB + e, pol_keep);
-  const uint2 ti = __ldg(g.tile_info + tile);
-  const uint32_t c = ti.x;
-  const bool valid = tid < ti.y;  // padding slots hold no factor
-  if (GBP_PREFETCH_TILES > 0 && MSG && warp == 0 && lane < 2) {
-    const uint32_t pt = tile + GBP_PREFETCH_TILES;
-    if (pt < g.n_tiles) bulk_prefetch_l2((lane ? g.recB : g.recA) + (size_t)pt * GBP_TILE, GBP_TILE * 16);
-  }
-  // the camera's packed belief/mean record goes through the stage as well (224 B per warp)
-  if (lane < GBP_SCAM / 4) cp_async16(s_cam + lane * 4, g.cam_rec + (size_t)c * 16 + lane);
-  if (MSG && valid) {
-#pragma unroll
-    for (int q = 0; q < GBP_FAC_QUADS; ++q)
-      cp_async16_hint<(GBP_L2_HINTS & 4)>(stage + q * 32 + lane, g.fac + (size_t)q * g.E_pad + e, pol_stream);
-#pragma unroll
-    for (int q = 0; q < GBP_MCAM_READ_QUADS; ++q)
-      cp_async16_hint<(GBP_L2_HINTS & 4)>(stage + (GBP_STAGE_MCAM + q) * 32 + lane, g.mcam + (size_t)q * g.E_pad + e, pol_stream);
-    if (GBP_STAGE_LMK) {
-#pragma unroll
-      for (int q = 0; q < GBP_MLMK_QUADS; ++q)
-        cp_async16(stage + (GBP_STAGE_MLMK + q) * 32 + lane, g.mlmk + e * GBP_MLMK_QUADS + q);
-    }
-  }
-  asm volatile("cp.async.commit_group;\n" ::: "memory");
-  float pl[12];  // previous f->lmk message: eta 0..2, lambda 3..11
-  if (MSG && !GBP_STAGE_LMK && valid) {
-    const float4* p = g.mlmk + e * GBP_MLMK_QUADS;
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      const float4 v = ld4_hint<(GBP_L2_HINTS & 1)>(p + q, pol_keep);
-      pl[q * 4] = v.x; pl[q * 4 + 1] = v.y; pl[q * 4 + 2] = v.z; pl[q * 4 + 3] = v.w;
-    }
-  }
+GBP_DEV void sweep_tile(const DeviceGraph& g, float4* stage, const float* s_cam, const uint32_t wt, const uint2 ti,
+                        const float (&lb)[20], const uint32_t lane) {
+  const size_t e = (size_t)wt * 32 + lane;
+  const bool valid = lane < ti.y;  // padding slots hold no factor
+  const float4 ra = stage[GBP_SQ_RECA * 32 + lane];
+  const float4 rb = stage[GBP_SQ_RECB * 32 + lane];
   float damping = ra.x;
   int dcount = __float_as_int(ra.y);
   uint32_t flags = __float_as_uint(ra.z);
   float dmu = ra.w;
   const bool active = valid && (flags & GBP_FLAG_ACTIVE) != 0;
-  const uint32_t l = __float_as_uint(rb.w);
-  float lb[16];  // landmark belief: eta 0..2 | lambda 3..11 | mean 12..14
-  if (active) {
-    const float4* p = g.lmk_b + (size_t)l * GBP_LMKB_QUADS;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 v = p[q];
-      lb[q * 4] = v.x; lb[q * 4 + 1] = v.y; lb[q * 4 + 2] = v.z; lb[q * 4 + 3] = v.w;
-    }
-  }
-  // everything staged so far (camera record + this warp's factor records) has landed
-  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-  __syncwarp();
+  const size_t lpos = __float_as_uint(rb.w);  // where this factor's landmark-bound message lives
 
   if (PREP && active) {
     if (dcount == 0) damping = g.hp.maxeta_damping;  // gbp_codelets.cpp:245-248
@@ -320,10 +337,9 @@ __global__ void __launch_bounds__(GBP_TILE, GBP_MIN_BLOCKS) k_sweep(const Device
 #pragma unroll
     for (int i = 0; i < 3; ++i) x_l[i] = lb[12 + i];
     if (flags & GBP_FLAG_MUVALID) {
-      const float4 mp = g.lmk_mean_prev[l];
 #pragma unroll
       for (int i = 0; i < 6; ++i) old[i] = s_cam[48 + i];
-      old[6] = mp.x; old[7] = mp.y; old[8] = mp.z;
+      old[6] = lb[16]; old[7] = lb[17]; old[8] = lb[18];
     } else {
 #pragma unroll
       for (int i = 0; i < 9; ++i) old[i] = g.oldmu_edge ? g.oldmu_edge[(size_t)i * g.E_pad + e] : 0.f;
@@ -344,59 +360,63 @@ __global__ void __launch_bounds__(GBP_TILE, GBP_MIN_BLOCKS) k_sweep(const Device
     if (dmu < g.hp.dmu_threshold && dcount > g.hp.min_linear_iters - g.hp.num_undamped_iters) {
       damping = 0.0f;  // gbp_codelets.cpp:280-283
       dcount = -g.hp.num_undamped_iters;
-      const uint32_t robust = relinearise_in_place(g.fac, g.E_pad, e, make_float4(g.K[0], g.K[1], g.K[2], g.K[3]), g.hp.Nstds,
-                                                   rb.x, rb.y, rb.z, x_kf[0], x_kf[1], x_kf[2], x_kf[3], x_kf[4], x_kf[5],
-                                                   x_l[0], x_l[1], x_l[2], false);
+      // the staged record is the current potential: accumulate onto it (quirk Q1), write it back
+      const uint32_t robust = relinearise_record(stage + lane, 32, g.fac + e, g.E_pad, stage + lane,
+                                                 make_float4(g.K[0], g.K[1], g.K[2], g.K[3]), g.hp.Nstds, rb.x, rb.y, g.var[e],
+                                                 x_kf[0], x_kf[1], x_kf[2], x_kf[3], x_kf[4], x_kf[5], x_l[0], x_l[1], x_l[2]);
       flags = (flags & ~GBP_FLAG_ROBUST) | (robust ? GBP_FLAG_ROBUST : 0u);
-      if (MSG) {  // re-stage the relinearised potential (plain loads: ordered after this thread's stores)
-#pragma unroll
-        for (int q = 0; q < GBP_FAC_QUADS; ++q) stage[q * 32 + lane] = g.fac[(size_t)q * g.E_pad + e];
-      }
     }
   }
 
-  float nc[GBP_MCAM_QUADS * 4];  // new f->cam message record
+  float nc[28];   // new f->cam message record: eta 0..5 | lower lambda 6..26 | pad
+  float ncu[16];  // its strict upper triangle (row-major, i<j): only summed into the camera partial
   if (MSG) {
-#ifdef GBP_EXPERIMENT_NOCOMPUTE
+#ifdef GBP_EXPERIMENT_NOCOMPUTE  // memory-only variant (tuning experiments): touch every staged quad, store every output
     if (active) {
-      float t[100];
-      stage_read<0, 25>(stage, lane, t);
+      float t[GBP_SQ * 4];
+      stage_read<0, GBP_SQ>(stage, lane, t);
+      float acc = lb[0] + lb[5] + lb[14] + lb[17] + s_cam[lane];
 #pragma unroll
-      for (int k = 0; k < 44; ++k) nc[k] = t[k] + t[k + 50] * lb[k % 16];
-      float nl[12];
+      for (int k = 0; k < GBP_SQ * 4; ++k) acc += t[k];
 #pragma unroll
-      for (int k = 0; k < 12; ++k) nl[k] = pl[k] + t[44 + k % 6];
+      for (int k = 0; k < 28; ++k) nc[k] = acc + t[k];
+#pragma unroll
+      for (int k = 0; k < 15; ++k) ncu[k] = acc;
       float4* p = g.mlmk + e * GBP_MLMK_QUADS;
 #pragma unroll
-      for (int q = 0; q < 3; ++q) p[q] = make_float4(nl[q * 4], nl[q * 4 + 1], nl[q * 4 + 2], nl[q * 4 + 3]);
-      store_quads<GBP_MCAM_QUADS>(g.mcam, g.E_pad, e, nc);
+      for (int q = 0; q < 3; ++q) p[q] = make_float4(acc, t[q], t[q + 4], t[q + 8]);
+#pragma unroll
+      for (int q = 0; q < GBP_MCAM_QUADS; ++q)
+        g.mcam[(size_t)q * g.E_pad + e] = make_float4(nc[q * 4], nc[q * 4 + 1], nc[q * 4 + 2], nc[q * 4 + 3]);
     } else if (false) {
 #else
     if (active) {
 #endif
       const float omd = fs(1.0f, damping);
-      float head[36];  // eta 0..8 | ll 9..17 | cl 18..35
-      stage_read<0, 9>(stage, lane, head);
+      float head[36];  // quads 0..8: eta 0..8 | ll(lower) 9..14 | cl 15..32 | cc(lower) 0..2 at 33..35
+      stage_read<GBP_SQ_FAC, 9>(stage, lane, head);
+      float tail[20];  // quads 9..13: cc(lower) 3..20 at 0..17 | pad
+      stage_read<GBP_SQ_FAC + 9, 5>(stage, lane, tail);
       const float* eta = head + GBP_FAC_ETA;
-      const float* ll = head + GBP_FAC_LL;
       const float* cl = head + GBP_FAC_CL;
-      if (GBP_STAGE_LMK) stage_read<GBP_STAGE_MLMK, 3>(stage, lane, pl);
-      float pc_eta[8];  // previous f->cam eta 0..5 (+2 lower-lambda entries)
-      stage_read<GBP_STAGE_MCAM, 2>(stage, lane, pc_eta);
+#define GBP_LLF(i, j) head[GBP_FAC_LL + gbp_sym(i, j)]
+#define GBP_CCF(i, j) ((gbp_sym(i, j) < 3) ? head[GBP_FAC_CC + gbp_sym(i, j)] : tail[gbp_sym(i, j) - 3])
+      float pl[12];  // previous f->lmk message: eta 0..2, lambda 3..11
+      stage_read<GBP_SQ_MLMK, 3>(stage, lane, pl);
+      float pc[28];  // previous f->cam message: eta 0..5, lower lambda 6..26
+      stage_read<GBP_SQ_MCAM, 7>(stage, lane, pc);
 
       // ---- message to the landmark (gbp_codelets.cpp:536-552, 691-699) ----
       float nl[12];
       {
         float Ai[36];
         {
-          float cc[36], pc[28], Ld[21];
-          stage_read<9, 9>(stage, lane, cc);
-          stage_read<GBP_STAGE_MCAM, 7>(stage, lane, pc);
+          float Ld[21];
 #pragma unroll
           for (int i = 0; i < 6; ++i)
 #pragma unroll
             for (int j = 0; j <= i; ++j)
-              Ld[lt(i, j)] = fs(fa(cc[i * 6 + j], s_cam[6 + i * 6 + j]), pc[GBP_MCAM_LOWER + lt(i, j)]);
+              Ld[lt(i, j)] = fs(fa(GBP_CCF(i, j), s_cam[6 + i * 6 + j]), pc[GBP_MCAM_LOWER + lt(i, j)]);
           inv6(Ld, Ai);
         }
         float P[18];  // Lambda_lc * inv  (3x6), Lambda_lc(i,k) = Lambda_cl(k,i)
@@ -411,7 +431,7 @@ __global__ void __launch_bounds__(GBP_TILE, GBP_MIN_BLOCKS) k_sweep(const Device
           }
         float ed[6];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) ed[i] = fs(fa(eta[i], s_cam[i]), pc_eta[i]);
+        for (int i = 0; i < 6; ++i) ed[i] = fs(fa(eta[i], s_cam[i]), pc[i]);
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
           float acc = fm(P[i * 6], ed[0]);
@@ -427,21 +447,22 @@ __global__ void __launch_bounds__(GBP_TILE, GBP_MIN_BLOCKS) k_sweep(const Device
             float acc = fm(P[i * 6], cl[j]);
 #pragma unroll
             for (int k = 1; k < 6; ++k) acc = fa(acc, fm(P[i * 6 + k], cl[k * 3 + j]));
-            nl[3 + i * 3 + j] = fs(ll[i * 3 + j], acc);
+            nl[3 + i * 3 + j] = fs(GBP_LLF(i, j), acc);
           }
       }
       {
-        float4* p = g.mlmk + e * GBP_MLMK_QUADS;
+        float4* p = g.mlmk + lpos * GBP_MLMK_QUADS;
 #pragma unroll
-        for (int q = 0; q < 3; ++q)
-          st4_hint<(GBP_L2_HINTS & 1)>(p + q, make_float4(nl[q * 4], nl[q * 4 + 1], nl[q * 4 + 2], nl[q * 4 + 3]), pol_keep);
+        for (int q = 0; q < 3; ++q) p[q] = make_float4(nl[q * 4], nl[q * 4 + 1], nl[q * 4 + 2], nl[q * 4 + 3]);
       }
 
       // ---- message to the camera (gbp_codelets.cpp:446-462, 619-627) ----
       {
         float Ld[9], Li[9];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) Ld[i] = fs(fa(ll[i], lb[3 + i]), pl[3 + i]);
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) Ld[i * 3 + j] = fs(fa(GBP_LLF(i, j), lb[3 + i * 3 + j]), pl[3 + i * 3 + j]);
         inv3(Ld, Li);
         float P[18];  // Lambda_cl * inv (6x3)
 #pragma unroll
@@ -456,41 +477,52 @@ __global__ void __launch_bounds__(GBP_TILE, GBP_MIN_BLOCKS) k_sweep(const Device
         for (int i = 0; i < 6; ++i) {
           const float acc = fa(fa(fm(P[i * 3], ed[0]), fm(P[i * 3 + 1], ed[1])), fm(P[i * 3 + 2], ed[2]));
           const float h = fs(eta[i], acc);
-          nc[i] = fa(fm(h, omd), fm(pc_eta[i], damping));
+          nc[i] = fa(fm(h, omd), fm(pc[i], damping));
         }
-        float cc[36];
-        stage_read<9, 9>(stage, lane, cc);
 #pragma unroll
         for (int i = 0; i < 6; ++i)
 #pragma unroll
           for (int j = 0; j < 6; ++j) {
             const float acc = fa(fa(fm(P[i * 3], cl[j * 3]), fm(P[i * 3 + 1], cl[j * 3 + 1])), fm(P[i * 3 + 2], cl[j * 3 + 2]));
-            nc[(i >= j) ? (GBP_MCAM_LOWER + lt(i, j)) : (GBP_MCAM_UPPER + (5 * i - i * (i - 1) / 2) + (j - i - 1))] =
-                fs(cc[i * 6 + j], acc);
+            const float v = fs(GBP_CCF(i, j), acc);
+            if (i >= j) nc[GBP_MCAM_LOWER + lt(i, j)] = v;
+            else ncu[gbp_upper(i, j)] = v;
           }
         nc[27] = 0.f;
-        nc[43] = 0.f;
       }
+#undef GBP_LLF
+#undef GBP_CCF
 #pragma unroll
       for (int q = 0; q < GBP_MCAM_QUADS; ++q)
-        st4_hint<(GBP_L2_HINTS & 8)>(g.mcam + (size_t)q * g.E_pad + e, make_float4(nc[q * 4], nc[q * 4 + 1], nc[q * 4 + 2], nc[q * 4 + 3]), pol_stream);
+        g.mcam[(size_t)q * g.E_pad + e] = make_float4(nc[q * 4], nc[q * 4 + 1], nc[q * 4 + 2], nc[q * 4 + 3]);
+      if (g.mcam_up) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          g.mcam_up[(size_t)q * g.E_pad + e] = make_float4(ncu[q * 4], ncu[q * 4 + 1], ncu[q * 4 + 2], q < 3 ? ncu[q * 4 + 3] : 0.f);
+      }
       flags |= GBP_FLAG_HASMSG;
     } else {
       // inactive (or padding) slot: its messages are zero (gbp_codelets.cpp:464-468 etc.)
 #pragma unroll
-      for (int k = 0; k < GBP_MCAM_QUADS * 4; ++k) nc[k] = 0.f;
+      for (int k = 0; k < 28; ++k) nc[k] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 15; ++k) ncu[k] = 0.f;
       if (valid && (flags & GBP_FLAG_HASMSG)) {
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int q = 0; q < GBP_MCAM_QUADS; ++q) g.mcam[(size_t)q * g.E_pad + e] = z4;
+        if (g.mcam_up) {
 #pragma unroll
-        for (int q = 0; q < 3; ++q) g.mlmk[e * GBP_MLMK_QUADS + q] = z4;
+          for (int q = 0; q < 4; ++q) g.mcam_up[(size_t)q * g.E_pad + e] = z4;
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q) g.mlmk[lpos * GBP_MLMK_QUADS + q] = z4;
         flags &= ~GBP_FLAG_HASMSG;
       }
     }
   }
   if (valid && (active || MSG))
-    st4_hint<(GBP_L2_HINTS & 2)>(g.recA + e, make_float4(damping, __int_as_float(dcount), __uint_as_float(flags), dmu), pol_keep);
+    g.recA[e] = make_float4(damping, __int_as_float(dcount), __uint_as_float(flags), dmu);
 
   if (MSG) {
     // lane-ordered reduction through the warp's own (now consumed) stage
@@ -503,16 +535,105 @@ __global__ void __launch_bounds__(GBP_TILE, GBP_MIN_BLOCKS) k_sweep(const Device
 #pragma unroll
       for (int j = 0; j < 6; ++j)
         red[(6 + i * 6 + j) * GBP_RED_STRIDE + lane] =
-            nc[(i >= j) ? (GBP_MCAM_LOWER + lt(i, j)) : (GBP_MCAM_UPPER + (5 * i - i * (i - 1) / 2) + (j - i - 1))];
+            (i >= j) ? nc[GBP_MCAM_LOWER + lt(i, j)] : ncu[gbp_upper(i, j)];
     __syncwarp();
-    warp_cam_reduce(red, lane, g.cam_partial + ((size_t)tile * GBP_WARPS + warp) * GBP_CAMPART);
+    warp_cam_reduce(red, lane, g.cam_partial + (size_t)wt * GBP_CAMPART);
+    __syncwarp();
   }
 }
 
+// L2 prefetch of one contiguous run (bytes % 16 == 0)
+GBP_DEV void bulk_prefetch_l2(const void* gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gmem), "r"(bytes) : "memory");
+}
+// DRAM -> L2 prefetch of every per-factor record of warp-tile wt: lane q fetches quad-row q (512 B)
+GBP_DEV void prefetch_tile_l2(const DeviceGraph& g, const uint32_t wt, const uint32_t lane) {
+  const size_t e0 = (size_t)wt * 32;
+  const void* p;
+  uint32_t bytes = 512;
+  if (lane < GBP_FAC_QUADS) p = g.fac + (size_t)lane * g.E_pad + e0;
+  else if (lane < GBP_FAC_QUADS + GBP_MCAM_QUADS) p = g.mcam + (size_t)(lane - GBP_FAC_QUADS) * g.E_pad + e0;
+  else if (lane == GBP_SQ_MLMK) return;  // landmark-ordered: no contiguous run per warp-tile
+  else if (lane == GBP_SQ_MLMK + 1) p = g.recA + e0;
+  else if (lane == GBP_SQ_MLMK + 2) p = g.recB + e0;
+  else return;
+  bulk_prefetch_l2(p, bytes);
+}
+
+template <bool PREP, bool MSG>
+__global__ void __launch_bounds__(GBP_SW_WARPS * 32, 1) k_sweep(const DeviceGraph g) {
+  extern __shared__ float4 smem4[];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4* stage_base = smem4 + warp * (GBP_NBUF * GBP_STAGE_QUADS);
+  float* scam_base = reinterpret_cast<float*>(smem4 + GBP_SW_WARPS * GBP_NBUF * GBP_STAGE_QUADS) + warp * (GBP_NBUF * GBP_SCAM);
+  const uint32_t n_wt = g.E_pad / 32;
+  const uint32_t stride = gridDim.x * GBP_SW_WARPS;
+  // consecutive warp-tiles go to different SMs, so small graphs spread over the whole chip
+  uint32_t wt = warp * gridDim.x + blockIdx.x;
+  if (wt >= n_wt) return;
+
+  // prologue: everything of the first warp-tile, ids of the second
+  uint2 ti = __ldg(g.wt_info + wt);
+  uint32_t buf = 0;
+  // {landmark id, message position} of a lane's factor = the second half of its recB record
+  const uint2* lrec = reinterpret_cast<const uint2*>(g.recB) + 1;
+  uint2 lid = __ldg(lrec + 2 * ((size_t)wt * 32 + lane));
+  issue_stage(g, stage_base, scam_base, wt, ti.x, lid.y, lane);
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  float lb[20];
+  load_lmk_belief(g, lid.x, lb);
+  uint32_t wt_n = wt + stride;
+  uint2 ti_n = make_uint2(0u, 0u);
+  uint2 lid_n = make_uint2(0u, 0u);
+  if (wt_n < n_wt) {
+    ti_n = __ldg(g.wt_info + wt_n);
+    lid_n = __ldg(lrec + 2 * ((size_t)wt_n * 32 + lane));
+    if (GBP_NBUF == 1) prefetch_tile_l2(g, wt_n, lane);
+  }
+  for (;;) {
+    const bool has_next = wt_n < n_wt;
+    float lb_n[20];
+    uint2 ti_nn = make_uint2(0u, 0u);
+    uint2 lid_nn = make_uint2(0u, 0u);
+    const uint32_t wt_nn = wt_n + stride;
+    if (has_next) {
+      if (GBP_NBUF == 2)
+        issue_stage(g, stage_base + (buf ^ 1) * GBP_STAGE_QUADS, scam_base + (buf ^ 1) * GBP_SCAM, wt_n, ti_n.x, lid_n.y, lane);
+      load_lmk_belief(g, lid_n.x, lb_n);
+      if (wt_nn < n_wt) {
+        ti_nn = __ldg(g.wt_info + wt_nn);
+        lid_nn = __ldg(lrec + 2 * ((size_t)wt_nn * 32 + lane));
+        if (GBP_NBUF == 1) prefetch_tile_l2(g, wt_nn, lane);
+      }
+    }
+    if (GBP_NBUF == 2) {
+      // the copies of THIS warp-tile were committed one iteration ago: leave the newest group in flight
+      asm volatile("cp.async.commit_group;\n cp.async.wait_group 1;\n" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    }
+    __syncwarp();
+    sweep_tile<PREP, MSG>(g, stage_base + buf * GBP_STAGE_QUADS, scam_base + buf * GBP_SCAM, wt, ti, lb, lane);
+    if (!has_next) break;
+    if (GBP_NBUF == 1) {  // single stage: refill it now (its records were pulled into L2 one tile ago)
+      issue_stage(g, stage_base, scam_base, wt_n, ti_n.x, lid_n.y, lane);
+      asm volatile("cp.async.commit_group;\n" ::: "memory");
+    }
+    wt = wt_n; wt_n = wt_nn;
+    ti = ti_n; ti_n = ti_nn;
+    lid_n = lid_nn;
+#pragma unroll
+    for (int i = 0; i < 20; ++i) lb[i] = lb_n[i];
+    if (GBP_NBUF == 2) buf ^= 1;
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+
 // Recompute the per-warp camera partial sums from the stored messages (used
-// after set_tensor on the camera message tensors).
+// after set_tensor on the camera message tensors; the strict upper triangle is
+// the mirrored lower one, see gbp_layout.h).
 __global__ void __launch_bounds__(GBP_TILE) k_cam_partials(const DeviceGraph g) {
-  __shared__ float s_red[GBP_WARPS][GBP_CAMPART * GBP_RED_STRIDE];
+  __shared__ float s_red[GBP_TILE / 32][GBP_CAMPART * GBP_RED_STRIDE];
   const uint32_t tile = blockIdx.x, tid = threadIdx.x;
   const uint32_t warp = tid >> 5, lane = tid & 31;
   const size_t e = (size_t)tile * GBP_TILE + tid;
@@ -524,39 +645,29 @@ __global__ void __launch_bounds__(GBP_TILE) k_cam_partials(const DeviceGraph g) 
 #pragma unroll
   for (int i = 0; i < 6; ++i)
 #pragma unroll
-    for (int j = 0; j < 6; ++j)
-      red[(6 + i * 6 + j) * GBP_RED_STRIDE + lane] =
-          m[(i >= j) ? (GBP_MCAM_LOWER + lt(i, j)) : (GBP_MCAM_UPPER + (5 * i - i * (i - 1) / 2) + (j - i - 1))];
+    for (int j = 0; j < 6; ++j) red[(6 + i * 6 + j) * GBP_RED_STRIDE + lane] = m[GBP_MCAM_LOWER + gbp_sym(i, j)];
+  if (g.mcam_up) {
+    float u[16];
+    load_quads<4>(g.mcam_up, g.E_pad, e, u);
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = i + 1; j < 6; ++j) red[(6 + i * 6 + j) * GBP_RED_STRIDE + lane] = u[gbp_upper(i, j)];
+  }
   __syncwarp();
-  warp_cam_reduce(red, lane, g.cam_partial + ((size_t)tile * GBP_WARPS + warp) * GBP_CAMPART);
+  warp_cam_reduce(red, lane, g.cam_partial + ((size_t)tile * (GBP_TILE / 32) + warp) * GBP_CAMPART);
 }
 
 // b += the factor->landmark messages of landmark l, strictly in slot order (= original
-// edge order, the reference's message slots 1..deg).  The gathers of four slots are
-// issued together (independent loads); the additions stay in order.
+// edge order, the reference's message slots 1..deg); they are contiguous in mlmk.
 GBP_DEV void lmk_accumulate(const DeviceGraph& g, const uint32_t l, float (&b)[12]) {
-  const uint64_t pol_keep = l2_policy_keep();
   const uint32_t k0 = g.lmk_ptr[l], k1 = g.lmk_ptr[l + 1];
-  for (uint32_t k = k0; k < k1; k += 4) {
-    uint32_t idx[4];
-    float4 v[4][3];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) idx[u] = (k + u < k1) ? __ldg(g.lmk_edges + k + u) : 0xffffffffu;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (idx[u] != 0xffffffffu) {
-        const float4* p = g.mlmk + (size_t)idx[u] * GBP_MLMK_QUADS;
-        v[u][0] = ld4_hint<(GBP_L2_HINTS & 1)>(p, pol_keep); v[u][1] = ld4_hint<(GBP_L2_HINTS & 1)>(p + 1, pol_keep); v[u][2] = ld4_hint<(GBP_L2_HINTS & 1)>(p + 2, pol_keep);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (idx[u] != 0xffffffffu) {
-        b[0] = fa(b[0], v[u][0].x); b[1] = fa(b[1], v[u][0].y); b[2] = fa(b[2], v[u][0].z); b[3] = fa(b[3], v[u][0].w);
-        b[4] = fa(b[4], v[u][1].x); b[5] = fa(b[5], v[u][1].y); b[6] = fa(b[6], v[u][1].z); b[7] = fa(b[7], v[u][1].w);
-        b[8] = fa(b[8], v[u][2].x); b[9] = fa(b[9], v[u][2].y); b[10] = fa(b[10], v[u][2].z); b[11] = fa(b[11], v[u][2].w);
-      }
-    }
+  for (uint32_t k = k0; k < k1; ++k) {
+    const float4* p = g.mlmk + (size_t)k * GBP_MLMK_QUADS;
+    const float4 v0 = p[0], v1 = p[1], v2 = p[2];
+    b[0] = fa(b[0], v0.x); b[1] = fa(b[1], v0.y); b[2] = fa(b[2], v0.z); b[3] = fa(b[3], v0.w);
+    b[4] = fa(b[4], v1.x); b[5] = fa(b[5], v1.y); b[6] = fa(b[6], v1.z); b[7] = fa(b[7], v1.w);
+    b[8] = fa(b[8], v2.x); b[9] = fa(b[9], v2.y); b[10] = fa(b[10], v2.z); b[11] = fa(b[11], v2.w);
   }
 }
 
@@ -589,70 +700,124 @@ GBP_DEV void lmk_load_prior(const DeviceGraph& g, const uint32_t l, float (&b)[1
   }
 }
 
-// Belief update + per-variable mean.  Blocks [0,C) own one camera each; the
-// remaining blocks own GBP_TILE landmarks each.  shift != 0: the mean that the
+#define GBP_LMK_PER_BLOCK (GBP_TILE / 4)  // four lanes per landmark
+// Belief update + per-variable mean (inf2mean hoisted out of PrepMessageVertex).  shift != 0: the mean that the
 // last PrepMessageVertex pass used becomes the "old mu" (Copy(mu, oldmu),
 // ba/ba.cpp:898) before the new mean is stored.
-__global__ void __launch_bounds__(GBP_TILE) k_update_vars(const DeviceGraph g, const int shift) {
+// Belief update of the cameras (prog_ub, ba/ba.cpp:104-139, camera half) + per-camera mean and
+// rotation.  One block per camera: 42 threads add the per-warp-tile partials of k_sweep to the
+// prior in warp-tile order, one thread inverts the 6x6 belief (latency bound: a serial LDL^T).
+GBP_DEV void update_camera(const DeviceGraph& g, const int shift, const uint32_t c) {
+  __shared__ float s_b[GBP_CAMPART];
   const uint32_t tid = threadIdx.x;
-  // landmark blocks come first so that the (latency-bound, mostly idle) camera blocks
-  // overlap with their tail instead of occupying the first wave
-  const uint32_t nb_lmk = (g.L + GBP_TILE - 1) / GBP_TILE;
-  if (blockIdx.x >= nb_lmk) {
-    __shared__ float s_b[GBP_CAMPART];
-    const uint32_t c = blockIdx.x - nb_lmk;
-    if (tid < GBP_CAMPART) {
-      // the sum starts from +0 like a zero-initialised accumulator: 0 + prior (turns a -0 prior into +0)
-      float acc = fa(0.0f, (tid < 6) ? g.cam_prior_eta[c * 6 + tid] : g.cam_prior_lam[c * 36 + (tid - 6)]);
-      const uint32_t t0 = g.cam_tile_begin[c], t1 = g.cam_tile_begin[c + 1];
-      // four partials (= one tile) are fetched together; the additions stay in order
-      for (uint32_t t = t0 * GBP_WARPS; t < t1 * GBP_WARPS; t += GBP_WARPS) {
-        float v[GBP_WARPS];
+  if (tid < GBP_CAMPART) {
+    // the sum starts from +0 like a zero-initialised accumulator: 0 + prior (turns a -0 prior into +0)
+    float acc = fa(0.0f, (tid < 6) ? g.cam_prior_eta[c * 6 + tid] : g.cam_prior_lam[c * 36 + (tid - 6)]);
+    const uint32_t t0 = g.cam_wt_begin[c], t1 = g.cam_wt_begin[c + 1];
+    // sixteen partials are fetched together; the additions stay in warp-tile order
+    for (uint32_t t = t0; t < t1; t += 16) {
+      float v[16];
 #pragma unroll
-        for (int u = 0; u < GBP_WARPS; ++u) v[u] = g.cam_partial[(size_t)(t + u) * GBP_CAMPART + tid];
+      for (int u = 0; u < 16; ++u) v[u] = (t + u < t1) ? g.cam_partial[(size_t)(t + u) * GBP_CAMPART + tid] : 0.f;
 #pragma unroll
-        for (int u = 0; u < GBP_WARPS; ++u) acc = fa(acc, v[u]);
-      }
-      s_b[tid] = acc;
-      if (tid < 6) g.cam_b_eta[c * 6 + tid] = acc;
-      else g.cam_b_lam[c * 36 + (tid - 6)] = acc;
+      for (int u = 0; u < 16; ++u)
+        if (t + u < t1) acc = fa(acc, v[u]);
     }
-    __syncthreads();
-    if (tid == 0) {
-      float eta[6], lamL[21], mean[6];
-#pragma unroll
-      for (int i = 0; i < 6; ++i) eta[i] = s_b[i];
-#pragma unroll
-      for (int i = 0; i < 6; ++i)
-#pragma unroll
-        for (int j = 0; j <= i; ++j) lamL[lt(i, j)] = s_b[6 + i * 6 + j];
-      inf2mean6(eta, lamL, mean);
-      const float w[3] = {mean[3], mean[4], mean[5]};
-      float R[9];
-      so3exp(w, R);
-      float* rec = reinterpret_cast<float*>(g.cam_rec + (size_t)c * 16);
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const float prev = shift ? g.cam_mean[c * 6 + i] : g.cam_mean_prev[c * 6 + i];
-        g.cam_mean_prev[c * 6 + i] = prev;
-        g.cam_mean[c * 6 + i] = mean[i];
-        rec[42 + i] = mean[i];
-        rec[48 + i] = prev;
-      }
-#pragma unroll
-      for (int i = 0; i < 9; ++i) g.cam_R[c * 9 + i] = R[i];
-    }
-    if (tid < GBP_CAMPART) reinterpret_cast<float*>(g.cam_rec + (size_t)c * 16)[tid] = s_b[tid];
-  } else {
-    const uint32_t l = blockIdx.x * GBP_TILE + tid;
-    if (l >= g.L) return;
-    // boundary landmarks of a multi-GPU shard are finished by k_boundary_finish
-    if (g.lmk_bslot && g.lmk_bslot[l] != 0xffffffffu) return;
-    float b[12];
-    lmk_load_prior(g, l, b);
-    lmk_accumulate(g, l, b);
-    lmk_store_belief(g, l, b, shift);
+    s_b[tid] = acc;
+    if (tid < 6) g.cam_b_eta[c * 6 + tid] = acc;
+    else g.cam_b_lam[c * 36 + (tid - 6)] = acc;
   }
+  __syncthreads();
+  if (tid == 0) {
+    float eta[6], lamL[21], mean[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) eta[i] = s_b[i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = 0; j <= i; ++j) lamL[lt(i, j)] = s_b[6 + i * 6 + j];
+    inf2mean6(eta, lamL, mean);
+    const float w[3] = {mean[3], mean[4], mean[5]};
+    float R[9];
+    so3exp(w, R);
+    float* rec = reinterpret_cast<float*>(g.cam_rec + (size_t)c * 16);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const float prev = shift ? g.cam_mean[c * 6 + i] : g.cam_mean_prev[c * 6 + i];
+      g.cam_mean_prev[c * 6 + i] = prev;
+      g.cam_mean[c * 6 + i] = mean[i];
+      rec[42 + i] = mean[i];
+      rec[48 + i] = prev;
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) g.cam_R[c * 9 + i] = R[i];
+  }
+  if (tid < GBP_CAMPART) reinterpret_cast<float*>(g.cam_rec + (size_t)c * 16)[tid] = s_b[tid];
+}
+
+// Belief update of the landmarks (prog_ub, landmark half) + per-landmark mean:
+// GBP_LMK_PER_BLOCK landmarks per block.
+GBP_DEV void update_landmarks(const DeviceGraph& g, const int shift, const uint32_t block) {
+  const uint32_t tid = threadIdx.x;
+  {
+    // four lanes per landmark: lane q < 3 sums quad q of [eta 3 | Lambda 9] over the landmark's
+    // factor->landmark messages, strictly in slot order (= original edge order, the reference's
+    // message slots 1..deg; contiguous in mlmk), four independent 16-byte loads in flight per lane
+    const uint32_t l = block * GBP_LMK_PER_BLOCK + (tid >> 2), q = tid & 3;
+    // boundary landmarks of a multi-GPU shard are finished by k_boundary_finish
+    const bool mine = l < g.L && !(g.lmk_bslot && g.lmk_bslot[l] != 0xffffffffu);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (mine && q < 3) {
+      // the sum starts from +0 like a zero-initialised accumulator: 0 + prior (turns a -0 prior into +0)
+      const float4 pr = g.lmk_prior[(size_t)l * 3 + q];
+      acc = make_float4(fa(0.0f, pr.x), fa(0.0f, pr.y), fa(0.0f, pr.z), fa(0.0f, pr.w));
+      const uint32_t k0 = g.lmk_ptr[l], k1 = g.lmk_ptr[l + 1];
+      for (uint32_t k = k0; k < k1; k += 4) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (k + u < k1) v[u] = g.mlmk[(size_t)(k + u) * GBP_MLMK_QUADS + q];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (k + u < k1) {
+            acc.x = fa(acc.x, v[u].x); acc.y = fa(acc.y, v[u].y); acc.z = fa(acc.z, v[u].z); acc.w = fa(acc.w, v[u].w);
+          }
+      }
+    }
+    // collect the 12 sums in the landmark's first lane for the mean
+    float b[12];
+    const uint32_t base = (tid & 31) & ~3u;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      b[j * 4 + 0] = __shfl_sync(0xffffffffu, acc.x, base + j);
+      b[j * 4 + 1] = __shfl_sync(0xffffffffu, acc.y, base + j);
+      b[j * 4 + 2] = __shfl_sync(0xffffffffu, acc.z, base + j);
+      b[j * 4 + 3] = __shfl_sync(0xffffffffu, acc.w, base + j);
+    }
+    if (!mine) return;
+    float4* o = g.lmk_b + (size_t)l * GBP_LMKB_QUADS;
+    if (q == 0) {
+      const float eta[3] = {b[0], b[1], b[2]};
+      float lam[9], mean[3];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) lam[i] = b[3 + i];
+      inf2mean3(eta, lam, mean);
+      if (shift) {
+        const float4 oldq = o[3];
+        g.lmk_mean_prev[l] = make_float4(oldq.x, oldq.y, oldq.z, 0.f);
+      }
+      o[3] = make_float4(mean[0], mean[1], mean[2], 0.f);
+    }
+    if (q < 3) o[q] = acc;
+  }
+}
+
+// prog_ub in one launch.  Camera blocks come first: few, long-running (a serial 6x6 inverse and a
+// Rodrigues formula per camera) and nearly idle, they overlap with the bandwidth-bound landmark
+// blocks that fill the rest of the chip.  The register budget (10 blocks per SM) fits both paths.
+__global__ void __launch_bounds__(GBP_TILE, 10) k_update_vars(const DeviceGraph g, const int shift) {
+  if (blockIdx.x < g.C) update_camera(g, shift, blockIdx.x);
+  else update_landmarks(g, shift, blockIdx.x - g.C);
 }
 
 // ---- multi-GPU boundary landmarks -------------------------------------
@@ -699,17 +864,17 @@ __global__ void __launch_bounds__(GBP_TILE) k_relinearise_all(const DeviceGraph 
   float4 ra = g.recA[e];
   uint32_t flags = __float_as_uint(ra.z);
   if (flags & GBP_FLAG_PAD) return;
-  const uint32_t c = g.tile_cam[tile];
+  const uint32_t c = g.wt_info[e >> 5].x;
   const float4 rb = g.recB[e];
-  const uint32_t l = __float_as_uint(rb.w);
+  const uint32_t l = __float_as_uint(rb.z);
   float x_kf[6], x_l[3];
 #pragma unroll
   for (int i = 0; i < 6; ++i) x_kf[i] = g.cam_mean[c * 6 + i];
   const float4 m = g.lmk_b[(size_t)l * GBP_LMKB_QUADS + 3];
   x_l[0] = m.x; x_l[1] = m.y; x_l[2] = m.z;
-  const uint32_t robust = relinearise_in_place(g.fac, g.E_pad, e, make_float4(g.K[0], g.K[1], g.K[2], g.K[3]), g.hp.Nstds,
-                                                   rb.x, rb.y, rb.z, x_kf[0], x_kf[1], x_kf[2], x_kf[3], x_kf[4], x_kf[5],
-                                                   x_l[0], x_l[1], x_l[2], true);
+  const uint32_t robust = relinearise_record(nullptr, 0, g.fac + e, g.E_pad, nullptr, make_float4(g.K[0], g.K[1], g.K[2], g.K[3]),
+                                             g.hp.Nstds, rb.x, rb.y, g.var[e], x_kf[0], x_kf[1], x_kf[2], x_kf[3], x_kf[4],
+                                             x_kf[5], x_l[0], x_l[1], x_l[2]);
   flags = (flags & ~GBP_FLAG_ROBUST) | (robust ? GBP_FLAG_ROBUST : 0u);
   ra.z = __uint_as_float(flags);
   g.recA[e] = ra;
@@ -750,14 +915,15 @@ struct MetricPartial {
 
 __global__ void __launch_bounds__(GBP_TILE) k_metric(const DeviceGraph g, const uint32_t n_active_total,
                                                     MetricPartial* __restrict__ out) {
-  __shared__ float s_cam[15];  // mean 6 | R 9
+  __shared__ float s_cam_all[GBP_TILE / 32][16];  // per warp-tile (= one camera): mean 6 | R 9
   __shared__ float s_f[2][GBP_TILE / 32];
   __shared__ uint32_t s_u[3][GBP_TILE / 32];
   const uint32_t tile = blockIdx.x, tid = threadIdx.x;
-  const uint32_t c = g.tile_cam[tile];
   const size_t e = (size_t)tile * GBP_TILE + tid;
-  if (tid < 6) s_cam[tid] = g.cam_mean[c * 6 + tid];
-  else if (tid < 15) s_cam[tid] = g.cam_R[c * 9 + (tid - 6)];
+  const uint32_t c = g.wt_info[e >> 5].x;
+  float* s_cam = s_cam_all[tid >> 5];
+  if ((tid & 31) < 6) s_cam[tid & 31] = g.cam_mean[c * 6 + (tid & 31)];
+  else if ((tid & 31) < 15) s_cam[tid & 31] = g.cam_R[c * 9 + ((tid & 31) - 6)];
   __syncthreads();
   const float4 ra = g.recA[e];
   const uint32_t flags = __float_as_uint(ra.z);
@@ -770,7 +936,7 @@ __global__ void __launch_bounds__(GBP_TILE) k_metric(const DeviceGraph g, const 
     // quirk Q7: the reference evaluates edges [0, n_active) of the ORIGINAL order
     if (g.edge_orig[e] < n_active_total) {
       const float4 rb = g.recB[e];
-      const float4 m = g.lmk_b[(size_t)__float_as_uint(rb.w) * GBP_LMKB_QUADS + 3];
+      const float4 m = g.lmk_b[(size_t)__float_as_uint(rb.z) * GBP_LMKB_QUADS + 3];
       float y[3];
 #pragma unroll
       for (int i = 0; i < 3; ++i)

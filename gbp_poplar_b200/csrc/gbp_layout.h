@@ -13,26 +13,38 @@
 
 #define GBP_TILE 128  // factors per thread block (one thread per factor)
 
-// ---- factor potential record: 72 floats = 18 quads -------------------------
-// [eta 9 | Lambda_ll 9 | Lambda_cl 18 (6x3) | Lambda_cc 36].  Lambda_lc is not
-// stored: the reference always sets it to Lambda_cl^T (gbp_codelets.cpp:158-162,363-367).
-#define GBP_FAC_QUADS 18
+// ---- factor potential record: 56 floats = 14 quads -------------------------
+// [eta 9 | Lambda_ll lower 6 | Lambda_cl 18 (6x3) | Lambda_cc lower 21 | pad 2].
+// Lambda_lc is not stored: the reference always sets it to Lambda_cl^T
+// (gbp_codelets.cpp:158-162,363-367).  Lambda_cc and Lambda_ll are stored as
+// packed lower triangles: the reference builds them as J^T J (+ the previous
+// block, quirk Q1) divided by a scalar, entry (i,j) and (j,i) by the very same
+// fp32 operations (matlib.cpp:60-68, gbp_codelets.cpp:109-125,313-329), so the
+// two triangles are bit-identical and storing one loses nothing.
+#define GBP_FAC_QUADS 14
 #define GBP_FAC_ETA 0
-#define GBP_FAC_LL 9
-#define GBP_FAC_CL 18
-#define GBP_FAC_CC 36
+#define GBP_FAC_LL 9    // 6 floats, lower triangle row-major (i>=j)
+#define GBP_FAC_CL 15   // 18 floats, 6x3 row-major
+#define GBP_FAC_CC 33   // 21 floats, lower triangle row-major (i>=j)
 
-// ---- factor->camera message record: 44 floats = 11 quads --------------------
-// [eta 6 | lower triangle of Lambda (21, row-major i>=j) | pad | strict upper (15) | pad]
-// The first 7 quads are everything a sweep READS back (inv6x6 only touches the
-// lower triangle, matlib.cpp:193-206); the upper part is kept for the belief sum.
-#define GBP_MCAM_QUADS 11
-#define GBP_MCAM_READ_QUADS 7
+// ---- factor->camera message record: 28 floats = 7 quads ----------------------
+// [eta 6 | lower triangle of Lambda (21, row-major i>=j) | pad].
+// This is everything the algorithm ever READS of a camera-bound message: inv6x6
+// only touches the lower triangle of (Lambda_cc + belief - message)
+// (matlib.cpp:193-206), and the belief sum over the FULL 6x6 message is formed
+// on chip by the kernel that computes it.  The strict upper triangle (equal to
+// the lower one up to fp32 rounding of the Schur complement) is therefore not
+// stored; get_tensor mirrors the lower triangle.
+#define GBP_MCAM_QUADS 7
 #define GBP_MCAM_LOWER 6
-#define GBP_MCAM_UPPER 28
 
-// ---- factor->landmark message record: 12 floats = 3 quads, AoS per edge slot
-// [eta 3 | Lambda 9] so the landmark-side gather reads 48 contiguous bytes.
+// ---- factor->landmark message record: 12 floats = 3 quads [eta 3 | Lambda 9] --------
+// Stored in LANDMARK order, not edge-slot order: the message of edge e lives at
+// lmk_ptr[landmark(e)] + (number of earlier edges of that landmark) -- the reference's
+// message slot (ba/ba.cpp:267-279) made dense.  The belief update then streams each
+// landmark's messages as one contiguous run (no index indirection, no gather), and the
+// scattered 48-byte accesses move into the factor kernel, whose software pipeline hides
+// their latency.
 #define GBP_MLMK_QUADS 3
 
 // ---- per-landmark belief record: 16 floats = 4 quads (64 B, sector aligned) --
@@ -41,7 +53,8 @@
 
 // ---- per-edge state quads -----------------------------------------------------
 // recA (read+write): {damping, damping_count (int bits), flags (uint bits), dmu}
-// recB (read only) : {z.x, z.y, meas_variance, landmark id (uint bits)}
+// recB (read only) : {z.x, z.y, landmark id, position of the landmark-bound message (uint bits)}
+// var  (read only) : meas_variance, separate because only a relinearising factor reads it
 #define GBP_FLAG_ACTIVE 1u    // active_flag                         ba/ba.cpp:765
 #define GBP_FLAG_ROBUST 2u    // robust_flag                         ba/ba.cpp:766
 #define GBP_FLAG_MUVALID 4u   // oldmu of this edge == previous mean of its variables
@@ -58,8 +71,8 @@
 #endif
 
 GBP_HD inline int gbp_lt(int i, int j) { return i * (i + 1) / 2 + j; }  // i >= j
-// field index of Lambda(i,j) inside the camera message record
-GBP_HD inline int gbp_mcam_lam_field(int i, int j) {
-  if (i >= j) return GBP_MCAM_LOWER + gbp_lt(i, j);
-  return GBP_MCAM_UPPER + (5 * i - i * (i - 1) / 2) + (j - i - 1);
-}
+GBP_HD inline int gbp_sym(int i, int j) { return i >= j ? gbp_lt(i, j) : gbp_lt(j, i); }
+// index of (i,j), i<j, in a row-major packed strict upper triangle of a 6x6
+GBP_HD inline int gbp_upper(int i, int j) { return (5 * i - i * (i - 1) / 2) + (j - i - 1); }
+// field index of Lambda(i,j) inside the camera message record (upper triangle mirrored)
+GBP_HD inline int gbp_mcam_lam_field(int i, int j) { return GBP_MCAM_LOWER + gbp_sym(i, j); }

@@ -18,6 +18,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace gbp {
 
 #define GBP_DEV __device__ __forceinline__
@@ -55,60 +57,82 @@ GBP_DEV void inv3(const float (&M)[9], float (&R)[9]) {
   R[8] = fd(fs(fm(M[0], M[4]), fm(M[3], M[1])), det);
 }
 
+// Compile-time loop: f(integral_constant<int, I>) for I in [B, E).  Used where every index
+// must be a constant expression so the small matrices are scalarised into registers (nvcc
+// gives up on `#pragma unroll` for the deepest triangular nests and falls back to a
+// local-memory array, which costs long-scoreboard stalls in the hot loop).
+template <int B, int E, class F>
+GBP_DEV void static_for(F&& f) {
+  if constexpr (B < E) {
+    f(std::integral_constant<int, B>{});
+    static_for<B + 1, E>(f);
+  }
+}
+
 // inv6x6 (matlib.cpp:163-222): un-pivoted LDL^T of the LOWER triangle,
 // explicit inverse of the unit upper factor, then L^-T D^-1 L^-1.
 // A: packed lower triangle (21).  Ai: full 6x6 row-major (not bitwise symmetric).
 GBP_DEV void inv6(const float (&A)[21], float (&Ai)[36]) {
   float D[6], rD[6];
-  float U[6][6];  // U[j][i], j<i : the reference's LT(j,i)
-#pragma unroll
-  for (int j = 0; j < 6; ++j) {
+  float U[36];  // U[j*6+i], j<i : the reference's LT(j,i)
+  static_for<0, 6>([&](auto jc) {
+    constexpr int j = decltype(jc)::value;
     float d = A[lt(j, j)];
-#pragma unroll
-    for (int k = 0; k < j; ++k) d = fs(d, fm(fm(U[k][j], U[k][j]), D[k]));
+    static_for<0, j>([&](auto kc) {
+      constexpr int k = decltype(kc)::value;
+      d = fs(d, fm(fm(U[k * 6 + j], U[k * 6 + j]), D[k]));
+    });
     D[j] = d;
     const float r = fd(1.0f, d);
     rD[j] = r;
-#pragma unroll
-    for (int i = j + 1; i < 6; ++i) {
+    static_for<j + 1, 6>([&](auto ic) {
+      constexpr int i = decltype(ic)::value;
       float v = fm(r, A[lt(i, j)]);
-#pragma unroll
-      for (int k = 0; k < j; ++k) v = fs(v, fm(fm(fm(r, U[k][i]), U[k][j]), D[k]));
-      U[j][i] = v;
-    }
-  }
+      static_for<0, j>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;
+        v = fs(v, fm(fm(fm(r, U[k * 6 + i]), U[k * 6 + j]), D[k]));
+      });
+      U[j * 6 + i] = v;
+    });
+  });
   // W = U^-1 (unit upper triangular), inv_uppertriang (matlib.cpp:163-178)
-  float W[6][6];
-#pragma unroll
-  for (int j = 1; j < 6; ++j) {
-#pragma unroll
-    for (int i = 0; i < j; ++i) {
-      float acc = U[i][j];  // 0 + 1*U(i,j)
-#pragma unroll
-      for (int k = i + 1; k < j; ++k) acc = fa(acc, fm(W[i][k], U[k][j]));
-      W[i][j] = -acc;  // /= -1
-    }
-  }
+  float W[36];
+  static_for<1, 6>([&](auto jc) {
+    constexpr int j = decltype(jc)::value;
+    static_for<0, j>([&](auto ic) {
+      constexpr int i = decltype(ic)::value;
+      float acc = U[i * 6 + j];  // 0 + 1*U(i,j)
+      static_for<i + 1, j>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;
+        acc = fa(acc, fm(W[i * 6 + k], U[k * 6 + j]));
+      });
+      W[i * 6 + j] = -acc;  // /= -1
+    });
+  });
   // T = W * D^-1 (upper triangular), Ai = T * W^T
-  float T[6][6];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) {
-    T[i][i] = rD[i];
-#pragma unroll
-    for (int k = i + 1; k < 6; ++k) T[i][k] = fm(W[i][k], rD[k]);
-  }
-#pragma unroll
-  for (int i = 0; i < 6; ++i) {
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      const int k0 = (i > j) ? i : j;
+  float T[36];
+  static_for<0, 6>([&](auto ic) {
+    constexpr int i = decltype(ic)::value;
+    T[i * 6 + i] = rD[i];
+    static_for<i + 1, 6>([&](auto kc) {
+      constexpr int k = decltype(kc)::value;
+      T[i * 6 + k] = fm(W[i * 6 + k], rD[k]);
+    });
+  });
+  static_for<0, 6>([&](auto ic) {
+    constexpr int i = decltype(ic)::value;
+    static_for<0, 6>([&](auto jc) {
+      constexpr int j = decltype(jc)::value;
+      constexpr int k0 = (i > j) ? i : j;
       // first non-zero term: T(i,k0) * W(j,k0), with W(j,j) == 1
-      float acc = (k0 == j) ? T[i][j] : fm(T[i][k0], W[j][k0]);
-#pragma unroll
-      for (int k = k0 + 1; k < 6; ++k) acc = fa(acc, fm(T[i][k], W[j][k]));
+      float acc = (k0 == j) ? T[i * 6 + j] : fm(T[i * 6 + k0], W[j * 6 + k0]);
+      static_for<k0 + 1, 6>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;
+        acc = fa(acc, fm(T[i * 6 + k], W[j * 6 + k]));
+      });
       Ai[i * 6 + j] = acc;
-    }
-  }
+    });
+  });
 }
 
 // mean = inv(lambda) * eta  (bafuncs.cpp:3-15), lambda given as packed lower triangle.

@@ -77,8 +77,15 @@ typedef struct gbp_opts {
   float dmu_threshold;        /* 3e-3  gbp_codelets.cpp:13 */
   int min_linear_iters;       /* 10    gbp_codelets.cpp:14 */
   float Nstds;                /* 2.5   gbp_codelets.cpp:16 */
-  int use_cuda_graph;         /* 1 = replay sweeps through a CUDA graph (default 1)     */
-  int reserved[7];
+  int use_cuda_graph;         /* reserved (sweeps are two launches; no graph needed)    */
+  int store_full_messages;    /* 0 (default): a factor->camera message keeps eta + the LOWER triangle of
+                                 Lambda -- all the algorithm ever reads back (inv6x6 works on the lower
+                                 triangle, matlib.cpp:193-206; the belief sum over the full 6x6 message is
+                                 formed on chip) -- and get_tensor("cam_messages_lambda") mirrors it.
+                                 1: the strict upper triangle is stored too (+64 B per factor and sweep),
+                                 so that tensor is bit-identical to the reference's as well.  Beliefs,
+                                 every other tensor and the trajectory are identical in both modes.     */
+  int reserved[6];
 } gbp_opts;
 
 /* Per-sweep metrics = what the reference's host computes after READ_PROG

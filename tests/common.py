@@ -14,6 +14,22 @@ BLOCK_DIMS = {
 }
 
 
+# Tensors of which the CUDA path stores only what the algorithm reads (gbp_layout.h): the strict
+# upper triangle of a factor->camera message Lambda is never read back (inv6x6 uses the lower
+# triangle, matlib.cpp:193-206; the belief sum is formed on chip from the full message), so
+# get_tensor mirrors the lower triangle.  canon() maps both sides to that form.
+LOWER_ONLY = ("cam_messages_lambda", "pcam_messages_lambda")
+
+
+def canon(name, a):
+    if name not in LOWER_ONLY:
+        return a
+    m = np.array(a).reshape(-1, 6, 6)
+    il = np.tril_indices(6, -1)
+    m[:, il[1], il[0]] = m[:, il[0], il[1]]
+    return m.reshape(-1)
+
+
 def load_sequence(name):
     """BALProblem of one of the reference sequences, from the frozen input fixture."""
     z = np.load(os.path.join(GOLDEN, f"seq_{name}.npz"))

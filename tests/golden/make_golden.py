@@ -35,6 +35,14 @@ def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
+def sha_all(eng):
+    """SHA-256 of every tensor; for the tensors of common.LOWER_ONLY also of their lower-triangle form."""
+    out = {t: sha(eng.get_tensor(t)) for t in TENSOR_NAMES}
+    for t in common.LOWER_ONLY:
+        out[t + ":lower"] = sha(common.canon(t, eng.get_tensor(t)))
+    return out
+
+
 def helpers():
     rng = np.random.default_rng(20201017)
     A6, A3, X, P = [], [], [], []
@@ -68,12 +76,12 @@ def runs():
             eng.set_reduce_order(order)
             key = f"{name}_ba_order{order}"
             m = {"init": eng.eval(), "sweeps": [], "sha": {}}
-            m["sha"]["init"] = {t: sha(eng.get_tensor(t)) for t in TENSOR_NAMES}
+            m["sha"]["init"] = sha_all(eng)
             for it in range(n_sweeps):
                 common.ba_schedule_step(eng, it)
                 m["sweeps"].append(eng.eval())
                 if it in checkpoints:
-                    m["sha"][str(it)] = {t: sha(eng.get_tensor(t)) for t in TENSOR_NAMES}
+                    m["sha"][str(it)] = sha_all(eng)
             b = eng.get_beliefs()
             for t in ("cam_beliefs_eta", "cam_beliefs_lambda", "lmk_beliefs_eta", "lmk_beliefs_lambda"):
                 arrays[f"{key}_{t}"] = b[t]
@@ -88,7 +96,7 @@ def runs():
         finals = common.slam_run(eng, st, 25, on_kf=lambda dc, n: new_lmks.append(n))
         key = f"fr2robot2_slam25_order{order}"
         meta[key] = {"finals": finals, "new_lmks": new_lmks,
-                     "sha": {"final": {t: sha(eng.get_tensor(t)) for t in TENSOR_NAMES}}}
+                     "sha": {"final": sha_all(eng)}}
         b = eng.get_beliefs()
         for t in ("cam_beliefs_eta", "cam_beliefs_lambda", "lmk_beliefs_eta", "lmk_beliefs_lambda"):
             arrays[f"{key}_{t}"] = b[t]

@@ -93,8 +93,8 @@ def check_against_global(ranks, ora, st, exact=True):
                                                    ("lmk_messages_eta", 3, SL, lSL, j, ll[j], slot_l[e]),
                                                    ("lmk_messages_lambda", 9, SL, lSL, j, ll[j], slot_l[e])):
                 gv = c if t.startswith("cam") else l
-                a = z[t].reshape(-1, lS, d)[v, s_loc + 1]
-                b = G[t].reshape(-1, S, d)[gv, s_glob + 1]
+                a = common.canon(t, z[t].reshape(-1, lS, d)[v, s_loc + 1])
+                b = common.canon(t, G[t].reshape(-1, S, d)[gv, s_glob + 1])
                 same(a, b, (t, int(e)))
             lc[i] += 1
             ll[j] += 1
