@@ -192,6 +192,8 @@ def main():
     init_s = time.time() - t_init0
     E_loc, C_loc, L_loc = eng.n_edges, eng.n_keyframes, eng.n_points   # this rank's shard (== global at N=1)
     n_boundary = eng.shard.n_boundary_points if eng.shard else 0
+    exchange_mode = {"p2p": "peer-to-peer stores over NVLink (CUDA IPC) from the kernel that forms them",
+                     "nccl": "NCCL all-gather", "none": "nothing"}[eng.exchange_mode()]
     ba_preroll(eng)
 
     sampler = ClockSampler(local_rank)
@@ -288,8 +290,8 @@ def main():
             "config": {"workload": "synthetic BAL 1k cameras / 100k landmarks / ~1M factors per GPU (configs[3]); at N>1 "
                                    "one N-times larger graph partitioned by camera range (N=8 ~ configs[4])",
                        "cameras": Cn, "landmarks": Ln, "factors": E, "per_gpu": False,
-                       "parallelism": f"camera-range shards x{world}, NCCL all-gather of boundary-landmark partials "
-                                      f"per sweep ({n_boundary} boundary landmarks, {48 * n_boundary} B per rank)"
+                       "parallelism": f"camera-range shards x{world}, boundary-landmark partials exchanged per sweep by "
+                                      f"{exchange_mode} ({n_boundary} boundary landmarks, {48 * n_boundary} B per rank and peer)"
                        if world > 1 else "single",
                        "rank0_shard": {"cameras": C_loc, "landmarks": L_loc, "factors": E_loc},
                        "cache": "per-sweep working set ~0.75 GB >> 126 MB L2 (no flush needed)",

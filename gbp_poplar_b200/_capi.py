@@ -57,7 +57,8 @@ class GbpOpts(C.Structure):
         ("Nstds", C.c_float),
         ("use_cuda_graph", C.c_int),
         ("store_full_messages", C.c_int),
-        ("reserved", C.c_int * 6),
+        ("exchange", C.c_int),
+        ("reserved", C.c_int * 5),
     ]
 
 
@@ -152,6 +153,7 @@ CUDA_ONLY_API = {
     "gbp_cuda_init_shard": (C.c_int, [C.POINTER(GbpProblem), C.POINTER(GbpOpts), C.c_uint32, C.c_uint32,
                                       C.c_void_p, C.POINTER(C.c_void_p)]),
     "gbp_cuda_shard_info": (C.c_void_p, [C.c_void_p]),
+    "gbp_cuda_exchange_mode": (C.c_int, [C.c_void_p]),
     # pure host: the rank-local sub-problem of a camera-range partition
     "gbp_shard_build": (C.c_int, [C.POINTER(GbpProblem), C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
     "gbp_shard_free": (None, [C.c_void_p]),

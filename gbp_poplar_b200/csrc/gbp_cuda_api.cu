@@ -111,6 +111,11 @@ struct gbp_handle {
   ncclComm_t comm = nullptr;
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_send = nullptr, ev_recv = nullptr;
+  // peer-to-peer exchange (CUDA IPC): one exported block per rank [flags | counters | receive buffer]
+  int p2p = 0;                      // 1 = boundary partials are pushed straight into the peers' buffers
+  void* p2p_block = nullptr;        // this rank's exported block
+  std::vector<void*> p2p_peers;     // the other ranks' blocks, mapped (nullptr for this rank)
+  uint32_t xstep = 0;               // exchange step counter (same sequence on every rank)
   double* d_metric_raw = nullptr;   // [8]         this rank's metric sums
   double* d_metric_all = nullptr;   // [world][8]  all-gathered
   uint64_t exchanges = 0;
@@ -180,27 +185,37 @@ int launch_update_vars(gbp_handle* h) {
   const uint32_t grid = lmks_grid(h);
   const bool exchange = h->shard && h->g.n_bnd_global > 0;
   const uint32_t bgrid = (h->g.n_bnd_local + GBP_TILE - 1) / GBP_TILE;
-  if (exchange) {
-    if (bgrid) {
-      gbp::k_boundary_partial<<<bgrid, GBP_TILE, 0, h->stream>>>(h->g);
+  if (exchange && h->p2p) {
+    // one launch: the first blocks form the partial sums and push them into every rank's receive buffer
+    // over NVLink, the last blocks finish the boundary landmarks once every rank's flag has arrived
+    const uint32_t n_x = std::max((h->g.n_bnd_local + GBP_LMK_PER_BLOCK - 1) / GBP_LMK_PER_BLOCK, 1u);
+    h->xstep++;
+    gbp::k_update_vars<<<n_x + h->C + grid + n_x, GBP_TILE, 0, h->stream>>>(h->g, shift, n_x, h->xstep);
+    h->kernels_launched++;
+    h->exchanges++;
+  } else {
+    if (exchange) {
+      if (bgrid) {
+        gbp::k_boundary_partial<<<bgrid, GBP_TILE, 0, h->stream>>>(h->g);
+        h->kernels_launched++;
+      }
+      GBP_CUDA_TRY(cudaEventRecord(h->ev_send, h->stream));
+      GBP_CUDA_TRY(cudaStreamWaitEvent(h->comm_stream, h->ev_send, 0));
+      GBP_NCCL_TRY(gbp::nccl_api().AllGather(h->g.bnd_send, (void*)h->g.bnd_recv, (size_t)h->g.n_bnd_global * 12, ncclFloat,
+                                             h->comm, h->comm_stream));
+      GBP_CUDA_TRY(cudaEventRecord(h->ev_recv, h->comm_stream));
+      h->exchanges++;
+    }
+    if (grid + h->C) {
+      gbp::k_update_vars<<<grid + h->C, GBP_TILE, 0, h->stream>>>(h->g, shift, 0u, 0u);
       h->kernels_launched++;
     }
-    GBP_CUDA_TRY(cudaEventRecord(h->ev_send, h->stream));
-    GBP_CUDA_TRY(cudaStreamWaitEvent(h->comm_stream, h->ev_send, 0));
-    GBP_NCCL_TRY(gbp::nccl_api().AllGather(h->g.bnd_send, (void*)h->g.bnd_recv, (size_t)h->g.n_bnd_global * 12, ncclFloat,
-                                           h->comm, h->comm_stream));
-    GBP_CUDA_TRY(cudaEventRecord(h->ev_recv, h->comm_stream));
-    h->exchanges++;
-  }
-  if (grid + h->C) {
-    gbp::k_update_vars<<<grid + h->C, GBP_TILE, 0, h->stream>>>(h->g, shift);
-    h->kernels_launched++;
-  }
-  if (exchange) {
-    GBP_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_recv, 0));
-    if (bgrid) {
-      gbp::k_boundary_finish<<<bgrid, GBP_TILE, 0, h->stream>>>(h->g, shift);
-      h->kernels_launched++;
+    if (exchange) {
+      GBP_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_recv, 0));
+      if (bgrid) {
+        gbp::k_boundary_finish<<<bgrid, GBP_TILE, 0, h->stream>>>(h->g, shift);
+        h->kernels_launched++;
+      }
     }
   }
   h->pending_shift = false;
@@ -407,6 +422,92 @@ int upload_lmk_priors(gbp_handle* h, const float* eta, const float* lam) {
   return GBP_OK;
 }
 
+// Peer-to-peer exchange set-up: every rank exports one block [arrival flags | counters | receive
+// buffer (2 parities x world x n_boundary x 3 quads)] through CUDA IPC, the handles travel over the
+// NCCL communicator once, and every rank maps every other rank's block.  Returns GBP_OK with
+// h->p2p == 0 when IPC is not available (the NCCL all-gather path is used instead).
+int setup_p2p(gbp_handle* h, int mode) {
+  DeviceGraph& g = h->g;
+  const uint32_t W = h->world;
+  h->p2p = 0;
+  if (mode == 1 || g.n_bnd_global == 0) return GBP_OK;
+  const size_t head = 4096;  // flags [W] at 0, done counter at 2048, error flag at 2052
+  const size_t recv_bytes = (size_t)2 * W * g.n_bnd_global * 3 * sizeof(float4);
+  const size_t total = ((head + recv_bytes + (2u << 20) - 1) >> 21) << 21;  // whole 2 MB pages
+  int ok = 1;
+  cudaIpcMemHandle_t mine;
+  std::memset(&mine, 0, sizeof(mine));
+  if (W > 1024 / sizeof(uint32_t)) ok = 0;
+  if (ok && cudaMalloc(&h->p2p_block, total) != cudaSuccess) ok = 0;
+  if (ok && cudaMemset(h->p2p_block, 0, total) != cudaSuccess) ok = 0;
+  if (ok && cudaIpcGetMemHandle(&mine, h->p2p_block) != cudaSuccess) ok = 0;
+  cudaGetLastError();
+  // all-gather {ok, handle} over the communicator (also tells every rank whether ALL ranks can do it)
+  struct Item { int ok; int pad[3]; cudaIpcMemHandle_t hd; };
+  static_assert(sizeof(Item) == 80, "item layout");
+  Item it;
+  it.ok = ok; it.pad[0] = it.pad[1] = it.pad[2] = 0; it.hd = mine;
+  Item* d_items = nullptr;
+  GBP_CUDA_TRY(cudaMalloc((void**)&d_items, sizeof(Item) * (W + 1)));
+  GBP_CUDA_TRY(cudaMemcpyAsync(d_items + W, &it, sizeof(Item), cudaMemcpyHostToDevice, h->comm_stream));
+  GBP_NCCL_TRY(gbp::nccl_api().AllGather(d_items + W, d_items, sizeof(Item), ncclChar, h->comm, h->comm_stream));
+  std::vector<Item> all(W);
+  GBP_CUDA_TRY(cudaMemcpyAsync(all.data(), d_items, sizeof(Item) * W, cudaMemcpyDeviceToHost, h->comm_stream));
+  GBP_CUDA_TRY(cudaStreamSynchronize(h->comm_stream));
+  cudaFree(d_items);
+  for (uint32_t r = 0; r < W; ++r) ok = ok && all[r].ok;
+  h->p2p_peers.assign(W, nullptr);
+  for (uint32_t r = 0; r < W && ok; ++r) {
+    if (r == h->rank) continue;
+    if (cudaIpcOpenMemHandle(&h->p2p_peers[r], all[r].hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      h->p2p_peers[r] = nullptr;
+      ok = 0;
+    }
+  }
+  cudaGetLastError();
+  // second round: fall back everywhere unless every rank mapped every peer
+  int* d_ok = nullptr;
+  GBP_CUDA_TRY(cudaMalloc((void**)&d_ok, sizeof(int) * (W + 1)));
+  GBP_CUDA_TRY(cudaMemcpyAsync(d_ok + W, &ok, sizeof(int), cudaMemcpyHostToDevice, h->comm_stream));
+  GBP_NCCL_TRY(gbp::nccl_api().AllGather(d_ok + W, d_ok, sizeof(int), ncclChar, h->comm, h->comm_stream));
+  std::vector<int> oks(W);
+  GBP_CUDA_TRY(cudaMemcpyAsync(oks.data(), d_ok, sizeof(int) * W, cudaMemcpyDeviceToHost, h->comm_stream));
+  GBP_CUDA_TRY(cudaStreamSynchronize(h->comm_stream));
+  cudaFree(d_ok);
+  for (uint32_t r = 0; r < W; ++r) ok = ok && oks[r];
+  if (!ok) {
+    for (void*& q : h->p2p_peers)
+      if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
+    if (h->p2p_block) cudaFree(h->p2p_block);
+    h->p2p_block = nullptr;
+    cudaGetLastError();
+    if (mode == 2) {
+      gbp_set_error("peer-to-peer exchange requested but CUDA IPC mapping of the peers failed");
+      return GBP_ERR_COMM;
+    }
+    return GBP_OK;
+  }
+  std::vector<float4*> recv(W);
+  std::vector<uint32_t*> flag(W);
+  for (uint32_t r = 0; r < W; ++r) {
+    char* base = (char*)(r == h->rank ? h->p2p_block : h->p2p_peers[r]);
+    flag[r] = (uint32_t*)base;
+    recv[r] = (float4*)(base + head);
+  }
+  int rc = h_alloc(h, &g.peer_recv, W);
+  if (!rc) rc = h_alloc(h, &g.peer_flag, W);
+  if (rc) return rc;
+  GBP_CUDA_TRY(cudaMemcpy(g.peer_recv, recv.data(), sizeof(float4*) * W, cudaMemcpyHostToDevice));
+  GBP_CUDA_TRY(cudaMemcpy(g.peer_flag, flag.data(), sizeof(uint32_t*) * W, cudaMemcpyHostToDevice));
+  char* own = (char*)h->p2p_block;
+  g.p2p_flag = (uint32_t*)own;
+  g.p2p_done = (uint32_t*)(own + 2048);
+  g.p2p_error = (uint32_t*)(own + 2052);
+  g.p2p_recv = (const float4*)(own + head);
+  h->p2p = 1;
+  return GBP_OK;
+}
+
 int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t* edge_global = nullptr) {
   const uint32_t C = p->n_keyframes, L = p->n_points, E = p->n_edges;
   h->C = C; h->L = L; h->E = E;
@@ -536,6 +637,7 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
     g.n_bnd_local = nbl;
     g.n_bnd_global = gbp_shard_get_plan(h->shard)->n_boundary_points;
     g.world = h->world;
+    g.rank = h->rank;
     lmk_bslot.assign(L, 0xffffffffu);
     for (uint32_t k = 0; k < nbl; ++k) lmk_bslot[gbp_shard_boundary_local(h->shard)[k]] = gbp_shard_boundary_slot(h->shard)[k];
     float4* recv = nullptr;
@@ -593,6 +695,10 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   GBP_CUDA_TRY(cudaFuncSetAttribute(gbp::k_sweep<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GBP_SWEEP_SMEM));
   GBP_CUDA_TRY(cudaFuncSetAttribute(gbp::k_sweep<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GBP_SWEEP_SMEM));
   GBP_CUDA_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
+  if (h->shard) {
+    rc = setup_p2p(h, o->exchange);
+    if (rc) return rc;
+  }
   // LINEARISE_PROG (ba/ba.cpp:890-893): beliefs <- priors, then linearise every factor
   h->pending_shift = false;
   rc = launch_update_vars(h);
@@ -676,6 +782,19 @@ int gbp_cuda_free(gbp_handle* h) {
   if (h->d_exp_robust) cudaFree(h->d_exp_robust);
   for (cudaEvent_t ev : h->prof_events) cudaEventDestroy(ev);
   if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);  // the communicator itself stays cached
+  if (h->p2p) {
+    // peers may still be pushing into this rank's block: freeing a sharded handle is collective
+    int* d_b = nullptr;
+    if (cudaMalloc((void**)&d_b, sizeof(int) * (h->world + 1)) == cudaSuccess) {
+      cudaMemsetAsync(d_b, 0, sizeof(int) * (h->world + 1), h->comm_stream);
+      gbp::nccl_api().AllGather(d_b + h->world, d_b, sizeof(int), ncclChar, h->comm, h->comm_stream);
+      cudaStreamSynchronize(h->comm_stream);
+      cudaFree(d_b);
+    }
+    for (void* q : h->p2p_peers)
+      if (q) cudaIpcCloseMemHandle(q);
+    cudaFree(h->p2p_block);
+  }
   if (h->ev_send) cudaEventDestroy(h->ev_send);
   if (h->ev_recv) cudaEventDestroy(h->ev_recv);
   if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
@@ -857,6 +976,14 @@ int gbp_cuda_get_beliefs(gbp_handle* h, float* cam_eta, float* cam_lambda, float
   if (rc) return rc;
   GBP_CUDA_TRY(cudaGetLastError());
   GBP_CUDA_TRY(cudaStreamSynchronize(s));
+  if (h->p2p) {  // a peer that never delivered its boundary partials (bounded wait in k_boundary_finish)
+    uint32_t err = 0;
+    GBP_CUDA_TRY(cudaMemcpy(&err, h->g.p2p_error, sizeof(err), cudaMemcpyDeviceToHost));
+    if (err) {
+      gbp_set_error("multi-GPU exchange: timed out waiting for a peer's boundary partials");
+      return GBP_ERR_COMM;
+    }
+  }
   return GBP_OK;
 }
 
@@ -1368,5 +1495,10 @@ int gbp_cuda_init_shard(const gbp_problem* p, const gbp_opts* o_in, uint32_t wor
 }
 
 const gbp_shard* gbp_cuda_shard_info(gbp_handle* h) { return h ? h->shard : nullptr; }
+
+int gbp_cuda_exchange_mode(gbp_handle* h) {
+  if (!h || !h->shard || h->g.n_bnd_global == 0) return 0;
+  return h->p2p ? 2 : 1;
+}
 
 }  // extern "C"

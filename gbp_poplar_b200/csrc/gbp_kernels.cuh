@@ -63,7 +63,15 @@ struct DeviceGraph {
   uint32_t* bnd_slot;     // [n_bnd_local] position in the global boundary list
   float4* bnd_send;       // [n_bnd_global][3]  this rank's partial sums (zero where it has no factor)
   const float4* bnd_recv; // [world][n_bnd_global][3]  all ranks' partial sums
-  uint32_t n_bnd_local, n_bnd_global, world;
+  uint32_t n_bnd_local, n_bnd_global, world, rank;
+  // peer-to-peer exchange over NVLink (null = the NCCL all-gather path): every rank maps the
+  // receive buffers and arrival flags of all ranks (CUDA IPC)
+  float4** peer_recv;     // [world] -> that rank's bnd_p2p buffer [2 parities][world][n_bnd_global][3]
+  uint32_t** peer_flag;   // [world] -> that rank's arrival flags [world]
+  const float4* p2p_recv; // this rank's own receive buffer
+  uint32_t* p2p_flag;     // this rank's own arrival flags: p2p_flag[r] = last exchange step rank r has delivered
+  uint32_t* p2p_done;     // block counter of k_boundary_push
+  uint32_t* p2p_error;    // set when a wait for a peer timed out
   float K[4];             // fx fy cx cy
   Hyper hp;
 };
@@ -757,70 +765,160 @@ GBP_DEV void update_camera(const DeviceGraph& g, const int shift, const uint32_t
 
 // Belief update of the landmarks (prog_ub, landmark half) + per-landmark mean:
 // GBP_LMK_PER_BLOCK landmarks per block.
+// Four lanes per landmark: lane q < 3 owns quad q of [eta 3 | Lambda 9].
+// acc += quad q of the landmark's factor->landmark messages, strictly in slot order (= original
+// edge order, the reference's message slots 1..deg; contiguous in mlmk), four independent
+// 16-byte loads in flight per lane.
+GBP_DEV float4 lmk_sum_quad(const DeviceGraph& g, const uint32_t l, const uint32_t q, float4 acc) {
+  const uint32_t k0 = g.lmk_ptr[l], k1 = g.lmk_ptr[l + 1];
+  for (uint32_t k = k0; k < k1; k += 4) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (k + u < k1) v[u] = g.mlmk[(size_t)(k + u) * GBP_MLMK_QUADS + q];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (k + u < k1) {
+        acc.x = fa(acc.x, v[u].x); acc.y = fa(acc.y, v[u].y); acc.z = fa(acc.z, v[u].z); acc.w = fa(acc.w, v[u].w);
+      }
+  }
+  return acc;
+}
+GBP_DEV float4 lmk_prior_quad(const DeviceGraph& g, const uint32_t l, const uint32_t q) {
+  // the sum starts from +0 like a zero-initialised accumulator: 0 + prior (turns a -0 prior into +0)
+  const float4 pr = g.lmk_prior[(size_t)l * 3 + q];
+  return make_float4(fa(0.0f, pr.x), fa(0.0f, pr.y), fa(0.0f, pr.z), fa(0.0f, pr.w));
+}
+// The landmark's first lane collects the 12 sums, forms the mean and stores the belief record
+// [eta 3 | Lambda 9 | mean 3 | pad].  Must be reached by all 32 lanes of the warp.
+GBP_DEV void lmk_finish_quads(const DeviceGraph& g, const uint32_t l, const uint32_t q, const float4 acc, const bool mine,
+                              const int shift) {
+  float b[12];
+  const uint32_t base = (threadIdx.x & 31) & ~3u;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    b[j * 4 + 0] = __shfl_sync(0xffffffffu, acc.x, base + j);
+    b[j * 4 + 1] = __shfl_sync(0xffffffffu, acc.y, base + j);
+    b[j * 4 + 2] = __shfl_sync(0xffffffffu, acc.z, base + j);
+    b[j * 4 + 3] = __shfl_sync(0xffffffffu, acc.w, base + j);
+  }
+  if (!mine) return;
+  float4* o = g.lmk_b + (size_t)l * GBP_LMKB_QUADS;
+  if (q == 0) {
+    const float eta[3] = {b[0], b[1], b[2]};
+    float lam[9], mean[3];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) lam[i] = b[3 + i];
+    inf2mean3(eta, lam, mean);
+    if (shift) {  // Copy(mu, oldmu), ba/ba.cpp:898
+      const float4 oldq = o[3];
+      g.lmk_mean_prev[l] = make_float4(oldq.x, oldq.y, oldq.z, 0.f);
+    }
+    o[3] = make_float4(mean[0], mean[1], mean[2], 0.f);
+  }
+  if (q < 3) o[q] = acc;
+}
+
 GBP_DEV void update_landmarks(const DeviceGraph& g, const int shift, const uint32_t block) {
-  const uint32_t tid = threadIdx.x;
-  {
-    // four lanes per landmark: lane q < 3 sums quad q of [eta 3 | Lambda 9] over the landmark's
-    // factor->landmark messages, strictly in slot order (= original edge order, the reference's
-    // message slots 1..deg; contiguous in mlmk), four independent 16-byte loads in flight per lane
-    const uint32_t l = block * GBP_LMK_PER_BLOCK + (tid >> 2), q = tid & 3;
-    // boundary landmarks of a multi-GPU shard are finished by k_boundary_finish
-    const bool mine = l < g.L && !(g.lmk_bslot && g.lmk_bslot[l] != 0xffffffffu);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (mine && q < 3) {
-      // the sum starts from +0 like a zero-initialised accumulator: 0 + prior (turns a -0 prior into +0)
-      const float4 pr = g.lmk_prior[(size_t)l * 3 + q];
-      acc = make_float4(fa(0.0f, pr.x), fa(0.0f, pr.y), fa(0.0f, pr.z), fa(0.0f, pr.w));
-      const uint32_t k0 = g.lmk_ptr[l], k1 = g.lmk_ptr[l + 1];
-      for (uint32_t k = k0; k < k1; k += 4) {
-        float4 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (k + u < k1) v[u] = g.mlmk[(size_t)(k + u) * GBP_MLMK_QUADS + q];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (k + u < k1) {
-            acc.x = fa(acc.x, v[u].x); acc.y = fa(acc.y, v[u].y); acc.z = fa(acc.z, v[u].z); acc.w = fa(acc.w, v[u].w);
-          }
-      }
-    }
-    // collect the 12 sums in the landmark's first lane for the mean
-    float b[12];
-    const uint32_t base = (tid & 31) & ~3u;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      b[j * 4 + 0] = __shfl_sync(0xffffffffu, acc.x, base + j);
-      b[j * 4 + 1] = __shfl_sync(0xffffffffu, acc.y, base + j);
-      b[j * 4 + 2] = __shfl_sync(0xffffffffu, acc.z, base + j);
-      b[j * 4 + 3] = __shfl_sync(0xffffffffu, acc.w, base + j);
-    }
-    if (!mine) return;
-    float4* o = g.lmk_b + (size_t)l * GBP_LMKB_QUADS;
-    if (q == 0) {
-      const float eta[3] = {b[0], b[1], b[2]};
-      float lam[9], mean[3];
-#pragma unroll
-      for (int i = 0; i < 9; ++i) lam[i] = b[3 + i];
-      inf2mean3(eta, lam, mean);
-      if (shift) {
-        const float4 oldq = o[3];
-        g.lmk_mean_prev[l] = make_float4(oldq.x, oldq.y, oldq.z, 0.f);
-      }
-      o[3] = make_float4(mean[0], mean[1], mean[2], 0.f);
-    }
-    if (q < 3) o[q] = acc;
+  const uint32_t l = block * GBP_LMK_PER_BLOCK + (threadIdx.x >> 2), q = threadIdx.x & 3;
+  // boundary landmarks of a multi-GPU shard are finished by the exchange blocks / kernels
+  const bool mine = l < g.L && !(g.lmk_bslot && g.lmk_bslot[l] != 0xffffffffu);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (mine && q < 3) acc = lmk_sum_quad(g, l, q, lmk_prior_quad(g, l, q));
+  lmk_finish_quads(g, l, q, acc, mine, shift);
+}
+
+// ---- multi-GPU: partial sums fused with their exchange over peer memory ----------------
+// Landmarks that other ranks observe too ("boundary") get
+//     belief = (0 + prior) + partial[rank 0] + partial[rank 1] + ...
+// where partial[r] is rank r's sum of its own messages (slot order, from +0): the same
+// operations on every rank, so all replicas stay bit-identical.
+// boundary_push: the blocks that form this rank's partial sums store them straight into the
+// receive buffer of EVERY rank (its own included) through NVLink-mapped peer pointers (CUDA
+// IPC); the last of them to finish publishes `step` in every rank's arrival flag.  No
+// collective call, no communication stream, no host synchronisation: the transfer is in
+// flight while the rest of the grid updates the cameras and the interior landmarks.
+// boundary_finish: the LAST blocks of the same grid wait (bounded) for every rank's flag and
+// finish the boundary landmarks from the receive buffer (read past L1).
+// Buffers are double-buffered by step parity: a peer may already push step s+1 while this
+// rank still reads step s, never s+2 (it needs this rank's step-s+1 flag first).
+GBP_DEV void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+GBP_DEV uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+GBP_DEV void boundary_push(const DeviceGraph& g, const uint32_t step, const uint32_t block, const uint32_t n_blocks) {
+  const uint32_t k = block * GBP_LMK_PER_BLOCK + (threadIdx.x >> 2), q = threadIdx.x & 3;
+  if (k < g.n_bnd_local && q < 3) {
+    const float4 acc = lmk_sum_quad(g, g.bnd_local[k], q, make_float4(0.f, 0.f, 0.f, 0.f));
+    const size_t off = ((size_t)((step & 1u) * g.world + g.rank) * g.n_bnd_global + g.bnd_slot[k]) * 3 + q;
+    for (uint32_t r = 0; r < g.world; ++r) g.peer_recv[r][off] = acc;
+  }
+  // threadFenceReduction pattern at system scope: every block fences its peer stores, the last
+  // one to arrive publishes the step to all ranks
+  __threadfence_system();
+  __syncthreads();
+  __shared__ uint32_t s_last;
+  if (threadIdx.x == 0) s_last = (atomicAdd(g.p2p_done, 1u) == n_blocks - 1) ? 1u : 0u;
+  __syncthreads();
+  if (s_last) {
+    if (threadIdx.x == 0) *g.p2p_done = 0u;
+    __threadfence_system();
+    if (threadIdx.x < g.world) st_release_sys(g.peer_flag[threadIdx.x] + g.rank, step);
   }
 }
 
-// prog_ub in one launch.  Camera blocks come first: few, long-running (a serial 6x6 inverse and a
-// Rodrigues formula per camera) and nearly idle, they overlap with the bandwidth-bound landmark
-// blocks that fill the rest of the chip.  The register budget (10 blocks per SM) fits both paths.
-__global__ void __launch_bounds__(GBP_TILE, 10) k_update_vars(const DeviceGraph g, const int shift) {
-  if (blockIdx.x < g.C) update_camera(g, shift, blockIdx.x);
-  else update_landmarks(g, shift, blockIdx.x - g.C);
+GBP_DEV void boundary_finish(const DeviceGraph& g, const int shift, const uint32_t step, const uint32_t block) {
+  if (threadIdx.x < g.world) {
+    const long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys(g.p2p_flag + threadIdx.x) - step) < 0) {
+      if (clock64() - t0 > 20000000000ll) {  // ~10 s: a peer died; do not hang the GPU
+        *g.p2p_error = 1u;
+        break;
+      }
+      __nanosleep(100);
+    }
+  }
+  __syncthreads();
+  const uint32_t k = block * GBP_LMK_PER_BLOCK + (threadIdx.x >> 2), q = threadIdx.x & 3;
+  const bool mine = k < g.n_bnd_local;
+  const uint32_t l = mine ? g.bnd_local[k] : 0u;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (mine && q < 3) {
+    acc = lmk_prior_quad(g, l, q);
+    const float4* base = g.p2p_recv + (size_t)(step & 1u) * g.world * g.n_bnd_global * 3 + (size_t)g.bnd_slot[k] * 3 + q;
+    for (uint32_t r = 0; r < g.world; ++r) {
+      const float4 v = __ldcg(base + (size_t)r * g.n_bnd_global * 3);
+      acc.x = fa(acc.x, v.x); acc.y = fa(acc.y, v.y); acc.z = fa(acc.z, v.z); acc.w = fa(acc.w, v.w);
+    }
+  }
+  lmk_finish_quads(g, l, q, acc, mine, shift);
 }
 
-// ---- multi-GPU boundary landmarks -------------------------------------
+// prog_ub in one launch.  Block roles, in dispatch order:
+//   [multi-GPU, peer-to-peer] boundary_push blocks  -- first, so the partials travel while the rest runs
+//   camera blocks     -- few, long-running (a serial 6x6 inverse + Rodrigues per camera), nearly idle:
+//                        they overlap with the bandwidth-bound landmark blocks that fill the chip
+//   landmark blocks   -- GBP_LMK_PER_BLOCK landmarks each
+//   [multi-GPU, peer-to-peer] boundary_finish blocks -- last; every block they wait for was dispatched before them
+// The register budget (10 blocks per SM) fits all paths.  n_push == 0: no fused exchange.
+__global__ void __launch_bounds__(GBP_TILE, 10) k_update_vars(const DeviceGraph g, const int shift, const uint32_t n_push,
+                                                             const uint32_t step) {
+  const uint32_t nb_lmk = (g.L + GBP_LMK_PER_BLOCK - 1) / GBP_LMK_PER_BLOCK;
+  uint32_t b = blockIdx.x;
+  if (b < n_push) return boundary_push(g, step, b, n_push);
+  b -= n_push;
+  if (b < g.C) return update_camera(g, shift, b);
+  b -= g.C;
+  if (b < nb_lmk) return update_landmarks(g, shift, b);
+  boundary_finish(g, shift, step, b - nb_lmk);
+}
+
+// ---- multi-GPU boundary landmarks, NCCL all-gather path (fallback when CUDA IPC is unavailable) ----
 // k_boundary_partial: this rank's partial sum (local factor->landmark messages in slot
 // order, starting from +0) of every boundary landmark it touches, written to its slot of
 // the exchange buffer.  k_boundary_finish, after the all-gather: belief = (0 + prior) +

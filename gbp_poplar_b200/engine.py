@@ -255,6 +255,10 @@ class GBPEngine:
         self._check(self._lib.gbp_cuda_last_kernel_times(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def exchange_mode(self):
+        """'none' | 'nccl' | 'p2p': how a sharded engine exchanges boundary-landmark partials."""
+        return ("none", "nccl", "p2p")[self._lib.gbp_cuda_exchange_mode(self._h)]
+
     def iterate_async(self, n_sweeps):
         self._check(self._lib.gbp_cuda_iterate_async(self._h, n_sweeps))
 

@@ -85,7 +85,10 @@ typedef struct gbp_opts {
                                  1: the strict upper triangle is stored too (+64 B per factor and sweep),
                                  so that tensor is bit-identical to the reference's as well.  Beliefs,
                                  every other tensor and the trajectory are identical in both modes.     */
-  int reserved[6];
+  int exchange;               /* multi-GPU boundary exchange: 0 = auto (peer-to-peer stores over NVLink via
+                                 CUDA IPC when every rank can map every peer, else NCCL all-gather),
+                                 1 = NCCL all-gather, 2 = peer-to-peer or fail                          */
+  int reserved[5];
 } gbp_opts;
 
 /* Per-sweep metrics = what the reference's host computes after READ_PROG
@@ -101,9 +104,8 @@ typedef struct gbp_iter_stats {
 
 typedef struct gbp_handle gbp_handle;
 
-/* Sharding description for the multi-GPU path (one process per GPU).  The
- * exchange itself is performed by the caller-provided callbacks or by NCCL
- * (gbp_cuda_attach_nccl). rank r owns cameras [cam_begin, cam_end). */
+/* Sharding description for the multi-GPU path (one process per GPU).
+ * rank r owns cameras [cam_begin, cam_end). */
 typedef struct gbp_shard_plan {
   uint32_t world;             /* number of ranks                                   */
   uint32_t rank;              /* this rank                                         */
@@ -216,8 +218,10 @@ void* gbp_cuda_stream(gbp_handle* h);
  * range (balanced by edge count), every factor of those cameras and a replica
  * of every landmark they observe.  Landmarks observed from more than one rank
  * are "boundary" landmarks; per sweep each rank contributes the partial sum of
- * its own factor->landmark messages (12 floats) for them, the partials are
- * all-gathered over NVLink (NCCL) and every rank forms
+ * its own factor->landmark messages (12 floats) for them -- the kernel that forms
+ * the partial sums stores them straight into every rank's receive buffer over
+ * NVLink (CUDA IPC peer mappings; NCCL all-gather as the fallback) -- and every
+ * rank forms
  *     belief = prior + partial[rank 0] + partial[rank 1] + ...
  * in rank order, so all replicas hold identical bits. */
 
@@ -257,6 +261,9 @@ int gbp_cuda_init_shard(const gbp_problem* p, const gbp_opts* o, uint32_t world,
                         const void* nccl_unique_id, gbp_handle** out);
 /* The shard a handle was built from (NULL for a single-GPU handle). */
 const gbp_shard* gbp_cuda_shard_info(gbp_handle* h);
+/* How this handle exchanges boundary partials: 0 = no exchange (single GPU or no boundary
+ * landmarks), 1 = NCCL all-gather, 2 = peer-to-peer stores over NVLink. */
+int gbp_cuda_exchange_mode(gbp_handle* h);
 
 #ifdef __cplusplus
 }

@@ -111,8 +111,12 @@ def main():
     st = make_problem(spec)
     stats = []
     if backend == "nccl":
-        eng = GBPEngine.sharded(st.problem, default_opts(device=rank))
+        want = os.environ.get("GBP_TEST_EXCHANGE", "auto")   # auto | nccl | p2p
+        eng = GBPEngine.sharded(st.problem, default_opts(device=rank, exchange={"auto": 0, "nccl": 1, "p2p": 2}[want]))
         shard = eng.shard
+        if want != "auto":
+            assert eng.exchange_mode() == want, eng.exchange_mode()
+        print(f"rank {rank}: exchange mode {eng.exchange_mode()}", flush=True)
         for it in range(n_sweeps):
             if (it + 1) % 2 == 0 and it < 10:
                 eng.weaken_priors()

@@ -20,9 +20,12 @@ def _n_gpus():
 
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs at least 2 GPUs")
-@pytest.mark.parametrize("spec,n", [("seq:fr1xyz", 40), ("synth:64:6000:9:11", 30)])
-def test_two_gpus_bit_identical_to_oracle_in_sharded_order(tmp_path, spec, n):
+@pytest.mark.parametrize("spec,n,exchange", [("seq:fr1xyz", 40, "p2p"), ("synth:64:6000:9:11", 30, "p2p"),
+                                              ("synth:64:6000:9:11", 30, "nccl")])
+def test_two_gpus_bit_identical_to_oracle_in_sharded_order(tmp_path, spec, n, exchange, monkeypatch):
+    """Both exchange paths: peer-to-peer stores over NVLink (CUDA IPC) and the NCCL all-gather."""
     world = 2
+    monkeypatch.setenv("GBP_TEST_EXCHANGE", exchange)
     ranks = run_ranks("nccl", world, spec, n, tmp_path)
     st = shard_worker.make_problem(spec)
     ora = oracle_lib.OracleEngine(st.problem, kind=KIND)

@@ -50,12 +50,15 @@ def check_against_global(ranks, ora, st, exact=True):
     C, L, E = p.n_keyframes, p.n_points, p.n_edges
     cam_ids, lmk_ids = np.array(st.array("cam_ids")), np.array(st.array("lmk_ids"))
     SK, SL = ora.max_nkfedges + 1, ora.max_nlmkedges + 1
-    slot_c = np.zeros(E, np.int64)
-    slot_l = np.zeros(E, np.int64)
-    cnt_c, cnt_l = np.zeros(C, np.int64), np.zeros(L, np.int64)
-    for e in range(E):
-        slot_c[e] = cnt_c[cam_ids[e]]; cnt_c[cam_ids[e]] += 1
-        slot_l[e] = cnt_l[lmk_ids[e]]; cnt_l[lmk_ids[e]] += 1
+    def running_count_global(keys):
+        order = np.argsort(keys, kind="stable")
+        ks = keys[order]
+        first = np.r_[0, np.flatnonzero(np.diff(ks)) + 1]
+        start = np.repeat(first, np.diff(np.r_[first, ks.size]))
+        out = np.empty(keys.size, np.int64)
+        out[order] = np.arange(keys.size) - start
+        return out
+    slot_c, slot_l = running_count_global(cam_ids.astype(np.int64)), running_count_global(lmk_ids.astype(np.int64))
     G = {t: ora.get_tensor(t) for t in ("cam_beliefs_eta", "cam_beliefs_lambda", "lmk_beliefs_eta", "lmk_beliefs_lambda",
                                         "cam_messages_eta", "cam_messages_lambda", "lmk_messages_eta",
                                         "lmk_messages_lambda", "factor_potentials_eta", "factor_potentials_lambda",
@@ -82,22 +85,26 @@ def check_against_global(ranks, ora, st, exact=True):
         # messages: local slot numbering follows the local edge order = global order restricted to the rank
         lSK = z["cam_messages_eta"].size // (6 * (c1 - c0)) if c1 > c0 else 1
         lSL = z["lmk_messages_eta"].size // (3 * lg.size) if lg.size else 1
-        lc = np.zeros(c1 - c0, np.int64)
-        ll = np.zeros(lg.size, np.int64)
-        lmk_local = {int(g): i for i, g in enumerate(lg)}
-        for e in eg:
-            c, l = cam_ids[e], lmk_ids[e]
-            i, j = c - c0, lmk_local[int(l)]
-            for t, d, S, lS, v, s_loc, s_glob in (("cam_messages_eta", 6, SK, lSK, i, lc[i], slot_c[e]),
-                                                   ("cam_messages_lambda", 36, SK, lSK, i, lc[i], slot_c[e]),
-                                                   ("lmk_messages_eta", 3, SL, lSL, j, ll[j], slot_l[e]),
-                                                   ("lmk_messages_lambda", 9, SL, lSL, j, ll[j], slot_l[e])):
-                gv = c if t.startswith("cam") else l
-                a = common.canon(t, z[t].reshape(-1, lS, d)[v, s_loc + 1])
-                b = common.canon(t, G[t].reshape(-1, S, d)[gv, s_glob + 1])
-                same(a, b, (t, int(e)))
-            lc[i] += 1
-            ll[j] += 1
+        lmk_local = np.full(L, -1, np.int64)
+        lmk_local[lg] = np.arange(lg.size)
+        ci, li = cam_ids[eg].astype(np.int64) - c0, lmk_local[lmk_ids[eg]]
+
+        def running_count(keys):   # number of earlier local edges with the same key (edges are in order)
+            order = np.argsort(keys, kind="stable")
+            ks = keys[order]
+            first = np.r_[0, np.flatnonzero(np.diff(ks)) + 1]
+            start = np.repeat(first, np.diff(np.r_[first, ks.size]))
+            out = np.empty(keys.size, np.int64)
+            out[order] = np.arange(keys.size) - start
+            return out
+        lc, ll = running_count(ci), running_count(li)
+        for t, d, S, lS, v, s_loc, gv, s_glob in (("cam_messages_eta", 6, SK, lSK, ci, lc, cam_ids[eg], slot_c[eg]),
+                                                   ("cam_messages_lambda", 36, SK, lSK, ci, lc, cam_ids[eg], slot_c[eg]),
+                                                   ("lmk_messages_eta", 3, SL, lSL, li, ll, lmk_ids[eg], slot_l[eg]),
+                                                   ("lmk_messages_lambda", 9, SL, lSL, li, ll, lmk_ids[eg], slot_l[eg])):
+            a = common.canon(t, z[t].reshape(-1, lS, d)[v, s_loc + 1].ravel())
+            b = common.canon(t, G[t].reshape(-1, S, d)[gv, s_glob + 1].ravel())
+            same(a, b, t)
     assert seen_edges.all()
 
 
