@@ -31,6 +31,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALGO_BYTES_PER_FACTOR = 896  # logical fp32/int32 tensor elements one sweep touches per factor
+# What the packed device layout actually moves per edge slot and sweep (gbp_layout.h): potential 224 r,
+# camera message 112 r + 112 w, landmark message 48 r + 48 w, state records 16 r + 16 w + 16 r  (+ 64 B of
+# landmark belief gathered through L2)
+MOVED_BYTES_PER_SLOT = 224 + 112 + 112 + 48 + 48 + 16 + 16 + 16
 ALGO_BYTES_PER_CAMERA = 504
 ALGO_BYTES_PER_LANDMARK = 144
 WORKLOAD = {"cameras": 1000, "landmarks": 100000, "obs_per_point": 10.5, "seed": 1234}
@@ -233,6 +237,9 @@ def main():
     roofline = {
         "bound": "hbm", "kernel": "k_sweep<true,true>", "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "note": "achieved/frac use the contract figure (896 B per factor = every logical tensor element of the "
+                "reference, SURVEY 8d); the packed layout moves fewer bytes, see achieved_moved / frac_moved",
+        "moved_bytes_per_launch_model": MOVED_BYTES_PER_SLOT * (-(-E_loc // 32) * 32),
         "algorithmic_bytes_per_launch": algo_bytes_factor_kernel,
         "avg_launch_us": t_factor * 1e6, "kernel_share_of_step": ms_factor / max(ms_prof, 1e-9),
         "variable_kernel_avg_us": ms_var / args.steps * 1e3,
@@ -245,6 +252,10 @@ def main():
             tr = json.load(f)
         if tr.get("factors") == E_loc:
             roofline["traffic"] = tr.get("dram_bytes_per_launch")
+            roofline["traffic_source"] = tr.get("source")
+    moved = roofline["traffic"] or roofline["moved_bytes_per_launch_model"]
+    roofline["achieved_moved"] = moved / t_factor / 1e9
+    roofline["frac_moved"] = roofline["achieved_moved"] / peak
 
     # ---- e2e: a whole ba-style job through the C ABI with host buffers (rank-local problem)
     e2e = None

@@ -246,9 +246,7 @@ __device__ __noinline__ uint32_t relinearise_record(const float4* src, size_t sr
 #ifndef GBP_SW_WARPS
 #define GBP_SW_WARPS 8   // warps per block (one block per SM)
 #endif
-#ifndef GBP_NBUF
-#define GBP_NBUF 2       // 2: double-buffered stage (DRAM latency hidden by the pipeline);
-#endif                   // 1: single stage refilled from L2 after an L2 prefetch one tile ahead (more warps fit)
+#define GBP_NBUF 2       // double-buffered stage
 #define GBP_WARPS (GBP_TILE / 32)  // warp-tiles per 128-slot tile
 #define GBP_SQ 26  // quads per factor in a stage
 #define GBP_SQ_FAC 0
@@ -320,6 +318,173 @@ GBP_DEV void warp_cam_reduce(float* red, uint32_t lane, float* __restrict__ out4
   }
 }
 
+GBP_DEV void store_cam_message(const DeviceGraph& g, const size_t e, const float (&nc)[28], const float (&ncu)[16]) {
+#pragma unroll
+  for (int q = 0; q < GBP_MCAM_QUADS; ++q)
+    g.mcam[(size_t)q * g.E_pad + e] = make_float4(nc[q * 4], nc[q * 4 + 1], nc[q * 4 + 2], nc[q * 4 + 3]);
+  if (g.mcam_up) {  // gbp_opts.store_full_messages
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      g.mcam_up[(size_t)q * g.E_pad + e] = make_float4(ncu[q * 4], ncu[q * 4 + 1], ncu[q * 4 + 2], ncu[q * 4 + 3]);
+  }
+}
+
+// ---- the two factor->variable messages, from a landed stage ------------------------
+// Staged factor record: quads 0..8 = eta 0..8 | ll(lower) 9..14 | cl 15..32 | cc(lower) 0..2 at 33..35,
+// quads 9..13 = cc(lower) 3..20 | pad.
+#define GBP_LLF(i, j) head[GBP_FAC_LL + gbp_sym(i, j)]
+#define GBP_CCF(i, j) ((gbp_sym(i, j) < 3) ? head[GBP_FAC_CC + gbp_sym(i, j)] : tail[gbp_sym(i, j) - 3])
+
+// Message to the landmark (gbp_codelets.cpp:536-552, 691-699): Schur complement over the camera block,
+// one inv6x6; eta damped with the previous message.  s_cam: camera belief eta 0..5 | lambda 6..41.
+GBP_DEV void msg_to_landmark(const float4* stage, const float* s_cam, const uint32_t lane, const float damping,
+                             float (&nl)[12]) {
+  const float omd = fs(1.0f, damping);
+  float head[36], tail[20];
+  stage_read<GBP_SQ_FAC, 9>(stage, lane, head);
+  stage_read<GBP_SQ_FAC + 9, 5>(stage, lane, tail);
+  const float* eta = head + GBP_FAC_ETA;
+  const float* cl = head + GBP_FAC_CL;
+  float pc[28];  // previous f->cam message: eta 0..5, lower lambda 6..26
+  stage_read<GBP_SQ_MCAM, 7>(stage, lane, pc);
+  const float4 ple = stage[GBP_SQ_MLMK * 32 + lane];  // previous f->lmk eta (x, y, z)
+  const float pl[3] = {ple.x, ple.y, ple.z};
+  float Ai[36];
+  {
+    float Ld[21];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = 0; j <= i; ++j)
+        Ld[lt(i, j)] = fs(fa(GBP_CCF(i, j), s_cam[6 + i * 6 + j]), pc[GBP_MCAM_LOWER + lt(i, j)]);
+    inv6(Ld, Ai);
+  }
+  float P[18];  // Lambda_lc * inv  (3x6), Lambda_lc(i,k) = Lambda_cl(k,i)
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      float acc = fm(cl[i], Ai[j]);
+#pragma unroll
+      for (int k = 1; k < 6; ++k) acc = fa(acc, fm(cl[k * 3 + i], Ai[k * 6 + j]));
+      P[i * 6 + j] = acc;
+    }
+  float ed[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) ed[i] = fs(fa(eta[i], s_cam[i]), pc[i]);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float acc = fm(P[i * 6], ed[0]);
+#pragma unroll
+    for (int k = 1; k < 6; ++k) acc = fa(acc, fm(P[i * 6 + k], ed[k]));
+    const float h = fs(eta[6 + i], acc);
+    nl[i] = fa(fm(h, omd), fm(pl[i], damping));
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float acc = fm(P[i * 6], cl[j]);
+#pragma unroll
+      for (int k = 1; k < 6; ++k) acc = fa(acc, fm(P[i * 6 + k], cl[k * 3 + j]));
+      nl[3 + i * 3 + j] = fs(GBP_LLF(i, j), acc);
+    }
+}
+
+// Message to the camera (gbp_codelets.cpp:446-462, 619-627): Schur complement over the landmark block,
+// one inv3x3.  nc: eta 0..5 | lower lambda 6..26 | pad; ncu: the strict upper triangle (row-major, i<j).
+GBP_DEV void msg_to_camera(const float4* stage, const uint32_t lane, const float (&lb)[20], const float damping,
+                           float (&nc)[28], float (&ncu)[16]) {
+  const float omd = fs(1.0f, damping);
+  float head[36], tail[20];
+  stage_read<GBP_SQ_FAC, 9>(stage, lane, head);
+  stage_read<GBP_SQ_FAC + 9, 5>(stage, lane, tail);
+  const float* eta = head + GBP_FAC_ETA;
+  const float* cl = head + GBP_FAC_CL;
+  float pl[12];  // previous f->lmk message: eta 0..2, lambda 3..11
+  stage_read<GBP_SQ_MLMK, 3>(stage, lane, pl);
+  float pc[8];  // previous f->cam eta 0..5
+  stage_read<GBP_SQ_MCAM, 2>(stage, lane, pc);
+  float Ld[9], Li[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) Ld[i * 3 + j] = fs(fa(GBP_LLF(i, j), lb[3 + i * 3 + j]), pl[3 + i * 3 + j]);
+  inv3(Ld, Li);
+  float P[18];  // Lambda_cl * inv (6x3)
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      P[i * 3 + j] = fa(fa(fm(cl[i * 3], Li[j]), fm(cl[i * 3 + 1], Li[3 + j])), fm(cl[i * 3 + 2], Li[6 + j]));
+  float ed[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) ed[i] = fs(fa(eta[6 + i], lb[i]), pl[i]);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const float acc = fa(fa(fm(P[i * 3], ed[0]), fm(P[i * 3 + 1], ed[1])), fm(P[i * 3 + 2], ed[2]));
+    const float h = fs(eta[i], acc);
+    nc[i] = fa(fm(h, omd), fm(pc[i], damping));
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const float acc = fa(fa(fm(P[i * 3], cl[j * 3]), fm(P[i * 3 + 1], cl[j * 3 + 1])), fm(P[i * 3 + 2], cl[j * 3 + 2]));
+      const float v = fs(GBP_CCF(i, j), acc);
+      if (i >= j) nc[GBP_MCAM_LOWER + lt(i, j)] = v;
+      else ncu[gbp_upper(i, j)] = v;
+    }
+  nc[27] = 0.f;
+  ncu[15] = 0.f;
+}
+#undef GBP_LLF
+#undef GBP_CCF
+
+// PrepMessageVertex on the hoisted per-variable means (gbp_codelets.cpp:241-378): damping state
+// machine, dmu, conditional accumulating relinearisation (quirk Q1) with Huber (quirk Q2).  The
+// staged factor record of a relinearising lane is rewritten in place (and in global memory).
+GBP_DEV void prep_factor(const DeviceGraph& g, float4* stage, const float* s_cam, const size_t e, const uint32_t lane,
+                         const float (&lb)[20], const float4 rb, float& damping, int& dcount, uint32_t& flags, float& dmu) {
+  if (dcount == 0) damping = g.hp.maxeta_damping;  // gbp_codelets.cpp:245-248
+  dcount += 1;
+  float x_kf[6], x_l[3], old[9];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) x_kf[i] = s_cam[42 + i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) x_l[i] = lb[12 + i];
+  if (flags & GBP_FLAG_MUVALID) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) old[i] = s_cam[48 + i];
+    old[6] = lb[16]; old[7] = lb[17]; old[8] = lb[18];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) old[i] = g.oldmu_edge ? g.oldmu_edge[(size_t)i * g.E_pad + e] : 0.f;
+  }
+  float acc = 0.f;  // gbp_codelets.cpp:268-277
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const float d = fs(old[i], x_kf[i]);
+    acc = fa(acc, fm(d, d));
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float d = fs(old[6 + i], x_l[i]);
+    acc = fa(acc, fm(d, d));
+  }
+  dmu = __fsqrt_rn(acc);
+  flags |= GBP_FLAG_MUVALID;
+  if (dmu < g.hp.dmu_threshold && dcount > g.hp.min_linear_iters - g.hp.num_undamped_iters) {
+    damping = 0.0f;  // gbp_codelets.cpp:280-283
+    dcount = -g.hp.num_undamped_iters;
+    // the staged record is the current potential: accumulate onto it (quirk Q1), write it back
+    const uint32_t robust = relinearise_record(stage + lane, 32, g.fac + e, g.E_pad, stage + lane,
+                                               make_float4(g.K[0], g.K[1], g.K[2], g.K[3]), g.hp.Nstds, rb.x, rb.y, g.var[e],
+                                               x_kf[0], x_kf[1], x_kf[2], x_kf[3], x_kf[4], x_kf[5], x_l[0], x_l[1], x_l[2]);
+    flags = (flags & ~GBP_FLAG_ROBUST) | (robust ? GBP_FLAG_ROBUST : 0u);
+  }
+}
+
 // One warp-tile: prep + messages of 32 factors from the landed stage.
 // lb: landmark record of this lane's factor (load_lmk_belief).
 template <bool PREP, bool MSG>
@@ -336,193 +501,29 @@ GBP_DEV void sweep_tile(const DeviceGraph& g, float4* stage, const float* s_cam,
   const bool active = valid && (flags & GBP_FLAG_ACTIVE) != 0;
   const size_t lpos = __float_as_uint(rb.w);  // where this factor's landmark-bound message lives
 
-  if (PREP && active) {
-    if (dcount == 0) damping = g.hp.maxeta_damping;  // gbp_codelets.cpp:245-248
-    dcount += 1;
-    float x_kf[6], x_l[3], old[9];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) x_kf[i] = s_cam[42 + i];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) x_l[i] = lb[12 + i];
-    if (flags & GBP_FLAG_MUVALID) {
-#pragma unroll
-      for (int i = 0; i < 6; ++i) old[i] = s_cam[48 + i];
-      old[6] = lb[16]; old[7] = lb[17]; old[8] = lb[18];
-    } else {
-#pragma unroll
-      for (int i = 0; i < 9; ++i) old[i] = g.oldmu_edge ? g.oldmu_edge[(size_t)i * g.E_pad + e] : 0.f;
-    }
-    float acc = 0.f;  // gbp_codelets.cpp:268-277
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      const float d = fs(old[i], x_kf[i]);
-      acc = fa(acc, fm(d, d));
-    }
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const float d = fs(old[6 + i], x_l[i]);
-      acc = fa(acc, fm(d, d));
-    }
-    dmu = __fsqrt_rn(acc);
-    flags |= GBP_FLAG_MUVALID;
-    if (dmu < g.hp.dmu_threshold && dcount > g.hp.min_linear_iters - g.hp.num_undamped_iters) {
-      damping = 0.0f;  // gbp_codelets.cpp:280-283
-      dcount = -g.hp.num_undamped_iters;
-      // the staged record is the current potential: accumulate onto it (quirk Q1), write it back
-      const uint32_t robust = relinearise_record(stage + lane, 32, g.fac + e, g.E_pad, stage + lane,
-                                                 make_float4(g.K[0], g.K[1], g.K[2], g.K[3]), g.hp.Nstds, rb.x, rb.y, g.var[e],
-                                                 x_kf[0], x_kf[1], x_kf[2], x_kf[3], x_kf[4], x_kf[5], x_l[0], x_l[1], x_l[2]);
-      flags = (flags & ~GBP_FLAG_ROBUST) | (robust ? GBP_FLAG_ROBUST : 0u);
-    }
-  }
+  if (PREP && active) prep_factor(g, stage, s_cam, e, lane, lb, rb, damping, dcount, flags, dmu);
 
   float nc[28];   // new f->cam message record: eta 0..5 | lower lambda 6..26 | pad
   float ncu[16];  // its strict upper triangle (row-major, i<j): only summed into the camera partial
   if (MSG) {
-#ifdef GBP_EXPERIMENT_NOCOMPUTE  // memory-only variant (tuning experiments): touch every staged quad, store every output
     if (active) {
-      float t[GBP_SQ * 4];
-      stage_read<0, GBP_SQ>(stage, lane, t);
-      float acc = lb[0] + lb[5] + lb[14] + lb[17] + s_cam[lane];
-#pragma unroll
-      for (int k = 0; k < GBP_SQ * 4; ++k) acc += t[k];
-#pragma unroll
-      for (int k = 0; k < 28; ++k) nc[k] = acc + t[k];
-#pragma unroll
-      for (int k = 0; k < 15; ++k) ncu[k] = acc;
-      float4* p = g.mlmk + e * GBP_MLMK_QUADS;
-#pragma unroll
-      for (int q = 0; q < 3; ++q) p[q] = make_float4(acc, t[q], t[q + 4], t[q + 8]);
-#pragma unroll
-      for (int q = 0; q < GBP_MCAM_QUADS; ++q)
-        g.mcam[(size_t)q * g.E_pad + e] = make_float4(nc[q * 4], nc[q * 4 + 1], nc[q * 4 + 2], nc[q * 4 + 3]);
-    } else if (false) {
-#else
-    if (active) {
-#endif
-      const float omd = fs(1.0f, damping);
-      float head[36];  // quads 0..8: eta 0..8 | ll(lower) 9..14 | cl 15..32 | cc(lower) 0..2 at 33..35
-      stage_read<GBP_SQ_FAC, 9>(stage, lane, head);
-      float tail[20];  // quads 9..13: cc(lower) 3..20 at 0..17 | pad
-      stage_read<GBP_SQ_FAC + 9, 5>(stage, lane, tail);
-      const float* eta = head + GBP_FAC_ETA;
-      const float* cl = head + GBP_FAC_CL;
-#define GBP_LLF(i, j) head[GBP_FAC_LL + gbp_sym(i, j)]
-#define GBP_CCF(i, j) ((gbp_sym(i, j) < 3) ? head[GBP_FAC_CC + gbp_sym(i, j)] : tail[gbp_sym(i, j) - 3])
-      float pl[12];  // previous f->lmk message: eta 0..2, lambda 3..11
-      stage_read<GBP_SQ_MLMK, 3>(stage, lane, pl);
-      float pc[28];  // previous f->cam message: eta 0..5, lower lambda 6..26
-      stage_read<GBP_SQ_MCAM, 7>(stage, lane, pc);
-
-      // ---- message to the landmark (gbp_codelets.cpp:536-552, 691-699) ----
       float nl[12];
-      {
-        float Ai[36];
-        {
-          float Ld[21];
+      msg_to_landmark(stage, s_cam, lane, damping, nl);
+      float4* p = g.mlmk + lpos * GBP_MLMK_QUADS;
 #pragma unroll
-          for (int i = 0; i < 6; ++i)
-#pragma unroll
-            for (int j = 0; j <= i; ++j)
-              Ld[lt(i, j)] = fs(fa(GBP_CCF(i, j), s_cam[6 + i * 6 + j]), pc[GBP_MCAM_LOWER + lt(i, j)]);
-          inv6(Ld, Ai);
-        }
-        float P[18];  // Lambda_lc * inv  (3x6), Lambda_lc(i,k) = Lambda_cl(k,i)
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-          for (int j = 0; j < 6; ++j) {
-            float acc = fm(cl[i], Ai[j]);
-#pragma unroll
-            for (int k = 1; k < 6; ++k) acc = fa(acc, fm(cl[k * 3 + i], Ai[k * 6 + j]));
-            P[i * 6 + j] = acc;
-          }
-        float ed[6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) ed[i] = fs(fa(eta[i], s_cam[i]), pc[i]);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          float acc = fm(P[i * 6], ed[0]);
-#pragma unroll
-          for (int k = 1; k < 6; ++k) acc = fa(acc, fm(P[i * 6 + k], ed[k]));
-          const float h = fs(eta[6 + i], acc);
-          nl[i] = fa(fm(h, omd), fm(pl[i], damping));
-        }
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            float acc = fm(P[i * 6], cl[j]);
-#pragma unroll
-            for (int k = 1; k < 6; ++k) acc = fa(acc, fm(P[i * 6 + k], cl[k * 3 + j]));
-            nl[3 + i * 3 + j] = fs(GBP_LLF(i, j), acc);
-          }
-      }
-      {
-        float4* p = g.mlmk + lpos * GBP_MLMK_QUADS;
-#pragma unroll
-        for (int q = 0; q < 3; ++q) p[q] = make_float4(nl[q * 4], nl[q * 4 + 1], nl[q * 4 + 2], nl[q * 4 + 3]);
-      }
-
-      // ---- message to the camera (gbp_codelets.cpp:446-462, 619-627) ----
-      {
-        float Ld[9], Li[9];
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-          for (int j = 0; j < 3; ++j) Ld[i * 3 + j] = fs(fa(GBP_LLF(i, j), lb[3 + i * 3 + j]), pl[3 + i * 3 + j]);
-        inv3(Ld, Li);
-        float P[18];  // Lambda_cl * inv (6x3)
-#pragma unroll
-        for (int i = 0; i < 6; ++i)
-#pragma unroll
-          for (int j = 0; j < 3; ++j)
-            P[i * 3 + j] = fa(fa(fm(cl[i * 3], Li[j]), fm(cl[i * 3 + 1], Li[3 + j])), fm(cl[i * 3 + 2], Li[6 + j]));
-        float ed[3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) ed[i] = fs(fa(eta[6 + i], lb[i]), pl[i]);
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          const float acc = fa(fa(fm(P[i * 3], ed[0]), fm(P[i * 3 + 1], ed[1])), fm(P[i * 3 + 2], ed[2]));
-          const float h = fs(eta[i], acc);
-          nc[i] = fa(fm(h, omd), fm(pc[i], damping));
-        }
-#pragma unroll
-        for (int i = 0; i < 6; ++i)
-#pragma unroll
-          for (int j = 0; j < 6; ++j) {
-            const float acc = fa(fa(fm(P[i * 3], cl[j * 3]), fm(P[i * 3 + 1], cl[j * 3 + 1])), fm(P[i * 3 + 2], cl[j * 3 + 2]));
-            const float v = fs(GBP_CCF(i, j), acc);
-            if (i >= j) nc[GBP_MCAM_LOWER + lt(i, j)] = v;
-            else ncu[gbp_upper(i, j)] = v;
-          }
-        nc[27] = 0.f;
-      }
-#undef GBP_LLF
-#undef GBP_CCF
-#pragma unroll
-      for (int q = 0; q < GBP_MCAM_QUADS; ++q)
-        g.mcam[(size_t)q * g.E_pad + e] = make_float4(nc[q * 4], nc[q * 4 + 1], nc[q * 4 + 2], nc[q * 4 + 3]);
-      if (g.mcam_up) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          g.mcam_up[(size_t)q * g.E_pad + e] = make_float4(ncu[q * 4], ncu[q * 4 + 1], ncu[q * 4 + 2], q < 3 ? ncu[q * 4 + 3] : 0.f);
-      }
+      for (int q = 0; q < 3; ++q) p[q] = make_float4(nl[q * 4], nl[q * 4 + 1], nl[q * 4 + 2], nl[q * 4 + 3]);
+      msg_to_camera(stage, lane, lb, damping, nc, ncu);
+      store_cam_message(g, e, nc, ncu);
       flags |= GBP_FLAG_HASMSG;
     } else {
       // inactive (or padding) slot: its messages are zero (gbp_codelets.cpp:464-468 etc.)
 #pragma unroll
       for (int k = 0; k < 28; ++k) nc[k] = 0.f;
 #pragma unroll
-      for (int k = 0; k < 15; ++k) ncu[k] = 0.f;
+      for (int k = 0; k < 16; ++k) ncu[k] = 0.f;
       if (valid && (flags & GBP_FLAG_HASMSG)) {
+        store_cam_message(g, e, nc, ncu);
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int q = 0; q < GBP_MCAM_QUADS; ++q) g.mcam[(size_t)q * g.E_pad + e] = z4;
-        if (g.mcam_up) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) g.mcam_up[(size_t)q * g.E_pad + e] = z4;
-        }
 #pragma unroll
         for (int q = 0; q < 3; ++q) g.mlmk[lpos * GBP_MLMK_QUADS + q] = z4;
         flags &= ~GBP_FLAG_HASMSG;
@@ -548,24 +549,6 @@ GBP_DEV void sweep_tile(const DeviceGraph& g, float4* stage, const float* s_cam,
     warp_cam_reduce(red, lane, g.cam_partial + (size_t)wt * GBP_CAMPART);
     __syncwarp();
   }
-}
-
-// L2 prefetch of one contiguous run (bytes % 16 == 0)
-GBP_DEV void bulk_prefetch_l2(const void* gmem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gmem), "r"(bytes) : "memory");
-}
-// DRAM -> L2 prefetch of every per-factor record of warp-tile wt: lane q fetches quad-row q (512 B)
-GBP_DEV void prefetch_tile_l2(const DeviceGraph& g, const uint32_t wt, const uint32_t lane) {
-  const size_t e0 = (size_t)wt * 32;
-  const void* p;
-  uint32_t bytes = 512;
-  if (lane < GBP_FAC_QUADS) p = g.fac + (size_t)lane * g.E_pad + e0;
-  else if (lane < GBP_FAC_QUADS + GBP_MCAM_QUADS) p = g.mcam + (size_t)(lane - GBP_FAC_QUADS) * g.E_pad + e0;
-  else if (lane == GBP_SQ_MLMK) return;  // landmark-ordered: no contiguous run per warp-tile
-  else if (lane == GBP_SQ_MLMK + 1) p = g.recA + e0;
-  else if (lane == GBP_SQ_MLMK + 2) p = g.recB + e0;
-  else return;
-  bulk_prefetch_l2(p, bytes);
 }
 
 template <bool PREP, bool MSG>
@@ -596,7 +579,6 @@ __global__ void __launch_bounds__(GBP_SW_WARPS * 32, 1) k_sweep(const DeviceGrap
   if (wt_n < n_wt) {
     ti_n = __ldg(g.wt_info + wt_n);
     lid_n = __ldg(lrec + 2 * ((size_t)wt_n * 32 + lane));
-    if (GBP_NBUF == 1) prefetch_tile_l2(g, wt_n, lane);
   }
   for (;;) {
     const bool has_next = wt_n < n_wt;
@@ -605,34 +587,24 @@ __global__ void __launch_bounds__(GBP_SW_WARPS * 32, 1) k_sweep(const DeviceGrap
     uint2 lid_nn = make_uint2(0u, 0u);
     const uint32_t wt_nn = wt_n + stride;
     if (has_next) {
-      if (GBP_NBUF == 2)
-        issue_stage(g, stage_base + (buf ^ 1) * GBP_STAGE_QUADS, scam_base + (buf ^ 1) * GBP_SCAM, wt_n, ti_n.x, lid_n.y, lane);
+      issue_stage(g, stage_base + (buf ^ 1) * GBP_STAGE_QUADS, scam_base + (buf ^ 1) * GBP_SCAM, wt_n, ti_n.x, lid_n.y, lane);
       load_lmk_belief(g, lid_n.x, lb_n);
       if (wt_nn < n_wt) {
         ti_nn = __ldg(g.wt_info + wt_nn);
         lid_nn = __ldg(lrec + 2 * ((size_t)wt_nn * 32 + lane));
-        if (GBP_NBUF == 1) prefetch_tile_l2(g, wt_nn, lane);
       }
     }
-    if (GBP_NBUF == 2) {
-      // the copies of THIS warp-tile were committed one iteration ago: leave the newest group in flight
-      asm volatile("cp.async.commit_group;\n cp.async.wait_group 1;\n" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-    }
+    // the copies of THIS warp-tile were committed one iteration ago: leave the newest group in flight
+    asm volatile("cp.async.commit_group;\n cp.async.wait_group 1;\n" ::: "memory");
     __syncwarp();
     sweep_tile<PREP, MSG>(g, stage_base + buf * GBP_STAGE_QUADS, scam_base + buf * GBP_SCAM, wt, ti, lb, lane);
     if (!has_next) break;
-    if (GBP_NBUF == 1) {  // single stage: refill it now (its records were pulled into L2 one tile ago)
-      issue_stage(g, stage_base, scam_base, wt_n, ti_n.x, lid_n.y, lane);
-      asm volatile("cp.async.commit_group;\n" ::: "memory");
-    }
     wt = wt_n; wt_n = wt_nn;
     ti = ti_n; ti_n = ti_nn;
     lid_n = lid_nn;
 #pragma unroll
     for (int i = 0; i < 20; ++i) lb[i] = lb_n[i];
-    if (GBP_NBUF == 2) buf ^= 1;
+    buf ^= 1;
   }
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 }
