@@ -598,7 +598,15 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   g.hp.min_linear_iters = o->min_linear_iters;
   g.hp.Nstds = o->Nstds;
   int rc = GBP_OK;
-#define A_(ptr, n) if (!rc) rc = h_alloc(h, &(ptr), (size_t)(n))
+  // one device arena for all per-handle buffers: a single cudaMalloc + cudaMemset instead of ~40
+  // (everything the reference relies on being zero IS zeroed, quirk Q4)
+  std::vector<std::pair<void**, size_t>> arena;
+  size_t arena_bytes = 0;
+  auto reserve = [&](void** pp, size_t bytes) {
+    arena.emplace_back(pp, arena_bytes);
+    arena_bytes += (std::max<size_t>(bytes, 16) + 255) & ~(size_t)255;
+  };
+#define A_(ptr, n) reserve((void**)&(ptr), (size_t)(n) * sizeof(*(ptr)))
   A_(g.fac, GBP_FAC_QUADS * EP);
   A_(g.mcam, GBP_MCAM_QUADS * EP);
   if (o->store_full_messages) A_(g.mcam_up, 4 * EP);
@@ -640,18 +648,22 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
     g.rank = h->rank;
     lmk_bslot.assign(L, 0xffffffffu);
     for (uint32_t k = 0; k < nbl; ++k) lmk_bslot[gbp_shard_boundary_local(h->shard)[k]] = gbp_shard_boundary_slot(h->shard)[k];
-    float4* recv = nullptr;
     A_(g.lmk_bslot, L);
     A_(g.bnd_local, nbl);
     A_(g.bnd_slot, nbl);
     A_(g.bnd_send, 3 * (size_t)g.n_bnd_global);
-    A_(recv, 3 * (size_t)g.n_bnd_global * h->world);
-    g.bnd_recv = recv;
+    reserve((void**)&g.bnd_recv, 3 * (size_t)g.n_bnd_global * h->world * sizeof(float4));
     A_(h->d_metric_raw, 8);
     A_(h->d_metric_all, 8 * (size_t)h->world);
   }
 #undef A_
-  if (rc) return rc;
+  {
+    char* base = nullptr;
+    rc = h_alloc(h, &base, arena_bytes, false);
+    if (rc) return rc;
+    GBP_CUDA_TRY(cudaMemsetAsync(base, 0, arena_bytes, h->stream));  // ordered before the uploads below
+    for (auto& r : arena) *r.first = base + r.second;
+  }
   cudaStream_t s = h->stream;
 #define U_(dst, src, n) if (!rc) rc = upload(dst, src, (size_t)(n), s)
   U_(g.recA, recA.data(), EP);

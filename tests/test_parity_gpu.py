@@ -317,3 +317,61 @@ def test_config4_full_size_properties():
     assert np.all(np.linalg.eigvalsh(0.5 * (lam + lam.transpose(0, 2, 1)))[:, 0] > 0)  # and positive definite
     e1 = gpu.eval()
     assert e1["n_active"] == bal.n_edges and e1["reproj_mean"] < 0.25 * e0["reproj_mean"]
+
+
+# ---- BASELINE.json configs 1-3 at their full horizons, against series frozen from the reference codelets
+# (tests/golden/make_golden.py, CUDA summation order); no oracle run is needed on the GPU box -------------
+def _golden_long():
+    z = np.load(os.path.join(common.GOLDEN, "golden_runs.npz"))
+    with open(os.path.join(common.GOLDEN, "golden_runs.json")) as f:
+        return z, json.load(f)["long_runs"]
+
+
+def _ba_series(gpu, n):
+    out = []
+    it = 0
+    while it < n:
+        if (it + 1) % 2 == 0 and it < 10:
+            gpu.weaken_priors()
+        m = 1 if it < 10 else min(250, n - it)
+        out += [s["reproj_mean"] for s in gpu.iterate(m, stats=True)]
+        it += m
+    return np.array(out)
+
+
+def test_config1_fr1xyz_1500_sweeps_matches_frozen_reference_series():
+    z, meta = _golden_long()
+    gold = z["long_fr1xyz_ba1500_reproj"]
+    gpu = GBPEngine(common.make_setup("fr1xyz").problem)
+    got = _ba_series(gpu, 1500)
+    assert np.allclose(got, gold, rtol=2e-3), float(np.abs(got / gold - 1).max())
+    assert got[-1] == pytest.approx(1.4242, rel=1e-3) and got[-1] == pytest.approx(1.4296, rel=0.01)
+    for t, h in meta["fr1xyz_ba1500"]["sha"].items():
+        assert sha(gpu.get_tensor(t)) == h, t          # the whole 1500-sweep trajectory is bit-identical
+
+
+def test_config2_fr1desk_descent_and_stop_rule():
+    z, _ = _golden_long()
+    gold = z["long_fr1desk_ba360_reproj"]
+    gpu = GBPEngine(common.make_setup("fr1desk").problem)
+    got = _ba_series(gpu, 360)
+    assert np.allclose(got, gold, rtol=2e-3), float(np.abs(got / gold - 1).max())
+    # "run to convergence": stop at the first sweep whose error exceeds twice the running minimum;
+    # in this summation order the run is still descending after 360 sweeps (the serial order diverges near 300)
+    run_min = np.minimum.accumulate(got)
+    assert not np.any(got > 2 * run_min) and run_min[-1] < 2.5 and got[0] > 100
+
+
+def test_config3_fr2robot2_slam_default_700_sweeps_per_keyframe():
+    z, _ = _golden_long()
+    gold = z["long_fr2robot2_slam700_reproj"]
+    st = common.make_setup("fr2robot2", mode=MODE_SLAM)
+    gpu = GBPEngine(st.problem)
+    got = np.array([f["reproj_mean"] for f in common.slam_run(gpu, st, 700)])
+    # The reference's SLAM schedule is only marginally stable on this sequence from keyframe 15 on (SURVEY 8c:
+    # a 1.86 px spike in the serial summation order; in the tile order the same instability runs away), so the
+    # comparison covers the stable prefix, where the two agree to the metric's rounding.
+    stable = int(np.flatnonzero(~(gold < 2.0))[0]) if np.any(~(gold < 2.0)) else gold.size
+    assert stable >= 14
+    assert np.allclose(got[:stable], gold[:stable], rtol=2e-3), (got[:stable], gold[:stable])
+    assert got[0] == pytest.approx(0.4644, rel=2e-3)      # SURVEY 8c known answer before the first insertion
