@@ -161,6 +161,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="config4", choices=["config4", "config5"],
+                    help="config4 (default): BASELINE.json configs[3] per GPU, one N-times larger graph at N>1 (weak "
+                         "scaling); config5: configs[4] exactly -- 10k cameras / 1M landmarks / ~10M factors in total, "
+                         "partitioned over the N GPUs (strong scaling)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -182,7 +186,7 @@ def main():
 
     from gbp_poplar_b200 import GBPEngine, default_opts
 
-    bal, setup = build_problem(scale=world)          # ONE graph, `world` times config-4 size
+    bal, setup = build_problem(scale=world if args.workload == "config4" else 10)   # ONE graph
     E, Cn, Ln = setup.problem.n_edges, setup.problem.n_keyframes, setup.problem.n_points
 
     def make_engine():
@@ -296,10 +300,13 @@ def main():
         line = {
             "metric": "factor_message_updates_per_sec", "value": value, "unit": "factor-updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak" if args.workload == "config4" else "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
             "sweeps_per_sec": args.steps / (ms / 1e3) * 1.0,
-            "config": {"workload": "synthetic BAL 1k cameras / 100k landmarks / ~1M factors per GPU (configs[3]); at N>1 "
-                                   "one N-times larger graph partitioned by camera range (N=8 ~ configs[4])",
+            "config": {"workload": ("synthetic BAL 1k cameras / 100k landmarks / ~1M factors per GPU (configs[3]); at N>1 "
+                                    "one N-times larger graph partitioned by camera range (N=8 ~ configs[4])")
+                       if args.workload == "config4" else
+                       "synthetic BAL 10k cameras / 1M landmarks / ~10M factors in total (configs[4]), partitioned by camera range",
                        "cameras": Cn, "landmarks": Ln, "factors": E, "per_gpu": False,
                        "parallelism": f"camera-range shards x{world}, boundary-landmark partials exchanged per sweep by "
                                       f"{exchange_mode} ({n_boundary} boundary landmarks, {48 * n_boundary} B per rank and peer)"
