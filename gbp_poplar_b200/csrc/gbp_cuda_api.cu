@@ -95,6 +95,8 @@ struct gbp_handle {
   uint32_t* d_exp_robust = nullptr;
   // metric
   gbp::MetricPartial* d_metric_parts = nullptr;
+  double* d_met_cam = nullptr;      // [C][16] double-precision camera means + rotations (metric only)
+  double* d_met_lmk = nullptr;      // [L][4]  double-precision landmark means (metric only)
   gbp::DeviceStats* d_stats = nullptr;
   size_t d_stats_cap = 0;
   // timing
@@ -240,8 +242,10 @@ int launch_sweep(gbp_handle* h) {
 
 int launch_metric(gbp_handle* h, gbp::DeviceStats* d_out) {
   if (h->n_tiles) {
-    gbp::k_metric<<<h->n_tiles, GBP_TILE, 0, h->stream>>>(h->g, h->n_active, h->d_metric_parts);
-    h->kernels_launched++;
+    const uint32_t nv = h->C + h->L;
+    gbp::k_metric_prep<<<(nv + 127) / 128, 128, 0, h->stream>>>(h->g, h->d_met_cam, h->d_met_lmk);
+    gbp::k_metric<<<h->n_tiles, GBP_TILE, 0, h->stream>>>(h->g, h->n_active, h->d_met_cam, h->d_met_lmk, h->d_metric_parts);
+    h->kernels_launched += 2;
   }
   gbp::k_metric_finish<<<1, 256, 0, h->stream>>>(h->d_metric_parts, h->n_tiles, d_out, h->shard ? h->d_metric_raw : nullptr);
   h->kernels_launched++;
@@ -636,6 +640,8 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   A_(g.lmk_ptr, L + 1);
   A_(h->d_pos_of_orig, E);
   A_(h->d_metric_parts, h->n_tiles);
+  A_(h->d_met_cam, 16 * (size_t)C);
+  A_(h->d_met_lmk, 4 * (size_t)L);
   A_(h->d_pprior_cam_eta, 6 * (size_t)C);
   A_(h->d_pprior_cam_lam, 36 * (size_t)C);
   A_(h->d_pprior_lmk, 3 * (size_t)L);

@@ -978,26 +978,94 @@ __global__ void k_weaken(const DeviceGraph g) {
 }
 
 // ---- metric (ba/util.cpp:74-144) ------------------------------------------------
+// The reference inverts every belief on the host (Eigen, fp32 LU) for the error it prints.  Here
+// the means used ONLY for the metric are solved in double precision (Gaussian elimination with
+// partial pivoting), so the reported error does not carry the fp32 inversion noise of weakly
+// constrained variables (a few 1e-3 relative); the sweep itself keeps using the codelets' fp32
+// LDL^T means.  k_metric_prep: one thread per variable; k_metric: one thread per factor.
 struct MetricPartial {
-  float sum_norm, sum_sq;
+  double sum_norm, sum_sq;
   uint32_t n_relins, n_robust, n_active, pad;
 };
 
+template <int N>
+GBP_DEV void solve_double(double (&A)[N * N], double (&b)[N], double (&x)[N]) {
+#pragma unroll 1
+  for (int k = 0; k < N; ++k) {
+    int piv = k;
+    double best = fabs(A[k * N + k]);
+    for (int r = k + 1; r < N; ++r)
+      if (fabs(A[r * N + k]) > best) { best = fabs(A[r * N + k]); piv = r; }
+    if (piv != k) {
+      for (int c = 0; c < N; ++c) { const double t = A[k * N + c]; A[k * N + c] = A[piv * N + c]; A[piv * N + c] = t; }
+      const double t = b[k]; b[k] = b[piv]; b[piv] = t;
+    }
+    const double inv = 1.0 / A[k * N + k];
+    for (int r = k + 1; r < N; ++r) {
+      const double f = A[r * N + k] * inv;
+      for (int c = k; c < N; ++c) A[r * N + c] -= f * A[k * N + c];
+      b[r] -= f * b[k];
+    }
+  }
+  for (int k = N - 1; k >= 0; --k) {
+    double acc = b[k];
+    for (int c = k + 1; c < N; ++c) acc -= A[k * N + c] * x[c];
+    x[k] = acc / A[k * N + k];
+  }
+}
+
+// met_cam: [C][16] doubles = mean 6 | R 9 | pad;  met_lmk: [L][4] doubles = mean 3 | pad
+__global__ void k_metric_prep(const DeviceGraph g, double* __restrict__ met_cam, double* __restrict__ met_lmk) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < g.C) {
+    double A[36], b[6], x[6];
+    for (int k = 0; k < 36; ++k) A[k] = (double)g.cam_b_lam[i * 36 + k];
+    for (int k = 0; k < 6; ++k) b[k] = (double)g.cam_b_eta[i * 6 + k];
+    solve_double<6>(A, b, x);
+    double* o = met_cam + (size_t)i * 16;
+    for (int k = 0; k < 6; ++k) o[k] = x[k];
+    // Rodrigues in double (bafuncs.cpp:32-55)
+    const double w0 = x[3], w1 = x[4], w2 = x[5];
+    const double th = sqrt(w0 * w0 + w1 * w1 + w2 * w2);
+    double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    if (th > 1e-6) {
+      const double a = sin(th) / th, c = (1.0 - cos(th)) / (th * th);
+      const double H[9] = {0, -w2, w1, w2, 0, -w0, -w1, w0, 0};
+      for (int r = 0; r < 3; ++r)
+        for (int q = 0; q < 3; ++q) {
+          double h2 = 0;
+          for (int k = 0; k < 3; ++k) h2 += H[r * 3 + k] * H[k * 3 + q];
+          R[r * 3 + q] += a * H[r * 3 + q] + c * h2;
+        }
+    }
+    for (int k = 0; k < 9; ++k) o[6 + k] = R[k];
+  } else if (i < g.C + g.L) {
+    const uint32_t l = i - g.C;
+    const float4* p = g.lmk_b + (size_t)l * GBP_LMKB_QUADS;
+    const float4 q0 = p[0], q1 = p[1], q2 = p[2];
+    double A[9] = {q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+    double b[3] = {q0.x, q0.y, q0.z}, x[3];
+    solve_double<3>(A, b, x);
+    double* o = met_lmk + (size_t)l * 4;
+    o[0] = x[0]; o[1] = x[1]; o[2] = x[2]; o[3] = 0.0;
+  }
+}
+
 __global__ void __launch_bounds__(GBP_TILE) k_metric(const DeviceGraph g, const uint32_t n_active_total,
+                                                    const double* __restrict__ met_cam, const double* __restrict__ met_lmk,
                                                     MetricPartial* __restrict__ out) {
-  __shared__ float s_cam_all[GBP_TILE / 32][16];  // per warp-tile (= one camera): mean 6 | R 9
-  __shared__ float s_f[2][GBP_TILE / 32];
+  __shared__ double s_cam_all[GBP_TILE / 32][16];  // per warp-tile (= one camera): mean 6 | R 9
+  __shared__ double s_f[2][GBP_TILE / 32];
   __shared__ uint32_t s_u[3][GBP_TILE / 32];
   const uint32_t tile = blockIdx.x, tid = threadIdx.x;
   const size_t e = (size_t)tile * GBP_TILE + tid;
   const uint32_t c = g.wt_info[e >> 5].x;
-  float* s_cam = s_cam_all[tid >> 5];
-  if ((tid & 31) < 6) s_cam[tid & 31] = g.cam_mean[c * 6 + (tid & 31)];
-  else if ((tid & 31) < 15) s_cam[tid & 31] = g.cam_R[c * 9 + ((tid & 31) - 6)];
+  double* s_cam = s_cam_all[tid >> 5];
+  if ((tid & 31) < 15) s_cam[tid & 31] = met_cam[(size_t)c * 16 + (tid & 31)];
   __syncthreads();
   const float4 ra = g.recA[e];
   const uint32_t flags = __float_as_uint(ra.z);
-  float nrm = 0.f, sq = 0.f;
+  double nrm = 0.0, sq = 0.0;
   uint32_t relin = 0, robust = 0, act = 0;
   if (!(flags & GBP_FLAG_PAD)) {
     robust = (flags & GBP_FLAG_ROBUST) ? 1u : 0u;
@@ -1006,17 +1074,17 @@ __global__ void __launch_bounds__(GBP_TILE) k_metric(const DeviceGraph g, const 
     // quirk Q7: the reference evaluates edges [0, n_active) of the ORIGINAL order
     if (g.edge_orig[e] < n_active_total) {
       const float4 rb = g.recB[e];
-      const float4 m = g.lmk_b[(size_t)__float_as_uint(rb.z) * GBP_LMKB_QUADS + 3];
-      float y[3];
+      const double* m = met_lmk + (size_t)__float_as_uint(rb.z) * 4;
+      const double m0 = m[0], m1 = m[1], m2 = m[2];
+      double y[3];
 #pragma unroll
-      for (int i = 0; i < 3; ++i)
-        y[i] = s_cam[6 + i * 3] * m.x + s_cam[6 + i * 3 + 1] * m.y + s_cam[6 + i * 3 + 2] * m.z + s_cam[i];
-      const float u = g.K[0] * y[0] / y[2] + g.K[2];
-      const float v = g.K[1] * y[1] / y[2] + g.K[3];
-      const float r0 = rb.x - u, r1 = rb.y - v;
-      const float s = r0 * r0 + r1 * r1;
-      nrm = sqrtf(s);
-      sq = 0.5f * s;
+      for (int i = 0; i < 3; ++i) y[i] = s_cam[6 + i * 3] * m0 + s_cam[6 + i * 3 + 1] * m1 + s_cam[6 + i * 3 + 2] * m2 + s_cam[i];
+      const double u = ((double)g.K[0] * y[0] + (double)g.K[2] * y[2]) / y[2];
+      const double v = ((double)g.K[1] * y[1] + (double)g.K[3] * y[2]) / y[2];
+      const double r0 = (double)rb.x - u, r1 = (double)rb.y - v;
+      const double s2 = r0 * r0 + r1 * r1;
+      nrm = sqrt(s2);
+      sq = 0.5 * s2;
     }
   }
 #pragma unroll
@@ -1034,7 +1102,7 @@ __global__ void __launch_bounds__(GBP_TILE) k_metric(const DeviceGraph g, const 
   }
   __syncthreads();
   if (tid == 0) {
-    MetricPartial p = {0.f, 0.f, 0u, 0u, 0u, 0u};
+    MetricPartial p = {0.0, 0.0, 0u, 0u, 0u, 0u};
     for (int i = 0; i < GBP_TILE / 32; ++i) {
       p.sum_norm += s_f[0][i]; p.sum_sq += s_f[1][i];
       p.n_relins += s_u[0][i]; p.n_robust += s_u[1][i]; p.n_active += s_u[2][i];
@@ -1059,7 +1127,7 @@ __global__ void __launch_bounds__(256) k_metric_finish(const MetricPartial* __re
   uint32_t r = 0, ro = 0, ac = 0;
   for (uint32_t t = tid; t < n_tiles; t += 256) {
     const MetricPartial p = parts[t];
-    a += (double)p.sum_norm; b += (double)p.sum_sq;
+    a += p.sum_norm; b += p.sum_sq;
     r += p.n_relins; ro += p.n_robust; ac += p.n_active;
   }
   s_d[0][tid] = a; s_d[1][tid] = b; s_u[0][tid] = r; s_u[1][tid] = ro; s_u[2][tid] = ac;

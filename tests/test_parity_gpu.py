@@ -328,14 +328,11 @@ def _golden_long():
 
 
 def _assert_series(got, gold):
-    """The device metric inverts the beliefs in fp32 (like the reference's Eigen float inverse, ba/util.cpp:103-109),
-    the frozen series comes from the oracle's double-precision solve: they agree to rounding on most sweeps and
-    to a few per cent on sweeps where a weakly constrained landmark sits near zero depth.  The trajectory
-    itself is pinned bit for bit through the belief hashes; the final error must agree within 1 %."""
+    """The device metric solves the means in double like the oracle's (the reference's own uses an fp32 Eigen
+    inverse, ba/util.cpp:103-109), so the two series agree to rounding; the trajectory itself is pinned bit
+    for bit through the belief hashes."""
     rel = np.abs(got / gold - 1)
-    assert rel[-1] < 0.01
-    assert np.median(rel) < 2e-3 and np.percentile(rel, 95) < 1e-2 and rel.max() < 0.1, \
-        (float(np.median(rel)), float(np.percentile(rel, 95)), float(rel.max()))
+    assert rel.max() < 1e-4, (float(np.median(rel)), float(rel.max()), int(rel.argmax()))
 
 
 def _ba_series(gpu, n):
@@ -386,5 +383,5 @@ def test_config3_fr2robot2_slam_default_700_sweeps_per_keyframe():
     # comparison covers the stable prefix, where the two agree to the metric's rounding.
     stable = int(np.flatnonzero(~(gold < 2.0))[0]) if np.any(~(gold < 2.0)) else gold.size
     assert stable >= 14
-    assert np.allclose(got[:stable], gold[:stable], rtol=1e-2), (got[:stable], gold[:stable])   # fp32 vs double metric
+    assert np.allclose(got[:stable], gold[:stable], rtol=1e-4), (got[:stable], gold[:stable])
     assert got[0] == pytest.approx(0.4644, rel=2e-3)      # SURVEY 8c known answer before the first insertion
