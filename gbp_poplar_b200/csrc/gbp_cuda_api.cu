@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -85,6 +86,14 @@ struct gbp_handle {
   float* d_pprior_cam_lam = nullptr;
   float4* d_pprior_lmk = nullptr;
   int use_graph = 0;
+  // CUDA-graph replay of one steady-state sweep (with / without the metric): one launch per sweep
+  // instead of 2-5, which is what bounds the small graphs of the reference sequences
+  cudaGraphExec_t sweep_graph[2] = {nullptr, nullptr};
+  DeviceGraph graph_g;               // the kernel arguments the graphs were captured with
+  gbp::DeviceStats* graph_stats = nullptr;
+  uint32_t graph_n_active = 0;      // k_metric's argument at capture time
+  bool capturing = false;
+  uint32_t* d_stat_cursor = nullptr;
   int num_sms = 148;
   // staging for READ_PROG
   uint32_t* d_pos_of_orig = nullptr;
@@ -247,7 +256,8 @@ int launch_metric(gbp_handle* h, gbp::DeviceStats* d_out) {
     gbp::k_metric<<<h->n_tiles, GBP_TILE, 0, h->stream>>>(h->g, h->n_active, h->d_met_cam, h->d_met_lmk, h->d_metric_parts);
     h->kernels_launched += 2;
   }
-  gbp::k_metric_finish<<<1, 256, 0, h->stream>>>(h->d_metric_parts, h->n_tiles, d_out, h->shard ? h->d_metric_raw : nullptr);
+  gbp::k_metric_finish<<<1, 256, 0, h->stream>>>(h->d_metric_parts, h->n_tiles, d_out, h->shard ? h->d_metric_raw : nullptr,
+                                                 h->capturing ? h->d_stat_cursor : nullptr);
   h->kernels_launched++;
   if (h->shard) {  // every rank reports the metric of the WHOLE graph
     GBP_CUDA_TRY(cudaEventRecord(h->ev_send, h->stream));
@@ -640,6 +650,7 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   A_(g.lmk_ptr, L + 1);
   A_(h->d_pos_of_orig, E);
   A_(h->d_metric_parts, h->n_tiles);
+  A_(h->d_stat_cursor, 1);
   A_(h->d_met_cam, 16 * (size_t)C);
   A_(h->d_met_lmk, 4 * (size_t)L);
   A_(h->d_pprior_cam_eta, 6 * (size_t)C);
@@ -730,6 +741,53 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   return GBP_OK;
 }
 
+void drop_graphs(gbp_handle* h) {
+  for (cudaGraphExec_t& e : h->sweep_graph) {
+    if (e) cudaGraphExecDestroy(e);
+    e = nullptr;
+  }
+}
+
+// The instantiated graph of ONE steady-state sweep: k_sweep, k_update_vars (shift = 1) and, with
+// stats, the three metric kernels writing to d_stats[cursor++].  Captured lazily, re-captured when
+// the kernel arguments (DeviceGraph, stats buffer) changed.
+int sweep_graph(gbp_handle* h, bool with_stats, cudaGraphExec_t* out) {
+  if (std::memcmp(&h->graph_g, &h->g, sizeof(DeviceGraph)) != 0 || h->graph_stats != h->d_stats ||
+      h->graph_n_active != h->n_active)
+    drop_graphs(h);
+  cudaGraphExec_t& exec = h->sweep_graph[with_stats ? 1 : 0];
+  if (!exec) {
+    const uint64_t k0 = h->kernels_launched;
+    cudaGraph_t graph = nullptr;
+    GBP_CUDA_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    h->capturing = true;
+    int rc = launch_sweep<true, true>(h);
+    if (!rc) rc = launch_update_vars(h);
+    if (!rc && with_stats) rc = launch_metric(h, h->d_stats);
+    h->capturing = false;
+    const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+    h->kernels_launched = k0;
+    if (rc || ce != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      gbp_set_error("CUDA graph capture of the sweep failed");
+      return rc ? rc : GBP_ERR_CUDA;
+    }
+    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) {
+      exec = nullptr;
+      gbp_set_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie));
+      return GBP_ERR_CUDA;
+    }
+    h->graph_g = h->g;
+    h->graph_stats = h->d_stats;
+    h->graph_n_active = h->n_active;
+  }
+  *out = exec;
+  return GBP_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -745,6 +803,8 @@ void gbp_opts_default(gbp_opts* o) {
   o->min_linear_iters = 10;
   o->Nstds = 2.5f;
   o->use_cuda_graph = 1;
+  const char* env = std::getenv("GBP_CUDA_GRAPH");  // "0" disables the graph replay (diagnostics)
+  if (env && env[0] == '0') o->use_cuda_graph = 0;
 }
 
 int gbp_cuda_init(const gbp_problem* p, const gbp_opts* o_in, gbp_handle** out) {
@@ -799,6 +859,7 @@ int gbp_cuda_free(gbp_handle* h) {
   if (h->d_exp_dcount) cudaFree(h->d_exp_dcount);
   if (h->d_exp_robust) cudaFree(h->d_exp_robust);
   for (cudaEvent_t ev : h->prof_events) cudaEventDestroy(ev);
+  drop_graphs(h);
   if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);  // the communicator itself stays cached
   if (h->p2p) {
     // peers may still be pushing into this rank's block: freeing a sharded handle is collective
@@ -892,8 +953,25 @@ int gbp_cuda_iterate(gbp_handle* h, int n_sweeps, gbp_iter_stats* stats) {
       h->prof_events.push_back(ev);
     }
   }
-  GBP_CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-  for (int i = 0; i < n_sweeps && !rc; ++i) {
+  // steady state on one GPU: replay the captured sweep (the very first sweep after a belief update without a
+  // preceding prep has shift = 0 and goes through the plain launches, as do profiling and sharded handles)
+  int first = 0;
+  if (h->use_graph && !prof && !h->shard && n_sweeps > 0 && h->n_tiles) {
+    GBP_CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+    if (stats) GBP_CUDA_TRY(cudaMemsetAsync(h->d_stat_cursor, 0, sizeof(uint32_t), h->stream));
+    cudaGraphExec_t exec = nullptr;
+    rc = sweep_graph(h, stats != nullptr, &exec);
+    if (rc) return rc;
+    const uint64_t per = stats ? 5 : 2;
+    for (int i = 0; i < n_sweeps; ++i) GBP_CUDA_TRY(cudaGraphLaunch(exec, h->stream));
+    h->kernels_launched += per * (uint64_t)n_sweeps;
+    h->pending_shift = false;
+    h->p_in_sync = true;
+    first = n_sweeps;
+  } else {
+    GBP_CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+  }
+  for (int i = first; i < n_sweeps && !rc; ++i) {
     if (prof) GBP_CUDA_TRY(cudaEventRecord(h->prof_events[3 * i], h->stream));
     rc = launch_sweep<true, true>(h);
     if (prof) GBP_CUDA_TRY(cudaEventRecord(h->prof_events[3 * i + 1], h->stream));

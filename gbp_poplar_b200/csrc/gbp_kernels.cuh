@@ -1118,8 +1118,10 @@ struct DeviceStats {  // == gbp_iter_stats
 
 // One block: fixed-order reduction of the per-tile partials in double.
 // raw != nullptr (multi-GPU): the five sums are written as doubles for k_metric_combine instead.
+// cursor != nullptr (CUDA-graph replay): the result goes to out[*cursor] and the cursor advances.
 __global__ void __launch_bounds__(256) k_metric_finish(const MetricPartial* __restrict__ parts, const uint32_t n_tiles,
-                                                      DeviceStats* __restrict__ out, double* __restrict__ raw) {
+                                                      DeviceStats* __restrict__ out, double* __restrict__ raw,
+                                                      uint32_t* __restrict__ cursor) {
   __shared__ double s_d[2][256];
   __shared__ uint32_t s_u[3][256];
   const uint32_t tid = threadIdx.x;
@@ -1151,7 +1153,12 @@ __global__ void __launch_bounds__(256) k_metric_finish(const MetricPartial* __re
     s.n_relins = s_u[0][0];
     s.n_robust = s_u[1][0];
     s.reserved = 0;
-    *out = s;
+    if (cursor) {
+      out[*cursor] = s;
+      *cursor += 1;
+    } else {
+      *out = s;
+    }
   }
 }
 

@@ -77,7 +77,8 @@ typedef struct gbp_opts {
   float dmu_threshold;        /* 3e-3  gbp_codelets.cpp:13 */
   int min_linear_iters;       /* 10    gbp_codelets.cpp:14 */
   float Nstds;                /* 2.5   gbp_codelets.cpp:16 */
-  int use_cuda_graph;         /* reserved (sweeps are two launches; no graph needed)    */
+  int use_cuda_graph;         /* 1 (default): gbp_cuda_iterate replays a captured CUDA graph of one sweep (one launch
+                                 per sweep instead of 2-5: what bounds the small graphs of the reference sequences) */
   int store_full_messages;    /* 0 (default): a factor->camera message keeps eta + the LOWER triangle of
                                  Lambda -- all the algorithm ever reads back (inv6x6 works on the lower
                                  triangle, matlib.cpp:193-206; the belief sum over the full 6x6 message is
