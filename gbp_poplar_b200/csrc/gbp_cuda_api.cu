@@ -8,11 +8,13 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/gbp_cuda.h"
@@ -522,7 +524,19 @@ int setup_p2p(gbp_handle* h, int mode) {
   return GBP_OK;
 }
 
+struct PhaseTimer {  // GBP_INIT_TIMING=1: wall time of the phases of gbp_cuda_init on stderr
+  bool on = std::getenv("GBP_INIT_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void lap(const char* what) {
+    if (!on) return;
+    const auto n = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[gbp init] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+    t = n;
+  }
+};
+
 int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t* edge_global = nullptr) {
+  PhaseTimer pt;
   const uint32_t C = p->n_keyframes, L = p->n_points, E = p->n_edges;
   h->C = C; h->L = L; h->E = E;
   h->cam_ids.assign(p->cam_ids, p->cam_ids + E);
@@ -572,35 +586,60 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   lmk_ptr.assign(L + 1, 0);
   for (uint32_t l = 0; l < L; ++l) lmk_ptr[l + 1] = lmk_ptr[l] + deg_l[l];
   std::vector<float> var(EP, 1.f);
-  // per-edge state records
+  pt.lap("index maps");
+  // per-edge state records (built by a few host threads: this is the largest part of gbp_cuda_init)
   std::vector<float4> recA(EP), recB(EP);
-  for (size_t s = 0; s < EP; ++s) {
-    recA[s] = make_float4(0.f, i2f(0), u2f(GBP_FLAG_PAD), 0.f);
-    recB[s] = make_float4(0.f, 0.f, u2f(0), u2f(0));
-  }
   h->active_host.assign(E, 1u);
   if (p->active_flag) h->active_host.assign(p->active_flag, p->active_flag + E);
-  h->n_active = 0;
-  for (uint32_t e = 0; e < E; ++e) {
-    const size_t s = h->pos_of_orig[e];
-    const uint32_t act = (h->active_host[e] == 1u) ? 1u : 0u;
-    h->n_active += act;
-    recA[s] = make_float4(p->damping ? p->damping[e] : 0.f, i2f(p->damping_count ? p->damping_count[e] : -15),
-                          u2f(act ? GBP_FLAG_ACTIVE : 0u), 0.f);
-    recB[s] = make_float4(p->measurements[2 * (size_t)e], p->measurements[2 * (size_t)e + 1], u2f(h->lmk_ids[e]),
-                          u2f(lmk_ptr[h->lmk_ids[e]] + h->slot_l[e]));
-    var[s] = p->meas_variances[e];
-  }
-  if (h->shard) h->n_active = gbp_shard_n_active_global(h->shard);
-  auto any_nonzero = [](const float* a, size_t n) {
-    if (!a) return false;
-    for (size_t i = 0; i < n; ++i)
-      if (a[i] != 0.f) return true;
-    return false;
+  const unsigned n_thr = (E > (1u << 16)) ? std::max(1u, std::min(8u, std::thread::hardware_concurrency())) : 1u;
+  std::vector<uint32_t> act_count(n_thr, 0);
+  std::vector<uint8_t> nz_mu(n_thr, 0), nz_oldmu(n_thr, 0);
+  auto worker = [&](unsigned t) {
+    for (size_t s = (size_t)EP * t / n_thr, s1 = (size_t)EP * (t + 1) / n_thr; s < s1; ++s) {
+      recA[s] = make_float4(0.f, i2f(0), u2f(GBP_FLAG_PAD), 0.f);
+      recB[s] = make_float4(0.f, 0.f, u2f(0), u2f(0));
+    }
   };
-  if (any_nonzero(p->mu, (size_t)9 * E)) h->mu_init.assign(p->mu, p->mu + (size_t)9 * E);
-  if (any_nonzero(p->oldmu, (size_t)9 * E)) h->oldmu_init.assign(p->oldmu, p->oldmu + (size_t)9 * E);
+  auto worker2 = [&](unsigned t) {
+    uint32_t n_act = 0;
+    const size_t e0 = (size_t)E * t / n_thr, e1 = (size_t)E * (t + 1) / n_thr;
+    for (size_t e = e0; e < e1; ++e) {
+      const size_t s = h->pos_of_orig[e];
+      const uint32_t act = (h->active_host[e] == 1u) ? 1u : 0u;
+      n_act += act;
+      recA[s] = make_float4(p->damping ? p->damping[e] : 0.f, i2f(p->damping_count ? p->damping_count[e] : -15),
+                            u2f(act ? GBP_FLAG_ACTIVE : 0u), 0.f);
+      recB[s] = make_float4(p->measurements[2 * e], p->measurements[2 * e + 1], u2f(h->lmk_ids[e]),
+                            u2f(lmk_ptr[h->lmk_ids[e]] + h->slot_l[e]));
+      var[s] = p->meas_variances[e];
+    }
+    act_count[t] = n_act;
+    auto any_nonzero = [&](const float* a) -> uint8_t {
+      if (!a) return 0;
+      for (size_t i = 9 * e0; i < 9 * e1; ++i)
+        if (a[i] != 0.f) return 1;
+      return 0;
+    };
+    nz_mu[t] = any_nonzero(p->mu);
+    nz_oldmu[t] = any_nonzero(p->oldmu);
+  };
+  auto run_parallel = [&](auto&& fn) {
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < n_thr; ++t) th.emplace_back(fn, t);
+    fn(0u);
+    for (std::thread& x : th) x.join();
+  };
+  run_parallel(worker);   // padding defaults first (edge slots of different threads interleave)
+  run_parallel(worker2);
+  h->n_active = 0;
+  for (unsigned t = 0; t < n_thr; ++t) h->n_active += act_count[t];
+  if (h->shard) h->n_active = gbp_shard_n_active_global(h->shard);
+  bool any_mu = false, any_oldmu = false;
+  for (unsigned t = 0; t < n_thr; ++t) { any_mu |= nz_mu[t] != 0; any_oldmu |= nz_oldmu[t] != 0; }
+  if (any_mu) h->mu_init.assign(p->mu, p->mu + (size_t)9 * E);
+  if (any_oldmu) h->oldmu_init.assign(p->oldmu, p->oldmu + (size_t)9 * E);
 
+  pt.lap("edge records (host)");
   // ---- device allocation (everything the reference relies on being zero IS zeroed, quirk Q4)
   DeviceGraph& g = h->g;
   std::memset(&g, 0, sizeof(g));
@@ -681,6 +720,7 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
     GBP_CUDA_TRY(cudaMemsetAsync(base, 0, arena_bytes, h->stream));  // ordered before the uploads below
     for (auto& r : arena) *r.first = base + r.second;
   }
+  pt.lap("cudaMalloc + memset");
   cudaStream_t s = h->stream;
 #define U_(dst, src, n) if (!rc) rc = upload(dst, src, (size_t)(n), s)
   U_(g.recA, recA.data(), EP);
@@ -724,6 +764,7 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   GBP_CUDA_TRY(cudaFuncSetAttribute(gbp::k_sweep<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GBP_SWEEP_SMEM));
   GBP_CUDA_TRY(cudaFuncSetAttribute(gbp::k_sweep<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GBP_SWEEP_SMEM));
   GBP_CUDA_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
+  pt.lap("uploads");
   if (h->shard) {
     rc = setup_p2p(h, o->exchange);
     if (rc) return rc;

@@ -979,8 +979,8 @@ __global__ void k_weaken(const DeviceGraph g) {
 
 // ---- metric (ba/util.cpp:74-144) ------------------------------------------------
 // The reference inverts every belief on the host (Eigen, fp32 LU) for the error it prints.  Here
-// the means used ONLY for the metric are solved in double precision (Gaussian elimination with
-// partial pivoting), so the reported error does not carry the fp32 inversion noise of weakly
+// the means used ONLY for the metric are solved in double precision (a register-resident
+// LU of the full matrix), so the reported error does not carry the fp32 inversion noise of weakly
 // constrained variables (a few 1e-3 relative); the sweep itself keeps using the codelets' fp32
 // LDL^T means.  k_metric_prep: one thread per variable; k_metric: one thread per factor.
 struct MetricPartial {
@@ -988,30 +988,45 @@ struct MetricPartial {
   uint32_t n_relins, n_robust, n_active, pad;
 };
 
+// x = A^-1 b in double for a belief precision A (positive definite up to the fp32 rounding of its
+// entries; the FULL matrix is used, like the reference's Eigen inverse, not just one triangle):
+// LU without pivoting, compile-time indices (registers only), forward and backward substitution.
 template <int N>
-GBP_DEV void solve_double(double (&A)[N * N], double (&b)[N], double (&x)[N]) {
-#pragma unroll 1
-  for (int k = 0; k < N; ++k) {
-    int piv = k;
-    double best = fabs(A[k * N + k]);
-    for (int r = k + 1; r < N; ++r)
-      if (fabs(A[r * N + k]) > best) { best = fabs(A[r * N + k]); piv = r; }
-    if (piv != k) {
-      for (int c = 0; c < N; ++c) { const double t = A[k * N + c]; A[k * N + c] = A[piv * N + c]; A[piv * N + c] = t; }
-      const double t = b[k]; b[k] = b[piv]; b[piv] = t;
-    }
-    const double inv = 1.0 / A[k * N + k];
-    for (int r = k + 1; r < N; ++r) {
-      const double f = A[r * N + k] * inv;
-      for (int c = k; c < N; ++c) A[r * N + c] -= f * A[k * N + c];
-      b[r] -= f * b[k];
-    }
-  }
-  for (int k = N - 1; k >= 0; --k) {
-    double acc = b[k];
-    for (int c = k + 1; c < N; ++c) acc -= A[k * N + c] * x[c];
-    x[k] = acc / A[k * N + k];
-  }
+GBP_DEV void solve_double(const double (&A)[N * N], const double (&b)[N], double (&x)[N]) {
+  double M[N * N], y[N];
+#pragma unroll
+  for (int i = 0; i < N * N; ++i) M[i] = A[i];
+  static_for<0, N>([&](auto kc) {  // Doolittle: rows below k are reduced, multipliers stored in place
+    constexpr int k = decltype(kc)::value;
+    const double inv = 1.0 / M[k * N + k];
+    static_for<k + 1, N>([&](auto rc) {
+      constexpr int r = decltype(rc)::value;
+      const double f = M[r * N + k] * inv;
+      M[r * N + k] = f;
+      static_for<k + 1, N>([&](auto cc) {
+        constexpr int c = decltype(cc)::value;
+        M[r * N + c] -= f * M[k * N + c];
+      });
+    });
+  });
+  static_for<0, N>([&](auto ic) {  // L y = b
+    constexpr int i = decltype(ic)::value;
+    double v = b[i];
+    static_for<0, i>([&](auto kc) {
+      constexpr int k = decltype(kc)::value;
+      v -= M[i * N + k] * y[k];
+    });
+    y[i] = v;
+  });
+  static_for<0, N>([&](auto rc) {  // U x = y
+    constexpr int i = N - 1 - decltype(rc)::value;
+    double v = y[i];
+    static_for<i + 1, N>([&](auto kc) {
+      constexpr int k = decltype(kc)::value;
+      v -= M[i * N + k] * x[k];
+    });
+    x[i] = v / M[i * N + i];
+  });
 }
 
 // met_cam: [C][16] doubles = mean 6 | R 9 | pad;  met_lmk: [L][4] doubles = mean 3 | pad
