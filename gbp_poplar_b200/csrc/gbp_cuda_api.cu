@@ -690,6 +690,11 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   A_(h->d_pos_of_orig, E);
   A_(h->d_metric_parts, h->n_tiles);
   A_(h->d_stat_cursor, 1);
+  A_(h->d_exp_lmk_eta, 3 * (size_t)L);   // READ_PROG staging (unpacked landmark beliefs, per-edge scalars in edge order)
+  A_(h->d_exp_lmk_lam, 9 * (size_t)L);
+  A_(h->d_exp_damping, E);
+  A_(h->d_exp_dcount, E);
+  A_(h->d_exp_robust, E);
   A_(h->d_met_cam, 16 * (size_t)C);
   A_(h->d_met_lmk, 4 * (size_t)L);
   A_(h->d_pprior_cam_eta, 6 * (size_t)C);
@@ -894,11 +899,6 @@ int gbp_cuda_free(gbp_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (void* p : h->allocs) cudaFree(p);
   if (h->d_stats) cudaFree(h->d_stats);
-  if (h->d_exp_lmk_eta) cudaFree(h->d_exp_lmk_eta);
-  if (h->d_exp_lmk_lam) cudaFree(h->d_exp_lmk_lam);
-  if (h->d_exp_damping) cudaFree(h->d_exp_damping);
-  if (h->d_exp_dcount) cudaFree(h->d_exp_dcount);
-  if (h->d_exp_robust) cudaFree(h->d_exp_robust);
   for (cudaEvent_t ev : h->prof_events) cudaEventDestroy(ev);
   drop_graphs(h);
   if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);  // the communicator itself stays cached
@@ -1084,10 +1084,6 @@ int gbp_cuda_get_beliefs(gbp_handle* h, float* cam_eta, float* cam_lambda, float
   if (cam_eta) rc = download(cam_eta, h->g.cam_b_eta, 6 * (size_t)h->C, s);
   if (!rc && cam_lambda) rc = download(cam_lambda, h->g.cam_b_lam, 36 * (size_t)h->C, s);
   if (!rc && (lmk_eta || lmk_lambda) && h->L) {
-    if (!h->d_exp_lmk_eta) {
-      rc = dev_alloc(&h->d_exp_lmk_eta, 3 * (size_t)h->L, false);
-      if (!rc) rc = dev_alloc(&h->d_exp_lmk_lam, 9 * (size_t)h->L, false);
-    }
     if (!rc) {
       gbp::k_export_lmk_beliefs<<<(h->L + 255) / 256, 256, 0, s>>>(h->g, h->d_exp_lmk_eta, h->d_exp_lmk_lam);
       h->kernels_launched++;
@@ -1096,11 +1092,6 @@ int gbp_cuda_get_beliefs(gbp_handle* h, float* cam_eta, float* cam_lambda, float
     }
   }
   if (!rc && (damping || damping_count || robust_flag) && h->E) {
-    if (!h->d_exp_damping) {
-      rc = dev_alloc(&h->d_exp_damping, (size_t)h->E, false);
-      if (!rc) rc = dev_alloc(&h->d_exp_dcount, (size_t)h->E, false);
-      if (!rc) rc = dev_alloc(&h->d_exp_robust, (size_t)h->E, false);
-    }
     if (!rc) {
       gbp::k_export_edges<<<(h->E + 255) / 256, 256, 0, s>>>(h->g, h->d_pos_of_orig, h->d_exp_damping,
                                                                h->d_exp_dcount, h->d_exp_robust);
