@@ -7,5 +7,7 @@ timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; pyt
 timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cut -c1-400 gpurun_out/bench_ref.json; tail -3 gpurun_out/bench_ref.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 44 --csv --log-file gpurun_out/launches.csv python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
 grep -E "k_sweep|k_update" gpurun_out/launches.csv | tail -6 | awk -F'","' '{print $5, $NF}' | tr -d '"'
+GBP_CUDA_GRAPH=0 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_stats.csv python scripts/metric_launches.py > /dev/null 2>&1
+grep -E "k_" gpurun_out/launches_stats.csv | tail -5 | awk -F'","' '{print $5, $NF}' | tr -d '"'
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_sweep|k_update_vars" -s 20 -c 2 -f -o gpurun_out/prof_sweep python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out | tail -4
