@@ -156,6 +156,7 @@ int download(T* dst, const T* src, size_t n, cudaStream_t s) {
   return GBP_OK;
 }
 
+inline uint32_t metric_grid(const gbp_handle* h) { return std::min<uint32_t>(h->n_tiles, 8u * (uint32_t)h->num_sms); }
 inline uint32_t lmks_grid(const gbp_handle* h) { return (h->L + GBP_LMK_PER_BLOCK - 1) / GBP_LMK_PER_BLOCK; }
 
 int priors_about_to_change(gbp_handle* h) {
@@ -255,10 +256,11 @@ int launch_metric(gbp_handle* h, gbp::DeviceStats* d_out) {
   if (h->n_tiles) {
     const uint32_t nv = h->C + h->L;
     gbp::k_metric_prep<<<(nv + 127) / 128, 128, 0, h->stream>>>(h->g, h->d_met_cam, h->d_met_lmk);
-    gbp::k_metric<<<h->n_tiles, GBP_TILE, 0, h->stream>>>(h->g, h->n_active, h->d_met_cam, h->d_met_lmk, h->d_metric_parts);
+    gbp::k_metric<<<metric_grid(h), GBP_TILE, 0, h->stream>>>(h->g, h->n_active, h->n_tiles, h->d_met_cam, h->d_met_lmk,
+                                                              h->d_metric_parts);
     h->kernels_launched += 2;
   }
-  gbp::k_metric_finish<<<1, 256, 0, h->stream>>>(h->d_metric_parts, h->n_tiles, d_out, h->shard ? h->d_metric_raw : nullptr,
+  gbp::k_metric_finish<<<1, 256, 0, h->stream>>>(h->d_metric_parts, h->n_tiles ? metric_grid(h) : 0u, d_out, h->shard ? h->d_metric_raw : nullptr,
                                                  h->capturing ? h->d_stat_cursor : nullptr);
   h->kernels_launched++;
   if (h->shard) {  // every rank reports the metric of the WHOLE graph

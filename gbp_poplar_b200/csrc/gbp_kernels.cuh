@@ -1066,40 +1066,43 @@ __global__ void k_metric_prep(const DeviceGraph g, double* __restrict__ met_cam,
   }
 }
 
-__global__ void __launch_bounds__(GBP_TILE) k_metric(const DeviceGraph g, const uint32_t n_active_total,
+// Persistent blocks: block b walks the 128-slot tiles b, b + gridDim.x, ... in order and every thread keeps
+// its own double sums, so the number of partials the finishing block has to add is the (small, fixed) grid size
+// and the summation order is fixed.
+__global__ void __launch_bounds__(GBP_TILE) k_metric(const DeviceGraph g, const uint32_t n_active_total, const uint32_t n_tiles,
                                                     const double* __restrict__ met_cam, const double* __restrict__ met_lmk,
                                                     MetricPartial* __restrict__ out) {
-  __shared__ double s_cam_all[GBP_TILE / 32][16];  // per warp-tile (= one camera): mean 6 | R 9
   __shared__ double s_f[2][GBP_TILE / 32];
   __shared__ uint32_t s_u[3][GBP_TILE / 32];
-  const uint32_t tile = blockIdx.x, tid = threadIdx.x;
-  const size_t e = (size_t)tile * GBP_TILE + tid;
-  const uint32_t c = g.wt_info[e >> 5].x;
-  double* s_cam = s_cam_all[tid >> 5];
-  if ((tid & 31) < 15) s_cam[tid & 31] = met_cam[(size_t)c * 16 + (tid & 31)];
-  __syncthreads();
-  const float4 ra = g.recA[e];
-  const uint32_t flags = __float_as_uint(ra.z);
+  const uint32_t tid = threadIdx.x;
   double nrm = 0.0, sq = 0.0;
   uint32_t relin = 0, robust = 0, act = 0;
-  if (!(flags & GBP_FLAG_PAD)) {
-    robust = (flags & GBP_FLAG_ROBUST) ? 1u : 0u;
-    relin = (__float_as_int(ra.y) == -g.hp.num_undamped_iters) ? 1u : 0u;
-    act = (flags & GBP_FLAG_ACTIVE) ? 1u : 0u;
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const size_t e = (size_t)tile * GBP_TILE + tid;
+    // the three coalesced per-slot loads are independent: issue them together
+    const float4 ra = g.recA[e];
+    const uint32_t eo = g.edge_orig[e];
+    const float4 rb = g.recB[e];
+    const uint32_t cam = g.wt_info[e >> 5].x;
+    const uint32_t flags = __float_as_uint(ra.z);
+    if (flags & GBP_FLAG_PAD) continue;
+    robust += (flags & GBP_FLAG_ROBUST) ? 1u : 0u;
+    relin += (__float_as_int(ra.y) == -g.hp.num_undamped_iters) ? 1u : 0u;
+    act += (flags & GBP_FLAG_ACTIVE) ? 1u : 0u;
     // quirk Q7: the reference evaluates edges [0, n_active) of the ORIGINAL order
-    if (g.edge_orig[e] < n_active_total) {
-      const float4 rb = g.recB[e];
+    if (eo < n_active_total) {
+      const double* cm = met_cam + (size_t)cam * 16;  // mean 6 | R 9 (same address across the warp)
       const double* m = met_lmk + (size_t)__float_as_uint(rb.z) * 4;
       const double m0 = m[0], m1 = m[1], m2 = m[2];
       double y[3];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) y[i] = s_cam[6 + i * 3] * m0 + s_cam[6 + i * 3 + 1] * m1 + s_cam[6 + i * 3 + 2] * m2 + s_cam[i];
+      for (int i = 0; i < 3; ++i) y[i] = cm[6 + i * 3] * m0 + cm[6 + i * 3 + 1] * m1 + cm[6 + i * 3 + 2] * m2 + cm[i];
       const double u = ((double)g.K[0] * y[0] + (double)g.K[2] * y[2]) / y[2];
       const double v = ((double)g.K[1] * y[1] + (double)g.K[3] * y[2]) / y[2];
       const double r0 = (double)rb.x - u, r1 = (double)rb.y - v;
       const double s2 = r0 * r0 + r1 * r1;
-      nrm = sqrt(s2);
-      sq = 0.5 * s2;
+      nrm += sqrt(s2);
+      sq += 0.5 * s2;
     }
   }
 #pragma unroll
@@ -1122,7 +1125,7 @@ __global__ void __launch_bounds__(GBP_TILE) k_metric(const DeviceGraph g, const 
       p.sum_norm += s_f[0][i]; p.sum_sq += s_f[1][i];
       p.n_relins += s_u[0][i]; p.n_robust += s_u[1][i]; p.n_active += s_u[2][i];
     }
-    out[tile] = p;
+    out[blockIdx.x] = p;
   }
 }
 
