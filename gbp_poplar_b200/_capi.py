@@ -143,6 +143,8 @@ CUDA_ONLY_API = {
     "gbp_cuda_version": (C.c_char_p, []),
     "gbp_opts_default": (None, [C.POINTER(GbpOpts)]),
     "gbp_cuda_last_timing": (C.c_int, [C.c_void_p, c_f32p, C.POINTER(C.c_uint64)]),
+    "gbp_cuda_iterate_until": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.POINTER(GbpIterStats),
+                                         C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "gbp_cuda_set_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "gbp_cuda_last_kernel_times": (C.c_int, [C.c_void_p, c_f32p, c_f32p]),
     "gbp_cuda_iterate_async": (C.c_int, [C.c_void_p, C.c_int]),
@@ -174,6 +176,7 @@ HOST_API = {
     "gbp_bal_from_arrays": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, c_f64p, c_u32p, c_u32p, c_f64p, c_f64p,
                                       c_f64p, C.POINTER(C.c_void_p)]),
     "gbp_bal_save": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "gbp_bal_with_means": (C.c_int, [C.c_void_p, c_f32p, c_f32p, c_f32p, c_f32p, C.POINTER(C.c_void_p)]),
     "gbp_bal_free": (None, [C.c_void_p]),
     "gbp_bal_dims": (C.c_int, [C.c_void_p, c_u32p, c_u32p, c_u32p]),
     "gbp_bal_camera_index": (c_u32p, [C.c_void_p]),

@@ -67,6 +67,12 @@ const Flag kFlags[] = {
     {"undamped_start", "arg (=15)", "Number of undamped iterations before damping GBP."},
     {"v", "arg (=0)", "Verbose: print beliefs"},
     {"seed", "arg (=0)", "Seed of the --tn/--rn/--ltn noise (0 = clock, like the reference)"},
+#ifndef GBP_CLI_SLAM
+    {"converge", "arg (=0)",
+     "If > 0: after the prior weakening, stop as soon as the reprojection error improves by less than this (relative) "
+     "over 10 sweeps, or exceeds twice its running minimum; --n_iters is then the maximum"},
+#endif
+    {"out", "arg", "Write the optimised problem (belief means) to this file, in the input format"},
 };
 
 void print_help() {
@@ -101,7 +107,8 @@ T parse_num(const std::string& name, const std::string& v) {
 
 struct Cli {
   gbp_cli_options opt;
-  std::string bal_file;
+  std::string bal_file, out_file;
+  float converge = 0.f;
   bool help = false;
 };
 
@@ -151,6 +158,8 @@ Cli parse(int argc, char** argv) {
     else if (a == "undamped_start") o.iters_before_damping = parse_num<int>(a, val);
     else if (a == "v") o.verbose = parse_bool(a, val);
     else if (a == "seed") o.noise_seed = parse_num<uint32_t>(a, val);
+    else if (a == "converge") c.converge = parse_num<float>(a, val);
+    else if (a == "out") c.out_file = val;
   }
   return c;
 }
@@ -342,7 +351,21 @@ int run(const Cli& cli, Ranks& rk) {
 
   if (!kSlam) {
     out << "Number of iterations: " << options.n_iters << "\n";
-    if (int e = stretch(0, (unsigned)std::max(options.n_iters, 0), 0)) return e;
+    const unsigned n_total = (unsigned)std::max(options.n_iters, 0);
+    if (cli.converge > 0.f && n_total > steps2) {
+      if (int e = stretch(0, steps2, 0)) return e;  // the weakening phase runs as scheduled
+      st.resize(n_total - steps2);
+      int n_done = 0, why = 0;
+      CHECK(gbp_cuda_iterate_until(h, (int)(n_total - steps2), 10, cli.converge, 2.0f, st.data(), &n_done, &why));
+      account(n_done);
+      for (int k = 0; k < n_done; ++k)
+        out << "Iter " << steps2 + k << " // Reprojection error " << st[k].reproj_mean << " // Cost " << st[k].cost
+            << " // n relins: " << st[k].n_relins << " // n robust edges " << st[k].n_robust << "\n";
+      out << "Stopped after " << steps2 + n_done << " iterations: "
+          << (why == GBP_STOP_CONVERGED ? "converged" : why == GBP_STOP_DIVERGED ? "diverging" : "iteration limit") << "\n";
+    } else if (int e = stretch(0, n_total, 0)) {
+      return e;
+    }
   } else {
     const unsigned ibk = (unsigned)std::max(options.iters_between_kfs, 1);
     const unsigned niters = (n_keyframes - 1) * ibk - 1;  // slam.cpp:1013
@@ -376,6 +399,19 @@ int run(const Cli& cli, Ranks& rk) {
     }
   }
   out << "\n Finished GBP.\n";
+  if (!cli.out_file.empty() && rk.world == 1) {
+    std::vector<float> ce(6 * (size_t)n_keyframes), cl(36 * (size_t)n_keyframes), le(3 * (size_t)n_points), ll(9 * (size_t)n_points);
+    CHECK(gbp_cuda_get_beliefs(h, ce.data(), cl.data(), le.data(), ll.data(), nullptr, nullptr, nullptr));
+    gbp_bal* opt = nullptr;
+    CHECK(gbp_bal_with_means(bal, ce.data(), cl.data(), le.data(), ll.data(), &opt));
+    const int wrc = gbp_bal_save(opt, cli.out_file.c_str());
+    gbp_bal_free(opt);
+    if (wrc != GBP_OK) {
+      std::cerr << "ERROR: " << gbp_cuda_last_error() << "\n";
+      return 2;
+    }
+    out << "Optimised problem written to " << cli.out_file << "\n";
+  }
   const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - time0).count();
   if (rk.rank == 0) {
     std::printf("Timing report: wall %.3f s; %llu sweeps, device time in sweeps %.3f ms (%.2f us/sweep, %.1f sweeps/s, "

@@ -1046,6 +1046,51 @@ int gbp_cuda_iterate(gbp_handle* h, int n_sweeps, gbp_iter_stats* stats) {
   return GBP_OK;
 }
 
+int gbp_cuda_iterate_until(gbp_handle* h, int max_sweeps, int check_every, float rel_tol, float diverge_factor,
+                           gbp_iter_stats* stats, int* n_done, int* stop_reason) {
+  if (!h || max_sweeps < 0 || check_every <= 0 || !n_done || !stop_reason) {
+    gbp_set_error("bad gbp_cuda_iterate_until arguments");
+    return GBP_ERR_ARG;
+  }
+  std::vector<gbp_iter_stats> block((size_t)check_every);
+  float run_min = 0.f, ms_total = 0.f;
+  float last_block_end = -1.f;
+  uint64_t kernels = 0;
+  bool have_min = false;
+  int done = 0, reason = GBP_STOP_MAX_SWEEPS;
+  while (done < max_sweeps) {
+    const int m = std::min(check_every, max_sweeps - done);
+    int rc = gbp_cuda_iterate(h, m, block.data());
+    if (rc) return rc;
+    ms_total += h->last_ms;
+    kernels += h->last_kernels;
+    if (stats) std::memcpy(stats + done, block.data(), (size_t)m * sizeof(gbp_iter_stats));
+    done += m;
+    bool diverged = false;
+    for (int i = 0; i < m; ++i) {
+      const float err = block[(size_t)i].reproj_mean;
+      if (!(err == err)) diverged = true;  // NaN
+      if (!have_min || err < run_min) { run_min = err; have_min = true; }
+      if (diverge_factor > 0.f && err > diverge_factor * run_min) diverged = true;
+    }
+    if (diverged) {
+      reason = GBP_STOP_DIVERGED;
+      break;
+    }
+    const float end = block[(size_t)m - 1].reproj_mean;
+    if (m == check_every && last_block_end >= 0.f && last_block_end - end < rel_tol * last_block_end) {
+      reason = GBP_STOP_CONVERGED;
+      break;
+    }
+    last_block_end = end;
+  }
+  h->last_ms = ms_total;
+  h->last_kernels = kernels;
+  *n_done = done;
+  *stop_reason = reason;
+  return GBP_OK;
+}
+
 int gbp_cuda_set_profile(gbp_handle* h, int enabled) {
   if (!h) return GBP_ERR_ARG;
   h->profile = enabled ? 1 : 0;

@@ -318,6 +318,44 @@ int gbp_bal_save(const gbp_bal* b, const char* path) {  // format: sequences/REA
   return GBP_OK;
 }
 
+// A copy of `b` whose camera / point parameters are the means of the given beliefs (mu = Lambda^-1 eta,
+// solved in double with partial pivoting).  What the reference's never-called save_cam_means /
+// save_lmk_means (ba/dataio.cpp:205-255) were meant to give: the optimised problem, here in the INPUT format.
+int gbp_bal_with_means(const gbp_bal* b, const float* cam_eta, const float* cam_lambda, const float* lmk_eta,
+                       const float* lmk_lambda, gbp_bal** out) {
+  if (!b || !cam_eta || !cam_lambda || !lmk_eta || !lmk_lambda || !out) return GBP_ERR_ARG;
+  auto solve = [](int n, const float* lam, const float* eta, double* x) {
+    double A[36], r[6];
+    for (int i = 0; i < n * n; ++i) A[i] = lam[i];
+    for (int i = 0; i < n; ++i) r[i] = eta[i];
+    for (int k = 0; k < n; ++k) {
+      int piv = k;
+      for (int i = k + 1; i < n; ++i)
+        if (std::fabs(A[i * n + k]) > std::fabs(A[piv * n + k])) piv = i;
+      if (piv != k) {
+        for (int c = 0; c < n; ++c) std::swap(A[k * n + c], A[piv * n + c]);
+        std::swap(r[k], r[piv]);
+      }
+      for (int i = k + 1; i < n; ++i) {
+        const double f = A[i * n + k] / A[k * n + k];
+        for (int c = k; c < n; ++c) A[i * n + c] -= f * A[k * n + c];
+        r[i] -= f * r[k];
+      }
+    }
+    for (int k = n - 1; k >= 0; --k) {
+      double acc = r[k];
+      for (int c = k + 1; c < n; ++c) acc -= A[k * n + c] * x[c];
+      x[k] = acc / A[k * n + k];
+    }
+  };
+  gbp_bal* o = new gbp_bal(*b);
+  for (uint32_t c = 0; c < b->C; ++c) solve(6, cam_lambda + (size_t)36 * c, cam_eta + (size_t)6 * c, &o->params[(size_t)6 * c]);
+  for (uint32_t l = 0; l < b->L; ++l)
+    solve(3, lmk_lambda + (size_t)9 * l, lmk_eta + (size_t)3 * l, &o->params[(size_t)6 * b->C + (size_t)3 * l]);
+  *out = o;
+  return GBP_OK;
+}
+
 void gbp_bal_free(gbp_bal* b) { delete b; }
 
 int gbp_bal_dims(const gbp_bal* b, uint32_t* C, uint32_t* L, uint32_t* E) {

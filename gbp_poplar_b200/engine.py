@@ -154,6 +154,16 @@ class GBPEngine:
         self._check(self._f["iterate"](self._h, n_sweeps, None))
         return None
 
+    def iterate_until(self, max_sweeps, check_every=10, rel_tol=1e-4, diverge_factor=2.0):
+        """Sweeps until the mean reprojection error stalls (relative improvement < rel_tol over `check_every`
+        sweeps) or exceeds diverge_factor x its running minimum.  Returns (per-sweep stats, reason) with reason in
+        {"max_sweeps", "converged", "diverged"}."""
+        arr = (GbpIterStats * max(max_sweeps, 1))()
+        n, why = C.c_int(), C.c_int()
+        self._check(self._lib.gbp_cuda_iterate_until(self._h, max_sweeps, check_every, rel_tol, diverge_factor, arr,
+                                                     C.byref(n), C.byref(why)))
+        return [stats_to_dict(arr[i]) for i in range(n.value)], ("max_sweeps", "converged", "diverged")[why.value]
+
     def eval(self):
         s = GbpIterStats()
         self._check(self._f["eval"](self._h, C.byref(s)))

@@ -81,6 +81,14 @@ class BALProblem:
     def save(self, path):
         _check(self._lib.gbp_bal_save(self._h, str(path).encode()), self._lib)
 
+    def with_means(self, beliefs):
+        """The optimised problem: a copy whose parameters are the means of `beliefs` (GBPEngine.get_beliefs())."""
+        f = lambda k: np.ascontiguousarray(beliefs[k], dtype=np.float32).ctypes.data_as(_capi.c_f32p)
+        h = C.c_void_p()
+        _check(self._lib.gbp_bal_with_means(self._h, f("cam_beliefs_eta"), f("cam_beliefs_lambda"), f("lmk_beliefs_eta"),
+                                            f("lmk_beliefs_lambda"), C.byref(h)), self._lib)
+        return BALProblem(h)
+
     @property
     def camera_index(self):
         return _view(self._lib.gbp_bal_camera_index(self._h), self.n_edges, np.uint32, self)

@@ -139,6 +139,21 @@ int gbp_cuda_weaken_priors(gbp_handle* h);
  * n_sweeps entries; entry i is evaluated on the beliefs after sweep i. */
 int gbp_cuda_iterate(gbp_handle* h, int n_sweeps, gbp_iter_stats* stats);
 
+/* Convergence control on top of gbp_cuda_iterate (the reference has none: it runs a
+ * fixed --n_iters and, on fr1desk, past the point where GBP diverges).  Runs at most max_sweeps
+ * sweeps in blocks of `check_every`, evaluating the metric on the device after every sweep, and stops
+ *   - GBP_STOP_CONVERGED: the mean reprojection error improved by less than rel_tol (relative) over the
+ *     last `check_every` sweeps, or
+ *   - GBP_STOP_DIVERGED:  the error exceeded `diverge_factor` x its running minimum (0 disables), or
+ *   - GBP_STOP_MAX_SWEEPS.
+ * Prior weakening is the caller's schedule (call this after the weakening phase).  stats (may be NULL)
+ * receives one entry per executed sweep (capacity max_sweeps); *n_done = executed sweeps. */
+#define GBP_STOP_MAX_SWEEPS 0
+#define GBP_STOP_CONVERGED 1
+#define GBP_STOP_DIVERGED 2
+int gbp_cuda_iterate_until(gbp_handle* h, int max_sweeps, int check_every, float rel_tol, float diverge_factor,
+                           gbp_iter_stats* stats, int* n_done, int* stop_reason);
+
 /* Metrics of the current beliefs (what the host prints as "Initial
  * Reprojection error", ba/ba.cpp:992-996). */
 int gbp_cuda_eval(gbp_handle* h, gbp_iter_stats* out);

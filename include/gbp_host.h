@@ -52,6 +52,11 @@ int gbp_bal_from_arrays(uint32_t C, uint32_t L, uint32_t E, const double intrins
                         const uint32_t* cam_idx, const uint32_t* lmk_idx, const double* observations,
                         const double* cameras, const double* points, gbp_bal** out);
 int gbp_bal_save(const gbp_bal* b, const char* path);
+/* A copy of `b` whose camera / point parameters are the means of the given beliefs (what READ_PROG
+ * returns): the optimised problem in the input format -- the purpose of the reference's never-called
+ * save_cam_means / save_lmk_means (ba/dataio.cpp:205-255). */
+int gbp_bal_with_means(const gbp_bal* b, const float* cam_beliefs_eta, const float* cam_beliefs_lambda,
+                       const float* lmk_beliefs_eta, const float* lmk_beliefs_lambda, gbp_bal** out);
 void gbp_bal_free(gbp_bal* b);
 int gbp_bal_dims(const gbp_bal* b, uint32_t* C, uint32_t* L, uint32_t* E);
 const uint32_t* gbp_bal_camera_index(const gbp_bal* b);

@@ -139,3 +139,22 @@ def test_ba_two_gpus(tmp_path):
     for x, y in zip(a[:8], b[:8]):     # same graph; the summation order differs at boundary landmarks (rounding)
         assert float(x[1]) == pytest.approx(float(y[1]), rel=1e-2)
     assert float(b[-1][1]) < 0.5 * float(b[0][1])
+
+
+@pytest.mark.gpu
+def test_ba_converge_and_out_round_trip(tmp_path):
+    """--converge stops early on the plateau; --out writes the optimised problem in the input format, and
+    loading that file back reproduces the final error as its initial error."""
+    path = write_fixture("fr1xyz", tmp_path)
+    out = os.path.join(str(tmp_path), "optimised.txt")
+    r = run([BA, "--bal_file", path, "--converge", "1e-4", "--out", out])
+    assert r.returncode == 0, r.stderr
+    rows = ITER_RE.findall(r.stdout)
+    m = re.search(r"Stopped after (\d+) iterations: (\w+)", r.stdout)
+    assert m and m.group(2) == "converged" and int(m.group(1)) == len(rows) < 1500
+    final = float(rows[-1][1])
+    assert final < 2.0
+    assert f"Optimised problem written to {out}" in r.stdout
+    r2 = run([BA, "--bal_file", out, "--n_iters", "0"])
+    m2 = re.search(r"Initial Reprojection error: ([-\w.+]+)", r2.stdout)
+    assert float(m2.group(1)) == pytest.approx(final, rel=2e-3)

@@ -385,3 +385,23 @@ def test_config3_fr2robot2_slam_default_700_sweeps_per_keyframe():
     assert stable >= 14
     assert np.allclose(got[:stable], gold[:stable], rtol=1e-4), (got[:stable], gold[:stable])
     assert got[0] == pytest.approx(0.4644, rel=2e-3)      # SURVEY 8c known answer before the first insertion
+
+
+def test_iterate_until_stop_rules():
+    """Convergence control: stalls -> converged; error above twice its running minimum -> diverged."""
+    st = common.make_setup("fr1xyz")
+    ref = GBPEngine(st.problem)
+    gpu = GBPEngine(st.problem)
+    for it in range(10):                      # the weakening phase is the caller's schedule
+        common.ba_schedule_step(ref, it)
+        common.ba_schedule_step(gpu, it)
+    stats, why = gpu.iterate_until(1490, check_every=10, rel_tol=1e-4, diverge_factor=2.0)
+    assert why == "converged" and 100 < len(stats) < 1490 and len(stats) % 10 == 0
+    series = [s["reproj_mean"] for s in ref.iterate(len(stats), stats=True)]
+    assert [s["reproj_mean"] for s in stats] == series                      # same sweeps as plain iterate
+    assert series[-10] - series[-1] < 1e-4 * series[-10] and series[-1] < 2.0
+    # divergence guard: a factor of 0.5 trips as soon as the error is above half of its minimum, i.e. immediately
+    stats, why = gpu.iterate_until(50, check_every=5, rel_tol=0.0, diverge_factor=0.5)
+    assert why == "diverged" and len(stats) == 5
+    stats, why = gpu.iterate_until(7, check_every=5, rel_tol=-1.0, diverge_factor=0.0)
+    assert why == "max_sweeps" and len(stats) == 7
