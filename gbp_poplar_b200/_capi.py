@@ -58,7 +58,8 @@ class GbpOpts(C.Structure):
         ("use_cuda_graph", C.c_int),
         ("store_full_messages", C.c_int),
         ("exchange", C.c_int),
-        ("reserved", C.c_int * 5),
+        ("relin_mode", C.c_int),
+        ("reserved", C.c_int * 4),
     ]
 
 

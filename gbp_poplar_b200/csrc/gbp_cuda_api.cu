@@ -21,6 +21,7 @@
 #include "gbp_kernels.cuh"
 #include "nccl_dyn.h"
 
+
 void gbp_set_error(const std::string& s);  // host_error.cpp
 
 namespace {
@@ -90,12 +91,17 @@ struct gbp_handle {
   int use_graph = 0;
   // CUDA-graph replay of one steady-state sweep (with / without the metric): one launch per sweep
   // instead of 2-5, which is what bounds the small graphs of the reference sequences
-  cudaGraphExec_t sweep_graph[2] = {nullptr, nullptr};
+  cudaGraphExec_t sweep_graph[4] = {nullptr, nullptr, nullptr, nullptr};  // [two_pass * 2 + with_stats]
   DeviceGraph graph_g;               // the kernel arguments the graphs were captured with
   gbp::DeviceStats* graph_stats = nullptr;
   uint32_t graph_n_active = 0;      // k_metric's argument at capture time
   bool capturing = false;
   uint32_t* d_stat_cursor = nullptr;
+  // sweep flavour: 0 = one fused kernel (prep + messages), 1 = prep pass + compacted relinearisation +
+  // message-only kernel.  Bit-identical; chosen from the relinearisation pattern of the last sweeps.
+  int relin_mode = 0;         // gbp_opts.relin_mode: 0 auto, 1 fused, 2 two-pass
+  int two_pass = 0;
+  uint32_t sweeps_since_choice = 0;
   int num_sms = 148;
   // staging for READ_PROG
   uint32_t* d_pos_of_orig = nullptr;
@@ -250,6 +256,27 @@ int launch_sweep(gbp_handle* h) {
   if (MSG) h->p_in_sync = true;
   GBP_CUDA_TRY(cudaGetLastError());
   return GBP_OK;
+}
+
+// PrepMessageVertex of every factor: state-machine pass, then the listed factors relinearise
+int launch_prep(gbp_handle* h) {
+  if (h->n_tiles) {
+    GBP_CUDA_TRY(cudaMemsetAsync(h->g.relin_count, 0, sizeof(uint32_t), h->stream));
+    gbp::k_prep_pass<<<h->n_tiles, GBP_TILE, 0, h->stream>>>(h->g);
+    gbp::k_relin_list<<<(h->E + GBP_TILE - 1) / GBP_TILE, GBP_TILE, 0, h->stream>>>(h->g);
+    h->kernels_launched += 2;
+  }
+  h->pending_shift = true;
+  GBP_CUDA_TRY(cudaGetLastError());
+  return GBP_OK;
+}
+
+// one full sweep of the factors (prep + messages)
+int launch_full_sweep(gbp_handle* h) {
+  if (!h->two_pass) return launch_sweep<true, true>(h);
+  int rc = launch_prep(h);
+  if (!rc) rc = launch_sweep<false, true>(h);
+  return rc;
 }
 
 int launch_metric(gbp_handle* h, gbp::DeviceStats* d_out) {
@@ -692,6 +719,9 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   A_(h->d_pos_of_orig, E);
   A_(h->d_metric_parts, h->n_tiles);
   A_(h->d_stat_cursor, 1);
+  A_(g.relin_list, E);
+  A_(g.relin_count, 1);
+  A_(g.relin_ring, GBP_RELIN_RING + 1);
   A_(h->d_exp_lmk_eta, 3 * (size_t)L);   // READ_PROG staging (unpacked landmark beliefs, per-edge scalars in edge order)
   A_(h->d_exp_lmk_lam, 9 * (size_t)L);
   A_(h->d_exp_damping, E);
@@ -789,6 +819,25 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   return GBP_OK;
 }
 
+// The fused sweep kernel is fastest while relinearisations come in lock step (all factors in one sweep out of
+// ~11, none in between: what the reference's uniform --undamped_start produces on a fresh graph); once they are
+// spread over the sweeps most warps contain a relinearising lane and the compacting two-pass sweep wins (config 4:
+// 171 us either way against 161 / 262 us for the fused kernel).  Decided from the last <= 32 sweeps.
+int choose_sweep_flavour(gbp_handle* h) {
+  if (h->relin_mode == 1) { h->two_pass = 0; return GBP_OK; }
+  if (h->relin_mode == 2) { h->two_pass = 1; return GBP_OK; }
+  uint32_t ring[GBP_RELIN_RING + 1];
+  GBP_CUDA_TRY(cudaMemcpyAsync(ring, h->g.relin_ring, sizeof(ring), cudaMemcpyDeviceToHost, h->stream));
+  GBP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  const uint32_t n = std::min<uint32_t>(ring[GBP_RELIN_RING], GBP_RELIN_RING);  // completed sweeps on record
+  if (n < 8) return GBP_OK;
+  uint32_t busy = 0;
+  for (uint32_t k = 1; k <= n; ++k)  // slot of the sweep counter itself is the (empty) next one
+    if (ring[(ring[GBP_RELIN_RING] - k) % GBP_RELIN_RING] > h->E / 500) busy++;
+  h->two_pass = (busy * 2 > n) ? 1 : 0;
+  return GBP_OK;
+}
+
 void drop_graphs(gbp_handle* h) {
   for (cudaGraphExec_t& e : h->sweep_graph) {
     if (e) cudaGraphExecDestroy(e);
@@ -803,13 +852,13 @@ int sweep_graph(gbp_handle* h, bool with_stats, cudaGraphExec_t* out) {
   if (std::memcmp(&h->graph_g, &h->g, sizeof(DeviceGraph)) != 0 || h->graph_stats != h->d_stats ||
       h->graph_n_active != h->n_active)
     drop_graphs(h);
-  cudaGraphExec_t& exec = h->sweep_graph[with_stats ? 1 : 0];
+  cudaGraphExec_t& exec = h->sweep_graph[(h->two_pass ? 2 : 0) + (with_stats ? 1 : 0)];
   if (!exec) {
     const uint64_t k0 = h->kernels_launched;
     cudaGraph_t graph = nullptr;
     GBP_CUDA_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
     h->capturing = true;
-    int rc = launch_sweep<true, true>(h);
+    int rc = launch_full_sweep(h);
     if (!rc) rc = launch_update_vars(h);
     if (!rc && with_stats) rc = launch_metric(h, h->d_stats);
     h->capturing = false;
@@ -880,6 +929,8 @@ int gbp_cuda_init(const gbp_problem* p, const gbp_opts* o_in, gbp_handle** out) 
   gbp_handle* h = new gbp_handle();
   h->device = o.device;
   h->use_graph = o.use_cuda_graph;
+  h->relin_mode = o.relin_mode;
+  h->two_pass = (o.relin_mode == 2) ? 1 : 0;
   int rc = set_device(h);
   if (!rc && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) rc = GBP_ERR_CUDA;
   if (!rc && cudaEventCreate(&h->ev0) != cudaSuccess) rc = GBP_ERR_CUDA;
@@ -973,7 +1024,7 @@ int gbp_cuda_iterate_async(gbp_handle* h, int n_sweeps) {
   if (!h || n_sweeps < 0) return GBP_ERR_ARG;
   int rc = set_device(h);
   for (int i = 0; i < n_sweeps && !rc; ++i) {
-    rc = launch_sweep<true, true>(h);
+    rc = launch_full_sweep(h);
     if (!rc) rc = launch_update_vars(h);
   }
   return rc;
@@ -1005,7 +1056,7 @@ int gbp_cuda_iterate(gbp_handle* h, int n_sweeps, gbp_iter_stats* stats) {
     cudaGraphExec_t exec = nullptr;
     rc = sweep_graph(h, stats != nullptr, &exec);
     if (rc) return rc;
-    const uint64_t per = stats ? 5 : 2;
+    const uint64_t per = (stats ? 5 : 2) + (h->two_pass ? 2 : 0);
     for (int i = 0; i < n_sweeps; ++i) GBP_CUDA_TRY(cudaGraphLaunch(exec, h->stream));
     h->kernels_launched += per * (uint64_t)n_sweeps;
     h->pending_shift = false;
@@ -1016,7 +1067,7 @@ int gbp_cuda_iterate(gbp_handle* h, int n_sweeps, gbp_iter_stats* stats) {
   }
   for (int i = first; i < n_sweeps && !rc; ++i) {
     if (prof) GBP_CUDA_TRY(cudaEventRecord(h->prof_events[3 * i], h->stream));
-    rc = launch_sweep<true, true>(h);
+    rc = launch_full_sweep(h);
     if (prof) GBP_CUDA_TRY(cudaEventRecord(h->prof_events[3 * i + 1], h->stream));
     if (!rc) rc = launch_update_vars(h);
     if (prof) GBP_CUDA_TRY(cudaEventRecord(h->prof_events[3 * i + 2], h->stream));
@@ -1030,6 +1081,12 @@ int gbp_cuda_iterate(gbp_handle* h, int n_sweeps, gbp_iter_stats* stats) {
   GBP_CUDA_TRY(cudaStreamSynchronize(h->stream));
   GBP_CUDA_TRY(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
   h->last_kernels = h->kernels_launched - k0;
+  h->sweeps_since_choice += (uint32_t)n_sweeps;
+  if (h->sweeps_since_choice >= 16 && h->E) {  // every 16 sweeps: one 132-byte read-back
+    h->sweeps_since_choice = 0;
+    rc = choose_sweep_flavour(h);
+    if (rc) return rc;
+  }
   h->last_ms_factor = h->last_ms_variable = 0.f;
   if (prof) {
     double a = 0, b = 0;
@@ -1225,7 +1282,7 @@ int gbp_cuda_prep_messages(gbp_handle* h) {
   if (!h) return GBP_ERR_ARG;
   int rc = set_device(h);
   if (rc) return rc;
-  return launch_sweep<true, false>(h);
+  return launch_prep(h);
 }
 
 int gbp_cuda_compute_messages(gbp_handle* h) {
@@ -1628,6 +1685,8 @@ int gbp_cuda_init_shard(const gbp_problem* p, const gbp_opts* o_in, uint32_t wor
   gbp_handle* h = new gbp_handle();
   h->device = o.device;
   h->use_graph = o.use_cuda_graph;
+  h->relin_mode = o.relin_mode;
+  h->two_pass = (o.relin_mode == 2) ? 1 : 0;
   h->shard = sh;
   h->world = world;
   h->rank = rank;

@@ -19,6 +19,8 @@
 #include "gbp_layout.h"
 #include "gbp_math.cuh"
 
+#define GBP_RELIN_RING 32  // sweeps of relinearisation history kept on the device
+
 namespace gbp {
 
 struct DeviceGraph {
@@ -72,6 +74,9 @@ struct DeviceGraph {
   uint32_t* p2p_flag;     // this rank's own arrival flags: p2p_flag[r] = last exchange step rank r has delivered
   uint32_t* p2p_done;     // block counter of k_boundary_push
   uint32_t* p2p_error;    // set when a wait for a peer timed out
+  uint32_t* relin_list;   // [E] edge slots that relinearise this sweep (compacted by k_prep_pass)
+  uint32_t* relin_count;  // [1]
+  uint32_t* relin_ring;   // [GBP_RELIN_RING + 1] relinearisations of the last sweeps; [GBP_RELIN_RING] = sweep counter
   float K[4];             // fx fy cx cy
   Hyper hp;
 };
@@ -501,7 +506,13 @@ GBP_DEV void sweep_tile(const DeviceGraph& g, float4* stage, const float* s_cam,
   const bool active = valid && (flags & GBP_FLAG_ACTIVE) != 0;
   const size_t lpos = __float_as_uint(rb.w);  // where this factor's landmark-bound message lives
 
-  if (PREP && active) prep_factor(g, stage, s_cam, e, lane, lb, rb, damping, dcount, flags, dmu);
+  if (PREP) {
+    const int dc_before = dcount;
+    if (active) prep_factor(g, stage, s_cam, e, lane, lb, rb, damping, dcount, flags, dmu);
+    // relinearisations of this sweep (drives the choice between the fused and the two-pass sweep)
+    const uint32_t m = __ballot_sync(0xffffffffu, active && dcount == -g.hp.num_undamped_iters && dc_before != dcount - 1);
+    if (m && lane == 0) atomicAdd(g.relin_ring + (g.relin_ring[GBP_RELIN_RING] % GBP_RELIN_RING), __popc(m));
+  }
 
   float nc[28];   // new f->cam message record: eta 0..5 | lower lambda 6..26 | pad
   float ncu[16];  // its strict upper triangle (row-major, i<j): only summed into the camera partial
@@ -530,7 +541,8 @@ GBP_DEV void sweep_tile(const DeviceGraph& g, float4* stage, const float* s_cam,
       }
     }
   }
-  if (valid && (active || MSG))
+  // the state record only changes in this kernel when prep ran here or the has-message flag toggled
+  if (valid && (PREP ? (active || MSG) : flags != __float_as_uint(ra.z)))
     g.recA[e] = make_float4(damping, __int_as_float(dcount), __uint_as_float(flags), dmu);
 
   if (MSG) {
@@ -607,6 +619,90 @@ __global__ void __launch_bounds__(GBP_SW_WARPS * 32, 1) k_sweep(const DeviceGrap
     buf ^= 1;
   }
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+
+// ---- PrepMessageVertex as its own pass, relinearisation by compaction ---------------------------
+// k_prep_pass runs the damping state machine of every factor (one thread per edge slot; it only
+// needs the 16-byte state record and the means of the two variables) and appends the slots whose
+// factor relinearises this sweep to a list; k_relin_list relinearises exactly those, one thread
+// each.  Whether 3 % of the factors relinearise per sweep (a de-synchronised graph) or all of them
+// in one sweep out of eleven, the heavy path runs in fully populated warps and stays out of the
+// instruction stream of the message kernel.
+__global__ void __launch_bounds__(GBP_TILE) k_prep_pass(const DeviceGraph g) {
+  const uint32_t tid = threadIdx.x, lane = tid & 31;
+  const size_t e = (size_t)blockIdx.x * GBP_TILE + tid;
+  const float4 ra = g.recA[e];
+  float damping = ra.x;
+  int dcount = __float_as_int(ra.y);
+  uint32_t flags = __float_as_uint(ra.z);
+  float dmu = ra.w;
+  const bool active = !(flags & GBP_FLAG_PAD) && (flags & GBP_FLAG_ACTIVE);
+  bool need = false;
+  if (active) {
+    const uint32_t cam = g.wt_info[e >> 5].x;
+    const uint32_t l = __float_as_uint(g.recB[e].z);
+    const float* crec = reinterpret_cast<const float*>(g.cam_rec + (size_t)cam * 16);  // ... | mean 42..47 | previous mean 48..53
+    const float4 lm = g.lmk_b[(size_t)l * GBP_LMKB_QUADS + 3];
+    if (dcount == 0) damping = g.hp.maxeta_damping;  // gbp_codelets.cpp:245-248
+    dcount += 1;
+    float old[9];
+    if (flags & GBP_FLAG_MUVALID) {
+      const float4 lp = g.lmk_mean_prev[l];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) old[i] = crec[48 + i];
+      old[6] = lp.x; old[7] = lp.y; old[8] = lp.z;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) old[i] = g.oldmu_edge ? g.oldmu_edge[(size_t)i * g.E_pad + e] : 0.f;
+    }
+    const float x_l[3] = {lm.x, lm.y, lm.z};
+    float acc = 0.f;  // gbp_codelets.cpp:268-277
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const float d = fs(old[i], crec[42 + i]);
+      acc = fa(acc, fm(d, d));
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const float d = fs(old[6 + i], x_l[i]);
+      acc = fa(acc, fm(d, d));
+    }
+    dmu = __fsqrt_rn(acc);
+    flags |= GBP_FLAG_MUVALID;
+    if (dmu < g.hp.dmu_threshold && dcount > g.hp.min_linear_iters - g.hp.num_undamped_iters) {
+      damping = 0.0f;  // gbp_codelets.cpp:280-283
+      dcount = -g.hp.num_undamped_iters;
+      need = true;
+    }
+    g.recA[e] = make_float4(damping, __int_as_float(dcount), __uint_as_float(flags), dmu);
+  }
+  // warp-aggregated append
+  const uint32_t mask = __ballot_sync(0xffffffffu, need);
+  if (mask) {
+    uint32_t base = 0;
+    if (lane == 0) {
+      base = atomicAdd(g.relin_count, __popc(mask));
+      atomicAdd(g.relin_ring + (g.relin_ring[GBP_RELIN_RING] % GBP_RELIN_RING), __popc(mask));
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (need) g.relin_list[base + __popc(mask & ((1u << lane) - 1u))] = (uint32_t)e;
+  }
+}
+
+__global__ void __launch_bounds__(GBP_TILE) k_relin_list(const DeviceGraph g) {
+  const uint32_t i = blockIdx.x * GBP_TILE + threadIdx.x;
+  if (i >= *g.relin_count) return;
+  const size_t e = g.relin_list[i];
+  const float4 rb = g.recB[e];
+  const uint32_t cam = g.wt_info[e >> 5].x;
+  const float* crec = reinterpret_cast<const float*>(g.cam_rec + (size_t)cam * 16);
+  const float4 lm = g.lmk_b[(size_t)__float_as_uint(rb.z) * GBP_LMKB_QUADS + 3];
+  // accumulate onto the current potential (quirk Q1), Huber re-evaluated (quirk Q2)
+  const uint32_t robust = relinearise_record(g.fac + e, g.E_pad, g.fac + e, g.E_pad, nullptr,
+                                             make_float4(g.K[0], g.K[1], g.K[2], g.K[3]), g.hp.Nstds, rb.x, rb.y, g.var[e], crec[42],
+                                             crec[43], crec[44], crec[45], crec[46], crec[47], lm.x, lm.y, lm.z);
+  uint32_t* fl = reinterpret_cast<uint32_t*>(g.recA + e) + 2;
+  *fl = (*fl & ~GBP_FLAG_ROBUST) | (robust ? GBP_FLAG_ROBUST : 0u);
 }
 
 // Recompute the per-warp camera partial sums from the stored messages (used
@@ -881,6 +977,11 @@ GBP_DEV void boundary_finish(const DeviceGraph& g, const int shift, const uint32
 __global__ void __launch_bounds__(GBP_TILE, 10) k_update_vars(const DeviceGraph g, const int shift, const uint32_t n_push,
                                                              const uint32_t step) {
   const uint32_t nb_lmk = (g.L + GBP_LMK_PER_BLOCK - 1) / GBP_LMK_PER_BLOCK;
+  if (shift && blockIdx.x == 0 && threadIdx.x == 0) {  // a sweep ended: open the next slot of the relinearisation ring
+    const uint32_t next = g.relin_ring[GBP_RELIN_RING] + 1;
+    g.relin_ring[next % GBP_RELIN_RING] = 0;
+    g.relin_ring[GBP_RELIN_RING] = next;
+  }
   uint32_t b = blockIdx.x;
   if (b < n_push) return boundary_push(g, step, b, n_push);
   b -= n_push;

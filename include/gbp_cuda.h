@@ -89,7 +89,11 @@ typedef struct gbp_opts {
   int exchange;               /* multi-GPU boundary exchange: 0 = auto (peer-to-peer stores over NVLink via
                                  CUDA IPC when every rank can map every peer, else NCCL all-gather),
                                  1 = NCCL all-gather, 2 = peer-to-peer or fail                          */
-  int reserved[5];
+  int relin_mode;             /* how a sweep handles the in-loop relinearisation (results are bit-identical):
+                                 1 = one fused kernel; 2 = state-machine pass + compacted relinearisation +
+                                 message-only kernel; 0 (default) = chosen from the pattern of the last sweeps
+                                 (fused while relinearisations come in lock step, two-pass once they are spread) */
+  int reserved[4];
 } gbp_opts;
 
 /* Per-sweep metrics = what the reference's host computes after READ_PROG

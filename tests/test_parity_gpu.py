@@ -405,3 +405,27 @@ def test_iterate_until_stop_rules():
     assert why == "diverged" and len(stats) == 5
     stats, why = gpu.iterate_until(7, check_every=5, rel_tol=-1.0, diverge_factor=0.0)
     assert why == "max_sweeps" and len(stats) == 7
+
+
+def test_fused_and_two_pass_sweeps_are_bit_identical():
+    """gbp_opts.relin_mode: one fused kernel vs state-machine pass + compacted relinearisation + message-only kernel
+    (and the automatic choice between them) give the same bits; fr1xyz relinearises 7-12 % of its factors per sweep."""
+    st, ora, fused = make_pair("fr1xyz")
+    fused.close()
+    engines = [GBPEngine(st.problem, default_opts(relin_mode=m)) for m in (1, 2, 0)]
+    relins = 0
+    for it in range(70):
+        common.ba_schedule_step(ora, it)
+        for e in engines:
+            common.ba_schedule_step(e, it)
+        if it in (17, 18, 19, 20, 40, 69):
+            relins += ora.eval()["n_relins"]
+            for e in engines:
+                assert_bit_identical(e, ora, f"relin_mode sweep {it}")
+    assert relins > 1000
+    # the automatic mode has seen scattered relinearisations for > 32 sweeps: a block of sweeps keeps matching
+    engines[2].iterate(40)
+    engines[0].iterate(40)
+    ora.iterate(40)
+    assert_bit_identical(engines[2], ora, "auto mode, block of sweeps")
+    assert_bit_identical(engines[0], engines[2], "fused vs auto")
