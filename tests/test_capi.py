@@ -87,3 +87,23 @@ def test_plan_shard_partitions_cameras(world):
         if world == 1:
             assert plan.n_boundary_points == 0
     assert prev_end == p.n_keyframes and tot_edges == p.n_edges
+
+
+def test_argument_validation_needs_no_gpu():
+    """Bad arguments are rejected before any CUDA call (same codes with or without a device)."""
+    lib = _capi.load_library()
+    h = C.c_void_p()
+    assert lib.gbp_cuda_init(None, None, C.byref(h)) == -1                      # GBP_ERR_ARG
+    p = _capi.GbpProblem()
+    p.n_edges = 5                                                               # arrays missing
+    assert lib.gbp_cuda_init(C.byref(p), None, C.byref(h)) == -1
+    assert b"null required array" in lib.gbp_cuda_last_error()
+    assert lib.gbp_cuda_free(None) == 0
+    assert lib.gbp_cuda_iterate(None, 1, None) == -1
+    n, why = C.c_int(), C.c_int()
+    assert lib.gbp_cuda_iterate_until(None, 10, 5, 1e-3, 2.0, None, C.byref(n), C.byref(why)) == -1
+    st = common.make_setup("fr2robot2")
+    plan = GbpShardPlan()
+    assert lib.gbp_cuda_plan_shard(C.byref(st.problem), 0, 0, C.byref(plan)) == -1
+    assert lib.gbp_cuda_plan_shard(C.byref(st.problem), 4, 4, C.byref(plan)) == -1
+    assert lib.gbp_cuda_exchange_mode(None) == 0

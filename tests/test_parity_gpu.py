@@ -429,3 +429,33 @@ def test_fused_and_two_pass_sweeps_are_bit_identical():
     ora.iterate(40)
     assert_bit_identical(engines[2], ora, "auto mode, block of sweeps")
     assert_bit_identical(engines[0], engines[2], "fused vs auto")
+
+
+def test_c_abi_error_codes():
+    """Error behaviour of the tensor / program entry points (negative codes + gbp_cuda_last_error text)."""
+    import ctypes as C
+    from gbp_poplar_b200 import _capi
+    lib = _capi.load_library()
+    st = common.make_setup("fr2robot2")
+    gpu = GBPEngine(st.problem)
+    n = C.c_size_t()
+    assert lib.gbp_cuda_tensor_nbytes(gpu.handle, b"no_such_tensor", C.byref(n)) == -3          # GBP_ERR_NAME
+    assert b"no_such_tensor" in lib.gbp_cuda_last_error()
+    buf = np.zeros(7, np.float32)
+    assert lib.gbp_cuda_get_tensor(gpu.handle, b"damping", buf.ctypes.data_as(C.c_void_p), buf.nbytes) == -4   # GBP_ERR_SIZE
+    assert lib.gbp_cuda_set_tensor(gpu.handle, b"damping", buf.ctypes.data_as(C.c_void_p), buf.nbytes) == -4
+    assert lib.gbp_cuda_iterate(gpu.handle, -1, None) == -1                                     # GBP_ERR_ARG
+    bad = default_opts(device=99)
+    with pytest.raises(RuntimeError, match="device ordinal out of range"):
+        GBPEngine(st.problem, bad)
+    ids = np.array(st.array("cam_ids")).copy()
+    ids[0] = 10 ** 6                                                                            # edge refers to a missing camera
+    from gbp_poplar_b200.host import problem_from_arrays
+    arrays = {k: np.array(st.array(k)) for k in ("lmk_ids", "measurements", "meas_variances", "cam_priors_eta",
+                                                 "cam_priors_lambda", "lmk_priors_eta", "lmk_priors_lambda", "cam_scaling",
+                                                 "lmk_scaling", "cam_weaken_flag", "lmk_weaken_flag")}
+    arrays["cam_ids"] = ids
+    with pytest.raises(RuntimeError, match="edge index out of range"):
+        GBPEngine(problem_from_arrays(arrays, st.K))
+    gpu.iterate(2)                                                                              # the good handle is unaffected
+    assert np.isfinite(gpu.eval()["reproj_mean"])
