@@ -487,6 +487,10 @@ GBP_DEV void prep_factor(const DeviceGraph& g, float4* stage, const float* s_cam
                                                make_float4(g.K[0], g.K[1], g.K[2], g.K[3]), g.hp.Nstds, rb.x, rb.y, g.var[e],
                                                x_kf[0], x_kf[1], x_kf[2], x_kf[3], x_kf[4], x_kf[5], x_l[0], x_l[1], x_l[2]);
     flags = (flags & ~GBP_FLAG_ROBUST) | (robust ? GBP_FLAG_ROBUST : 0u);
+    // relinearisations of this sweep, one atomic per warp that has any (drives the choice between the
+    // fused and the two-pass sweep); costs nothing on the common path
+    const uint32_t m = __activemask();
+    if (lane == (uint32_t)__ffs(m) - 1u) atomicAdd(g.relin_ring + (g.relin_ring[GBP_RELIN_RING] % GBP_RELIN_RING), __popc(m));
   }
 }
 
@@ -506,13 +510,7 @@ GBP_DEV void sweep_tile(const DeviceGraph& g, float4* stage, const float* s_cam,
   const bool active = valid && (flags & GBP_FLAG_ACTIVE) != 0;
   const size_t lpos = __float_as_uint(rb.w);  // where this factor's landmark-bound message lives
 
-  if (PREP) {
-    const int dc_before = dcount;
-    if (active) prep_factor(g, stage, s_cam, e, lane, lb, rb, damping, dcount, flags, dmu);
-    // relinearisations of this sweep (drives the choice between the fused and the two-pass sweep)
-    const uint32_t m = __ballot_sync(0xffffffffu, active && dcount == -g.hp.num_undamped_iters && dc_before != dcount - 1);
-    if (m && lane == 0) atomicAdd(g.relin_ring + (g.relin_ring[GBP_RELIN_RING] % GBP_RELIN_RING), __popc(m));
-  }
+  if (PREP && active) prep_factor(g, stage, s_cam, e, lane, lb, rb, damping, dcount, flags, dmu);
 
   float nc[28];   // new f->cam message record: eta 0..5 | lower lambda 6..26 | pad
   float ncu[16];  // its strict upper triangle (row-major, i<j): only summed into the camera partial
