@@ -312,7 +312,7 @@ def main():
                                       f"{exchange_mode} ({n_boundary} boundary landmarks, {48 * n_boundary} B per rank and peer)"
                        if world > 1 else "single",
                        "rank0_shard": {"cameras": C_loc, "landmarks": L_loc, "factors": E_loc},
-                       "cache": "per-sweep working set ~0.75 GB >> 126 MB L2 (no flush needed)",
+                       "cache": "per-sweep working set ~0.65 GB per GPU >> 126 MB L2 (no flush needed)",
                        "preroll": f"{BA_PREROLL} sweeps of the ba.cpp schedule incl. prior weakening, untimed",
                        "init_s": init_s},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
