@@ -18,6 +18,13 @@ COMMON_FLAGS = ["help", "bal_file", "profile", "ipus", "camspertile", "tn", "rn"
                 "reproj_meas_var", "prior_std_weaker_factor", "first_cam_prior_std", "steps", "undamped_start", "v"]
 
 
+@pytest.fixture(scope="module", autouse=True)
+def _built_tools():
+    """The tools are build artefacts (gbp_poplar_b200/bin/, not in git): build them on demand."""
+    if not (os.path.exists(BA) and os.path.exists(SLAM)):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "gbp_poplar_b200", "csrc"), "ba", "slam"])
+
+
 def run(cmd, **kw):
     return subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600, **kw)
 
