@@ -134,7 +134,6 @@ struct gbp_handle {
   int p2p = 0;                      // 1 = boundary partials are pushed straight into the peers' buffers
   void* p2p_block = nullptr;        // this rank's exported block
   std::vector<void*> p2p_peers;     // the other ranks' blocks, mapped (nullptr for this rank)
-  uint32_t xstep = 0;               // exchange step counter (same sequence on every rank)
   double* d_metric_raw = nullptr;   // [8]         this rank's metric sums
   double* d_metric_all = nullptr;   // [world][8]  all-gathered
   uint64_t exchanges = 0;
@@ -209,8 +208,7 @@ int launch_update_vars(gbp_handle* h) {
     // one launch: the first blocks form the partial sums and push them into every rank's receive buffer
     // over NVLink, the last blocks finish the boundary landmarks once every rank's flag has arrived
     const uint32_t n_x = std::max((h->g.n_bnd_local + GBP_LMK_PER_BLOCK - 1) / GBP_LMK_PER_BLOCK, 1u);
-    h->xstep++;
-    gbp::k_update_vars<<<n_x + h->C + grid + n_x, GBP_TILE, 0, h->stream>>>(h->g, shift, n_x, h->xstep);
+    gbp::k_update_vars<<<n_x + h->C + grid + n_x, GBP_TILE, 0, h->stream>>>(h->g, shift, n_x);
     h->kernels_launched++;
     h->exchanges++;
   } else {
@@ -227,7 +225,7 @@ int launch_update_vars(gbp_handle* h) {
       h->exchanges++;
     }
     if (grid + h->C) {
-      gbp::k_update_vars<<<grid + h->C, GBP_TILE, 0, h->stream>>>(h->g, shift, 0u, 0u);
+      gbp::k_update_vars<<<grid + h->C, GBP_TILE, 0, h->stream>>>(h->g, shift, 0u);
       h->kernels_launched++;
     }
     if (exchange) {
@@ -746,6 +744,7 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
     A_(g.bnd_slot, nbl);
     A_(g.bnd_send, 3 * (size_t)g.n_bnd_global);
     reserve((void**)&g.bnd_recv, 3 * (size_t)g.n_bnd_global * h->world * sizeof(float4));
+    A_(g.p2p_step, 2);
     A_(h->d_metric_raw, 8);
     A_(h->d_metric_all, 8 * (size_t)h->world);
   }
@@ -1050,7 +1049,10 @@ int gbp_cuda_iterate(gbp_handle* h, int n_sweeps, gbp_iter_stats* stats) {
   // steady state on one GPU: replay the captured sweep (the very first sweep after a belief update without a
   // preceding prep has shift = 0 and goes through the plain launches, as do profiling and sharded handles)
   int first = 0;
-  if (h->use_graph && !prof && !h->shard && n_sweeps > 0 && h->n_tiles) {
+  // (a sharded handle qualifies when its exchange is the fused peer-to-peer one and no metric -- an NCCL
+  // all-gather on the communication stream -- is requested)
+  const bool graph_ok = !h->shard || (h->p2p && !stats) || h->g.n_bnd_global == 0;
+  if (h->use_graph && !prof && graph_ok && !(h->shard && stats) && n_sweeps > 0 && h->n_tiles) {
     GBP_CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
     if (stats) GBP_CUDA_TRY(cudaMemsetAsync(h->d_stat_cursor, 0, sizeof(uint32_t), h->stream));
     cudaGraphExec_t exec = nullptr;

@@ -74,6 +74,7 @@ struct DeviceGraph {
   uint32_t* p2p_flag;     // this rank's own arrival flags: p2p_flag[r] = last exchange step rank r has delivered
   uint32_t* p2p_done;     // block counter of k_boundary_push
   uint32_t* p2p_error;    // set when a wait for a peer timed out
+  uint32_t* p2p_step;     // [2] {completed exchange steps, blocks of the current k_update_vars that are done}
   uint32_t* relin_list;   // [E] edge slots that relinearise this sweep (compacted by k_prep_pass)
   uint32_t* relin_count;  // [1]
   uint32_t* relin_ring;   // [GBP_RELIN_RING + 1] relinearisations of the last sweeps; [GBP_RELIN_RING] = sweep counter
@@ -972,21 +973,34 @@ GBP_DEV void boundary_finish(const DeviceGraph& g, const int shift, const uint32
 //   landmark blocks   -- GBP_LMK_PER_BLOCK landmarks each
 //   [multi-GPU, peer-to-peer] boundary_finish blocks -- last; every block they wait for was dispatched before them
 // The register budget (10 blocks per SM) fits all paths.  n_push == 0: no fused exchange.
-__global__ void __launch_bounds__(GBP_TILE, 10) k_update_vars(const DeviceGraph g, const int shift, const uint32_t n_push,
-                                                             const uint32_t step) {
+__global__ void __launch_bounds__(GBP_TILE, 10) k_update_vars(const DeviceGraph g, const int shift, const uint32_t n_push) {
   const uint32_t nb_lmk = (g.L + GBP_LMK_PER_BLOCK - 1) / GBP_LMK_PER_BLOCK;
   if (shift && blockIdx.x == 0 && threadIdx.x == 0) {  // a sweep ended: open the next slot of the relinearisation ring
     const uint32_t next = g.relin_ring[GBP_RELIN_RING] + 1;
     g.relin_ring[next % GBP_RELIN_RING] = 0;
     g.relin_ring[GBP_RELIN_RING] = next;
   }
+  // The exchange step lives on the device (the same sequence on every rank), so the launch has no
+  // per-sweep argument and can be replayed from a CUDA graph: every block reads it, the last block
+  // of the grid to finish advances it.
+  const uint32_t step = n_push ? g.p2p_step[0] + 1u : 0u;
   uint32_t b = blockIdx.x;
-  if (b < n_push) return boundary_push(g, step, b, n_push);
-  b -= n_push;
-  if (b < g.C) return update_camera(g, shift, b);
-  b -= g.C;
-  if (b < nb_lmk) return update_landmarks(g, shift, b);
-  boundary_finish(g, shift, step, b - nb_lmk);
+  if (b < n_push) {
+    boundary_push(g, step, b, n_push);
+  } else if ((b -= n_push) < g.C) {
+    update_camera(g, shift, b);
+  } else if ((b -= g.C) < nb_lmk) {
+    update_landmarks(g, shift, b);
+  } else {
+    boundary_finish(g, shift, step, b - nb_lmk);
+  }
+  if (n_push) {
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(g.p2p_step + 1, 1u) == gridDim.x - 1) {
+      g.p2p_step[1] = 0u;
+      g.p2p_step[0] = step;
+    }
+  }
 }
 
 // ---- multi-GPU boundary landmarks, NCCL all-gather path (fallback when CUDA IPC is unavailable) ----
