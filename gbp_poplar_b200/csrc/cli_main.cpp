@@ -71,6 +71,10 @@ const Flag kFlags[] = {
     {"converge", "arg (=0)",
      "If > 0: after the prior weakening, stop as soon as the reprojection error improves by less than this (relative) "
      "over 10 sweeps, or exceeds twice its running minimum; --n_iters is then the maximum"},
+#else
+    {"host_keyframes", "arg (=0)",
+     "bool: insert keyframes through the reference's READ_PRIORS / host / NEW_KEYFRAME round trip instead of on the "
+     "device (same result bit for bit)"},
 #endif
     {"out", "arg", "Write the optimised problem (belief means) to this file, in the input format"},
 };
@@ -109,6 +113,7 @@ struct Cli {
   gbp_cli_options opt;
   std::string bal_file, out_file;
   float converge = 0.f;
+  bool host_keyframes = false;
   bool help = false;
 };
 
@@ -159,6 +164,7 @@ Cli parse(int argc, char** argv) {
     else if (a == "v") o.verbose = parse_bool(a, val);
     else if (a == "seed") o.noise_seed = parse_num<uint32_t>(a, val);
     else if (a == "converge") c.converge = parse_num<float>(a, val);
+    else if (a == "host_keyframes") c.host_keyframes = parse_bool(a, val);
     else if (a == "out") c.out_file = val;
   }
   return c;
@@ -278,6 +284,8 @@ int run(const Cli& cli, Ranks& rk) {
   o.device = rk.rank;
   gbp_handle* h = nullptr;
   const auto time0 = std::chrono::steady_clock::now();
+  double kf_seconds = 0.0;
+  unsigned kf_inserted = 0;
   out << "Running program to stream initial data to GPU\n";
   const int rc = (rk.world > 1) ? gbp_cuda_init_shard(p, &o, (uint32_t)rk.world, (uint32_t)rk.rank, rk.nccl_id, &h)
                                 : gbp_cuda_init(p, &o, &h);
@@ -378,18 +386,26 @@ int run(const Cli& cli, Ranks& rk) {
     while (i < niters) {
       if ((i + 1) % ibk == 0) {  // slam.cpp:1020-1046
         int n_new = 0;
-        CHECK(gbp_cuda_get_beliefs(h, cbe.data(), cbl.data(), nullptr, nullptr, nullptr, nullptr, nullptr));
-        CHECK(gbp_cuda_get_priors(h, cpe.data(), cpl.data(), lpe.data(), lpl.data()));  // READ_PRIORS
-        CHECK(gbp_setup_next_keyframe(setup, cbe.data(), cbl.data(), cpe.data(), cpl.data(), lpe.data(), lpl.data(),
-                                      dcount.data(), &n_new));
-        data_counter = (unsigned)gbp_setup_data_counter(setup);
+        const auto t_kf = std::chrono::steady_clock::now();
+        if (cli.host_keyframes) {
+          CHECK(gbp_cuda_get_beliefs(h, cbe.data(), cbl.data(), nullptr, nullptr, nullptr, nullptr, nullptr));
+          CHECK(gbp_cuda_get_priors(h, cpe.data(), cpl.data(), lpe.data(), lpl.data()));  // READ_PRIORS
+          CHECK(gbp_setup_next_keyframe(setup, cbe.data(), cbl.data(), cpe.data(), cpl.data(), lpe.data(), lpl.data(),
+                                        dcount.data(), &n_new));
+          data_counter = (unsigned)gbp_setup_data_counter(setup);
+          const gbp_problem* q = gbp_setup_problem(setup);
+          CHECK(gbp_cuda_add_keyframe(h, dcount.data(), cpe.data(), cpl.data(), lpe.data(), lpl.data(), q->active_flag,
+                                      q->cam_weaken_flag, q->lmk_weaken_flag));  // NEW_KEYFRAME
+        } else {  // the same insertion where the data lives: 4 bytes cross the bus
+          data_counter += 1;
+          CHECK(gbp_cuda_add_keyframe_device(h, data_counter + 1, (uint32_t)cli.opt.steps, &n_new));
+        }
+        kf_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_kf).count();
+        kf_inserted += 1;
         out << "\n**********************************************************";
         out << "\n Adding keyframe " << data_counter + 1;
         out << "\n Adding " << n_new << " new landmarks";
         out << "\n**********************************************************\n\n";
-        const gbp_problem* q = gbp_setup_problem(setup);
-        CHECK(gbp_cuda_add_keyframe(h, dcount.data(), cpe.data(), cpl.data(), lpe.data(), lpl.data(), q->active_flag,
-                                    q->cam_weaken_flag, q->lmk_weaken_flag));  // NEW_KEYFRAME
       }
       // sweeps up to (not including) the next insertion point
       const unsigned next = ((i + 1) % ibk == 0) ? i + ibk : (i / ibk + 1) * ibk - 1;
@@ -419,6 +435,9 @@ int run(const Cli& cli, Ranks& rk) {
                 wall, (unsigned long long)sweeps, device_ms, sweeps ? 1e3 * device_ms / sweeps : 0.0,
                 device_ms > 0 ? 1e3 * sweeps / device_ms : 0.0, device_ms > 0 ? 1e3 * (double)n_edges * sweeps / device_ms : 0.0,
                 (unsigned long long)launches);
+    if (kf_inserted)
+      std::printf("Keyframe insertions: %u, %.3f ms each (%s)\n", kf_inserted, 1e3 * kf_seconds / kf_inserted,
+                  cli.host_keyframes ? "READ_PRIORS / host / NEW_KEYFRAME round trip" : "on the device");
     if (options.profile) {
       const char* log_dir = std::getenv("GC_PROFILE_LOG_DIR");  // same variable as the reference (ba.cpp:1062)
       const std::string path = std::string(log_dir ? log_dir : ".") + "/gbp_profile.json";

@@ -105,6 +105,11 @@ struct gbp_handle {
   int num_sms = 148;
   // staging for READ_PROG
   uint32_t* d_pos_of_orig = nullptr;
+  // device-side keyframe insertion (gbp_cuda_add_keyframe_device)
+  uint32_t* d_lmk_first_cam = nullptr;      // [L] lowest camera index observing the landmark (0xffffffff: none)
+  float* d_kf_scratch = nullptr;            // [4] see k_kf_pose
+  std::vector<uint32_t> new_lmks_at_cam;    // [C] landmarks first observed by each camera
+  std::vector<uint32_t> cam_degree;         // [C]
   float* d_exp_lmk_eta = nullptr;
   float* d_exp_lmk_lam = nullptr;
   float* d_exp_damping = nullptr;
@@ -715,6 +720,8 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   A_(g.lmk_wflag, L);
   A_(g.lmk_ptr, L + 1);
   A_(h->d_pos_of_orig, E);
+  A_(h->d_lmk_first_cam, L);
+  A_(h->d_kf_scratch, 4);
   A_(h->d_metric_parts, h->n_tiles);
   A_(h->d_stat_cursor, 1);
   A_(g.relin_list, E);
@@ -773,6 +780,15 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   U_(g.lmk_ptr, lmk_ptr.data(), L + 1);
   U_(g.var, var.data(), EP);
   U_(h->d_pos_of_orig, h->pos_of_orig.data(), E);
+  {
+    std::vector<uint32_t> first_cam(L, 0xffffffffu);
+    for (uint32_t e = 0; e < E; ++e) first_cam[h->lmk_ids[e]] = std::min(first_cam[h->lmk_ids[e]], h->cam_ids[e]);
+    h->new_lmks_at_cam.assign(C, 0u);
+    for (uint32_t l = 0; l < L; ++l)
+      if (first_cam[l] != 0xffffffffu) h->new_lmks_at_cam[first_cam[l]]++;
+    h->cam_degree = deg_c;
+    U_(h->d_lmk_first_cam, first_cam.data(), L);
+  }
   if (h->shard) {
     U_(g.lmk_bslot, lmk_bslot.data(), L);
     U_(g.bnd_local, gbp_shard_boundary_local(h->shard), g.n_bnd_local);
@@ -1265,6 +1281,48 @@ int gbp_cuda_add_keyframe(gbp_handle* h, const int32_t* damping_count, const flo
   if (!rc) rc = launch_update_vars(h);  // prog_ub at the end of NEW_KEYFRAME (slam.cpp:928)
   if (rc) return rc;
   GBP_CUDA_TRY(cudaStreamSynchronize(s));
+  return GBP_OK;
+}
+
+int gbp_cuda_add_keyframe_device(gbp_handle* h, uint32_t new_cam, uint32_t steps, int* n_new_lmks) {
+  if (!h) return GBP_ERR_ARG;
+  if (h->shard) {
+    gbp_set_error("add_keyframe (incremental SLAM) is single-GPU only");
+    return GBP_ERR_ARG;
+  }
+  if (new_cam < 1 || new_cam >= h->C) {
+    gbp_set_error("add_keyframe_device: keyframe index out of range");
+    return GBP_ERR_ARG;
+  }
+  int rc = set_device(h);
+  if (rc) return rc;
+  cudaStream_t s = h->stream;
+  rc = priors_about_to_change(h);
+  if (rc) return rc;
+  gbp::k_kf_pose<<<1, 32, 0, s>>>(h->g, new_cam, h->d_kf_scratch);
+  const uint32_t n = std::max(std::max(h->E_pad, h->L), h->C);
+  gbp::k_kf_apply<<<(n + GBP_TILE - 1) / GBP_TILE, GBP_TILE, 0, s>>>(h->g, new_cam, steps, -15, h->d_lmk_first_cam,
+                                                                    h->d_kf_scratch);
+  h->kernels_launched += 2;
+  GBP_CUDA_TRY(cudaGetLastError());
+  rc = launch_update_vars(h);  // prog_ub at the end of NEW_KEYFRAME (slam.cpp:928)
+  if (rc) return rc;
+  uint32_t status = 0;
+  GBP_CUDA_TRY(cudaMemcpyAsync(&status, h->d_kf_scratch + 3, sizeof(status), cudaMemcpyDeviceToHost, s));
+  GBP_CUDA_TRY(cudaStreamSynchronize(s));
+  if (status) {
+    gbp_set_error("singular belief of the previous keyframe");
+    return GBP_ERR_ARG;
+  }
+  // host mirrors of the flags (get_tensor("active_flag"), the metric's active-edge count)
+  uint32_t newly = 0;
+  for (uint32_t e = 0; e < h->E; ++e)
+    if (h->cam_ids[e] == new_cam && h->active_host[e] != 1u) {
+      h->active_host[e] = 1u;
+      ++newly;
+    }
+  h->n_active += newly;
+  if (n_new_lmks) *n_new_lmks = (int)h->new_lmks_at_cam[new_cam];
   return GBP_OK;
 }
 

@@ -1090,6 +1090,123 @@ __global__ void k_weaken(const DeviceGraph g) {
   }
 }
 
+// ---- SLAM keyframe insertion on the device (ba/slam.cpp:1020-1046) ---------------------
+// The reference reads the camera beliefs and all priors back (READ_PROG / READ_PRIORS), runs
+// update_flags (ba/dataio.cpp:477-508) and initialise_new_kf (ba/util.cpp:183-223) on the host and
+// streams priors, flags and damping counts in again (NEW_KEYFRAME).  Here the same arithmetic runs
+// where the data lives.  k_kf_pose: one thread -- mean of the previous keyframe (double-precision
+// LU with partial pivoting, the host restatement's solve_small), prior eta of the new keyframe,
+// and the world point 1 m in front of the previous keyframe (prior mean of the new landmarks).
+// kf_scratch: {pw.x, pw.y, pw.z, status bits (1 = singular belief)}.
+__global__ void k_kf_pose(const DeviceGraph g, const uint32_t new_cam, float* __restrict__ kf_scratch) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const uint32_t prev = new_cam - 1;
+  double A[36], b[6], x[6];
+  for (int i = 0; i < 36; ++i) A[i] = (double)g.cam_b_lam[(size_t)prev * 36 + i];
+  for (int i = 0; i < 6; ++i) b[i] = (double)g.cam_b_eta[(size_t)prev * 6 + i];
+  bool singular = false;
+  for (int k = 0; k < 6 && !singular; ++k) {
+    int p = k;
+    for (int i = k + 1; i < 6; ++i)
+      if (fabs(A[i * 6 + k]) > fabs(A[p * 6 + k])) p = i;
+    if (A[p * 6 + k] == 0.0) {
+      singular = true;
+      break;
+    }
+    if (p != k) {
+      for (int j = 0; j < 6; ++j) {
+        const double t = A[k * 6 + j];
+        A[k * 6 + j] = A[p * 6 + j];
+        A[p * 6 + j] = t;
+      }
+      const double t = b[k];
+      b[k] = b[p];
+      b[p] = t;
+    }
+    for (int i = k + 1; i < 6; ++i) {
+      const double f = __ddiv_rn(A[i * 6 + k], A[k * 6 + k]);
+      for (int j = k; j < 6; ++j) A[i * 6 + j] = __dsub_rn(A[i * 6 + j], __dmul_rn(f, A[k * 6 + j]));
+      b[i] = __dsub_rn(b[i], __dmul_rn(f, b[k]));
+    }
+  }
+  if (singular) {
+    kf_scratch[3] = __uint_as_float(1u);
+    return;
+  }
+  for (int i = 5; i >= 0; --i) {
+    double s = b[i];
+    for (int j = i + 1; j < 6; ++j) s = __dsub_rn(s, __dmul_rn(A[i * 6 + j], x[j]));
+    x[i] = __ddiv_rn(s, A[i * 6 + i]);
+  }
+  float mu[6];
+  for (int i = 0; i < 6; ++i) mu[i] = (float)x[i];
+  // eta of the new keyframe's prior = its (current) prior Lambda times the previous keyframe's mean
+  const float* lam_new = g.cam_prior_lam + (size_t)new_cam * 36;
+  for (int i = 0; i < 6; ++i) {
+    float v = 0.f;
+    for (int j = 0; j < 6; ++j) v = fa(v, fm(lam_new[i * 6 + j], mu[j]));
+    g.cam_prior_eta[(size_t)new_cam * 6 + i] = v;
+  }
+  // point 1 m in front of the previous keyframe: R(w)^T ([0 0 1] - t), R in the term order of
+  // ba/util.cpp:20-32 (sin/cos in double, rounded once)
+  float R[9];
+  for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.f : 0.f;
+  const float w[3] = {mu[3], mu[4], mu[5]};
+  const float theta = __fsqrt_rn(fa(fa(fm(w[0], w[0]), fm(w[1], w[1])), fm(w[2], w[2])));
+  if (!((double)theta < 1e-6)) {
+    const float H[9] = {0.f, -w[2], w[1], w[2], 0.f, -w[0], -w[1], w[0], 0.f};
+    const float sn = (float)sin((double)theta), cs = (float)cos((double)theta);
+    const float a = fd(sn, theta), bb = fd(fs(1.f, cs), fm(theta, theta));
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        float h2 = 0.f;
+        for (int k = 0; k < 3; ++k) h2 = fa(h2, fm(H[i * 3 + k], H[k * 3 + j]));
+        R[i * 3 + j] = fa(R[i * 3 + j], fa(fm(a, H[i * 3 + j]), fm(bb, h2)));
+      }
+  }
+  const float d[3] = {fs(0.f, mu[0]), fs(0.f, mu[1]), fs(1.f, mu[2])};
+  for (int i = 0; i < 3; ++i) kf_scratch[i] = fa(fa(fm(R[i], d[0]), fm(R[3 + i], d[1])), fm(R[6 + i], d[2]));
+  kf_scratch[3] = __uint_as_float(0u);
+}
+
+// k_kf_apply: thread i handles edge slot i (activate the factors of the new keyframe, reset every
+// damping count: ba/slam.cpp:1039-1041, quirk Q10), landmark i (weaken flag = steps for the
+// landmarks this keyframe observes first, 0 otherwise; their prior eta = prior Lambda x the point in
+// front of the previous keyframe -- quirk Q6, intended semantics: the test is `flag == 5` whatever
+// `steps` is, ba/util.cpp:214) and camera i (weaken flag).
+__global__ void __launch_bounds__(GBP_TILE) k_kf_apply(const DeviceGraph g, const uint32_t new_cam, const uint32_t steps,
+                                                       const int dcount_reset, const uint32_t* __restrict__ lmk_first_cam,
+                                                       const float* __restrict__ kf_scratch) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (__float_as_uint(kf_scratch[3]) != 0u) return;  // singular belief: leave the state untouched
+  if (i < g.E_pad) {
+    float4 ra = g.recA[i];
+    uint32_t flags = __float_as_uint(ra.z);
+    if (!(flags & GBP_FLAG_PAD)) {
+      if (g.wt_info[i >> 5].x == new_cam) flags |= GBP_FLAG_ACTIVE;
+      ra.y = __int_as_float(dcount_reset);
+      ra.z = __uint_as_float(flags);
+      g.recA[i] = ra;
+    }
+  }
+  if (i < g.L) {
+    const uint32_t fl = (lmk_first_cam[i] == new_cam) ? steps : 0u;
+    g.lmk_wflag[i] = fl;
+    if (fl == 5u) {
+      const float pw[3] = {kf_scratch[0], kf_scratch[1], kf_scratch[2]};
+      float4* p = g.lmk_prior + (size_t)i * 3;
+      float4 q0 = p[0];
+      const float4 q1 = p[1], q2 = p[2];
+      const float lam[9] = {q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+      q0.x = fa(fa(fm(lam[0], pw[0]), fm(lam[1], pw[1])), fm(lam[2], pw[2]));
+      q0.y = fa(fa(fm(lam[3], pw[0]), fm(lam[4], pw[1])), fm(lam[5], pw[2]));
+      q0.z = fa(fa(fm(lam[6], pw[0]), fm(lam[7], pw[1])), fm(lam[8], pw[2]));
+      p[0] = q0;
+    }
+  }
+  if (i < g.C) g.cam_wflag[i] = (i == new_cam) ? steps : 0u;
+}
+
 // ---- metric (ba/util.cpp:74-144) ------------------------------------------------
 // The reference inverts every belief on the host (Eigen, fp32 LU) for the error it prints.  Here
 // the means used ONLY for the metric are solved in double precision (a register-resident

@@ -53,12 +53,17 @@ struct gbp_setup {
 namespace {
 
 // ---- small fp32 helpers (Eigen-free restatements of ba/util.cpp:11-46) -----
-void so3exp_f(const float* w, float* R) {  // ba/util.cpp:20-32
+// trig_in_double: sin/cos evaluated in double and rounded once (what a correctly rounded sinf/cosf
+// returns; glibc's differ from that by 1 ulp for <0.1 % of the arguments).  Used where the device
+// evaluates the same expression (k_kf_pose), so that host and device keyframe insertion agree bit for bit.
+void so3exp_f(const float* w, float* R, bool trig_in_double = false) {  // ba/util.cpp:20-32
   const float theta = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
   for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.f : 0.f;
   if (theta < 1e-6) return;
   const float H[9] = {0.f, -w[2], w[1], w[2], 0.f, -w[0], -w[1], w[0], 0.f};
-  const float a = std::sin(theta) / theta, b = (1 - std::cos(theta)) / (theta * theta);
+  const float sn = trig_in_double ? (float)std::sin((double)theta) : std::sin(theta);
+  const float cs = trig_in_double ? (float)std::cos((double)theta) : std::cos(theta);
+  const float a = sn / theta, b = (1 - cs) / (theta * theta);
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j) {
       float h2 = 0.f;
@@ -134,9 +139,9 @@ bool solve_small(int n, const float* A_in, const float* b_in, float* x_out) {
 
 // World position of the point 1 m in front of a camera with pose x[6]
 // (Tw2c.inverse() * (0,0,1,1), ba/dataio.cpp:427-440, ba/util.cpp:199-211).
-void point_in_front(const float* x, float* p_world) {
+void point_in_front(const float* x, float* p_world, bool trig_in_double = false) {
   float R[9];
-  so3exp_f(x + 3, R);
+  so3exp_f(x + 3, R, trig_in_double);
   const float d[3] = {0.f - x[0], 0.f - x[1], 1.f - x[2]};
   for (int i = 0; i < 3; ++i) p_world[i] = R[i] * d[0] + R[3 + i] * d[1] + R[6 + i] * d[2];  // R^T d
 }
@@ -589,7 +594,7 @@ int gbp_setup_next_keyframe(gbp_setup* s, const float* cam_b_eta, const float* c
     cam_p_eta[(size_t)(dc + 1) * 6 + i] = v;
   }
   float pw[3];
-  point_in_front(prev_mu, pw);
+  point_in_front(prev_mu, pw, true);
   for (uint32_t l = 0; l < L; ++l) {
     // Quirk Q6: the reference indexes lmk_weaken_flag_[data_counter*n_points + i]
     // (out of bounds); the intended test is "newly observed landmark".

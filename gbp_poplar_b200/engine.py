@@ -208,6 +208,13 @@ class GBPEngine:
             p(lmk_prior_lambda, _F32, _capi.c_f32p), p(active_flag, np.uint32, _capi.c_u32p),
             p(cam_weaken_flag, np.uint32, _capi.c_u32p), p(lmk_weaken_flag, np.uint32, _capi.c_u32p)))
 
+    def add_keyframe_device(self, new_cam, steps=5):
+        """The whole insertion of slam.cpp:1020-1046 (update_flags + initialise_new_kf + NEW_KEYFRAME)
+        on the device; returns the number of newly observed landmarks.  CUDA library only."""
+        n_new = C.c_int()
+        self._check(self._lib.gbp_cuda_add_keyframe_device(self._h, int(new_cam), int(steps), C.byref(n_new)))
+        return n_new.value
+
     # -- codelet-level entry points (Execute(cs_*)) -------------------------
     def relinearise_factors(self):
         self._check(self._f["relinearise_factors"](self._h))

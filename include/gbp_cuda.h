@@ -179,6 +179,20 @@ int gbp_cuda_add_keyframe(gbp_handle* h, const int32_t* damping_count, const flo
                           const float* lmk_prior_lambda, const uint32_t* active_flag,
                           const uint32_t* cam_weaken_flag, const uint32_t* lmk_weaken_flag);
 
+/* The whole keyframe insertion of slam.cpp:1020-1046 on the device, without the
+ * READ_PROG / READ_PRIORS / NEW_KEYFRAME host round trip: update_flags
+ * (ba/dataio.cpp:477-508: factors of camera `new_cam` become active, `new_cam` and the
+ * landmarks it is the first camera to observe get weaken flag `steps`, every other
+ * weaken flag 0), initialise_new_kf (ba/util.cpp:183-223: prior eta of `new_cam` =
+ * its prior Lambda x the mean of keyframe new_cam-1; prior eta of the new landmarks =
+ * their prior Lambda x the point 1 m in front of keyframe new_cam-1), damping_count
+ * reset to -15 (slam.cpp:1039-1041) and NEW_KEYFRAME's trailing belief update.
+ * new_cam = data_counter + 1 of slam.cpp.  Leaves the handle in exactly (bit for bit)
+ * the state that gbp_cuda_get_beliefs + gbp_cuda_get_priors +
+ * gbp_setup_next_keyframe + gbp_cuda_add_keyframe produce.  Four bytes cross the bus.
+ * *n_new_lmks (may be NULL) = number of newly observed landmarks. */
+int gbp_cuda_add_keyframe_device(gbp_handle* h, uint32_t new_cam, uint32_t steps, int* n_new_lmks);
+
 /* Codelet-level entry points = Execute(cs_*) of one compute set on the
  * handle's state (used by the parity tests).
  *   relinearise_factors      cs_relinearise         ba/ba.cpp:68-97   gbp_codelets.cpp:20-172

@@ -69,9 +69,11 @@ def block_rel_err(a, b, d):
     return out
 
 
-def slam_run(engine, setup, iters_between_kfs, steps=5, stats_every_kf=True, on_kf=None):
-    """The slam.cpp loop (ba/slam.cpp:1013-1103) against any engine."""
+def slam_run(engine, setup, iters_between_kfs, steps=5, stats_every_kf=True, on_kf=None, device_kf=False):
+    """The slam.cpp loop (ba/slam.cpp:1013-1103) against any engine.  device_kf: keyframe insertion
+    through gbp_cuda_add_keyframe_device instead of the READ_PRIORS / host / NEW_KEYFRAME round trip."""
     C = setup.problem.n_keyframes
+    data_counter = 0
     niters = (C - 1) * iters_between_kfs - 1
     it = 0
     finals = []
@@ -80,6 +82,14 @@ def slam_run(engine, setup, iters_between_kfs, steps=5, stats_every_kf=True, on_
             if stats_every_kf:
                 finals.append(engine.eval())
             it = 0
+            data_counter += 1
+            if device_kf:
+                n_new = engine.add_keyframe_device(data_counter + 1, steps)
+                if on_kf:
+                    on_kf(data_counter, n_new)
+                ba_schedule_step(engine, it, steps)
+                it += 1
+                continue
             b = engine.get_beliefs()
             pr = engine.get_priors()
             n_new, dc = setup.next_keyframe(b["cam_beliefs_eta"], b["cam_beliefs_lambda"], pr["cam_priors_eta"],

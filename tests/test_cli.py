@@ -129,6 +129,13 @@ def test_slam_log_matches_engine(tmp_path):
     finals = common.slam_run(gpu, st, 25)
     assert float(rows[-1][2]) == pytest.approx(finals[-1]["reproj_mean"], rel=1e-5)
     assert float(rows[23][2]) == pytest.approx(finals[0]["reproj_mean"], rel=1e-5)
+    # keyframes are inserted on the device by default; the reference's host round trip gives the same log
+    assert "on the device" in r.stdout
+    rh = run([SLAM, "--bal_file", path, "--iters_between_kfs", "25", "--host_keyframes", "1"])
+    assert rh.returncode == 0, rh.stderr
+    assert "READ_PRIORS / host / NEW_KEYFRAME round trip" in rh.stdout
+    strip = lambda t: [ln for ln in t.splitlines() if not ln.startswith(("Timing report", "Keyframe insertions"))]
+    assert strip(rh.stdout) == strip(r.stdout)
 
 
 @pytest.mark.gpu
