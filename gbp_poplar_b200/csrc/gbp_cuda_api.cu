@@ -89,6 +89,7 @@ struct gbp_handle {
   float* d_pprior_cam_lam = nullptr;
   float4* d_pprior_lmk = nullptr;
   int use_graph = 0;
+  cudaAccessPolicyWindow l2_window{};  // num_bytes == 0: none
   // CUDA-graph replay of one steady-state sweep (with / without the metric): one launch per sweep
   // instead of 2-5, which is what bounds the small graphs of the reference sequences
   cudaGraphExec_t sweep_graph[4] = {nullptr, nullptr, nullptr, nullptr};  // [two_pass * 2 + with_stats]
@@ -695,15 +696,23 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   A_(g.fac, GBP_FAC_QUADS * EP);
   A_(g.mcam, GBP_MCAM_QUADS * EP);
   if (o->store_full_messages) A_(g.mcam_up, 4 * EP);
+  // buffers that are touched again within a sweep or by the next one (landmark-bound messages: written and
+  // read back by k_sweep, streamed by k_update_vars; edge state; camera partials; landmark records) are kept
+  // together so that ONE access-policy window can pin them in L2 (l2_persist below)
+  const size_t reuse_begin = arena_bytes;
   A_(g.mlmk, GBP_MLMK_QUADS * (size_t)E);
-  A_(g.var, EP);
+  const size_t reuse_mlmk_end = arena_bytes;
   A_(g.recA, EP);
+  A_(g.cam_partial, (size_t)n_wt * GBP_CAMPART);
+  A_(g.lmk_b, GBP_LMKB_QUADS * (size_t)L);
+  A_(g.lmk_mean_prev, L);
+  const size_t reuse_end = arena_bytes;
+  A_(g.var, EP);
   A_(g.recB, EP);
   A_(g.edge_orig, EP);
   A_(g.wt_info, n_wt);
   A_(g.cam_rec, 16 * (size_t)C);
   A_(g.cam_wt_begin, C + 1);
-  A_(g.cam_partial, (size_t)n_wt * GBP_CAMPART);
   A_(g.cam_b_eta, 6 * (size_t)C);
   A_(g.cam_b_lam, 36 * (size_t)C);
   A_(g.cam_mean, 6 * (size_t)C);
@@ -713,8 +722,6 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   A_(g.cam_prior_lam, 36 * (size_t)C);
   A_(g.cam_scaling, C);
   A_(g.cam_wflag, C);
-  A_(g.lmk_b, GBP_LMKB_QUADS * (size_t)L);
-  A_(g.lmk_mean_prev, L);
   A_(g.lmk_prior, 3 * (size_t)L);
   A_(g.lmk_scaling, L);
   A_(g.lmk_wflag, L);
@@ -762,6 +769,43 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
     if (rc) return rc;
     GBP_CUDA_TRY(cudaMemsetAsync(base, 0, arena_bytes, h->stream));  // ordered before the uploads below
     for (auto& r : arena) *r.first = base + r.second;
+    // L2 residency of the re-used buffers (B200: 126 MB L2, at most 79 MB of it can be set aside).
+    // GBP_L2_PERSIST: 0 off, 1 (default) the landmark-bound messages, 2 all re-used buffers.  Measured on
+    // config 4 (profiles/): 161.9 us per sweep without, 155.1 us with the 48 MB of landmark-bound messages
+    // pinned (k_update_vars 28 -> 23.5 us, k_sweep 142 -> 140 us), 167 us with all 77 MB (too little L2 is
+    // left for the streams); windows with a hit ratio below 1 only lose.
+    int mode = 1;
+    if (const char* env = std::getenv("GBP_L2_PERSIST")) mode = std::atoi(env);
+    h->l2_window = cudaAccessPolicyWindow{};
+    h->l2_window.num_bytes = 0;
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, h->device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, h->device);
+    size_t want = (mode == 1 ? reuse_mlmk_end : reuse_end) - reuse_begin;
+    if (const char* env = std::getenv("GBP_L2_WINDOW_MB")) want = std::min(want, (size_t)std::atoi(env) << 20);
+    size_t cap_mb = 1u << 20;
+    if (const char* env = std::getenv("GBP_L2_SETASIDE_MB")) cap_mb = (size_t)std::atoi(env);
+    if (mode > 0 && max_persist > 0 && max_window > 0 && want >= ((size_t)8 << 20)) {  // small graphs live in L2 anyway
+      const size_t win = std::min(want, (size_t)max_window);
+      size_t cur = 0;
+      cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize);
+      const size_t set_aside = std::min(std::min(std::max(cur, win), (size_t)max_persist), cap_mb << 20);
+      if (set_aside != cur) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside);
+      h->l2_window.base_ptr = base + reuse_begin;
+      h->l2_window.num_bytes = win;
+      h->l2_window.hitRatio = std::min(1.0f, (float)((double)set_aside / (double)win));
+      h->l2_window.hitProp = cudaAccessPropertyPersisting;
+      h->l2_window.missProp = cudaAccessPropertyStreaming;
+      cudaStreamAttrValue av;
+      av.accessPolicyWindow = h->l2_window;
+      if (cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) {
+        cudaGetLastError();
+        h->l2_window.num_bytes = 0;
+      }
+      if (std::getenv("GBP_INIT_TIMING"))
+        std::fprintf(stderr, "[gbp init] L2 window %.1f MB, set-aside %.1f MB (max %.1f MB), hit ratio %.2f\n", win / 1048576.0,
+                     set_aside / 1048576.0, max_persist / 1048576.0, h->l2_window.hitRatio);
+    }
   }
   pt.lap("cudaMalloc + memset");
   cudaStream_t s = h->stream;
@@ -885,6 +929,20 @@ int sweep_graph(gbp_handle* h, bool with_stats, cudaGraphExec_t* out) {
       gbp_set_error("CUDA graph capture of the sweep failed");
       return rc ? rc : GBP_ERR_CUDA;
     }
+    if (h->l2_window.num_bytes) {  // captured kernel nodes do not inherit the stream's access-policy window
+      size_t n_nodes = 0;
+      cudaGraphGetNodes(graph, nullptr, &n_nodes);
+      std::vector<cudaGraphNode_t> nodes(n_nodes);
+      if (n_nodes) cudaGraphGetNodes(graph, nodes.data(), &n_nodes);
+      for (cudaGraphNode_t nd : nodes) {
+        cudaGraphNodeType ty;
+        if (cudaGraphNodeGetType(nd, &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+        cudaKernelNodeAttrValue av;
+        av.accessPolicyWindow = h->l2_window;
+        cudaGraphKernelNodeSetAttribute(nd, cudaKernelNodeAttributeAccessPolicyWindow, &av);
+      }
+      cudaGetLastError();
+    }
     const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
     if (ie != cudaSuccess) {
@@ -965,6 +1023,7 @@ int gbp_cuda_free(gbp_handle* h) {
   if (!h) return GBP_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->l2_window.num_bytes) cudaCtxResetPersistingL2Cache();  // do not leave this handle's lines pinned
   for (void* p : h->allocs) cudaFree(p);
   if (h->d_stats) cudaFree(h->d_stats);
   for (cudaEvent_t ev : h->prof_events) cudaEventDestroy(ev);

@@ -836,15 +836,18 @@ GBP_DEV void update_camera(const DeviceGraph& g, const int shift, const uint32_t
 // acc += quad q of the landmark's factor->landmark messages, strictly in slot order (= original
 // edge order, the reference's message slots 1..deg; contiguous in mlmk), four independent
 // 16-byte loads in flight per lane.
+#ifndef GBP_LMK_BATCH
+#define GBP_LMK_BATCH 4
+#endif
 GBP_DEV float4 lmk_sum_quad(const DeviceGraph& g, const uint32_t l, const uint32_t q, float4 acc) {
   const uint32_t k0 = g.lmk_ptr[l], k1 = g.lmk_ptr[l + 1];
-  for (uint32_t k = k0; k < k1; k += 4) {
-    float4 v[4];
+  for (uint32_t k = k0; k < k1; k += GBP_LMK_BATCH) {
+    float4 v[GBP_LMK_BATCH];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < GBP_LMK_BATCH; ++u)
       if (k + u < k1) v[u] = g.mlmk[(size_t)(k + u) * GBP_MLMK_QUADS + q];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < GBP_LMK_BATCH; ++u)
       if (k + u < k1) {
         acc.x = fa(acc.x, v[u].x); acc.y = fa(acc.y, v[u].y); acc.z = fa(acc.z, v[u].z); acc.w = fa(acc.w, v[u].w);
       }
@@ -973,7 +976,10 @@ GBP_DEV void boundary_finish(const DeviceGraph& g, const int shift, const uint32
 //   landmark blocks   -- GBP_LMK_PER_BLOCK landmarks each
 //   [multi-GPU, peer-to-peer] boundary_finish blocks -- last; every block they wait for was dispatched before them
 // The register budget (10 blocks per SM) fits all paths.  n_push == 0: no fused exchange.
-__global__ void __launch_bounds__(GBP_TILE, 10) k_update_vars(const DeviceGraph g, const int shift, const uint32_t n_push) {
+#ifndef GBP_UV_BLOCKS
+#define GBP_UV_BLOCKS 10
+#endif
+__global__ void __launch_bounds__(GBP_TILE, GBP_UV_BLOCKS) k_update_vars(const DeviceGraph g, const int shift, const uint32_t n_push) {
   const uint32_t nb_lmk = (g.L + GBP_LMK_PER_BLOCK - 1) / GBP_LMK_PER_BLOCK;
   if (shift && blockIdx.x == 0 && threadIdx.x == 0) {  // a sweep ended: open the next slot of the relinearisation ring
     const uint32_t next = g.relin_ring[GBP_RELIN_RING] + 1;
