@@ -717,7 +717,7 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   A_(g.cam_b_lam, 36 * (size_t)C);
   A_(g.cam_mean, 6 * (size_t)C);
   A_(g.cam_mean_prev, 6 * (size_t)C);
-  A_(g.cam_R, 9 * (size_t)C);
+  A_(g.cam_lin, 5 * (size_t)C);
   A_(g.cam_prior_eta, 6 * (size_t)C);
   A_(g.cam_prior_lam, 36 * (size_t)C);
   A_(g.cam_scaling, C);

@@ -45,7 +45,7 @@ struct DeviceGraph {
   float* cam_b_lam;      // [C][36]
   float* cam_mean;       // [C][6]
   float* cam_mean_prev;  // [C][6]
-  float* cam_R;          // [C][9] so3exp(mean[3:6]) for the metric
+  float4* cam_lin;       // [C][5] camera-only linearisation constants of the mean: R 9 | num 9 | den | pad (cam_lin_consts)
   float4* cam_rec;       // [C][16] packed {belief eta 6 | belief lambda 36 | mean 6 | previous mean 6 | pad}: what k_sweep stages
   float* cam_prior_eta;  // [C][6]
   float* cam_prior_lam;  // [C][36]
@@ -195,7 +195,8 @@ GBP_DEV void fac_pack(const float (&f)[72], float (&r)[GBP_FAC_QUADS * 4]) {
 // is given, into the caller's shared-memory stage slot as well.  Arguments are passed by
 // value so the kernel parameter block never has its address taken.
 __device__ __noinline__ uint32_t relinearise_record(const float4* src, size_t src_stride, float4* dst, size_t dst_stride,
-                                                    float4* stage, float4 K4, float Nstds, float z0, float z1, float var,
+                                                    float4* stage, const float4* cam_lin, float4 K4, float Nstds, float z0,
+                                                    float z1, float var,
                                                     float c0, float c1, float c2, float c3, float c4, float c5, float l0,
                                                     float l1, float l2) {
   float f[72];
@@ -218,7 +219,15 @@ __device__ __noinline__ uint32_t relinearise_record(const float4* src, size_t sr
   float(&ll)[9] = *reinterpret_cast<float(*)[9]>(f + GBP_F_LL);
   float(&cl)[18] = *reinterpret_cast<float(*)[18]>(f + GBP_F_CL);
   float(&cc)[36] = *reinterpret_cast<float(*)[36]>(f + GBP_F_CC);
-  const uint32_t robust = linearise_accumulate(z0, z1, var, K, x_kf, x_l, Nstds, eta, ll, cl, cc);
+  float Rn[20];  // R 9 | num 9 | den | pad of this factor's camera
+#pragma unroll
+  for (int q = 0; q < 5; ++q) {
+    const float4 v = __ldg(cam_lin + q);
+    Rn[q * 4] = v.x; Rn[q * 4 + 1] = v.y; Rn[q * 4 + 2] = v.z; Rn[q * 4 + 3] = v.w;
+  }
+  const float(&R)[9] = *reinterpret_cast<const float(*)[9]>(Rn);
+  const float(&num)[9] = *reinterpret_cast<const float(*)[9]>(Rn + 9);
+  const uint32_t robust = linearise_accumulate(z0, z1, var, K, x_kf, x_l, R, num, Rn[18], Nstds, eta, ll, cl, cc);
   float r[GBP_FAC_QUADS * 4];
   fac_pack(f, r);
 #pragma unroll
@@ -253,6 +262,9 @@ __device__ __noinline__ uint32_t relinearise_record(const float4* src, size_t sr
 #define GBP_SW_WARPS 8   // warps per block (one block per SM)
 #endif
 #define GBP_NBUF 2       // double-buffered stage
+#ifndef GBP_L2_PREFETCH
+#define GBP_L2_PREFETCH 0  // 1: bulk, 2: per-line L2 prefetch of warp-tile t+2 (measured: 138 -> 145 / 143 us, kept for experiments)
+#endif
 #define GBP_WARPS (GBP_TILE / 32)  // warp-tiles per 128-slot tile
 #define GBP_SQ 26  // quads per factor in a stage
 #define GBP_SQ_FAC 0
@@ -450,8 +462,8 @@ GBP_DEV void msg_to_camera(const float4* stage, const uint32_t lane, const float
 // PrepMessageVertex on the hoisted per-variable means (gbp_codelets.cpp:241-378): damping state
 // machine, dmu, conditional accumulating relinearisation (quirk Q1) with Huber (quirk Q2).  The
 // staged factor record of a relinearising lane is rewritten in place (and in global memory).
-GBP_DEV void prep_factor(const DeviceGraph& g, float4* stage, const float* s_cam, const size_t e, const uint32_t lane,
-                         const float (&lb)[20], const float4 rb, float& damping, int& dcount, uint32_t& flags, float& dmu) {
+GBP_DEV void prep_factor(const DeviceGraph& g, float4* stage, const float* s_cam, const uint32_t cam, const size_t e,
+                         const uint32_t lane, const float (&lb)[20], const float4 rb, float& damping, int& dcount, uint32_t& flags, float& dmu) {
   if (dcount == 0) damping = g.hp.maxeta_damping;  // gbp_codelets.cpp:245-248
   dcount += 1;
   float x_kf[6], x_l[3], old[9];
@@ -484,7 +496,7 @@ GBP_DEV void prep_factor(const DeviceGraph& g, float4* stage, const float* s_cam
     damping = 0.0f;  // gbp_codelets.cpp:280-283
     dcount = -g.hp.num_undamped_iters;
     // the staged record is the current potential: accumulate onto it (quirk Q1), write it back
-    const uint32_t robust = relinearise_record(stage + lane, 32, g.fac + e, g.E_pad, stage + lane,
+    const uint32_t robust = relinearise_record(stage + lane, 32, g.fac + e, g.E_pad, stage + lane, g.cam_lin + (size_t)cam * 5,
                                                make_float4(g.K[0], g.K[1], g.K[2], g.K[3]), g.hp.Nstds, rb.x, rb.y, g.var[e],
                                                x_kf[0], x_kf[1], x_kf[2], x_kf[3], x_kf[4], x_kf[5], x_l[0], x_l[1], x_l[2]);
     flags = (flags & ~GBP_FLAG_ROBUST) | (robust ? GBP_FLAG_ROBUST : 0u);
@@ -511,7 +523,7 @@ GBP_DEV void sweep_tile(const DeviceGraph& g, float4* stage, const float* s_cam,
   const bool active = valid && (flags & GBP_FLAG_ACTIVE) != 0;
   const size_t lpos = __float_as_uint(rb.w);  // where this factor's landmark-bound message lives
 
-  if (PREP && active) prep_factor(g, stage, s_cam, e, lane, lb, rb, damping, dcount, flags, dmu);
+  if (PREP && active) prep_factor(g, stage, s_cam, ti.x, e, lane, lb, rb, damping, dcount, flags, dmu);
 
   float nc[28];   // new f->cam message record: eta 0..5 | lower lambda 6..26 | pad
   float ncu[16];  // its strict upper triangle (row-major, i<j): only summed into the camera partial
@@ -603,6 +615,29 @@ __global__ void __launch_bounds__(GBP_SW_WARPS * 32, 1) k_sweep(const DeviceGrap
       if (wt_nn < n_wt) {
         ti_nn = __ldg(g.wt_info + wt_nn);
         lid_nn = __ldg(lrec + 2 * ((size_t)wt_nn * 32 + lane));
+#if GBP_L2_PREFETCH == 1
+        // warp-tile t+2: pull its 23 contiguous 512-byte rows (potential 14, camera message 7, the two
+        // edge-state records) into L2 now, one bulk prefetch per lane, so that the cp.async copies issued
+        // at the top of the next iteration are served from L2 instead of queueing behind DRAM
+        const float4* row = nullptr;
+        if (lane < GBP_FAC_QUADS) row = g.fac + (size_t)lane * g.E_pad;
+        else if (lane < GBP_FAC_QUADS + GBP_MCAM_QUADS) row = g.mcam + (size_t)(lane - GBP_FAC_QUADS) * g.E_pad;
+        else if (lane == GBP_FAC_QUADS + GBP_MCAM_QUADS) row = g.recA;
+        else if (lane == GBP_FAC_QUADS + GBP_MCAM_QUADS + 1) row = g.recB;
+        if (row) asm volatile("cp.async.bulk.prefetch.L2.global [%0], 512;\n" ::"l"(row + (size_t)wt_nn * 32) : "memory");
+#elif GBP_L2_PREFETCH == 2
+        // the same 23 rows x 4 lines of 128 B, one prefetch.global.L2 per line, three per lane
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const uint32_t i = lane + 32u * k, r = i >> 2;
+          if (r < GBP_FAC_QUADS + GBP_MCAM_QUADS + 2) {
+            const float4* row = (r < GBP_FAC_QUADS) ? g.fac + (size_t)r * g.E_pad
+                                : (r < GBP_FAC_QUADS + GBP_MCAM_QUADS) ? g.mcam + (size_t)(r - GBP_FAC_QUADS) * g.E_pad
+                                : (r == GBP_FAC_QUADS + GBP_MCAM_QUADS) ? g.recA : g.recB;
+            asm volatile("prefetch.global.L2 [%0];\n" ::"l"(row + (size_t)wt_nn * 32 + (i & 3u) * 8) : "memory");
+          }
+        }
+#endif
       }
     }
     // the copies of THIS warp-tile were committed one iteration ago: leave the newest group in flight
@@ -697,7 +732,7 @@ __global__ void __launch_bounds__(GBP_TILE) k_relin_list(const DeviceGraph g) {
   const float* crec = reinterpret_cast<const float*>(g.cam_rec + (size_t)cam * 16);
   const float4 lm = g.lmk_b[(size_t)__float_as_uint(rb.z) * GBP_LMKB_QUADS + 3];
   // accumulate onto the current potential (quirk Q1), Huber re-evaluated (quirk Q2)
-  const uint32_t robust = relinearise_record(g.fac + e, g.E_pad, g.fac + e, g.E_pad, nullptr,
+  const uint32_t robust = relinearise_record(g.fac + e, g.E_pad, g.fac + e, g.E_pad, nullptr, g.cam_lin + (size_t)cam * 5,
                                              make_float4(g.K[0], g.K[1], g.K[2], g.K[3]), g.hp.Nstds, rb.x, rb.y, g.var[e], crec[42],
                                              crec[43], crec[44], crec[45], crec[46], crec[47], lm.x, lm.y, lm.z);
   uint32_t* fl = reinterpret_cast<uint32_t*>(g.recA + e) + 2;
@@ -813,8 +848,8 @@ GBP_DEV void update_camera(const DeviceGraph& g, const int shift, const uint32_t
       for (int j = 0; j <= i; ++j) lamL[lt(i, j)] = s_b[6 + i * 6 + j];
     inf2mean6(eta, lamL, mean);
     const float w[3] = {mean[3], mean[4], mean[5]};
-    float R[9];
-    so3exp(w, R);
+    float R[9], num[9], den;
+    cam_lin_consts(w, R, num, den);
     float* rec = reinterpret_cast<float*>(g.cam_rec + (size_t)c * 16);
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
@@ -824,8 +859,13 @@ GBP_DEV void update_camera(const DeviceGraph& g, const int shift, const uint32_t
       rec[42 + i] = mean[i];
       rec[48 + i] = prev;
     }
+    float* lin = reinterpret_cast<float*>(g.cam_lin + (size_t)c * 5);
 #pragma unroll
-    for (int i = 0; i < 9; ++i) g.cam_R[c * 9 + i] = R[i];
+    for (int i = 0; i < 9; ++i) {
+      lin[i] = R[i];
+      lin[9 + i] = num[i];
+    }
+    lin[18] = den;
   }
   if (tid < GBP_CAMPART) reinterpret_cast<float*>(g.cam_rec + (size_t)c * 16)[tid] = s_b[tid];
 }
@@ -1061,7 +1101,7 @@ __global__ void __launch_bounds__(GBP_TILE) k_relinearise_all(const DeviceGraph 
   for (int i = 0; i < 6; ++i) x_kf[i] = g.cam_mean[c * 6 + i];
   const float4 m = g.lmk_b[(size_t)l * GBP_LMKB_QUADS + 3];
   x_l[0] = m.x; x_l[1] = m.y; x_l[2] = m.z;
-  const uint32_t robust = relinearise_record(nullptr, 0, g.fac + e, g.E_pad, nullptr, make_float4(g.K[0], g.K[1], g.K[2], g.K[3]),
+  const uint32_t robust = relinearise_record(nullptr, 0, g.fac + e, g.E_pad, nullptr, g.cam_lin + (size_t)c * 5, make_float4(g.K[0], g.K[1], g.K[2], g.K[3]),
                                              g.hp.Nstds, rb.x, rb.y, g.var[e], x_kf[0], x_kf[1], x_kf[2], x_kf[3], x_kf[4],
                                              x_kf[5], x_l[0], x_l[1], x_l[2]);
   flags = (flags & ~GBP_FLAG_ROBUST) | (robust ? GBP_FLAG_ROBUST : 0u);
@@ -1490,8 +1530,8 @@ __global__ void k_means_from_beliefs(const DeviceGraph g) {
       for (int j = 0; j <= r; ++j) lamL[lt(r, j)] = g.cam_b_lam[i * 36 + r * 6 + j];
     inf2mean6(eta, lamL, mean);
     const float w[3] = {mean[3], mean[4], mean[5]};
-    float R[9];
-    so3exp(w, R);
+    float R[9], num[9], den;
+    cam_lin_consts(w, R, num, den);
     float* rec = reinterpret_cast<float*>(g.cam_rec + (size_t)i * 16);
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
@@ -1502,8 +1542,13 @@ __global__ void k_means_from_beliefs(const DeviceGraph g) {
     }
 #pragma unroll
     for (int k = 0; k < 36; ++k) rec[6 + k] = g.cam_b_lam[i * 36 + k];
+    float* lin = reinterpret_cast<float*>(g.cam_lin + (size_t)i * 5);
 #pragma unroll
-    for (int k = 0; k < 9; ++k) g.cam_R[i * 9 + k] = R[k];
+    for (int k = 0; k < 9; ++k) {
+      lin[k] = R[k];
+      lin[9 + k] = num[k];
+    }
+    lin[18] = den;
   } else if (i < g.C + g.L) {
     const uint32_t l = i - g.C;
     float4* o = g.lmk_b + (size_t)l * GBP_LMKB_QUADS;

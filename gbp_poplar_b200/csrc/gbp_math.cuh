@@ -201,15 +201,31 @@ GBP_DEV void mul_hat(const float (&A)[9], const float (&h)[3], float (&O)[9]) {
 // terms are ADDED onto the incoming blocks (zero them first for
 // RelineariseFactorVertex; leave them for the in-loop relinearisation, quirk Q1).
 // Layout of the blocks: eta[9], ll[9], cl[18] (6x3), cc[36]; lc is cl^T.
+// Camera-only part of Jac (bafuncs.cpp:107-213): R = so3exp(w), num = (R^T - I)[w]x + w w^T and
+// den = |w|^2 of dRp/dw = -R [p]x num / den.  The reference recomputes them per factor; here they
+// are formed once per camera when its mean changes (k_update_vars) -- same operations, same values.
+GBP_DEV void cam_lin_consts(const float (&w)[3], float (&R)[9], float (&num)[9], float& den) {
+  so3exp(w, R);
+  float RtI[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) RtI[i * 3 + j] = (i == j) ? fa(-1.0f, R[i * 3 + i]) : R[j * 3 + i];
+  mul_hat(RtI, w, num);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) num[i * 3 + j] = fa(num[i * 3 + j], fm(w[i], w[j]));
+  den = fa(fa(fm(w[0], w[0]), fm(w[1], w[1])), fm(w[2], w[2]));
+}
+
 GBP_DEV uint32_t linearise_accumulate(const float z0, const float z1, const float var,
                                       const float (&K)[4] /* fx fy cx cy */,
                                       const float (&x_kf)[6], const float (&x_l)[3],
+                                      const float (&R)[9], const float (&num)[9], const float den,
                                       const float Nstds, float (&eta)[9], float (&ll)[9],
                                       float (&cl)[18], float (&cc)[36]) {
   const float fx = K[0], fy = K[1], cx = K[2], cy = K[3];
-  const float w[3] = {x_kf[3], x_kf[4], x_kf[5]};
-  float R[9];
-  so3exp(w, R);
   float y[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
@@ -228,18 +244,8 @@ GBP_DEV uint32_t linearise_accumulate(const float z0, const float z1, const floa
   Jk[0] = ja; Jk[1] = 0.f; Jk[2] = jb;
   Jk[6] = 0.f; Jk[7] = jc; Jk[8] = jd;
   // rotation part: dRp/dw = -R [p]x (w w^T + (R^T - I)[w]x) / |w|^2
-  float Rph[9], RtI[9], num[9], dR[9];
+  float Rph[9], dR[9];
   mul_hat(R, x_l, Rph);
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) RtI[i * 3 + j] = (i == j) ? fa(-1.0f, R[i * 3 + i]) : R[j * 3 + i];
-  mul_hat(RtI, w, num);
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) num[i * 3 + j] = fa(num[i * 3 + j], fm(w[i], w[j]));
-  const float den = fa(fa(fm(w[0], w[0]), fm(w[1], w[1])), fm(w[2], w[2]));
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
