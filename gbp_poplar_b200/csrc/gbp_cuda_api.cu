@@ -92,7 +92,8 @@ struct gbp_handle {
   cudaAccessPolicyWindow l2_window{};  // num_bytes == 0: none
   // CUDA-graph replay of one steady-state sweep (with / without the metric): one launch per sweep
   // instead of 2-5, which is what bounds the small graphs of the reference sequences
-  cudaGraphExec_t sweep_graph[4] = {nullptr, nullptr, nullptr, nullptr};  // [two_pass * 2 + with_stats]
+  cudaGraphExec_t sweep_graph[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [skip_upper * 4 + two_pass * 2 + with_stats]
+  int skip_upper = 1;               // all sweeps of a gbp_cuda_iterate call but the last skip the upper triangle of the camera messages (GBP_SKIP_UPPER=0 disables)
   DeviceGraph graph_g;               // the kernel arguments the graphs were captured with
   gbp::DeviceStats* graph_stats = nullptr;
   uint32_t graph_n_active = 0;      // k_metric's argument at capture time
@@ -122,6 +123,11 @@ struct gbp_handle {
   double* d_met_lmk = nullptr;      // [L][4]  double-precision landmark means (metric only)
   gbp::DeviceStats* d_stats = nullptr;
   size_t d_stats_cap = 0;
+  // pinned staging for the small per-call read-backs (per-sweep metrics, relinearisation ring): one
+  // asynchronous copy each and ONE stream synchronisation per gbp_cuda_iterate call
+  gbp_iter_stats* pin_stats = nullptr;
+  size_t pin_stats_cap = 0;
+  uint32_t* pin_ring = nullptr;
   // timing
   int profile = 0;
   std::vector<cudaEvent_t> prof_events;
@@ -205,7 +211,7 @@ std::vector<CommEntry>& comm_cache() {
 // prog_ub (ba/ba.cpp:104-139).  On a shard the boundary landmarks go first: their partial
 // sums are all-gathered on the communication stream while the main stream updates the
 // interior landmarks and the cameras; k_boundary_finish then waits for the gather.
-int launch_update_vars(gbp_handle* h) {
+int launch_update_vars(gbp_handle* h, bool lower_only = false) {
   const int shift = h->pending_shift ? 1 : 0;
   const uint32_t grid = lmks_grid(h);
   const bool exchange = h->shard && h->g.n_bnd_global > 0;
@@ -214,7 +220,7 @@ int launch_update_vars(gbp_handle* h) {
     // one launch: the first blocks form the partial sums and push them into every rank's receive buffer
     // over NVLink, the last blocks finish the boundary landmarks once every rank's flag has arrived
     const uint32_t n_x = std::max((h->g.n_bnd_local + GBP_LMK_PER_BLOCK - 1) / GBP_LMK_PER_BLOCK, 1u);
-    gbp::k_update_vars<<<n_x + h->C + grid + n_x, GBP_TILE, 0, h->stream>>>(h->g, shift, n_x);
+    gbp::k_update_vars<<<n_x + h->C + grid + n_x, GBP_TILE, 0, h->stream>>>(h->g, shift, n_x, lower_only ? 1 : 0);
     h->kernels_launched++;
     h->exchanges++;
   } else {
@@ -231,7 +237,7 @@ int launch_update_vars(gbp_handle* h) {
       h->exchanges++;
     }
     if (grid + h->C) {
-      gbp::k_update_vars<<<grid + h->C, GBP_TILE, 0, h->stream>>>(h->g, shift, 0u);
+      gbp::k_update_vars<<<grid + h->C, GBP_TILE, 0, h->stream>>>(h->g, shift, 0u, lower_only ? 1 : 0);
       h->kernels_launched++;
     }
     if (exchange) {
@@ -247,13 +253,18 @@ int launch_update_vars(gbp_handle* h) {
   return GBP_OK;
 }
 
+// upper == false: the strict upper triangle of the camera messages is skipped (see k_sweep); only valid when the
+// following belief update runs with lower_only and another, complete sweep follows before anything is read
 template <bool PREP, bool MSG>
-int launch_sweep(gbp_handle* h) {
+int launch_sweep(gbp_handle* h, bool upper = true) {
   if (h->n_tiles) {
     // persistent: one block per SM (fewer when the graph has fewer warp-tiles than that)
     const uint32_t n_wt = h->E_pad / 32;
     const uint32_t grid = std::min<uint32_t>((uint32_t)h->num_sms, n_wt);
-    gbp::k_sweep<PREP, MSG><<<grid, GBP_SW_WARPS * 32, GBP_SWEEP_SMEM, h->stream>>>(h->g);
+    if (upper || !MSG || h->g.mcam_up)
+      gbp::k_sweep<PREP, MSG, true><<<grid, GBP_SW_WARPS * 32, GBP_SWEEP_SMEM, h->stream>>>(h->g);
+    else
+      gbp::k_sweep<PREP, MSG, false><<<grid, GBP_SW_WARPS * 32, GBP_SWEEP_SMEM, h->stream>>>(h->g);
     h->kernels_launched++;
   }
   if (PREP) h->pending_shift = true;
@@ -276,12 +287,14 @@ int launch_prep(gbp_handle* h) {
 }
 
 // one full sweep of the factors (prep + messages)
-int launch_full_sweep(gbp_handle* h) {
-  if (!h->two_pass) return launch_sweep<true, true>(h);
+int launch_full_sweep(gbp_handle* h, bool upper = true) {
+  if (!h->two_pass) return launch_sweep<true, true>(h, upper);
   int rc = launch_prep(h);
-  if (!rc) rc = launch_sweep<false, true>(h);
+  if (!rc) rc = launch_sweep<false, true>(h, upper);
   return rc;
 }
+// may the sweeps of a call other than the last skip the upper triangle of the camera messages?
+inline bool can_skip_upper(const gbp_handle* h) { return h->skip_upper && !h->g.mcam_up; }
 
 int launch_metric(gbp_handle* h, gbp::DeviceStats* d_out) {
   if (h->n_tiles) {
@@ -308,6 +321,13 @@ int launch_metric(gbp_handle* h, gbp::DeviceStats* d_out) {
 }
 
 int ensure_stats(gbp_handle* h, size_t n) {
+  if (n > h->pin_stats_cap) {
+    if (h->pin_stats) cudaFreeHost(h->pin_stats);
+    h->pin_stats = nullptr;
+    h->pin_stats_cap = 0;
+    GBP_CUDA_TRY(cudaHostAlloc((void**)&h->pin_stats, std::max<size_t>(n, 64) * sizeof(gbp_iter_stats), cudaHostAllocDefault));
+    h->pin_stats_cap = std::max<size_t>(n, 64);
+  }
   if (n <= h->d_stats_cap) return GBP_OK;
   if (h->d_stats) cudaFree(h->d_stats);
   h->d_stats = nullptr;
@@ -856,9 +876,11 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
 #undef U_
   if (rc) return rc;
   GBP_CUDA_TRY(cudaStreamSynchronize(s));
-  GBP_CUDA_TRY(cudaFuncSetAttribute(gbp::k_sweep<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GBP_SWEEP_SMEM));
-  GBP_CUDA_TRY(cudaFuncSetAttribute(gbp::k_sweep<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GBP_SWEEP_SMEM));
-  GBP_CUDA_TRY(cudaFuncSetAttribute(gbp::k_sweep<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GBP_SWEEP_SMEM));
+  GBP_CUDA_TRY(cudaFuncSetAttribute(gbp::k_sweep<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GBP_SWEEP_SMEM));
+  GBP_CUDA_TRY(cudaFuncSetAttribute(gbp::k_sweep<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GBP_SWEEP_SMEM));
+  GBP_CUDA_TRY(cudaFuncSetAttribute(gbp::k_sweep<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GBP_SWEEP_SMEM));
+  GBP_CUDA_TRY(cudaFuncSetAttribute(gbp::k_sweep<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GBP_SWEEP_SMEM));
+  GBP_CUDA_TRY(cudaFuncSetAttribute(gbp::k_sweep<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GBP_SWEEP_SMEM));
   GBP_CUDA_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
   pt.lap("uploads");
   if (h->shard) {
@@ -882,12 +904,16 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
 // ~11, none in between: what the reference's uniform --undamped_start produces on a fresh graph); once they are
 // spread over the sweeps most warps contain a relinearising lane and the compacting two-pass sweep wins (config 4:
 // 171 us either way against 161 / 262 us for the fused kernel).  Decided from the last <= 32 sweeps.
-int choose_sweep_flavour(gbp_handle* h) {
+int choose_sweep_flavour(gbp_handle* h, const uint32_t* ring_in = nullptr) {
   if (h->relin_mode == 1) { h->two_pass = 0; return GBP_OK; }
   if (h->relin_mode == 2) { h->two_pass = 1; return GBP_OK; }
-  uint32_t ring[GBP_RELIN_RING + 1];
-  GBP_CUDA_TRY(cudaMemcpyAsync(ring, h->g.relin_ring, sizeof(ring), cudaMemcpyDeviceToHost, h->stream));
-  GBP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  uint32_t local[GBP_RELIN_RING + 1];
+  const uint32_t* ring = ring_in;
+  if (!ring) {
+    GBP_CUDA_TRY(cudaMemcpyAsync(local, h->g.relin_ring, sizeof(local), cudaMemcpyDeviceToHost, h->stream));
+    GBP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    ring = local;
+  }
   const uint32_t n = std::min<uint32_t>(ring[GBP_RELIN_RING], GBP_RELIN_RING);  // completed sweeps on record
   if (n < 8) return GBP_OK;
   uint32_t busy = 0;
@@ -907,18 +933,18 @@ void drop_graphs(gbp_handle* h) {
 // The instantiated graph of ONE steady-state sweep: k_sweep, k_update_vars (shift = 1) and, with
 // stats, the three metric kernels writing to d_stats[cursor++].  Captured lazily, re-captured when
 // the kernel arguments (DeviceGraph, stats buffer) changed.
-int sweep_graph(gbp_handle* h, bool with_stats, cudaGraphExec_t* out) {
+int sweep_graph(gbp_handle* h, bool with_stats, bool upper, cudaGraphExec_t* out) {
   if (std::memcmp(&h->graph_g, &h->g, sizeof(DeviceGraph)) != 0 || h->graph_stats != h->d_stats ||
       h->graph_n_active != h->n_active)
     drop_graphs(h);
-  cudaGraphExec_t& exec = h->sweep_graph[(h->two_pass ? 2 : 0) + (with_stats ? 1 : 0)];
+  cudaGraphExec_t& exec = h->sweep_graph[(upper ? 0 : 4) + (h->two_pass ? 2 : 0) + (with_stats ? 1 : 0)];
   if (!exec) {
     const uint64_t k0 = h->kernels_launched;
     cudaGraph_t graph = nullptr;
     GBP_CUDA_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
     h->capturing = true;
-    int rc = launch_full_sweep(h);
-    if (!rc) rc = launch_update_vars(h);
+    int rc = launch_full_sweep(h, upper);
+    if (!rc) rc = launch_update_vars(h, !upper);
     if (!rc && with_stats) rc = launch_metric(h, h->d_stats);
     h->capturing = false;
     const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
@@ -1002,6 +1028,7 @@ int gbp_cuda_init(const gbp_problem* p, const gbp_opts* o_in, gbp_handle** out) 
   gbp_handle* h = new gbp_handle();
   h->device = o.device;
   h->use_graph = o.use_cuda_graph;
+  if (const char* env = std::getenv("GBP_SKIP_UPPER")) h->skip_upper = std::atoi(env) != 0;
   h->relin_mode = o.relin_mode;
   h->two_pass = (o.relin_mode == 2) ? 1 : 0;
   int rc = set_device(h);
@@ -1026,6 +1053,8 @@ int gbp_cuda_free(gbp_handle* h) {
   if (h->l2_window.num_bytes) cudaCtxResetPersistingL2Cache();  // do not leave this handle's lines pinned
   for (void* p : h->allocs) cudaFree(p);
   if (h->d_stats) cudaFree(h->d_stats);
+  if (h->pin_stats) cudaFreeHost(h->pin_stats);
+  if (h->pin_ring) cudaFreeHost(h->pin_ring);
   for (cudaEvent_t ev : h->prof_events) cudaEventDestroy(ev);
   drop_graphs(h);
   if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);  // the communicator itself stays cached
@@ -1098,8 +1127,9 @@ int gbp_cuda_iterate_async(gbp_handle* h, int n_sweeps) {
   if (!h || n_sweeps < 0) return GBP_ERR_ARG;
   int rc = set_device(h);
   for (int i = 0; i < n_sweeps && !rc; ++i) {
-    rc = launch_full_sweep(h);
-    if (!rc) rc = launch_update_vars(h);
+    const bool upper = i == n_sweeps - 1 || !can_skip_upper(h);
+    rc = launch_full_sweep(h, upper);
+    if (!rc) rc = launch_update_vars(h, !upper);
   }
   return rc;
 }
@@ -1130,11 +1160,15 @@ int gbp_cuda_iterate(gbp_handle* h, int n_sweeps, gbp_iter_stats* stats) {
   if (h->use_graph && !prof && graph_ok && !(h->shard && stats) && n_sweeps > 0 && h->n_tiles) {
     GBP_CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
     if (stats) GBP_CUDA_TRY(cudaMemsetAsync(h->d_stat_cursor, 0, sizeof(uint32_t), h->stream));
-    cudaGraphExec_t exec = nullptr;
-    rc = sweep_graph(h, stats != nullptr, &exec);
+    // every sweep but the last skips the strict upper triangle of the camera messages (see k_sweep)
+    cudaGraphExec_t exec = nullptr, exec_lower = nullptr;
+    rc = sweep_graph(h, stats != nullptr, true, &exec);
+    // (not when per-sweep metrics are requested: the metric inverts the FULL camera belief, like the reference's)
+    if (!rc && n_sweeps > 1 && !stats && can_skip_upper(h)) rc = sweep_graph(h, false, false, &exec_lower);
     if (rc) return rc;
     const uint64_t per = (stats ? 5 : 2) + (h->two_pass ? 2 : 0);
-    for (int i = 0; i < n_sweeps; ++i) GBP_CUDA_TRY(cudaGraphLaunch(exec, h->stream));
+    for (int i = 0; i < n_sweeps; ++i)
+      GBP_CUDA_TRY(cudaGraphLaunch((exec_lower && i + 1 < n_sweeps) ? exec_lower : exec, h->stream));
     h->kernels_launched += per * (uint64_t)n_sweeps;
     h->pending_shift = false;
     h->p_in_sync = true;
@@ -1143,25 +1177,34 @@ int gbp_cuda_iterate(gbp_handle* h, int n_sweeps, gbp_iter_stats* stats) {
     GBP_CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
   }
   for (int i = first; i < n_sweeps && !rc; ++i) {
+    const bool upper = i == n_sweeps - 1 || stats || !can_skip_upper(h);
     if (prof) GBP_CUDA_TRY(cudaEventRecord(h->prof_events[3 * i], h->stream));
-    rc = launch_full_sweep(h);
+    rc = launch_full_sweep(h, upper);
     if (prof) GBP_CUDA_TRY(cudaEventRecord(h->prof_events[3 * i + 1], h->stream));
-    if (!rc) rc = launch_update_vars(h);
+    if (!rc) rc = launch_update_vars(h, !upper);
     if (prof) GBP_CUDA_TRY(cudaEventRecord(h->prof_events[3 * i + 2], h->stream));
     if (!rc && stats) rc = launch_metric(h, h->d_stats + i);
   }
   if (rc) return rc;
   GBP_CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
   if (stats && n_sweeps)
-    GBP_CUDA_TRY(cudaMemcpyAsync(stats, h->d_stats, (size_t)n_sweeps * sizeof(gbp_iter_stats), cudaMemcpyDeviceToHost,
+    GBP_CUDA_TRY(cudaMemcpyAsync(h->pin_stats, h->d_stats, (size_t)n_sweeps * sizeof(gbp_iter_stats), cudaMemcpyDeviceToHost,
                                  h->stream));
+  // every 16 sweeps the relinearisation ring (132 bytes) rides along with the same synchronisation
+  h->sweeps_since_choice += (uint32_t)n_sweeps;
+  const bool want_ring = h->sweeps_since_choice >= 16 && h->E && h->relin_mode == 0;
+  if (want_ring) {
+    if (!h->pin_ring) GBP_CUDA_TRY(cudaHostAlloc((void**)&h->pin_ring, (GBP_RELIN_RING + 1) * sizeof(uint32_t), cudaHostAllocDefault));
+    GBP_CUDA_TRY(cudaMemcpyAsync(h->pin_ring, h->g.relin_ring, (GBP_RELIN_RING + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                 h->stream));
+  }
   GBP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (stats && n_sweeps) std::memcpy(stats, h->pin_stats, (size_t)n_sweeps * sizeof(gbp_iter_stats));
   GBP_CUDA_TRY(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
   h->last_kernels = h->kernels_launched - k0;
-  h->sweeps_since_choice += (uint32_t)n_sweeps;
-  if (h->sweeps_since_choice >= 16 && h->E) {  // every 16 sweeps: one 132-byte read-back
+  if (h->sweeps_since_choice >= 16 && h->E) {
     h->sweeps_since_choice = 0;
-    rc = choose_sweep_flavour(h);
+    rc = choose_sweep_flavour(h, want_ring ? h->pin_ring : nullptr);
     if (rc) return rc;
   }
   h->last_ms_factor = h->last_ms_variable = 0.f;
@@ -1804,6 +1847,7 @@ int gbp_cuda_init_shard(const gbp_problem* p, const gbp_opts* o_in, uint32_t wor
   gbp_handle* h = new gbp_handle();
   h->device = o.device;
   h->use_graph = o.use_cuda_graph;
+  if (const char* env = std::getenv("GBP_SKIP_UPPER")) h->skip_upper = std::atoi(env) != 0;
   h->relin_mode = o.relin_mode;
   h->two_pass = (o.relin_mode == 2) ? 1 : 0;
   h->shard = sh;

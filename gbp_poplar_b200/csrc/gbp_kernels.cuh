@@ -318,21 +318,40 @@ GBP_DEV void load_lmk_belief(const DeviceGraph& g, const uint32_t l, float (&lb)
   lb[16] = mp.x; lb[17] = mp.y; lb[18] = mp.z; lb[19] = mp.w;
 }
 
-// lane-ordered sum of the 42 camera-message values of the warp's 32 factors
+// lane-ordered sum of the 42 camera-message values of the warp's 32 factors.
+// UPPER == false: only eta and the lower triangle of Lambda (27 values, rows 0..26 of `red` in the order
+// [eta 6 | lower 21]) are summed -- one pass over the lanes instead of two; the strict upper triangle of the
+// partial is left untouched (see k_sweep).
+template <bool UPPER>
 GBP_DEV void warp_cam_reduce(float* red, uint32_t lane, float* __restrict__ out42) {
-  {
+  if (UPPER) {
+    {
+      const float* row = red + lane * GBP_RED_STRIDE;
+      float acc = row[0];
+#pragma unroll 8
+      for (int i = 1; i < 32; ++i) acc = fa(acc, row[i]);
+      out42[lane] = acc;
+    }
+    if (lane < GBP_CAMPART - 32) {
+      const float* row = red + (32 + lane) * GBP_RED_STRIDE;
+      float acc = row[0];
+#pragma unroll 8
+      for (int i = 1; i < 32; ++i) acc = fa(acc, row[i]);
+      out42[32 + lane] = acc;
+    }
+  } else if (lane < 27) {
     const float* row = red + lane * GBP_RED_STRIDE;
     float acc = row[0];
 #pragma unroll 8
     for (int i = 1; i < 32; ++i) acc = fa(acc, row[i]);
-    out42[lane] = acc;
-  }
-  if (lane < GBP_CAMPART - 32) {
-    const float* row = red + (32 + lane) * GBP_RED_STRIDE;
-    float acc = row[0];
-#pragma unroll 8
-    for (int i = 1; i < 32; ++i) acc = fa(acc, row[i]);
-    out42[32 + lane] = acc;
+    // position of value `lane` of [eta 6 | lower 21] inside [eta 6 | Lambda 36 row-major]
+    uint32_t pos = lane;
+    if (lane >= 6) {
+      const uint32_t k = lane - 6;
+      const uint32_t i = (k >= 15) ? 5u : (k >= 10) ? 4u : (k >= 6) ? 3u : (k >= 3) ? 2u : (k >= 1) ? 1u : 0u;
+      pos = 6 + i * 6 + (k - i * (i + 1) / 2);
+    }
+    out42[pos] = acc;
   }
 }
 
@@ -411,6 +430,7 @@ GBP_DEV void msg_to_landmark(const float4* stage, const float* s_cam, const uint
 
 // Message to the camera (gbp_codelets.cpp:446-462, 619-627): Schur complement over the landmark block,
 // one inv3x3.  nc: eta 0..5 | lower lambda 6..26 | pad; ncu: the strict upper triangle (row-major, i<j).
+template <bool UPPER>
 GBP_DEV void msg_to_camera(const float4* stage, const uint32_t lane, const float (&lb)[20], const float damping,
                            float (&nc)[28], float (&ncu)[16]) {
   const float omd = fs(1.0f, damping);
@@ -448,10 +468,14 @@ GBP_DEV void msg_to_camera(const float4* stage, const uint32_t lane, const float
   for (int i = 0; i < 6; ++i)
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
-      const float acc = fa(fa(fm(P[i * 3], cl[j * 3]), fm(P[i * 3 + 1], cl[j * 3 + 1])), fm(P[i * 3 + 2], cl[j * 3 + 2]));
-      const float v = fs(GBP_CCF(i, j), acc);
-      if (i >= j) nc[GBP_MCAM_LOWER + lt(i, j)] = v;
-      else ncu[gbp_upper(i, j)] = v;
+      if (i >= j || UPPER) {
+        const float acc = fa(fa(fm(P[i * 3], cl[j * 3]), fm(P[i * 3 + 1], cl[j * 3 + 1])), fm(P[i * 3 + 2], cl[j * 3 + 2]));
+        const float v = fs(GBP_CCF(i, j), acc);
+        if (i >= j) nc[GBP_MCAM_LOWER + lt(i, j)] = v;
+        else ncu[gbp_upper(i, j)] = v;
+      } else {
+        ncu[gbp_upper(i, j)] = 0.f;
+      }
     }
   nc[27] = 0.f;
   ncu[15] = 0.f;
@@ -509,7 +533,7 @@ GBP_DEV void prep_factor(const DeviceGraph& g, float4* stage, const float* s_cam
 
 // One warp-tile: prep + messages of 32 factors from the landed stage.
 // lb: landmark record of this lane's factor (load_lmk_belief).
-template <bool PREP, bool MSG>
+template <bool PREP, bool MSG, bool UPPER>
 GBP_DEV void sweep_tile(const DeviceGraph& g, float4* stage, const float* s_cam, const uint32_t wt, const uint2 ti,
                         const float (&lb)[20], const uint32_t lane) {
   const size_t e = (size_t)wt * 32 + lane;
@@ -534,7 +558,7 @@ GBP_DEV void sweep_tile(const DeviceGraph& g, float4* stage, const float* s_cam,
       float4* p = g.mlmk + lpos * GBP_MLMK_QUADS;
 #pragma unroll
       for (int q = 0; q < 3; ++q) p[q] = make_float4(nl[q * 4], nl[q * 4 + 1], nl[q * 4 + 2], nl[q * 4 + 3]);
-      msg_to_camera(stage, lane, lb, damping, nc, ncu);
+      msg_to_camera<UPPER>(stage, lane, lb, damping, nc, ncu);
       store_cam_message(g, e, nc, ncu);
       flags |= GBP_FLAG_HASMSG;
     } else {
@@ -562,19 +586,30 @@ GBP_DEV void sweep_tile(const DeviceGraph& g, float4* stage, const float* s_cam,
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < 6; ++i) red[i * GBP_RED_STRIDE + lane] = nc[i];
+    if (UPPER) {
 #pragma unroll
-    for (int i = 0; i < 6; ++i)
+      for (int i = 0; i < 6; ++i)
 #pragma unroll
-      for (int j = 0; j < 6; ++j)
-        red[(6 + i * 6 + j) * GBP_RED_STRIDE + lane] =
-            (i >= j) ? nc[GBP_MCAM_LOWER + lt(i, j)] : ncu[gbp_upper(i, j)];
+        for (int j = 0; j < 6; ++j)
+          red[(6 + i * 6 + j) * GBP_RED_STRIDE + lane] =
+              (i >= j) ? nc[GBP_MCAM_LOWER + lt(i, j)] : ncu[gbp_upper(i, j)];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 21; ++k) red[(6 + k) * GBP_RED_STRIDE + lane] = nc[GBP_MCAM_LOWER + k];
+    }
     __syncwarp();
-    warp_cam_reduce(red, lane, g.cam_partial + (size_t)wt * GBP_CAMPART);
+    warp_cam_reduce<UPPER>(red, lane, g.cam_partial + (size_t)wt * GBP_CAMPART);
     __syncwarp();
   }
 }
 
-template <bool PREP, bool MSG>
+// UPPER == false: the strict upper triangle of the factor->camera message Lambda is neither computed nor
+// summed.  Nothing in the algorithm ever reads it back (inv6x6 and the staged camera belief use the lower
+// triangle only); it only reaches the caller through cam_beliefs_lambda.  gbp_cuda_iterate therefore runs
+// every sweep of a call without per-sweep metrics but the LAST in this mode (k_update_vars mirrors the lower triangle meanwhile): the
+// belief of a camera is the sum of the messages of the latest sweep alone, so after the call every tensor is
+// what the all-UPPER sequence would have produced, bit for bit.
+template <bool PREP, bool MSG, bool UPPER>
 __global__ void __launch_bounds__(GBP_SW_WARPS * 32, 1) k_sweep(const DeviceGraph g) {
   extern __shared__ float4 smem4[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -643,7 +678,7 @@ __global__ void __launch_bounds__(GBP_SW_WARPS * 32, 1) k_sweep(const DeviceGrap
     // the copies of THIS warp-tile were committed one iteration ago: leave the newest group in flight
     asm volatile("cp.async.commit_group;\n cp.async.wait_group 1;\n" ::: "memory");
     __syncwarp();
-    sweep_tile<PREP, MSG>(g, stage_base + buf * GBP_STAGE_QUADS, scam_base + buf * GBP_SCAM, wt, ti, lb, lane);
+    sweep_tile<PREP, MSG, UPPER>(g, stage_base + buf * GBP_STAGE_QUADS, scam_base + buf * GBP_SCAM, wt, ti, lb, lane);
     if (!has_next) break;
     wt = wt_n; wt_n = wt_nn;
     ti = ti_n; ti_n = ti_nn;
@@ -765,7 +800,7 @@ __global__ void __launch_bounds__(GBP_TILE) k_cam_partials(const DeviceGraph g) 
       for (int j = i + 1; j < 6; ++j) red[(6 + i * 6 + j) * GBP_RED_STRIDE + lane] = u[gbp_upper(i, j)];
   }
   __syncwarp();
-  warp_cam_reduce(red, lane, g.cam_partial + ((size_t)tile * (GBP_TILE / 32) + warp) * GBP_CAMPART);
+  warp_cam_reduce<true>(red, lane, g.cam_partial + ((size_t)tile * (GBP_TILE / 32) + warp) * GBP_CAMPART);
 }
 
 // b += the factor->landmark messages of landmark l, strictly in slot order (= original
@@ -817,10 +852,14 @@ GBP_DEV void lmk_load_prior(const DeviceGraph& g, const uint32_t l, float (&b)[1
 // Belief update of the cameras (prog_ub, ba/ba.cpp:104-139, camera half) + per-camera mean and
 // rotation.  One block per camera: 42 threads add the per-warp-tile partials of k_sweep to the
 // prior in warp-tile order, one thread inverts the 6x6 belief (latency bound: a serial LDL^T).
-GBP_DEV void update_camera(const DeviceGraph& g, const int shift, const uint32_t c) {
+GBP_DEV void update_camera(const DeviceGraph& g, const int shift, const uint32_t c, const int lower_only) {
   __shared__ float s_b[GBP_CAMPART];
   const uint32_t tid = threadIdx.x;
-  if (tid < GBP_CAMPART) {
+  // entry tid of [eta 6 | Lambda 36 row-major]; after a sweep that skipped the strict upper triangle of the
+  // camera messages (k_sweep<.., UPPER = false>) the upper entries of the belief mirror the lower ones
+  const uint32_t bi = (tid >= 6 && tid < GBP_CAMPART) ? (tid - 6) / 6 : 0u, bj = (tid >= 6 && tid < GBP_CAMPART) ? (tid - 6) % 6 : 0u;
+  const bool skip = lower_only && tid >= 6 && bi < bj;
+  if (tid < GBP_CAMPART && !skip) {
     // the sum starts from +0 like a zero-initialised accumulator: 0 + prior (turns a -0 prior into +0)
     float acc = fa(0.0f, (tid < 6) ? g.cam_prior_eta[c * 6 + tid] : g.cam_prior_lam[c * 36 + (tid - 6)]);
     const uint32_t t0 = g.cam_wt_begin[c], t1 = g.cam_wt_begin[c + 1];
@@ -834,10 +873,14 @@ GBP_DEV void update_camera(const DeviceGraph& g, const int shift, const uint32_t
         if (t + u < t1) acc = fa(acc, v[u]);
     }
     s_b[tid] = acc;
-    if (tid < 6) g.cam_b_eta[c * 6 + tid] = acc;
-    else g.cam_b_lam[c * 36 + (tid - 6)] = acc;
   }
   __syncthreads();
+  if (tid < GBP_CAMPART) {
+    const float v = skip ? s_b[6 + bj * 6 + bi] : s_b[tid];
+    if (tid < 6) g.cam_b_eta[c * 6 + tid] = v;
+    else g.cam_b_lam[c * 36 + (tid - 6)] = v;
+    reinterpret_cast<float*>(g.cam_rec + (size_t)c * 16)[tid] = v;
+  }
   if (tid == 0) {
     float eta[6], lamL[21], mean[6];
 #pragma unroll
@@ -867,7 +910,6 @@ GBP_DEV void update_camera(const DeviceGraph& g, const int shift, const uint32_t
     }
     lin[18] = den;
   }
-  if (tid < GBP_CAMPART) reinterpret_cast<float*>(g.cam_rec + (size_t)c * 16)[tid] = s_b[tid];
 }
 
 // Belief update of the landmarks (prog_ub, landmark half) + per-landmark mean:
@@ -1019,7 +1061,8 @@ GBP_DEV void boundary_finish(const DeviceGraph& g, const int shift, const uint32
 #ifndef GBP_UV_BLOCKS
 #define GBP_UV_BLOCKS 10
 #endif
-__global__ void __launch_bounds__(GBP_TILE, GBP_UV_BLOCKS) k_update_vars(const DeviceGraph g, const int shift, const uint32_t n_push) {
+__global__ void __launch_bounds__(GBP_TILE, GBP_UV_BLOCKS) k_update_vars(const DeviceGraph g, const int shift, const uint32_t n_push,
+                                                                         const int lower_only) {
   const uint32_t nb_lmk = (g.L + GBP_LMK_PER_BLOCK - 1) / GBP_LMK_PER_BLOCK;
   if (shift && blockIdx.x == 0 && threadIdx.x == 0) {  // a sweep ended: open the next slot of the relinearisation ring
     const uint32_t next = g.relin_ring[GBP_RELIN_RING] + 1;
@@ -1034,7 +1077,7 @@ __global__ void __launch_bounds__(GBP_TILE, GBP_UV_BLOCKS) k_update_vars(const D
   if (b < n_push) {
     boundary_push(g, step, b, n_push);
   } else if ((b -= n_push) < g.C) {
-    update_camera(g, shift, b);
+    update_camera(g, shift, b, lower_only);
   } else if ((b -= g.C) < nb_lmk) {
     update_landmarks(g, shift, b);
   } else {

@@ -475,6 +475,38 @@ def test_fused_and_two_pass_sweeps_are_bit_identical():
     assert_bit_identical(engines[0], engines[2], "fused vs auto")
 
 
+@pytest.mark.parametrize("name", ["fr1xyz", "synth"])
+def test_blocks_of_sweeps_skip_the_upper_triangle_until_the_last(name, monkeypatch):
+    """Inside one gbp_cuda_iterate(n) call without per-sweep metrics every sweep but the last skips the strict upper
+    triangle of the camera messages (nothing reads it back; k_update_vars mirrors the lower one meanwhile).  After
+    the call every tensor, cam_beliefs_lambda included, equals the oracle's and the all-complete sequence's bit for
+    bit; with metrics every sweep is complete and the metrics are those of the all-complete sequence."""
+    if name == "synth":
+        st = Setup(BALProblem.synthetic(12, 1500, 8.0, seed=3))
+    else:
+        st = common.make_setup(name)
+    ora = oracle_lib.OracleEngine(st.problem, kind=KIND)
+    ora.set_reduce_order(1)
+    fast = GBPEngine(st.problem)
+    monkeypatch.setenv("GBP_SKIP_UPPER", "0")
+    full = GBPEngine(st.problem)
+    monkeypatch.delenv("GBP_SKIP_UPPER")
+    for e in (ora, fast, full):
+        common.run_ba(e, 12)
+    for n, with_stats in ((7, False), (1, False), (13, True), (2, False), (30, True)):
+        so = ora.iterate(n, stats=with_stats)
+        sf = fast.iterate(n, stats=with_stats)
+        su = full.iterate(n, stats=with_stats)
+        assert_bit_identical(fast, ora, f"{name}: block of {n}")
+        assert_bit_identical(fast, full, f"{name}: block of {n}, skipping vs complete")
+        if with_stats:
+            for a, b, c in zip(sf, su, so):
+                assert a == b
+                assert (a["n_relins"], a["n_robust"], a["n_active"]) == (c["n_relins"], c["n_robust"], c["n_active"])
+        fast.weaken_priors(); full.weaken_priors(); ora.weaken_priors()      # a belief update between calls
+        assert_bit_identical(fast, ora, f"{name}: after weaken")
+
+
 def test_c_abi_error_codes():
     """Error behaviour of the tensor / program entry points (negative codes + gbp_cuda_last_error text)."""
     import ctypes as C
