@@ -10,4 +10,7 @@ grep -E "k_sweep|k_update" gpurun_out/launches.csv | tail -6 | awk -F'","' '{pri
 GBP_CUDA_GRAPH=0 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_stats.csv python scripts/metric_launches.py > /dev/null 2>&1
 grep -E "k_" gpurun_out/launches_stats.csv | tail -5 | awk -F'","' '{print $5, $NF}' | tr -d '"'
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_sweep|k_update_vars" -s 20 -c 2 -f -o gpurun_out/prof_sweep python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+# the same capture with the caches left as they are between replays: DRAM traffic with the landmark-bound messages resident in the
+# persisting L2 window (the default capture flushes L2 before every replay)
+timeout 900 ncu --set full --clock-control none --cache-control none -k regex:"k_sweep|k_update_vars" -s 20 -c 2 -f -o gpurun_out/prof_sweep_warm python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/ncu_full_warm.log 2>&1
 ls -la gpurun_out | tail -4
