@@ -140,7 +140,11 @@ int gbp_cuda_free(gbp_handle* h);
 int gbp_cuda_weaken_priors(gbp_handle* h);
 
 /* GBP_PROG x n_sweeps (ba/ba.cpp:895-905).  If stats != NULL it must hold
- * n_sweeps entries; entry i is evaluated on the beliefs after sweep i. */
+ * n_sweeps entries; entry i is evaluated on the beliefs after sweep i.
+ * When the call returns every tensor equals what n_sweeps x GBP_PROG leave behind.
+ * With stats == NULL the sweeps before the last one do not form the strict upper
+ * triangle of the factor->camera message Lambda (the algorithm never reads it back;
+ * it only reaches cam_beliefs_lambda, which the last sweep of the call rebuilds). */
 int gbp_cuda_iterate(gbp_handle* h, int n_sweeps, gbp_iter_stats* stats);
 
 /* Convergence control on top of gbp_cuda_iterate (the reference has none: it runs a
