@@ -119,6 +119,7 @@ struct gbp_handle {
   uint32_t* d_exp_robust = nullptr;
   // metric
   gbp::MetricPartial* d_metric_parts = nullptr;
+  uint32_t* d_metric_ticket = nullptr;  // blocks of k_metric that are done (the last one finishes)
   double* d_met_cam = nullptr;      // [C][16] double-precision camera means + rotations (metric only)
   double* d_met_lmk = nullptr;      // [L][4]  double-precision landmark means (metric only)
   gbp::DeviceStats* d_stats = nullptr;
@@ -301,12 +302,15 @@ int launch_metric(gbp_handle* h, gbp::DeviceStats* d_out) {
     const uint32_t nv = h->C + h->L;
     gbp::k_metric_prep<<<(nv + 127) / 128, 128, 0, h->stream>>>(h->g, h->d_met_cam, h->d_met_lmk);
     gbp::k_metric<<<metric_grid(h), GBP_TILE, 0, h->stream>>>(h->g, h->n_active, h->n_tiles, h->d_met_cam, h->d_met_lmk,
-                                                              h->d_metric_parts);
+                                                              h->d_metric_parts, h->d_metric_ticket, d_out,
+                                                              h->shard ? h->d_metric_raw : nullptr,
+                                                              h->capturing ? h->d_stat_cursor : nullptr);
     h->kernels_launched += 2;
+  } else {
+    gbp::k_metric_finish<<<1, GBP_TILE, 0, h->stream>>>(h->d_metric_parts, 0u, d_out, h->shard ? h->d_metric_raw : nullptr,
+                                                        h->capturing ? h->d_stat_cursor : nullptr);
+    h->kernels_launched++;
   }
-  gbp::k_metric_finish<<<1, 256, 0, h->stream>>>(h->d_metric_parts, h->n_tiles ? metric_grid(h) : 0u, d_out, h->shard ? h->d_metric_raw : nullptr,
-                                                 h->capturing ? h->d_stat_cursor : nullptr);
-  h->kernels_launched++;
   if (h->shard) {  // every rank reports the metric of the WHOLE graph
     GBP_CUDA_TRY(cudaEventRecord(h->ev_send, h->stream));
     GBP_CUDA_TRY(cudaStreamWaitEvent(h->comm_stream, h->ev_send, 0));
@@ -750,6 +754,7 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   A_(h->d_lmk_first_cam, L);
   A_(h->d_kf_scratch, 4);
   A_(h->d_metric_parts, h->n_tiles);
+  A_(h->d_metric_ticket, 1);
   A_(h->d_stat_cursor, 1);
   A_(g.relin_list, E);
   A_(g.relin_count, 1);
@@ -1166,7 +1171,7 @@ int gbp_cuda_iterate(gbp_handle* h, int n_sweeps, gbp_iter_stats* stats) {
     // (not when per-sweep metrics are requested: the metric inverts the FULL camera belief, like the reference's)
     if (!rc && n_sweeps > 1 && !stats && can_skip_upper(h)) rc = sweep_graph(h, false, false, &exec_lower);
     if (rc) return rc;
-    const uint64_t per = (stats ? 5 : 2) + (h->two_pass ? 2 : 0);
+    const uint64_t per = (stats ? 4 : 2) + (h->two_pass ? 2 : 0);
     for (int i = 0; i < n_sweeps; ++i)
       GBP_CUDA_TRY(cudaGraphLaunch((exec_lower && i + 1 < n_sweeps) ? exec_lower : exec, h->stream));
     h->kernels_launched += per * (uint64_t)n_sweeps;

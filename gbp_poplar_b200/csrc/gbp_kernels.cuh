@@ -1385,12 +1385,68 @@ __global__ void k_metric_prep(const DeviceGraph g, double* __restrict__ met_cam,
   }
 }
 
+struct DeviceStats {  // == gbp_iter_stats
+  float reproj_mean, cost;
+  uint32_t n_relins, n_robust, n_active, reserved;
+};
+
+// Fixed-order reduction of the per-block partials in double by ONE block of NT threads, then the result.
+// raw != nullptr (multi-GPU): the five sums are written as doubles for k_metric_combine instead.
+// cursor != nullptr (CUDA-graph replay): the result goes to out[*cursor] and the cursor advances.
+template <int NT>
+GBP_DEV void metric_finish(const MetricPartial* parts, const uint32_t n_parts, DeviceStats* __restrict__ out,
+                           double* __restrict__ raw, uint32_t* __restrict__ cursor) {
+  __shared__ double s_d[2][NT];
+  __shared__ uint32_t s_u[3][NT];
+  const uint32_t tid = threadIdx.x;
+  double a = 0.0, b = 0.0;
+  uint32_t r = 0, ro = 0, ac = 0;
+  for (uint32_t t = tid; t < n_parts; t += NT) {
+    // written by other blocks of the same launch: read past L1
+    const double2 d = __ldcg(reinterpret_cast<const double2*>(parts + t));
+    const uint4 u = __ldcg(reinterpret_cast<const uint4*>(parts + t) + 1);
+    a += d.x; b += d.y;
+    r += u.x; ro += u.y; ac += u.z;
+  }
+  s_d[0][tid] = a; s_d[1][tid] = b; s_u[0][tid] = r; s_u[1][tid] = ro; s_u[2][tid] = ac;
+  __syncthreads();
+  for (int o = NT / 2; o > 0; o >>= 1) {
+    if (tid < o) {
+      s_d[0][tid] += s_d[0][tid + o]; s_d[1][tid] += s_d[1][tid + o];
+      s_u[0][tid] += s_u[0][tid + o]; s_u[1][tid] += s_u[1][tid + o]; s_u[2][tid] += s_u[2][tid + o];
+    }
+    __syncthreads();
+  }
+  if (tid == 0 && raw) {
+    raw[0] = s_d[0][0]; raw[1] = s_d[1][0];
+    raw[2] = (double)s_u[0][0]; raw[3] = (double)s_u[1][0]; raw[4] = (double)s_u[2][0];
+    raw[5] = raw[6] = raw[7] = 0.0;
+  } else if (tid == 0) {
+    DeviceStats s;
+    s.n_active = s_u[2][0];
+    s.reproj_mean = (float)(s_d[0][0] / (double)s.n_active);
+    s.cost = (float)s_d[1][0];
+    s.n_relins = s_u[0][0];
+    s.n_robust = s_u[1][0];
+    s.reserved = 0;
+    if (cursor) {
+      out[*cursor] = s;
+      *cursor += 1;
+    } else {
+      *out = s;
+    }
+  }
+}
+
 // Persistent blocks: block b walks the 128-slot tiles b, b + gridDim.x, ... in order and every thread keeps
 // its own double sums, so the number of partials the finishing block has to add is the (small, fixed) grid size
-// and the summation order is fixed.
+// and the summation order is fixed.  The last block to finish (a ticket counter) adds them up and writes the
+// result: no separate finishing launch.
 __global__ void __launch_bounds__(GBP_TILE) k_metric(const DeviceGraph g, const uint32_t n_active_total, const uint32_t n_tiles,
                                                     const double* __restrict__ met_cam, const double* __restrict__ met_lmk,
-                                                    MetricPartial* __restrict__ out) {
+                                                    MetricPartial* out, uint32_t* __restrict__ ticket,
+                                                    DeviceStats* __restrict__ stats_out, double* __restrict__ raw,
+                                                    uint32_t* __restrict__ cursor) {
   __shared__ double s_f[2][GBP_TILE / 32];
   __shared__ uint32_t s_u[3][GBP_TILE / 32];
   const uint32_t tid = threadIdx.x;
@@ -1416,8 +1472,9 @@ __global__ void __launch_bounds__(GBP_TILE) k_metric(const DeviceGraph g, const 
       double y[3];
 #pragma unroll
       for (int i = 0; i < 3; ++i) y[i] = cm[6 + i * 3] * m0 + cm[6 + i * 3 + 1] * m1 + cm[6 + i * 3 + 2] * m2 + cm[i];
-      const double u = ((double)g.K[0] * y[0] + (double)g.K[2] * y[2]) / y[2];
-      const double v = ((double)g.K[1] * y[1] + (double)g.K[3] * y[2]) / y[2];
+      const double iz = 1.0 / y[2];
+      const double u = ((double)g.K[0] * y[0] + (double)g.K[2] * y[2]) * iz;
+      const double v = ((double)g.K[1] * y[1] + (double)g.K[3] * y[2]) * iz;
       const double r0 = (double)rb.x - u, r1 = (double)rb.y - v;
       const double s2 = r0 * r0 + r1 * r1;
       nrm += sqrt(s2);
@@ -1446,57 +1503,24 @@ __global__ void __launch_bounds__(GBP_TILE) k_metric(const DeviceGraph g, const 
     }
     out[blockIdx.x] = p;
   }
+  __shared__ uint32_t s_last;
+  if (tid == 0) {
+    __threadfence();
+    s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  metric_finish<GBP_TILE>(out, gridDim.x, stats_out, raw, cursor);
+  if (tid == 0) *ticket = 0u;
 }
 
-struct DeviceStats {  // == gbp_iter_stats
-  float reproj_mean, cost;
-  uint32_t n_relins, n_robust, n_active, reserved;
-};
 
-// One block: fixed-order reduction of the per-tile partials in double.
-// raw != nullptr (multi-GPU): the five sums are written as doubles for k_metric_combine instead.
-// cursor != nullptr (CUDA-graph replay): the result goes to out[*cursor] and the cursor advances.
-__global__ void __launch_bounds__(256) k_metric_finish(const MetricPartial* __restrict__ parts, const uint32_t n_tiles,
-                                                      DeviceStats* __restrict__ out, double* __restrict__ raw,
-                                                      uint32_t* __restrict__ cursor) {
-  __shared__ double s_d[2][256];
-  __shared__ uint32_t s_u[3][256];
-  const uint32_t tid = threadIdx.x;
-  double a = 0.0, b = 0.0;
-  uint32_t r = 0, ro = 0, ac = 0;
-  for (uint32_t t = tid; t < n_tiles; t += 256) {
-    const MetricPartial p = parts[t];
-    a += p.sum_norm; b += p.sum_sq;
-    r += p.n_relins; ro += p.n_robust; ac += p.n_active;
-  }
-  s_d[0][tid] = a; s_d[1][tid] = b; s_u[0][tid] = r; s_u[1][tid] = ro; s_u[2][tid] = ac;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (tid < o) {
-      s_d[0][tid] += s_d[0][tid + o]; s_d[1][tid] += s_d[1][tid + o];
-      s_u[0][tid] += s_u[0][tid + o]; s_u[1][tid] += s_u[1][tid + o]; s_u[2][tid] += s_u[2][tid + o];
-    }
-    __syncthreads();
-  }
-  if (tid == 0 && raw) {
-    raw[0] = s_d[0][0]; raw[1] = s_d[1][0];
-    raw[2] = (double)s_u[0][0]; raw[3] = (double)s_u[1][0]; raw[4] = (double)s_u[2][0];
-    raw[5] = raw[6] = raw[7] = 0.0;
-  } else if (tid == 0) {
-    DeviceStats s;
-    s.n_active = s_u[2][0];
-    s.reproj_mean = (float)(s_d[0][0] / (double)s.n_active);
-    s.cost = (float)s_d[1][0];
-    s.n_relins = s_u[0][0];
-    s.n_robust = s_u[1][0];
-    s.reserved = 0;
-    if (cursor) {
-      out[*cursor] = s;
-      *cursor += 1;
-    } else {
-      *out = s;
-    }
-  }
+// The empty graph (no k_metric launch): zero sums through the same finishing code.
+__global__ void __launch_bounds__(GBP_TILE) k_metric_finish(const MetricPartial* __restrict__ parts, const uint32_t n_parts,
+                                                           DeviceStats* __restrict__ out, double* __restrict__ raw,
+                                                           uint32_t* __restrict__ cursor) {
+  metric_finish<GBP_TILE>(parts, n_parts, out, raw, cursor);
 }
 
 // multi-GPU: sum the all-gathered per-rank metric sums [world][8] in rank order
