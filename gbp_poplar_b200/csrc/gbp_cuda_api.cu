@@ -111,7 +111,8 @@ struct gbp_handle {
   uint32_t* d_lmk_first_cam = nullptr;      // [L] lowest camera index observing the landmark (0xffffffff: none)
   float* d_kf_scratch = nullptr;            // [4] see k_kf_pose
   std::vector<uint32_t> new_lmks_at_cam;    // [C] landmarks first observed by each camera
-  std::vector<uint32_t> cam_degree;         // [C]
+  std::vector<uint32_t> cam_edge_ptr;       // [C+1] CSR over original edge ids: the factors of every camera
+  std::vector<uint32_t> cam_edge_ids;       // [E]
   float* d_exp_lmk_eta = nullptr;
   float* d_exp_lmk_lam = nullptr;
   float* d_exp_damping = nullptr;
@@ -855,7 +856,10 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
     h->new_lmks_at_cam.assign(C, 0u);
     for (uint32_t l = 0; l < L; ++l)
       if (first_cam[l] != 0xffffffffu) h->new_lmks_at_cam[first_cam[l]]++;
-    h->cam_degree = deg_c;
+    h->cam_edge_ptr.assign(C + 1, 0u);
+    for (uint32_t c = 0; c < C; ++c) h->cam_edge_ptr[c + 1] = h->cam_edge_ptr[c] + deg_c[c];
+    h->cam_edge_ids.resize(E);
+    for (uint32_t e = 0; e < E; ++e) h->cam_edge_ids[h->cam_edge_ptr[h->cam_ids[e]] + h->slot_c[e]] = e;
     U_(h->d_lmk_first_cam, first_cam.data(), L);
   }
   if (h->shard) {
@@ -1423,11 +1427,13 @@ int gbp_cuda_add_keyframe_device(gbp_handle* h, uint32_t new_cam, uint32_t steps
   }
   // host mirrors of the flags (get_tensor("active_flag"), the metric's active-edge count)
   uint32_t newly = 0;
-  for (uint32_t e = 0; e < h->E; ++e)
-    if (h->cam_ids[e] == new_cam && h->active_host[e] != 1u) {
+  for (uint32_t k = h->cam_edge_ptr[new_cam]; k < h->cam_edge_ptr[new_cam + 1]; ++k) {
+    const uint32_t e = h->cam_edge_ids[k];
+    if (h->active_host[e] != 1u) {
       h->active_host[e] = 1u;
       ++newly;
     }
+  }
   h->n_active += newly;
   if (n_new_lmks) *n_new_lmks = (int)h->new_lmks_at_cam[new_cam];
   return GBP_OK;

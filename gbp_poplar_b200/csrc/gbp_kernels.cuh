@@ -274,7 +274,7 @@ __device__ __noinline__ uint32_t relinearise_record(const float4* src, size_t sr
 #define GBP_SQ_RECB (GBP_SQ_RECA + 1)                  // 25
 #define GBP_STAGE_QUADS (GBP_SQ * 32)
 #define GBP_SCAM 56  // per-warp copy of: belief eta 6 | belief lambda 36 | mean 6 | previous mean 6
-#define GBP_RED_STRIDE 33
+#define GBP_RED_STRIDE 36  // floats per row of the reduction scratch: 32 lanes + 4 pad, rows 16-byte aligned for LDS.128
 #define GBP_SWEEP_SMEM (GBP_SW_WARPS * GBP_NBUF * (GBP_STAGE_QUADS * 16 + GBP_SCAM * 4))
 
 GBP_DEV void cp_async16(void* smem, const void* gmem) {
@@ -322,28 +322,26 @@ GBP_DEV void load_lmk_belief(const DeviceGraph& g, const uint32_t l, float (&lb)
 // UPPER == false: only eta and the lower triangle of Lambda (27 values, rows 0..26 of `red` in the order
 // [eta 6 | lower 21]) are summed -- one pass over the lanes instead of two; the strict upper triangle of the
 // partial is left untouched (see k_sweep).
+// one row of the scratch (the 32 lanes' values of one message entry), summed in lane order; eight 16-byte reads
+GBP_DEV float row_sum_lane_order(const float* row) {
+  const float4* r4 = reinterpret_cast<const float4*>(row);
+  float4 v = r4[0];
+  float acc = fa(fa(fa(v.x, v.y), v.z), v.w);
+#pragma unroll
+  for (int k = 1; k < 8; ++k) {
+    v = r4[k];
+    acc = fa(fa(fa(fa(acc, v.x), v.y), v.z), v.w);
+  }
+  return acc;
+}
+
 template <bool UPPER>
 GBP_DEV void warp_cam_reduce(float* red, uint32_t lane, float* __restrict__ out42) {
   if (UPPER) {
-    {
-      const float* row = red + lane * GBP_RED_STRIDE;
-      float acc = row[0];
-#pragma unroll 8
-      for (int i = 1; i < 32; ++i) acc = fa(acc, row[i]);
-      out42[lane] = acc;
-    }
-    if (lane < GBP_CAMPART - 32) {
-      const float* row = red + (32 + lane) * GBP_RED_STRIDE;
-      float acc = row[0];
-#pragma unroll 8
-      for (int i = 1; i < 32; ++i) acc = fa(acc, row[i]);
-      out42[32 + lane] = acc;
-    }
+    out42[lane] = row_sum_lane_order(red + lane * GBP_RED_STRIDE);
+    if (lane < GBP_CAMPART - 32) out42[32 + lane] = row_sum_lane_order(red + (32 + lane) * GBP_RED_STRIDE);
   } else if (lane < 27) {
-    const float* row = red + lane * GBP_RED_STRIDE;
-    float acc = row[0];
-#pragma unroll 8
-    for (int i = 1; i < 32; ++i) acc = fa(acc, row[i]);
+    const float acc = row_sum_lane_order(red + lane * GBP_RED_STRIDE);
     // position of value `lane` of [eta 6 | lower 21] inside [eta 6 | Lambda 36 row-major]
     uint32_t pos = lane;
     if (lane >= 6) {
@@ -778,7 +776,7 @@ __global__ void __launch_bounds__(GBP_TILE) k_relin_list(const DeviceGraph g) {
 // after set_tensor on the camera message tensors; the strict upper triangle is
 // the mirrored lower one, see gbp_layout.h).
 __global__ void __launch_bounds__(GBP_TILE) k_cam_partials(const DeviceGraph g) {
-  __shared__ float s_red[GBP_TILE / 32][GBP_CAMPART * GBP_RED_STRIDE];
+  __shared__ __align__(16) float s_red[GBP_TILE / 32][GBP_CAMPART * GBP_RED_STRIDE];
   const uint32_t tile = blockIdx.x, tid = threadIdx.x;
   const uint32_t warp = tid >> 5, lane = tid & 31;
   const size_t e = (size_t)tile * GBP_TILE + tid;

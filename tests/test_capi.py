@@ -65,6 +65,8 @@ def test_null_arguments_are_rejected():
     assert fns["init"](None, None, C.byref(h)) == -1
     assert fns["iterate"](None, 1, None) == -1
     assert fns["get_tensor"](None, b"mu", None, 0) == -1
+    assert fns["add_keyframe"](None, None, None, None, None, None, None, None, None) == -1
+    assert lib.gbp_cuda_add_keyframe_device(None, 2, 5, None) == -1
 
 
 @pytest.mark.parametrize("world", [1, 2, 4, 8])
