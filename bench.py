@@ -268,6 +268,7 @@ def main():
 
     # ---- e2e: a whole ba-style job through the C ABI with host buffers (rank-local problem)
     e2e = None
+    eng.close()                                        # the e2e job below is a fresh one: nothing of the timed engine is kept
     if rank == 0 or world > 1:
         barrier()
         t0 = time.time()

@@ -138,6 +138,7 @@ struct gbp_handle {
   uint64_t kernels_launched = 0;
   uint64_t last_kernels = 0;
   std::vector<void*> allocs;
+  std::vector<void*> pool_allocs;  // from the stream-ordered pool (arena_alloc)
   // multi-GPU shard (null / 0 on a single-GPU handle)
   gbp_shard* shard = nullptr;
   uint32_t world = 1, rank = 0;
@@ -154,6 +155,30 @@ struct gbp_handle {
 };
 
 namespace {
+
+// The per-handle arena comes from the device's default stream-ordered memory pool with its release threshold
+// lifted, so the block of a freed handle is handed to the next gbp_cuda_init of the process without a trip to
+// the driver (a fresh cudaMalloc of 0.65 GB costs anything between 1 and 200 ms depending on the box).
+int arena_alloc(gbp_handle* h, char** p, size_t bytes) {
+  *p = nullptr;
+  int pools = 0;
+  cudaDeviceGetAttribute(&pools, cudaDevAttrMemoryPoolsSupported, h->device);
+  if (pools) {
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, h->device) == cudaSuccess) {
+      uint64_t keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      if (cudaMallocAsync((void**)p, std::max<size_t>(bytes, 16), h->stream) == cudaSuccess) {
+        h->pool_allocs.push_back((void*)*p);
+        return GBP_OK;
+      }
+    }
+    cudaGetLastError();
+  }
+  GBP_CUDA_TRY(cudaMalloc((void**)p, std::max<size_t>(bytes, 16)));
+  h->allocs.push_back((void*)*p);
+  return GBP_OK;
+}
 
 template <class T>
 int h_alloc(gbp_handle* h, T** p, size_t n, bool zero = true) {
@@ -791,7 +816,7 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
 #undef A_
   {
     char* base = nullptr;
-    rc = h_alloc(h, &base, arena_bytes, false);
+    rc = arena_alloc(h, &base, arena_bytes);
     if (rc) return rc;
     GBP_CUDA_TRY(cudaMemsetAsync(base, 0, arena_bytes, h->stream));  // ordered before the uploads below
     for (auto& r : arena) *r.first = base + r.second;
@@ -1061,6 +1086,8 @@ int gbp_cuda_free(gbp_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->l2_window.num_bytes) cudaCtxResetPersistingL2Cache();  // do not leave this handle's lines pinned
   for (void* p : h->allocs) cudaFree(p);
+  for (void* p : h->pool_allocs) cudaFreeAsync(p, h->stream);  // stays in the pool for the next handle
+  if (h->stream && !h->pool_allocs.empty()) cudaStreamSynchronize(h->stream);
   if (h->d_stats) cudaFree(h->d_stats);
   if (h->pin_stats) cudaFreeHost(h->pin_stats);
   if (h->pin_ring) cudaFreeHost(h->pin_ring);
