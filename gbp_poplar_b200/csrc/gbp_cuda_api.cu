@@ -163,6 +163,7 @@ int arena_alloc(gbp_handle* h, char** p, size_t bytes) {
   *p = nullptr;
   int pools = 0;
   cudaDeviceGetAttribute(&pools, cudaDevAttrMemoryPoolsSupported, h->device);
+  if (const char* env = std::getenv("GBP_ARENA_POOL")) pools = pools && std::atoi(env) != 0;
   if (pools) {
     cudaMemPool_t pool = nullptr;
     if (cudaDeviceGetDefaultMemPool(&pool, h->device) == cudaSuccess) {
@@ -833,7 +834,11 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
     cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, h->device);
     cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, h->device);
     size_t want = (mode == 1 ? reuse_mlmk_end : reuse_end) - reuse_begin;
-    if (const char* env = std::getenv("GBP_L2_WINDOW_MB")) want = std::min(want, (size_t)std::atoi(env) << 20);
+    // never more than 48 MB: a window that needs a hit ratio below 1, or a set-aside that leaves the streams less
+    // than ~70 MB of L2, loses (measured); on larger graphs the window covers the first 48 MB of the messages
+    size_t window_cap_mb = 48;
+    if (const char* env = std::getenv("GBP_L2_WINDOW_MB")) window_cap_mb = (size_t)std::atoi(env);
+    want = std::min(want, window_cap_mb << 20);
     size_t cap_mb = 1u << 20;
     if (const char* env = std::getenv("GBP_L2_SETASIDE_MB")) cap_mb = (size_t)std::atoi(env);
     if (mode > 0 && max_persist > 0 && max_window > 0 && want >= ((size_t)8 << 20)) {  // small graphs live in L2 anyway
