@@ -234,6 +234,31 @@ def main():
     stats = eng.eval()
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    clocks = sampler.summary()
+    if world > 1:
+        # every rank samples its own GPU: one power-capped GPU slows the whole lock-step job
+        try:
+            per_rank = [None] * world
+            dist.all_gather_object(per_rank, clocks)
+            mhz = [c["sm_mhz"] for c in per_rank if c and c.get("sm_mhz")]
+            clocks = dict(clocks)
+            clocks["ranks"] = [{"sm_mhz": c.get("sm_mhz"), "reasons": c.get("reasons")} for c in per_rank if c]
+            if mhz:
+                clocks["sm_mhz"] = min(mhz)
+            clocks["reasons"] = sorted(set(r for c in per_rank if c for r in (c.get("reasons") or [])))
+        except Exception as e:  # never let the diagnostics break the measurement
+            clocks = dict(clocks)
+            clocks["ranks_error"] = repr(e)
+
+    per_rank_kernels = None
+    if world > 1:
+        # factor / variable kernel time of every rank: the lock-step job runs at the slowest rank's pace and
+        # the others show the difference as waiting time inside k_update_vars
+        try:
+            per_rank_kernels = [None] * world
+            dist.all_gather_object(per_rank_kernels, [ms_factor / args.steps * 1e3, ms_var / args.steps * 1e3])
+        except Exception as e:
+            per_rank_kernels = repr(e)
 
     peak, peak_src = read_peaks()
     algo_bytes_factor_kernel = ALGO_BYTES_PER_FACTOR * E_loc   # one launch = this rank's factors
@@ -248,6 +273,7 @@ def main():
         "algorithmic_bytes_per_launch": algo_bytes_factor_kernel,
         "avg_launch_us": t_factor * 1e6, "kernel_share_of_step": ms_factor / max(ms_prof, 1e-9),
         "variable_kernel_avg_us": ms_var / args.steps * 1e3,
+        "per_rank_kernel_us": per_rank_kernels,
         "whole_sweep_algorithmic_GBps": (algo_bytes_factor_kernel + ALGO_BYTES_PER_CAMERA * Cn +
                                          ALGO_BYTES_PER_LANDMARK * Ln) * args.steps / (ms / 1e3) / 1e9,
     }
@@ -322,7 +348,7 @@ def main():
                        "preroll": f"{BA_PREROLL} sweeps of the ba.cpp schedule incl. prior weakening, untimed",
                        "init_s": init_s},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": sampler.summary(),
+            "clocks": clocks,
             "final": stats,
         }
         print(json.dumps(line), flush=True)
