@@ -160,6 +160,7 @@ CUDA_ONLY_API = {
     "gbp_cuda_exchange_mode": (C.c_int, [C.c_void_p]),
     # pure host: the rank-local sub-problem of a camera-range partition
     "gbp_shard_build": (C.c_int, [C.POINTER(GbpProblem), C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "gbp_shard_build_view": (C.c_int, [C.POINTER(GbpProblem), C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
     "gbp_shard_free": (None, [C.c_void_p]),
     "gbp_shard_problem": (C.POINTER(GbpProblem), [C.c_void_p]),
     "gbp_shard_get_plan": (C.POINTER(GbpShardPlan), [C.c_void_p]),

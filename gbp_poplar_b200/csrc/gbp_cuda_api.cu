@@ -1885,7 +1885,7 @@ int gbp_cuda_init_shard(const gbp_problem* p, const gbp_opts* o_in, uint32_t wor
     return GBP_ERR_COMM;
   }
   gbp_shard* sh = nullptr;
-  int rc = gbp_shard_build(p, world, rank, &sh);
+  int rc = gbp_shard_build_view(p, world, rank, &sh);  // p's arrays are only read during this call
   if (rc) return rc;
   gbp_handle* h = new gbp_handle();
   h->device = o.device;

@@ -6,6 +6,9 @@
 // tiles of 2^k IPUs (ba/ba.cpp:617-631,717-753,795-834); the exchange Poplar compiles
 // from graph.connect + reduce becomes one explicit all-gather of boundary partials.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -32,12 +35,20 @@ namespace {
 int camera_bounds(const gbp_problem* p, uint32_t world, std::vector<uint32_t>& bounds) {
   const uint32_t C = p->n_keyframes, L = p->n_points, E = p->n_edges;
   std::vector<uint64_t> deg(C, 0);
-  for (uint32_t e = 0; e < E; ++e) {
-    if (p->cam_ids[e] >= C || p->lmk_ids[e] >= L) {
+  for (uint32_t e = 0; e < E;) {  // by runs of one camera (the shipped files are camera-sorted)
+    const uint32_t c = p->cam_ids[e];
+    if (c >= C) {
       gbp_set_error("edge index out of range");
       return GBP_ERR_ARG;
     }
-    deg[p->cam_ids[e]]++;
+    const uint32_t e0 = e;
+    uint32_t bad = 0;
+    while (e < E && p->cam_ids[e] == c) bad |= (p->lmk_ids[e++] >= L) ? 1u : 0u;
+    if (bad) {
+      gbp_set_error("edge index out of range");
+      return GBP_ERR_ARG;
+    }
+    deg[c] += e - e0;
   }
   bounds.assign(world + 1, C);
   bounds[0] = 0;
@@ -52,29 +63,63 @@ int camera_bounds(const gbp_problem* p, uint32_t world, std::vector<uint32_t>& b
   return GBP_OK;
 }
 
-inline uint32_t rank_of_camera(const std::vector<uint32_t>& bounds, uint32_t c) {
-  return (uint32_t)(std::upper_bound(bounds.begin() + 1, bounds.end(), c) - bounds.begin() - 1);
+// owner rank of every camera (a table: one lookup per edge instead of a binary search)
+std::vector<uint32_t> camera_ranks(const std::vector<uint32_t>& bounds, uint32_t C) {
+  std::vector<uint32_t> rank(C, 0u);
+  for (uint32_t r = 0; r + 1 < bounds.size(); ++r)
+    for (uint32_t c = bounds[r]; c < bounds[r + 1] && c < C; ++c) rank[c] = r;
+  return rank;
 }
 
 // first / last rank observing each landmark (0xffffffff = unobserved)
-void landmark_rank_span(const gbp_problem* p, const std::vector<uint32_t>& bounds, std::vector<uint32_t>& lo,
+void landmark_rank_span(const gbp_problem* p, const std::vector<uint32_t>& cam_rank, std::vector<uint32_t>& lo,
                         std::vector<uint32_t>& hi) {
   lo.assign(p->n_points, 0xffffffffu);
   hi.assign(p->n_points, 0u);
   for (uint32_t e = 0; e < p->n_edges; ++e) {
-    const uint32_t r = rank_of_camera(bounds, p->cam_ids[e]);
+    const uint32_t r = cam_rank[p->cam_ids[e]];
     const uint32_t l = p->lmk_ids[e];
     lo[l] = std::min(lo[l], r);
     hi[l] = std::max(hi[l], r);
   }
 }
 
+// sel = src[idx] (rows of `width` elements), returned as a pointer: into `dst` (a copy) or -- when `view` is set
+// and idx is one contiguous ascending run (the edges of a camera range in a camera-sorted file, a range of
+// cameras) -- straight into src, without touching memory.  skip_if_zero: nullptr when every selected element is
+// zero (the streamed mu / oldmu of a fresh problem: the library treats a null array as zeros).
 template <class T>
-void slice(std::vector<T>& dst, const T* src, const std::vector<uint32_t>& idx, size_t width) {
+const T* slice(std::vector<T>& dst, const T* src, const std::vector<uint32_t>& idx, size_t width, bool view,
+               bool skip_if_zero = false) {
   dst.clear();
-  if (!src) return;
+  if (!src || idx.empty()) return nullptr;
+  const bool contiguous = (size_t)idx.back() - (size_t)idx.front() + 1 == idx.size();
+  if (skip_if_zero) {
+    bool any = false;
+    if (contiguous) {
+      // block-wise, branch-free inside a block so the compiler vectorises it (-0.0f counts as non-zero: harmless)
+      const unsigned char* b = reinterpret_cast<const unsigned char*>(src + (size_t)idx.front() * width);
+      const size_t n = idx.size() * width * sizeof(T);
+      for (size_t i = 0; i < n && !any; i += 4096) {
+        unsigned char acc = 0;
+        for (size_t k = i, k1 = std::min(n, i + 4096); k < k1; ++k) acc |= b[k];
+        any = acc != 0;
+      }
+    } else {
+      for (size_t i = 0; i < idx.size() && !any; ++i)
+        for (size_t k = 0; k < width && !any; ++k) any = src[(size_t)idx[i] * width + k] != T(0);
+    }
+    if (!any) return nullptr;
+  }
+  if (contiguous) {
+    const T* b = src + (size_t)idx.front() * width;
+    if (view) return b;
+    dst.assign(b, b + idx.size() * width);
+    return dst.data();
+  }
   dst.resize(idx.size() * width);
   for (size_t i = 0; i < idx.size(); ++i) std::memcpy(&dst[i * width], src + (size_t)idx[i] * width, width * sizeof(T));
+  return dst.data();
 }
 
 }  // namespace
@@ -89,11 +134,12 @@ int gbp_cuda_plan_shard(const gbp_problem* p, uint32_t world, uint32_t rank, gbp
   std::vector<uint32_t> bounds, lo, hi;
   int rc = camera_bounds(p, world, bounds);
   if (rc) return rc;
-  landmark_rank_span(p, bounds, lo, hi);
+  const std::vector<uint32_t> cam_rank = camera_ranks(bounds, p->n_keyframes);
+  landmark_rank_span(p, cam_rank, lo, hi);
   uint32_t n_local_edges = 0, n_local_points = 0, n_boundary = 0;
   std::vector<uint8_t> touched(p->n_points, 0);
   for (uint32_t e = 0; e < p->n_edges; ++e)
-    if (rank_of_camera(bounds, p->cam_ids[e]) == rank) {
+    if (cam_rank[p->cam_ids[e]] == rank) {
       n_local_edges++;
       touched[p->lmk_ids[e]] = 1;
     }
@@ -112,7 +158,7 @@ int gbp_cuda_plan_shard(const gbp_problem* p, uint32_t world, uint32_t rank, gbp
   return GBP_OK;
 }
 
-int gbp_shard_build(const gbp_problem* p, uint32_t world, uint32_t rank, gbp_shard** out) {
+static int shard_build_impl(const gbp_problem* p, uint32_t world, uint32_t rank, bool view, gbp_shard** out) {
   if (!p || !out || world == 0 || rank >= world) {
     gbp_set_error("bad shard arguments");
     return GBP_ERR_ARG;
@@ -124,25 +170,40 @@ int gbp_shard_build(const gbp_problem* p, uint32_t world, uint32_t rank, gbp_sha
     return GBP_ERR_ARG;
   }
   gbp_shard* s = new gbp_shard();
+  const bool timing = std::getenv("GBP_INIT_TIMING") != nullptr;
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[gbp shard] %-30s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+    t_last = now;
+  };
   int rc = camera_bounds(p, world, s->cam_bounds);
+  lap("camera bounds");
   if (rc) {
     delete s;
     return rc;
   }
   const uint32_t L = p->n_points, E = p->n_edges;
   const uint32_t c0 = s->cam_bounds[rank], c1 = s->cam_bounds[rank + 1];
-  std::vector<uint32_t> lo, hi;
-  landmark_rank_span(p, s->cam_bounds, lo, hi);
-  // local edges (global order), local landmarks (ascending global id)
+  // one pass over the global edge list: first / last rank of every landmark, this rank's edges (global
+  // order) and landmarks, the active-edge count of the whole graph
+  const std::vector<uint32_t> cam_rank = camera_ranks(s->cam_bounds, p->n_keyframes);
+  std::vector<uint32_t> lo(L, 0xffffffffu), hi(L, 0u);
   std::vector<uint32_t> lmk_local(L, 0xffffffffu);
+  s->edge_global.reserve((size_t)E / world + (size_t)E / (8 * world) + 64);
   for (uint32_t e = 0; e < E; ++e) {
-    const uint32_t c = p->cam_ids[e];
-    if (c >= c0 && c < c1) {
+    const uint32_t r = cam_rank[p->cam_ids[e]];
+    const uint32_t l = p->lmk_ids[e];
+    lo[l] = std::min(lo[l], r);
+    hi[l] = std::max(hi[l], r);
+    if (r == rank) {
       s->edge_global.push_back(e);
-      lmk_local[p->lmk_ids[e]] = 0;
+      lmk_local[l] = 0;
     }
     if (!p->active_flag || p->active_flag[e] == 1u) s->n_active_global++;
   }
+  lap("edge pass");
   uint32_t n_boundary = 0;
   for (uint32_t l = 0; l < L; ++l) {
     const bool boundary = lo[l] != 0xffffffffu && lo[l] != hi[l];
@@ -164,47 +225,35 @@ int gbp_shard_build(const gbp_problem* p, uint32_t world, uint32_t rank, gbp_sha
     s->cam_ids[i] = p->cam_ids[e] - c0;
     s->lmk_ids[i] = lmk_local[p->lmk_ids[e]];
   }
+  lap("landmark pass + local ids");
   std::vector<uint32_t> cams(nC);
   for (uint32_t i = 0; i < nC; ++i) cams[i] = c0 + i;
-  slice(s->z, p->measurements, s->edge_global, 2);
-  slice(s->var, p->meas_variances, s->edge_global, 1);
-  slice(s->active, p->active_flag, s->edge_global, 1);
-  slice(s->damping, p->damping, s->edge_global, 1);
-  slice(s->dcount, p->damping_count, s->edge_global, 1);
-  slice(s->mu, p->mu, s->edge_global, 9);
-  slice(s->oldmu, p->oldmu, s->edge_global, 9);
-  slice(s->cam_pe, p->cam_priors_eta, cams, 6);
-  slice(s->cam_pl, p->cam_priors_lambda, cams, 36);
-  slice(s->cam_sc, p->cam_scaling, cams, 1);
-  slice(s->cam_wflag, p->cam_weaken_flag, cams, 1);
-  slice(s->lmk_pe, p->lmk_priors_eta, s->lmk_global, 3);
-  slice(s->lmk_pl, p->lmk_priors_lambda, s->lmk_global, 9);
-  slice(s->lmk_sc, p->lmk_scaling, s->lmk_global, 1);
-  slice(s->lmk_wflag, p->lmk_weaken_flag, s->lmk_global, 1);
   gbp_problem& q = s->prob;
   std::memset(&q, 0, sizeof(q));
   q.n_keyframes = nC;
   q.n_points = nL;
   q.n_edges = nE;
   std::memcpy(q.K, p->K, sizeof(q.K));
-  auto ptr = [](auto& v) { return v.empty() ? nullptr : v.data(); };
   q.cam_ids = s->cam_ids.data();
   q.lmk_ids = s->lmk_ids.data();
-  q.measurements = s->z.data();
-  q.meas_variances = s->var.data();
-  q.cam_priors_eta = s->cam_pe.data();
-  q.cam_priors_lambda = s->cam_pl.data();
-  q.lmk_priors_eta = s->lmk_pe.data();
-  q.lmk_priors_lambda = s->lmk_pl.data();
-  q.cam_scaling = s->cam_sc.data();
-  q.lmk_scaling = s->lmk_sc.data();
-  q.cam_weaken_flag = s->cam_wflag.data();
-  q.lmk_weaken_flag = s->lmk_wflag.data();
-  q.active_flag = ptr(s->active);
-  q.damping = ptr(s->damping);
-  q.damping_count = ptr(s->dcount);
-  q.mu = ptr(s->mu);
-  q.oldmu = ptr(s->oldmu);
+  q.measurements = slice(s->z, p->measurements, s->edge_global, 2, view);
+  q.meas_variances = slice(s->var, p->meas_variances, s->edge_global, 1, view);
+  q.active_flag = slice(s->active, p->active_flag, s->edge_global, 1, view);
+  q.damping = slice(s->damping, p->damping, s->edge_global, 1, view);
+  q.damping_count = slice(s->dcount, p->damping_count, s->edge_global, 1, view);
+  lap("slices: z var active damping dcount");
+  q.mu = slice(s->mu, p->mu, s->edge_global, 9, view, true);
+  q.oldmu = slice(s->oldmu, p->oldmu, s->edge_global, 9, view, true);
+  lap("slices: mu oldmu");
+  q.cam_priors_eta = slice(s->cam_pe, p->cam_priors_eta, cams, 6, view);
+  q.cam_priors_lambda = slice(s->cam_pl, p->cam_priors_lambda, cams, 36, view);
+  q.cam_scaling = slice(s->cam_sc, p->cam_scaling, cams, 1, view);
+  q.cam_weaken_flag = slice(s->cam_wflag, p->cam_weaken_flag, cams, 1, view);
+  q.lmk_priors_eta = slice(s->lmk_pe, p->lmk_priors_eta, s->lmk_global, 3, view);
+  q.lmk_priors_lambda = slice(s->lmk_pl, p->lmk_priors_lambda, s->lmk_global, 9, view);
+  q.lmk_scaling = slice(s->lmk_sc, p->lmk_scaling, s->lmk_global, 1, view);
+  q.lmk_weaken_flag = slice(s->lmk_wflag, p->lmk_weaken_flag, s->lmk_global, 1, view);
+  lap("slices: variables");
   s->plan.world = world;
   s->plan.rank = rank;
   s->plan.cam_begin = c0;
@@ -215,6 +264,13 @@ int gbp_shard_build(const gbp_problem* p, uint32_t world, uint32_t rank, gbp_sha
   s->plan.reserved = 0;
   *out = s;
   return GBP_OK;
+}
+
+int gbp_shard_build(const gbp_problem* p, uint32_t world, uint32_t rank, gbp_shard** out) {
+  return shard_build_impl(p, world, rank, false, out);
+}
+int gbp_shard_build_view(const gbp_problem* p, uint32_t world, uint32_t rank, gbp_shard** out) {
+  return shard_build_impl(p, world, rank, true, out);
 }
 
 void gbp_shard_free(gbp_shard* s) { delete s; }

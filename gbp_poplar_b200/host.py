@@ -211,13 +211,14 @@ class Shard:
     IPUs (ba/ba.cpp:617-631,717-753,795-834).  Pure host code; `owner` keeps the global
     problem's arrays alive."""
 
-    def __init__(self, problem, world, rank, owner=None, handle=None):
+    def __init__(self, problem, world, rank, owner=None, handle=None, view=False):
         self._lib = _capi.load_library()
         self._owner = owner
         self._owned = handle is None
         if handle is None:
             h = C.c_void_p()
-            _check(self._lib.gbp_shard_build(C.byref(problem), world, rank, C.byref(h)), self._lib)
+            build = self._lib.gbp_shard_build_view if view else self._lib.gbp_shard_build
+            _check(build(C.byref(problem), world, rank, C.byref(h)), self._lib)
             handle = h
         self._h = handle
         pl = self._lib.gbp_shard_get_plan(self._h).contents

@@ -271,8 +271,13 @@ int gbp_cuda_plan_shard(const gbp_problem* p, uint32_t world, uint32_t rank, gbp
  * local edges touch, in ascending global id; local edges keep their global order. */
 typedef struct gbp_shard gbp_shard;
 int gbp_shard_build(const gbp_problem* p, uint32_t world, uint32_t rank, gbp_shard** out);
+/* The same shard without copying what is one contiguous run of the global arrays (the per-edge arrays of a
+ * camera range in a camera-sorted problem, the per-camera arrays): those members of gbp_shard_problem() then
+ * point INTO p's arrays, which must outlive every use of them.  gbp_cuda_init_shard builds its shard this way
+ * (it only reads the arrays during the call). */
+int gbp_shard_build_view(const gbp_problem* p, uint32_t world, uint32_t rank, gbp_shard** out);
 void gbp_shard_free(gbp_shard* s);
-const gbp_problem* gbp_shard_problem(const gbp_shard* s);    /* local ids, arrays owned by s */
+const gbp_problem* gbp_shard_problem(const gbp_shard* s);    /* local ids, arrays owned by s (see _view) */
 const gbp_shard_plan* gbp_shard_get_plan(const gbp_shard* s);
 const uint32_t* gbp_shard_lmk_global(const gbp_shard* s);    /* [n_local_points] global landmark id */
 const uint32_t* gbp_shard_edge_global(const gbp_shard* s);   /* [n_local_edges]  global edge id     */

@@ -124,7 +124,7 @@ def main():
         stats = [[s["reproj_mean"], s["cost"], s["n_relins"], s["n_robust"], s["n_active"]] for s in stats]
     else:
         import oracle_lib
-        shard = Shard(st.problem, world, rank, owner=st)
+        shard = Shard(st.problem, world, rank, owner=st, view=True)   # the build gbp_cuda_init_shard uses
         kind = "reference" if oracle_lib.available("reference") else "port"
         ora = oracle_lib.OracleEngine(shard.problem, kind=kind, threads=2)
         ora.set_reduce_order(1)

@@ -149,6 +149,63 @@ def test_shard_build_partitions_the_graph(world):
         assert max(loads) < 1.35 * E / world   # balanced by edge count (camera granularity)
 
 
+_FIELDS = [  # (member of gbp_problem, elements per local edge / camera / landmark, which count)
+    ("cam_ids", 1, "E"), ("lmk_ids", 1, "E"), ("measurements", 2, "E"), ("meas_variances", 1, "E"),
+    ("active_flag", 1, "E"), ("damping", 1, "E"), ("damping_count", 1, "E"), ("mu", 9, "E"), ("oldmu", 9, "E"),
+    ("cam_priors_eta", 6, "C"), ("cam_priors_lambda", 36, "C"), ("cam_scaling", 1, "C"), ("cam_weaken_flag", 1, "C"),
+    ("lmk_priors_eta", 3, "L"), ("lmk_priors_lambda", 9, "L"), ("lmk_scaling", 1, "L"), ("lmk_weaken_flag", 1, "L"),
+]
+
+
+def _problem_arrays(q):
+    n = {"E": q.n_edges, "C": q.n_keyframes, "L": q.n_points}
+    out = {}
+    for name, width, kind in _FIELDS:
+        ptr = getattr(q, name)
+        out[name] = None if not ptr or n[kind] == 0 else np.ctypeslib.as_array(ptr, shape=(width * n[kind],)).copy()
+    return out
+
+
+@pytest.mark.parametrize("sorted_by_camera", [True, False])
+@pytest.mark.parametrize("world", [1, 2, 3, 5])
+def test_shard_view_equals_owning_shard(world, sorted_by_camera):
+    """gbp_shard_build_view (what gbp_cuda_init_shard uses: contiguous runs of the global arrays are referenced, not
+    copied) describes exactly the same sub-problem as gbp_shard_build, also when the edge list is not camera-sorted
+    (nothing is contiguous then and everything is copied) and when mu / oldmu are not all zero."""
+    st = common.make_setup("fr2robot2")
+    p = st.problem
+    E = p.n_edges
+    keep = [st]
+    if not sorted_by_camera:
+        bal = common.load_sequence("fr2robot2")
+        perm = np.random.default_rng(3).permutation(bal.n_edges)
+        params = bal.parameters
+        C = bal.n_keyframes
+        shuffled = BALProblem.from_arrays(bal.intrinsics, bal.camera_index[perm], bal.point_index[perm],
+                                          bal.observations.reshape(-1, 2)[perm], params[:6 * C], params[6 * C:])
+        st = Setup(shuffled)
+        p = st.problem
+        keep += [shuffled, st]
+    mu = np.ctypeslib.as_array(p.mu, shape=(9 * E,))
+    mu[:] = np.random.default_rng(1).normal(size=9 * E).astype(np.float32)     # oldmu stays all zero
+    for r in range(world):
+        own, view = Shard(p, world, r, owner=st), Shard(p, world, r, owner=st, view=True)
+        a, b = _problem_arrays(own.problem), _problem_arrays(view.problem)
+        assert (own.problem.n_keyframes, own.problem.n_points, own.problem.n_edges) == \
+               (view.problem.n_keyframes, view.problem.n_points, view.problem.n_edges)
+        for name, _, _ in _FIELDS:
+            assert (a[name] is None) == (b[name] is None), name
+            if a[name] is not None:
+                assert a[name].tobytes() == b[name].tobytes(), name
+        assert a["oldmu"] is None                                      # all zero: left to the library's default
+        if own.problem.n_edges:
+            assert a["mu"] is not None and np.array_equal(a["mu"].reshape(-1, 9), mu.reshape(-1, 9)[np.array(own.edge_global)])
+        for f in ("edge_global", "lmk_global", "boundary_local", "boundary_slot", "cam_bounds"):
+            assert np.array_equal(np.array(getattr(own, f)), np.array(getattr(view, f))), f
+        assert (own.n_boundary_points, own.n_active_global) == (view.n_boundary_points, view.n_active_global)
+    mu[:] = 0
+
+
 def _plan(p, world, rank):
     import ctypes as C
     from gbp_poplar_b200 import _capi
