@@ -53,3 +53,17 @@ def test_four_gpus_bit_identical_to_oracle_in_sharded_order(tmp_path):
     ora.set_shard_bounds(ranks[0]["cam_bounds"])
     common.run_ba(ora, n)
     check_against_global(ranks, ora, st, exact=True)
+
+
+def test_world_of_one_sharded_handle_equals_plain_handle():
+    """The sharded entry point on ONE GPU (gbp_cuda_init_shard with world = 1: the view shard build, the shard-aware
+    build, no boundary landmarks) against gbp_cuda_init: every tensor bit-identical after a block of sweeps.  Runs
+    in its own process because it creates a NCCL process group."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "shard_world1_check.py")], capture_output=True,
+                       text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    assert "world-1 sharded vs plain: IDENTICAL" in r.stdout, r.stdout[-2000:]
