@@ -1,8 +1,12 @@
 """A sharded handle with world = 1 on one GPU (gbp_cuda_init_shard -> gbp_shard_build_view -> build) against the plain
 handle: every tensor bit-identical after a few sweeps."""
-import os, sys
-sys.path.insert(0, "."); sys.path.insert(0, "tests")
-os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT="29544", RANK="0", WORLD_SIZE="1", LOCAL_RANK="0")
+import os, socket, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+with socket.socket() as _s:
+    _s.bind(("127.0.0.1", 0))
+    _port = _s.getsockname()[1]
+os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(_port), RANK="0", WORLD_SIZE="1", LOCAL_RANK="0")
 import torch, torch.distributed as dist
 import common
 from gbp_poplar_b200 import GBPEngine, default_opts
