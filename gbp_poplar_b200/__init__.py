@@ -5,7 +5,7 @@ and thin ctypes mirrors of the reference's host-side interface (host.py,
 engine.py).  Nothing here imports the test-only CPU oracle under oracle/.
 """
 from . import _capi  # noqa: F401
-from .engine import GBPEngine, default_opts  # noqa: F401
+from .engine import GBPEngine, GBPGroup, default_opts  # noqa: F401
 from .host import BALProblem, Setup, cli_options, MODE_BA, MODE_SLAM  # noqa: F401
 
-__all__ = ["GBPEngine", "default_opts", "BALProblem", "Setup", "cli_options", "MODE_BA", "MODE_SLAM"]
+__all__ = ["GBPEngine", "GBPGroup", "default_opts", "BALProblem", "Setup", "cli_options", "MODE_BA", "MODE_SLAM"]

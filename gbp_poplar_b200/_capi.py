@@ -156,6 +156,13 @@ CUDA_ONLY_API = {
     "gbp_cuda_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "gbp_cuda_init_shard": (C.c_int, [C.POINTER(GbpProblem), C.POINTER(GbpOpts), C.c_uint32, C.c_uint32,
                                       C.c_void_p, C.POINTER(C.c_void_p)]),
+    "gbp_cuda_init_group": (C.c_int, [C.POINTER(GbpProblem), C.POINTER(GbpOpts), C.c_uint32, C.POINTER(C.c_int),
+                                      C.POINTER(C.c_void_p)]),
+    "gbp_cuda_group_iterate": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32, C.c_int, C.POINTER(GbpIterStats)]),
+    "gbp_cuda_group_weaken_priors": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32]),
+    "gbp_cuda_group_eval": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32, C.POINTER(GbpIterStats)]),
+    "gbp_cuda_group_free": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32]),
+    "gbp_cuda_release_cached_memory": (C.c_int, []),
     "gbp_cuda_shard_info": (C.c_void_p, [C.c_void_p]),
     "gbp_cuda_exchange_mode": (C.c_int, [C.c_void_p]),
     # pure host: the rank-local sub-problem of a camera-range partition

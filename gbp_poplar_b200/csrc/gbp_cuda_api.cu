@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -23,6 +24,7 @@
 
 
 void gbp_set_error(const std::string& s);  // host_error.cpp
+extern "C" void gbp_shard_detach_views(gbp_shard* s);  // shard.cpp
 
 namespace {
 
@@ -152,33 +154,100 @@ struct gbp_handle {
   double* d_metric_raw = nullptr;   // [8]         this rank's metric sums
   double* d_metric_all = nullptr;   // [world][8]  all-gathered
   uint64_t exchanges = 0;
+  uint32_t* p2p_err_host = nullptr; // host-mapped word a kernel sets when a wait for a peer timed out (sticky)
+  struct GroupShared* group = nullptr;  // single-process group (gbp_cuda_init_group): owner of the exchange blocks
+  // state of the gbp_cuda_iterate call in flight (iterate_begin .. iterate_finish)
+  cudaGraphExec_t it_exec = nullptr, it_exec_lower = nullptr;
+  bool it_graph = false, it_prof = false;
+  uint64_t it_k0 = 0;
+  bool l2_limit_changed = false;
+  // TMA-staged sweep kernel (k_sweep_tma): descriptors of the two big quad-SoA arrays
+  gbp::SweepMaps maps;
+  int use_tma = 0;
+};
+
+// A single-process group of shard handles: the exchange blocks of all ranks live (and die) together, so that
+// freeing one handle never pulls memory from under a peer that is still pushing into it.
+struct GroupShared {
+  std::vector<void*> blocks;
+  std::vector<int> devices;
+  int refs = 0;
 };
 
 namespace {
 
-// The per-handle arena comes from the device's default stream-ordered memory pool with its release threshold
-// lifted, so the block of a freed handle is handed to the next gbp_cuda_init of the process without a trip to
-// the driver (a fresh cudaMalloc of 0.65 GB costs anything between 1 and 200 ms depending on the box).
-int arena_alloc(gbp_handle* h, char** p, size_t bytes) {
-  *p = nullptr;
-  int pools = 0;
-  cudaDeviceGetAttribute(&pools, cudaDevAttrMemoryPoolsSupported, h->device);
-  if (const char* env = std::getenv("GBP_ARENA_POOL")) pools = pools && std::atoi(env) != 0;
-  if (pools) {
-    cudaMemPool_t pool = nullptr;
-    if (cudaDeviceGetDefaultMemPool(&pool, h->device) == cudaSuccess) {
+// The per-handle arena comes from a stream-ordered memory pool PRIVATE to this library (one per device, release
+// threshold lifted), so the block of a freed handle is handed to the next gbp_cuda_init of the process without a
+// trip to the driver (a fresh cudaMalloc of 0.65 GB costs anything between 1 and 200 ms depending on the box) and
+// the host application's own default pool is left alone.  gbp_cuda_release_cached_memory() returns it.
+struct DevicePool {
+  int device;
+  cudaMemPool_t pool;
+};
+std::vector<DevicePool>& pools() {
+  static std::vector<DevicePool> v;
+  return v;
+}
+std::mutex& pools_mutex() {
+  static std::mutex m;
+  return m;
+}
+cudaMemPool_t private_pool(int device) {
+  std::lock_guard<std::mutex> lk(pools_mutex());
+  for (const DevicePool& d : pools())
+    if (d.device == device) return d.pool;
+  int supported = 0;
+  cudaDeviceGetAttribute(&supported, cudaDevAttrMemoryPoolsSupported, device);
+  if (const char* env = std::getenv("GBP_ARENA_POOL")) supported = supported && std::atoi(env) != 0;
+  cudaMemPool_t pool = nullptr;
+  if (supported) {
+    cudaMemPoolProps props{};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    if (cudaMemPoolCreate(&pool, &props) == cudaSuccess) {
       uint64_t keep = ~0ull;
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-      if (cudaMallocAsync((void**)p, std::max<size_t>(bytes, 16), h->stream) == cudaSuccess) {
-        h->pool_allocs.push_back((void*)*p);
-        return GBP_OK;
-      }
+    } else {
+      pool = nullptr;
+      cudaGetLastError();
+    }
+  }
+  pools().push_back({device, pool});
+  return pool;
+}
+
+int arena_alloc(gbp_handle* h, char** p, size_t bytes) {
+  *p = nullptr;
+  if (cudaMemPool_t pool = private_pool(h->device)) {
+    if (cudaMallocFromPoolAsync((void**)p, std::max<size_t>(bytes, 16), pool, h->stream) == cudaSuccess) {
+      h->pool_allocs.push_back((void*)*p);
+      return GBP_OK;
     }
     cudaGetLastError();
   }
   GBP_CUDA_TRY(cudaMalloc((void**)p, std::max<size_t>(bytes, 16)));
   h->allocs.push_back((void*)*p);
   return GBP_OK;
+}
+
+// Persisting-L2 set-aside: a context-wide limit.  The first handle that raises it remembers the previous value;
+// the last handle with a window to go restores it (and only then resets the persisting lines).
+struct L2State {
+  int device;
+  int users;
+  size_t prev_limit;
+};
+std::vector<L2State>& l2_states() {
+  static std::vector<L2State> v;
+  return v;
+}
+L2State& l2_state(int device) {
+  for (L2State& s : l2_states())
+    if (s.device == device) return s;
+  l2_states().push_back({device, 0, 0});
+  return l2_states().back();
 }
 
 template <class T>
@@ -289,10 +358,19 @@ int launch_sweep(gbp_handle* h, bool upper = true) {
     // persistent: one block per SM (fewer when the graph has fewer warp-tiles than that)
     const uint32_t n_wt = h->E_pad / 32;
     const uint32_t grid = std::min<uint32_t>((uint32_t)h->num_sms, n_wt);
-    if (upper || !MSG || h->g.mcam_up)
+    const bool full = upper || !MSG || h->g.mcam_up;
+    if constexpr (MSG) {
+      if (h->use_tma) {
+        if (full) gbp::k_sweep_tma<PREP, true, true><<<grid, GBP_TW * 32, GBP_T_SMEM, h->stream>>>(h->g, h->maps);
+        else gbp::k_sweep_tma<PREP, true, false><<<grid, GBP_TW * 32, GBP_T_SMEM, h->stream>>>(h->g, h->maps);
+      } else if (full) {
+        gbp::k_sweep<PREP, true, true><<<grid, GBP_SW_WARPS * 32, GBP_SWEEP_SMEM, h->stream>>>(h->g);
+      } else {
+        gbp::k_sweep<PREP, true, false><<<grid, GBP_SW_WARPS * 32, GBP_SWEEP_SMEM, h->stream>>>(h->g);
+      }
+    } else {
       gbp::k_sweep<PREP, MSG, true><<<grid, GBP_SW_WARPS * 32, GBP_SWEEP_SMEM, h->stream>>>(h->g);
-    else
-      gbp::k_sweep<PREP, MSG, false><<<grid, GBP_SW_WARPS * 32, GBP_SWEEP_SMEM, h->stream>>>(h->g);
+    }
     h->kernels_launched++;
   }
   if (PREP) h->pending_shift = true;
@@ -325,29 +403,43 @@ int launch_full_sweep(gbp_handle* h, bool upper = true) {
 inline bool can_skip_upper(const gbp_handle* h) { return h->skip_upper && !h->g.mcam_up; }
 
 int launch_metric(gbp_handle* h, gbp::DeviceStats* d_out) {
+  uint32_t* cursor = h->capturing ? h->d_stat_cursor : nullptr;
   if (h->n_tiles) {
     const uint32_t nv = h->C + h->L;
     gbp::k_metric_prep<<<(nv + 127) / 128, 128, 0, h->stream>>>(h->g, h->d_met_cam, h->d_met_lmk);
     gbp::k_metric<<<metric_grid(h), GBP_TILE, 0, h->stream>>>(h->g, h->n_active, h->n_tiles, h->d_met_cam, h->d_met_lmk,
                                                               h->d_metric_parts, h->d_metric_ticket, d_out,
-                                                              h->shard ? h->d_metric_raw : nullptr,
-                                                              h->capturing ? h->d_stat_cursor : nullptr);
+                                                              h->shard ? h->d_metric_raw : nullptr, h->shard ? nullptr : cursor);
     h->kernels_launched += 2;
   } else {
-    gbp::k_metric_finish<<<1, GBP_TILE, 0, h->stream>>>(h->d_metric_parts, 0u, d_out, h->shard ? h->d_metric_raw : nullptr,
-                                                        h->capturing ? h->d_stat_cursor : nullptr);
+    gbp::k_metric_finish<<<1, GBP_TILE, 0, h->stream>>>(h->g, h->d_metric_parts, 0u, d_out, h->shard ? h->d_metric_raw : nullptr,
+                                                        h->shard ? nullptr : cursor);
     h->kernels_launched++;
   }
   if (h->shard) {  // every rank reports the metric of the WHOLE graph
-    GBP_CUDA_TRY(cudaEventRecord(h->ev_send, h->stream));
-    GBP_CUDA_TRY(cudaStreamWaitEvent(h->comm_stream, h->ev_send, 0));
-    GBP_NCCL_TRY(gbp::nccl_api().AllGather(h->d_metric_raw, h->d_metric_all, 8, ncclDouble, h->comm, h->comm_stream));
-    GBP_CUDA_TRY(cudaEventRecord(h->ev_recv, h->comm_stream));
-    GBP_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_recv, 0));
-    gbp::k_metric_combine<<<1, 32, 0, h->stream>>>(h->d_metric_all, h->world, d_out);
+    if (h->p2p) {
+      // the finishing block of k_metric pushed this rank's sums into every rank's receive buffer; wait for all
+      gbp::k_metric_combine<<<1, 32, 0, h->stream>>>(h->g, nullptr, d_out, cursor);
+    } else {
+      GBP_CUDA_TRY(cudaEventRecord(h->ev_send, h->stream));
+      GBP_CUDA_TRY(cudaStreamWaitEvent(h->comm_stream, h->ev_send, 0));
+      GBP_NCCL_TRY(gbp::nccl_api().AllGather(h->d_metric_raw, h->d_metric_all, 8, ncclDouble, h->comm, h->comm_stream));
+      GBP_CUDA_TRY(cudaEventRecord(h->ev_recv, h->comm_stream));
+      GBP_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_recv, 0));
+      gbp::k_metric_combine<<<1, 32, 0, h->stream>>>(h->g, h->d_metric_all, d_out, cursor);
+    }
     h->kernels_launched++;
   }
   GBP_CUDA_TRY(cudaGetLastError());
+  return GBP_OK;
+}
+
+// a kernel of this handle gave up waiting for a peer (bounded spin in boundary_finish / k_metric_combine)
+int check_peer_error(gbp_handle* h) {
+  if (h->p2p_err_host && *(volatile uint32_t*)h->p2p_err_host) {
+    gbp_set_error("multi-GPU exchange: timed out waiting for a peer's boundary partials; the handle's state is invalid");
+    return GBP_ERR_COMM;
+  }
   return GBP_OK;
 }
 
@@ -522,22 +614,78 @@ int upload_lmk_priors(gbp_handle* h, const float* eta, const float* lam) {
   return GBP_OK;
 }
 
-// Peer-to-peer exchange set-up: every rank exports one block [arrival flags | counters | receive
-// buffer (2 parities x world x n_boundary x 3 quads)] through CUDA IPC, the handles travel over the
-// NCCL communicator once, and every rank maps every other rank's block.  Returns GBP_OK with
-// h->p2p == 0 when IPC is not available (the NCCL all-gather path is used instead).
+// ---- peer-to-peer exchange set-up ------------------------------------------------------------
+// Every rank owns one block
+//   [boundary arrival flags W | metric arrival flags W | counters | metric receive buffer 2 x W x 8 doubles |
+//    boundary receive buffer 2 parities x W x n_boundary x 3 quads]
+// that every other rank maps: through CUDA IPC when the ranks are processes (the handles travel over the NCCL
+// communicator once), directly (same device, or cudaDeviceEnablePeerAccess) when they are the handles of a
+// single-process group.
+constexpr size_t P2P_OFF_FLAG = 0, P2P_OFF_MFLAG = 1024, P2P_OFF_DONE = 2048, P2P_OFF_METRIC = 4096;
+constexpr size_t P2P_OFF_RECV = 4096 + 2 * 256 * 8 * sizeof(double);  // metric buffer sized for <= 256 ranks
+constexpr uint32_t P2P_MAX_WORLD = 256;
+
+size_t p2p_block_bytes(uint32_t W, uint32_t n_bnd_global) {
+  const size_t recv_bytes = (size_t)2 * W * n_bnd_global * 3 * sizeof(float4);
+  return ((P2P_OFF_RECV + recv_bytes + (2u << 20) - 1) >> 21) << 21;  // whole 2 MB pages
+}
+
+// bases[r] = rank r's block as seen from this rank's device (bases[rank] = its own)
+int p2p_wire(gbp_handle* h, const std::vector<void*>& bases) {
+  DeviceGraph& g = h->g;
+  const uint32_t W = h->world;
+  std::vector<float4*> recv(W);
+  std::vector<uint32_t*> flag(W), mflag(W);
+  std::vector<double*> metric(W);
+  for (uint32_t r = 0; r < W; ++r) {
+    char* base = (char*)bases[r];
+    flag[r] = (uint32_t*)(base + P2P_OFF_FLAG);
+    mflag[r] = (uint32_t*)(base + P2P_OFF_MFLAG);
+    metric[r] = (double*)(base + P2P_OFF_METRIC);
+    recv[r] = (float4*)(base + P2P_OFF_RECV);
+  }
+  int rc = h_alloc(h, &g.peer_recv, W);
+  if (!rc) rc = h_alloc(h, &g.peer_flag, W);
+  if (!rc) rc = h_alloc(h, &g.peer_mflag, W);
+  if (!rc) rc = h_alloc(h, &g.peer_metric, W);
+  if (rc) return rc;
+  GBP_CUDA_TRY(cudaMemcpy(g.peer_recv, recv.data(), sizeof(float4*) * W, cudaMemcpyHostToDevice));
+  GBP_CUDA_TRY(cudaMemcpy(g.peer_flag, flag.data(), sizeof(uint32_t*) * W, cudaMemcpyHostToDevice));
+  GBP_CUDA_TRY(cudaMemcpy(g.peer_mflag, mflag.data(), sizeof(uint32_t*) * W, cudaMemcpyHostToDevice));
+  GBP_CUDA_TRY(cudaMemcpy(g.peer_metric, metric.data(), sizeof(double*) * W, cudaMemcpyHostToDevice));
+  char* own = (char*)bases[h->rank];
+  g.p2p_flag = (uint32_t*)(own + P2P_OFF_FLAG);
+  g.metric_flag = (uint32_t*)(own + P2P_OFF_MFLAG);
+  g.p2p_done = (uint32_t*)(own + P2P_OFF_DONE);
+  g.metric_recv = (const double*)(own + P2P_OFF_METRIC);
+  g.p2p_recv = (const float4*)(own + P2P_OFF_RECV);
+  // the error word lives in mapped host memory: a timed-out kernel sets it, every synchronising entry point reads it
+  GBP_CUDA_TRY(cudaHostAlloc((void**)&h->p2p_err_host, sizeof(uint32_t), cudaHostAllocMapped));
+  *h->p2p_err_host = 0u;
+  GBP_CUDA_TRY(cudaHostGetDevicePointer((void**)&g.p2p_error, h->p2p_err_host, 0));
+  // how long a block waits for its peers: generous (a peer may be instantiating a graph or sit in a debugger),
+  // GBP_P2P_TIMEOUT_S overrides
+  double seconds = 60.0;
+  if (const char* env = std::getenv("GBP_P2P_TIMEOUT_S")) seconds = std::max(0.001, std::atof(env));
+  int khz = 0;
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device);
+  g.p2p_timeout = (long long)(seconds * 1e3 * (khz > 0 ? khz : 1965000));
+  h->p2p = 1;
+  return GBP_OK;
+}
+
+// Processes (one per GPU): returns GBP_OK with h->p2p == 0 when IPC is not available (the NCCL all-gather path
+// is used instead).
 int setup_p2p(gbp_handle* h, int mode) {
   DeviceGraph& g = h->g;
   const uint32_t W = h->world;
   h->p2p = 0;
   if (mode == 1 || g.n_bnd_global == 0) return GBP_OK;
-  const size_t head = 4096;  // flags [W] at 0, done counter at 2048, error flag at 2052
-  const size_t recv_bytes = (size_t)2 * W * g.n_bnd_global * 3 * sizeof(float4);
-  const size_t total = ((head + recv_bytes + (2u << 20) - 1) >> 21) << 21;  // whole 2 MB pages
+  const size_t total = p2p_block_bytes(W, g.n_bnd_global);
   int ok = 1;
   cudaIpcMemHandle_t mine;
   std::memset(&mine, 0, sizeof(mine));
-  if (W > 1024 / sizeof(uint32_t)) ok = 0;
+  if (W > P2P_MAX_WORLD) ok = 0;
   if (ok && cudaMalloc(&h->p2p_block, total) != cudaSuccess) ok = 0;
   if (ok && cudaMemset(h->p2p_block, 0, total) != cudaSuccess) ok = 0;
   if (ok && cudaIpcGetMemHandle(&mine, h->p2p_block) != cudaSuccess) ok = 0;
@@ -587,25 +735,78 @@ int setup_p2p(gbp_handle* h, int mode) {
     }
     return GBP_OK;
   }
-  std::vector<float4*> recv(W);
-  std::vector<uint32_t*> flag(W);
-  for (uint32_t r = 0; r < W; ++r) {
-    char* base = (char*)(r == h->rank ? h->p2p_block : h->p2p_peers[r]);
-    flag[r] = (uint32_t*)base;
-    recv[r] = (float4*)(base + head);
+  std::vector<void*> bases(W);
+  for (uint32_t r = 0; r < W; ++r) bases[r] = (r == h->rank) ? h->p2p_block : h->p2p_peers[r];
+  return p2p_wire(h, bases);
+}
+
+// TMA descriptors for k_sweep_tma: the factor potentials and the camera-bound messages seen as 2-D fp32 tensors
+// [rows][E_pad * 4] whose box is one warp-tile: [rows] x [128 floats = the 32 lanes' quads of one row].
+// GBP_SWEEP=cpasync selects the cp.async kernel (k_sweep) instead.
+int setup_tma(gbp_handle* h) {
+  h->use_tma = 1;
+  if (const char* env = std::getenv("GBP_SWEEP")) h->use_tma = std::strcmp(env, "cpasync") != 0;
+  if (!h->use_tma || !h->n_tiles) return GBP_OK;
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+        qres != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      gbp_set_error("cuTensorMapEncodeTiled is not available from this driver");
+      return GBP_ERR_CUDA;
+    }
+    encode = (EncodeFn)fn;
   }
-  int rc = h_alloc(h, &g.peer_recv, W);
-  if (!rc) rc = h_alloc(h, &g.peer_flag, W);
+  int promo = 2;  // CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+  if (const char* env = std::getenv("GBP_TMA_L2PROMO")) promo = std::max(0, std::min(3, std::atoi(env)));
+  auto make = [&](CUtensorMap* m, void* base, uint32_t rows) -> int {
+    const cuuint64_t dims[2] = {(cuuint64_t)h->E_pad * 4, rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)h->E_pad * 16};
+    const cuuint32_t box[2] = {128, rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, (CUtensorMapL2promotion)promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      gbp_set_error("cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
+      return GBP_ERR_CUDA;
+    }
+    return GBP_OK;
+  };
+  int rc = make(&h->maps.fac, h->g.fac, GBP_FAC_QUADS);
+  if (!rc) rc = make(&h->maps.mcam, h->g.mcam, GBP_MCAM_QUADS);
   if (rc) return rc;
-  GBP_CUDA_TRY(cudaMemcpy(g.peer_recv, recv.data(), sizeof(float4*) * W, cudaMemcpyHostToDevice));
-  GBP_CUDA_TRY(cudaMemcpy(g.peer_flag, flag.data(), sizeof(uint32_t*) * W, cudaMemcpyHostToDevice));
-  char* own = (char*)h->p2p_block;
-  g.p2p_flag = (uint32_t*)own;
-  g.p2p_done = (uint32_t*)(own + 2048);
-  g.p2p_error = (uint32_t*)(own + 2052);
-  g.p2p_recv = (const float4*)(own + head);
-  h->p2p = 1;
+  GBP_CUDA_TRY(cudaFuncSetAttribute(gbp::k_sweep_tma<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GBP_T_SMEM));
+  GBP_CUDA_TRY(cudaFuncSetAttribute(gbp::k_sweep_tma<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GBP_T_SMEM));
+  GBP_CUDA_TRY(cudaFuncSetAttribute(gbp::k_sweep_tma<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GBP_T_SMEM));
+  GBP_CUDA_TRY(cudaFuncSetAttribute(gbp::k_sweep_tma<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GBP_T_SMEM));
   return GBP_OK;
+}
+
+// CUDA loads kernels lazily, and loading one can need a context-wide synchronisation.  In a single-process group
+// rank A's belief update spins on its peers while rank B launches a kernel for the first time: if that launch had
+// to load the kernel it would wait for A, which waits for B.  Every kernel of the library is therefore loaded
+// up front (cudaFuncGetAttributes forces the load).
+template <class K>
+void preload(K kernel) {
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, kernel);
+}
+void preload_kernels() {
+  preload(gbp::k_sweep<true, true, true>); preload(gbp::k_sweep<true, true, false>);
+  preload(gbp::k_sweep<false, true, true>); preload(gbp::k_sweep<false, true, false>);
+  preload(gbp::k_sweep_tma<true, true, true>); preload(gbp::k_sweep_tma<true, true, false>);
+  preload(gbp::k_sweep_tma<false, true, true>); preload(gbp::k_sweep_tma<false, true, false>);
+  preload(gbp::k_prep_pass); preload(gbp::k_relin_list); preload(gbp::k_cam_partials); preload(gbp::k_update_vars);
+  preload(gbp::k_boundary_partial); preload(gbp::k_boundary_finish); preload(gbp::k_relinearise_all); preload(gbp::k_weaken);
+  preload(gbp::k_kf_pose); preload(gbp::k_kf_apply); preload(gbp::k_metric_prep); preload(gbp::k_metric);
+  preload(gbp::k_metric_finish); preload(gbp::k_metric_combine); preload(gbp::k_export_edges);
+  preload(gbp::k_export_lmk_beliefs); preload(gbp::k_import_edges); preload(gbp::k_means_from_beliefs);
+  cudaGetLastError();
 }
 
 struct PhaseTimer {  // GBP_INIT_TIMING=1: wall time of the phases of gbp_cuda_init on stderr
@@ -757,6 +958,7 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   A_(g.cam_partial, (size_t)n_wt * GBP_CAMPART);
   A_(g.lmk_b, GBP_LMKB_QUADS * (size_t)L);
   A_(g.lmk_mean_prev, L);
+  A_(g.lmk_sq, L);
   const size_t reuse_end = arena_bytes;
   A_(g.var, EP);
   A_(g.recB, EP);
@@ -786,6 +988,7 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   A_(g.relin_list, E);
   A_(g.relin_count, 1);
   A_(g.relin_ring, GBP_RELIN_RING + 1);
+  A_(g.tile_queue, 2);
   A_(h->d_exp_lmk_eta, 3 * (size_t)L);   // READ_PROG staging (unpacked landmark beliefs, per-edge scalars in edge order)
   A_(h->d_exp_lmk_lam, 9 * (size_t)L);
   A_(h->d_exp_damping, E);
@@ -846,6 +1049,13 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
       size_t cur = 0;
       cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize);
       const size_t set_aside = std::min(std::min(std::max(cur, win), (size_t)max_persist), cap_mb << 20);
+      {
+        std::lock_guard<std::mutex> lk(pools_mutex());
+        L2State& ls = l2_state(h->device);
+        if (ls.users == 0) ls.prev_limit = cur;  // restored by the last handle with a window (gbp_cuda_free)
+        ls.users++;
+        h->l2_limit_changed = true;
+      }
       if (set_aside != cur) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside);
       h->l2_window.base_ptr = base + reuse_begin;
       h->l2_window.num_bytes = win;
@@ -921,22 +1131,29 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   GBP_CUDA_TRY(cudaFuncSetAttribute(gbp::k_sweep<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GBP_SWEEP_SMEM));
   GBP_CUDA_TRY(cudaFuncSetAttribute(gbp::k_sweep<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GBP_SWEEP_SMEM));
   GBP_CUDA_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
+  rc = setup_tma(h);
+  if (rc) return rc;
   pt.lap("uploads");
-  if (h->shard) {
-    rc = setup_p2p(h, o->exchange);
-    if (rc) return rc;
-  }
-  // LINEARISE_PROG (ba/ba.cpp:890-893): beliefs <- priors, then linearise every factor
+  return GBP_OK;
+}
+
+// LINEARISE_PROG (ba/ba.cpp:890-893): beliefs <- priors, then linearise every factor.  Enqueued only: on a
+// multi-GPU handle the belief update contains the first boundary exchange, so every rank must have enqueued it
+// before any rank waits (linearise_wait).
+int linearise_prog(gbp_handle* h) {
   h->pending_shift = false;
-  rc = launch_update_vars(h);
+  int rc = launch_update_vars(h);
   if (rc) return rc;
   if (h->n_tiles) {
-    gbp::k_relinearise_all<<<h->n_tiles, GBP_TILE, 0, s>>>(h->g);
+    gbp::k_relinearise_all<<<h->n_tiles, GBP_TILE, 0, h->stream>>>(h->g);
     h->kernels_launched++;
   }
   GBP_CUDA_TRY(cudaGetLastError());
-  GBP_CUDA_TRY(cudaStreamSynchronize(s));
   return GBP_OK;
+}
+int linearise_wait(gbp_handle* h) {
+  GBP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return check_peer_error(h);
 }
 
 // The fused sweep kernel is fastest while relinearisations come in lock step (all factors in one sweep out of
@@ -1076,6 +1293,8 @@ int gbp_cuda_init(const gbp_problem* p, const gbp_opts* o_in, gbp_handle** out) 
   if (!rc && cudaEventCreate(&h->ev1) != cudaSuccess) rc = GBP_ERR_CUDA;
 
   if (!rc) rc = build(h, p, &o);
+  if (!rc) rc = linearise_prog(h);
+  if (!rc) rc = linearise_wait(h);
   if (rc) {
     if (rc == GBP_ERR_CUDA && !*gbp_cuda_last_error()) gbp_set_error("CUDA initialisation failed");
     gbp_cuda_free(h);
@@ -1085,11 +1304,29 @@ int gbp_cuda_init(const gbp_problem* p, const gbp_opts* o_in, gbp_handle** out) 
   return GBP_OK;
 }
 
+int gbp_cuda_release_cached_memory(void) {
+  std::lock_guard<std::mutex> lk(pools_mutex());
+  for (const DevicePool& d : pools())
+    if (d.pool) cudaMemPoolTrimTo(d.pool, 0);
+  cudaGetLastError();
+  return GBP_OK;
+}
+
 int gbp_cuda_free(gbp_handle* h) {
   if (!h) return GBP_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  if (h->l2_window.num_bytes) cudaCtxResetPersistingL2Cache();  // do not leave this handle's lines pinned
+  if (h->l2_limit_changed) {
+    // the last handle with a persisting window on this device un-pins the lines and restores the set-aside the
+    // application had; while other handles are alive their windows are left alone
+    std::lock_guard<std::mutex> lk(pools_mutex());
+    L2State& ls = l2_state(h->device);
+    if (--ls.users == 0) {
+      cudaCtxResetPersistingL2Cache();
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, ls.prev_limit);
+      cudaGetLastError();
+    }
+  }
   for (void* p : h->allocs) cudaFree(p);
   for (void* p : h->pool_allocs) cudaFreeAsync(p, h->stream);  // stays in the pool for the next handle
   if (h->stream && !h->pool_allocs.empty()) cudaStreamSynchronize(h->stream);
@@ -1099,7 +1336,7 @@ int gbp_cuda_free(gbp_handle* h) {
   for (cudaEvent_t ev : h->prof_events) cudaEventDestroy(ev);
   drop_graphs(h);
   if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);  // the communicator itself stays cached
-  if (h->p2p) {
+  if (h->p2p && !h->group) {
     // peers may still be pushing into this rank's block: freeing a sharded handle is collective
     int* d_b = nullptr;
     if (cudaMalloc((void**)&d_b, sizeof(int) * (h->world + 1)) == cudaSuccess) {
@@ -1112,6 +1349,15 @@ int gbp_cuda_free(gbp_handle* h) {
       if (q) cudaIpcCloseMemHandle(q);
     cudaFree(h->p2p_block);
   }
+  if (h->group && --h->group->refs == 0) {  // the last handle of a single-process group frees every rank's block
+    for (size_t r = 0; r < h->group->blocks.size(); ++r) {
+      cudaSetDevice(h->group->devices[r]);
+      cudaFree(h->group->blocks[r]);
+    }
+    cudaSetDevice(h->device);
+    delete h->group;
+  }
+  if (h->p2p_err_host) cudaFreeHost(h->p2p_err_host);
   if (h->ev_send) cudaEventDestroy(h->ev_send);
   if (h->ev_recv) cudaEventDestroy(h->ev_recv);
   if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
@@ -1140,7 +1386,7 @@ int gbp_cuda_synchronize(gbp_handle* h) {
   int rc = set_device(h);
   if (rc) return rc;
   GBP_CUDA_TRY(cudaStreamSynchronize(h->stream));
-  return GBP_OK;
+  return check_peer_error(h);
 }
 
 int gbp_cuda_weaken_priors(gbp_handle* h) {
@@ -1175,57 +1421,73 @@ int gbp_cuda_iterate_async(gbp_handle* h, int n_sweeps) {
   return rc;
 }
 
-int gbp_cuda_iterate(gbp_handle* h, int n_sweeps, gbp_iter_stats* stats) {
-  if (!h || n_sweeps < 0) return GBP_ERR_ARG;
+}  // extern "C"
+
+namespace {
+
+// gbp_cuda_iterate in four phases, so that a single-process group can interleave the ranks (every rank's sweep i
+// must be enqueued before any rank waits: the belief update of a sweep spins on its peers' partials):
+//   iterate_begin    buffers, events, the CUDA graphs to replay
+//   iterate_enqueue  sweep i of n
+//   iterate_end      closing event + the asynchronous read-backs
+//   iterate_finish   ONE stream synchronisation, results, the sweep-flavour choice
+int iterate_begin(gbp_handle* h, int n_sweeps, bool stats) {
   int rc = set_device(h);
+  if (!rc) rc = check_peer_error(h);
   if (rc) return rc;
   if (stats) {
     rc = ensure_stats(h, (size_t)n_sweeps);
     if (rc) return rc;
   }
-  const uint64_t k0 = h->kernels_launched;
-  const bool prof = h->profile != 0;
-  if (prof) {
+  h->it_k0 = h->kernels_launched;
+  h->it_prof = h->profile != 0;
+  if (h->it_prof) {
     while (h->prof_events.size() < (size_t)3 * n_sweeps) {
       cudaEvent_t ev;
       GBP_CUDA_TRY(cudaEventCreate(&ev));
       h->prof_events.push_back(ev);
     }
   }
-  // steady state on one GPU: replay the captured sweep (the very first sweep after a belief update without a
-  // preceding prep has shift = 0 and goes through the plain launches, as do profiling and sharded handles)
-  int first = 0;
-  // (a sharded handle qualifies when its exchange is the fused peer-to-peer one and no metric -- an NCCL
-  // all-gather on the communication stream -- is requested)
-  const bool graph_ok = !h->shard || (h->p2p && !stats) || h->g.n_bnd_global == 0;
-  if (h->use_graph && !prof && graph_ok && !(h->shard && stats) && n_sweeps > 0 && h->n_tiles) {
-    GBP_CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+  // steady state: replay the captured sweep (profiling goes through the plain launches, as does a sharded handle
+  // whose exchange is the NCCL all-gather on the communication stream)
+  const bool graph_ok = !h->shard || h->p2p || h->g.n_bnd_global == 0;
+  h->it_graph = h->use_graph && !h->it_prof && graph_ok && !(h->shard && stats && !h->p2p) && n_sweeps > 0 && h->n_tiles;
+  h->it_exec = h->it_exec_lower = nullptr;
+  GBP_CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+  if (h->it_graph) {
     if (stats) GBP_CUDA_TRY(cudaMemsetAsync(h->d_stat_cursor, 0, sizeof(uint32_t), h->stream));
     // every sweep but the last skips the strict upper triangle of the camera messages (see k_sweep)
-    cudaGraphExec_t exec = nullptr, exec_lower = nullptr;
-    rc = sweep_graph(h, stats != nullptr, true, &exec);
+    rc = sweep_graph(h, stats, true, &h->it_exec);
     // (not when per-sweep metrics are requested: the metric inverts the FULL camera belief, like the reference's)
-    if (!rc && n_sweeps > 1 && !stats && can_skip_upper(h)) rc = sweep_graph(h, false, false, &exec_lower);
+    if (!rc && n_sweeps > 1 && !stats && can_skip_upper(h)) rc = sweep_graph(h, false, false, &h->it_exec_lower);
     if (rc) return rc;
-    const uint64_t per = (stats ? 4 : 2) + (h->two_pass ? 2 : 0);
-    for (int i = 0; i < n_sweeps; ++i)
-      GBP_CUDA_TRY(cudaGraphLaunch((exec_lower && i + 1 < n_sweeps) ? exec_lower : exec, h->stream));
-    h->kernels_launched += per * (uint64_t)n_sweeps;
+  }
+  return GBP_OK;
+}
+
+int iterate_enqueue(gbp_handle* h, int i, int n_sweeps, bool stats) {
+  int rc = set_device(h);
+  if (rc) return rc;
+  if (h->it_graph) {
+    GBP_CUDA_TRY(cudaGraphLaunch((h->it_exec_lower && i + 1 < n_sweeps) ? h->it_exec_lower : h->it_exec, h->stream));
+    h->kernels_launched += (uint64_t)((stats ? (h->shard ? 5 : 4) : 2) + (h->two_pass ? 2 : 0));
     h->pending_shift = false;
     h->p_in_sync = true;
-    first = n_sweeps;
-  } else {
-    GBP_CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+    return GBP_OK;
   }
-  for (int i = first; i < n_sweeps && !rc; ++i) {
-    const bool upper = i == n_sweeps - 1 || stats || !can_skip_upper(h);
-    if (prof) GBP_CUDA_TRY(cudaEventRecord(h->prof_events[3 * i], h->stream));
-    rc = launch_full_sweep(h, upper);
-    if (prof) GBP_CUDA_TRY(cudaEventRecord(h->prof_events[3 * i + 1], h->stream));
-    if (!rc) rc = launch_update_vars(h, !upper);
-    if (prof) GBP_CUDA_TRY(cudaEventRecord(h->prof_events[3 * i + 2], h->stream));
-    if (!rc && stats) rc = launch_metric(h, h->d_stats + i);
-  }
+  const bool prof = h->it_prof;
+  const bool upper = i == n_sweeps - 1 || stats || !can_skip_upper(h);
+  if (prof) GBP_CUDA_TRY(cudaEventRecord(h->prof_events[3 * i], h->stream));
+  rc = launch_full_sweep(h, upper);
+  if (prof) GBP_CUDA_TRY(cudaEventRecord(h->prof_events[3 * i + 1], h->stream));
+  if (!rc) rc = launch_update_vars(h, !upper);
+  if (prof) GBP_CUDA_TRY(cudaEventRecord(h->prof_events[3 * i + 2], h->stream));
+  if (!rc && stats) rc = launch_metric(h, h->d_stats + i);
+  return rc;
+}
+
+int iterate_end(gbp_handle* h, int n_sweeps, bool stats) {
+  int rc = set_device(h);
   if (rc) return rc;
   GBP_CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
   if (stats && n_sweeps)
@@ -1233,23 +1495,30 @@ int gbp_cuda_iterate(gbp_handle* h, int n_sweeps, gbp_iter_stats* stats) {
                                  h->stream));
   // every 16 sweeps the relinearisation ring (132 bytes) rides along with the same synchronisation
   h->sweeps_since_choice += (uint32_t)n_sweeps;
-  const bool want_ring = h->sweeps_since_choice >= 16 && h->E && h->relin_mode == 0;
-  if (want_ring) {
+  if (h->sweeps_since_choice >= 16 && h->E && h->relin_mode == 0) {
     if (!h->pin_ring) GBP_CUDA_TRY(cudaHostAlloc((void**)&h->pin_ring, (GBP_RELIN_RING + 1) * sizeof(uint32_t), cudaHostAllocDefault));
     GBP_CUDA_TRY(cudaMemcpyAsync(h->pin_ring, h->g.relin_ring, (GBP_RELIN_RING + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                                  h->stream));
   }
+  return GBP_OK;
+}
+
+int iterate_finish(gbp_handle* h, int n_sweeps, gbp_iter_stats* stats) {
+  int rc = set_device(h);
+  if (rc) return rc;
   GBP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  rc = check_peer_error(h);
+  if (rc) return rc;
   if (stats && n_sweeps) std::memcpy(stats, h->pin_stats, (size_t)n_sweeps * sizeof(gbp_iter_stats));
   GBP_CUDA_TRY(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
-  h->last_kernels = h->kernels_launched - k0;
+  h->last_kernels = h->kernels_launched - h->it_k0;
   if (h->sweeps_since_choice >= 16 && h->E) {
     h->sweeps_since_choice = 0;
-    rc = choose_sweep_flavour(h, want_ring ? h->pin_ring : nullptr);
+    rc = choose_sweep_flavour(h, h->relin_mode == 0 ? h->pin_ring : nullptr);
     if (rc) return rc;
   }
   h->last_ms_factor = h->last_ms_variable = 0.f;
-  if (prof) {
+  if (h->it_prof) {
     double a = 0, b = 0;
     for (int i = 0; i < n_sweeps; ++i) {
       float t;
@@ -1262,6 +1531,19 @@ int gbp_cuda_iterate(gbp_handle* h, int n_sweeps, gbp_iter_stats* stats) {
     h->last_ms_variable = (float)b;
   }
   return GBP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gbp_cuda_iterate(gbp_handle* h, int n_sweeps, gbp_iter_stats* stats) {
+  if (!h || n_sweeps < 0) return GBP_ERR_ARG;
+  int rc = iterate_begin(h, n_sweeps, stats != nullptr);
+  for (int i = 0; i < n_sweeps && !rc; ++i) rc = iterate_enqueue(h, i, n_sweeps, stats != nullptr);
+  if (!rc) rc = iterate_end(h, n_sweeps, stats != nullptr);
+  if (!rc) rc = iterate_finish(h, n_sweeps, stats);
+  return rc;
 }
 
 int gbp_cuda_iterate_until(gbp_handle* h, int max_sweeps, int check_every, float rel_tol, float diverge_factor,
@@ -1296,7 +1578,10 @@ int gbp_cuda_iterate_until(gbp_handle* h, int max_sweeps, int check_every, float
       break;
     }
     const float end = block[(size_t)m - 1].reproj_mean;
-    if (m == check_every && last_block_end >= 0.f && last_block_end - end < rel_tol * last_block_end) {
+    // converged: the error still went down (or stood still) over the block, by less than rel_tol.  A block over
+    // which it ROSE is not convergence: the run goes on until the rise trips the divergence rule or max_sweeps
+    const float gain = last_block_end - end;
+    if (m == check_every && last_block_end >= 0.f && gain >= 0.f && gain < rel_tol * last_block_end) {
       reason = GBP_STOP_CONVERGED;
       break;
     }
@@ -1337,7 +1622,7 @@ int gbp_cuda_eval(gbp_handle* h, gbp_iter_stats* out) {
   if (rc) return rc;
   GBP_CUDA_TRY(cudaMemcpyAsync(out, h->d_stats, sizeof(gbp_iter_stats), cudaMemcpyDeviceToHost, h->stream));
   GBP_CUDA_TRY(cudaStreamSynchronize(h->stream));
-  return GBP_OK;
+  return check_peer_error(h);
 }
 
 int gbp_cuda_get_beliefs(gbp_handle* h, float* cam_eta, float* cam_lambda, float* lmk_eta, float* lmk_lambda,
@@ -1369,15 +1654,7 @@ int gbp_cuda_get_beliefs(gbp_handle* h, float* cam_eta, float* cam_lambda, float
   if (rc) return rc;
   GBP_CUDA_TRY(cudaGetLastError());
   GBP_CUDA_TRY(cudaStreamSynchronize(s));
-  if (h->p2p) {  // a peer that never delivered its boundary partials (bounded wait in k_boundary_finish)
-    uint32_t err = 0;
-    GBP_CUDA_TRY(cudaMemcpy(&err, h->g.p2p_error, sizeof(err), cudaMemcpyDeviceToHost));
-    if (err) {
-      gbp_set_error("multi-GPU exchange: timed out waiting for a peer's boundary partials");
-      return GBP_ERR_COMM;
-    }
-  }
-  return GBP_OK;
+  return check_peer_error(h);
 }
 
 int gbp_cuda_get_priors(gbp_handle* h, float* cam_eta, float* cam_lambda, float* lmk_eta, float* lmk_lambda) {
@@ -1676,7 +1953,7 @@ int gbp_cuda_get_tensor(gbp_handle* h, const char* name, void* dst, size_t nbyte
   }
   if (rc) return rc;
   GBP_CUDA_TRY(cudaStreamSynchronize(s));
-  return GBP_OK;
+  return check_peer_error(h);
 }
 
 int gbp_cuda_set_tensor(gbp_handle* h, const char* name, const void* src, size_t nbytes) {
@@ -1925,12 +2202,216 @@ int gbp_cuda_init_shard(const gbp_problem* p, const gbp_opts* o_in, uint32_t wor
     }
   }
   if (!rc) rc = build(h, gbp_shard_problem(sh), &o, gbp_shard_edge_global(sh));
+  gbp_shard_detach_views(sh);  // the caller may free p's arrays after this call: the retained shard keeps no pointer into them
+  if (!rc) rc = setup_p2p(h, o.exchange);
+  if (!rc) rc = linearise_prog(h);
+  if (!rc) rc = linearise_wait(h);
   if (rc) {
     if (rc == GBP_ERR_CUDA && !*gbp_cuda_last_error()) gbp_set_error("CUDA initialisation failed");
     gbp_cuda_free(h);
     return rc;
   }
   *out = h;
+  return GBP_OK;
+}
+
+// ---- single-process group: `world` shard handles of one problem driven by one host thread -------------------
+int gbp_cuda_init_group(const gbp_problem* p, const gbp_opts* o_in, uint32_t world, const int* devices, gbp_handle** out) {
+  if (!p || !out || world == 0 || world > P2P_MAX_WORLD) {
+    gbp_set_error("bad gbp_cuda_init_group arguments");
+    return GBP_ERR_ARG;
+  }
+  gbp_opts o;
+  if (o_in) o = *o_in; else gbp_opts_default(&o);
+  for (uint32_t r = 0; r < world; ++r) out[r] = nullptr;
+  if (world == 1) {
+    if (devices) o.device = devices[0];
+    return gbp_cuda_init(p, &o, out);
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    gbp_set_error("no CUDA device available (the GBP hot path has no CPU fallback)");
+    return GBP_ERR_CUDA;
+  }
+  std::vector<int> dev(world);
+  for (uint32_t r = 0; r < world; ++r) {
+    dev[r] = devices ? devices[r] : (int)(r % (uint32_t)ndev);
+    if (dev[r] < 0 || dev[r] >= ndev) {
+      gbp_set_error("device ordinal out of range");
+      return GBP_ERR_ARG;
+    }
+  }
+  auto fail = [&](int rc) {
+    if (rc == GBP_ERR_CUDA && !*gbp_cuda_last_error()) gbp_set_error("CUDA initialisation failed");
+    for (uint32_t r = 0; r < world; ++r)
+      if (out[r]) {
+        cudaSetDevice(out[r]->device);
+        cudaStreamSynchronize(out[r]->stream);
+      }
+    for (uint32_t r = 0; r < world; ++r)
+      if (out[r]) {
+        gbp_cuda_free(out[r]);
+        out[r] = nullptr;
+      }
+    return rc;
+  };
+  int rc = GBP_OK;
+  // every device of the group must be able to address every other one's memory
+  for (uint32_t a = 0; a < world && !rc; ++a)
+    for (uint32_t b = 0; b < world && !rc; ++b) {
+      if (dev[a] == dev[b]) continue;
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, dev[a], dev[b]);
+      if (!can) {
+        gbp_set_error("gbp_cuda_init_group: the devices of the group cannot access each other's memory");
+        rc = GBP_ERR_COMM;
+        break;
+      }
+      cudaSetDevice(dev[a]);
+      const cudaError_t e = cudaDeviceEnablePeerAccess(dev[b], 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+        gbp_set_error(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+        rc = GBP_ERR_COMM;
+      }
+      cudaGetLastError();
+    }
+  if (rc) return rc;
+  for (uint32_t r = 0; r < world && !rc; ++r) {
+    gbp_shard* sh = nullptr;
+    rc = gbp_shard_build_view(p, world, r, &sh);
+    if (rc) break;
+    gbp_handle* h = new gbp_handle();
+    out[r] = h;
+    h->device = dev[r];
+    h->use_graph = o.use_cuda_graph;
+    if (const char* env = std::getenv("GBP_SKIP_UPPER")) h->skip_upper = std::atoi(env) != 0;
+    h->relin_mode = o.relin_mode;
+    h->two_pass = (o.relin_mode == 2) ? 1 : 0;
+    h->shard = sh;
+    h->world = world;
+    h->rank = r;
+    rc = set_device(h);
+    if (!rc && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) rc = GBP_ERR_CUDA;
+    if (!rc && cudaEventCreate(&h->ev0) != cudaSuccess) rc = GBP_ERR_CUDA;
+    if (!rc && cudaEventCreate(&h->ev1) != cudaSuccess) rc = GBP_ERR_CUDA;
+    if (!rc) preload_kernels();
+    gbp_opts or_ = o;
+    or_.device = dev[r];
+    if (!rc) rc = build(h, gbp_shard_problem(sh), &or_, gbp_shard_edge_global(sh));
+    gbp_shard_detach_views(sh);
+  }
+  if (rc) return fail(rc);
+  // Shards that SHARE a device (a test configuration: the whole multi-GPU protocol on a one-GPU box) can only make
+  // progress while the blocks spinning for a peer leave room for that peer's kernels: refuse graphs whose
+  // boundary would fill the device with waiting blocks.
+  for (uint32_t a = 0; a < world; ++a)
+    for (uint32_t b = a + 1; b < world; ++b)
+      if (dev[a] == dev[b]) {
+        const uint32_t n_x = (std::max(out[a]->g.n_bnd_local, out[b]->g.n_bnd_local) + GBP_LMK_PER_BLOCK - 1) / GBP_LMK_PER_BLOCK;
+        // (a waiting block holds ~1/10 of an SM's registers, a sweep block of the peer needs ~9/10: two waiting
+        // blocks on every SM would starve it; at most world - 1 ranks wait at a time)
+        if (n_x * (world - 1) > (uint32_t)out[a]->num_sms) {
+          gbp_set_error("gbp_cuda_init_group: too many boundary landmarks for shards that share one device");
+          return fail(GBP_ERR_ARG);
+        }
+      }
+  // one exchange block per rank on its device, addressed directly by every peer
+  GroupShared* gs = new GroupShared();
+  gs->blocks.assign(world, nullptr);
+  gs->devices = dev;
+  const size_t total = p2p_block_bytes(world, out[0]->g.n_bnd_global);
+  for (uint32_t r = 0; r < world && !rc; ++r) {
+    cudaSetDevice(dev[r]);
+    if (cudaMalloc(&gs->blocks[r], total) != cudaSuccess || cudaMemset(gs->blocks[r], 0, total) != cudaSuccess) rc = GBP_ERR_CUDA;
+  }
+  if (rc) {
+    for (uint32_t r = 0; r < world; ++r)
+      if (gs->blocks[r]) {
+        cudaSetDevice(dev[r]);
+        cudaFree(gs->blocks[r]);
+      }
+    delete gs;
+    cudaGetLastError();
+    return fail(rc);
+  }
+  for (uint32_t r = 0; r < world; ++r) {
+    out[r]->group = gs;
+    gs->refs++;
+  }
+  for (uint32_t r = 0; r < world && !rc; ++r) {
+    rc = set_device(out[r]);
+    if (!rc) rc = p2p_wire(out[r], gs->blocks);
+  }
+  for (uint32_t r = 0; r < world && !rc; ++r) {
+    rc = set_device(out[r]);
+    if (!rc) rc = linearise_prog(out[r]);
+  }
+  for (uint32_t r = 0; r < world && !rc; ++r) {
+    rc = set_device(out[r]);
+    if (!rc) rc = linearise_wait(out[r]);
+  }
+  if (rc) return fail(rc);
+  return GBP_OK;
+}
+
+int gbp_cuda_group_iterate(gbp_handle** hs, uint32_t world, int n_sweeps, gbp_iter_stats* stats) {
+  if (!hs || world == 0 || n_sweeps < 0) return GBP_ERR_ARG;
+  for (uint32_t r = 0; r < world; ++r)
+    if (!hs[r]) return GBP_ERR_ARG;
+  int rc = GBP_OK;
+  for (uint32_t r = 0; r < world && !rc; ++r) rc = iterate_begin(hs[r], n_sweeps, stats != nullptr);
+  // sweep by sweep over the ranks: no rank's launch queue can fill up with work that waits for a peer that has
+  // not been enqueued yet
+  for (int i = 0; i < n_sweeps && !rc; ++i)
+    for (uint32_t r = 0; r < world && !rc; ++r) rc = iterate_enqueue(hs[r], i, n_sweeps, stats != nullptr);
+  for (uint32_t r = 0; r < world && !rc; ++r) rc = iterate_end(hs[r], n_sweeps, stats != nullptr);
+  // every rank reports the metric of the whole graph: rank 0's copy is returned
+  std::vector<gbp_iter_stats> scratch(stats ? (size_t)n_sweeps : 0);
+  for (uint32_t r = 0; r < world && !rc; ++r) rc = iterate_finish(hs[r], n_sweeps, stats ? (r == 0 ? stats : scratch.data()) : nullptr);
+  return rc;
+}
+
+int gbp_cuda_group_weaken_priors(gbp_handle** hs, uint32_t world) {
+  if (!hs || world == 0) return GBP_ERR_ARG;
+  int rc = GBP_OK;
+  for (uint32_t r = 0; r < world && !rc; ++r) rc = hs[r] ? gbp_cuda_weaken_priors(hs[r]) : GBP_ERR_ARG;  // enqueues only
+  return rc;
+}
+
+int gbp_cuda_group_eval(gbp_handle** hs, uint32_t world, gbp_iter_stats* out) {
+  if (!hs || world == 0 || !out) return GBP_ERR_ARG;
+  int rc = GBP_OK;
+  for (uint32_t r = 0; r < world && !rc; ++r) {
+    gbp_handle* h = hs[r];
+    if (!h) return GBP_ERR_ARG;
+    rc = set_device(h);
+    if (!rc) rc = ensure_stats(h, 1);
+    if (!rc) rc = launch_metric(h, h->d_stats);
+  }
+  for (uint32_t r = 0; r < world && !rc; ++r) {
+    gbp_handle* h = hs[r];
+    rc = set_device(h);
+    if (rc) break;
+    gbp_iter_stats tmp;
+    GBP_CUDA_TRY(cudaMemcpyAsync(r == 0 ? out : &tmp, h->d_stats, sizeof(gbp_iter_stats), cudaMemcpyDeviceToHost, h->stream));
+    GBP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    rc = check_peer_error(h);
+  }
+  return rc;
+}
+
+int gbp_cuda_group_free(gbp_handle** hs, uint32_t world) {
+  if (!hs) return GBP_OK;
+  for (uint32_t r = 0; r < world; ++r)
+    if (hs[r]) {
+      cudaSetDevice(hs[r]->device);
+      if (hs[r]->stream) cudaStreamSynchronize(hs[r]->stream);
+    }
+  for (uint32_t r = 0; r < world; ++r)
+    if (hs[r]) {
+      gbp_cuda_free(hs[r]);
+      hs[r] = nullptr;
+    }
   return GBP_OK;
 }
 

@@ -54,6 +54,7 @@ struct DeviceGraph {
   // landmarks
   float4* lmk_b;          // [L][4] {eta3, lam9, mean3, pad}
   float4* lmk_mean_prev;  // [L]
+  float4* lmk_sq;         // [L] {(old - new)^2 of the three mean components, 0}: the landmark's terms of dmu (k_sweep_tma)
   float4* lmk_prior;      // [L][3] {eta3, lam9}
   float* lmk_scaling;     // [L]
   uint32_t* lmk_wflag;    // [L]
@@ -75,9 +76,17 @@ struct DeviceGraph {
   uint32_t* p2p_done;     // block counter of k_boundary_push
   uint32_t* p2p_error;    // set when a wait for a peer timed out
   uint32_t* p2p_step;     // [2] {completed exchange steps, blocks of the current k_update_vars that are done}
+  long long p2p_timeout;  // clock64 ticks a block waits for its peers before it gives up (p2p_error)
+  // metric exchange over the same peer mappings (no collective call in a sweep that asks for the metric)
+  double** peer_metric;       // [world] -> that rank's metric receive buffer [2 parities][world][8]
+  uint32_t** peer_mflag;      // [world] -> that rank's metric arrival flags [world]
+  const double* metric_recv;  // this rank's own receive buffer
+  uint32_t* metric_flag;      // this rank's own arrival flags
+  uint32_t* metric_step;      // [1] completed metric exchanges
   uint32_t* relin_list;   // [E] edge slots that relinearise this sweep (compacted by k_prep_pass)
   uint32_t* relin_count;  // [1]
   uint32_t* relin_ring;   // [GBP_RELIN_RING + 1] relinearisations of the last sweeps; [GBP_RELIN_RING] = sweep counter
+  uint32_t* tile_queue;   // [1] next warp-tile k_sweep_tma hands out (reset by k_update_vars)
   float K[4];             // fx fy cx cy
   Hyper hp;
 };
@@ -814,6 +823,12 @@ GBP_DEV void lmk_accumulate(const DeviceGraph& g, const uint32_t l, float (&b)[1
   }
 }
 
+// the landmark's three terms of dmu (gbp_codelets.cpp:268-277): (old - new)^2 per mean component
+GBP_DEV float4 lmk_sq_terms(const float4 prev, const float (&mean)[3]) {
+  const float d0 = fs(prev.x, mean[0]), d1 = fs(prev.y, mean[1]), d2 = fs(prev.z, mean[2]);
+  return make_float4(fm(d0, d0), fm(d1, d1), fm(d2, d2), 0.f);
+}
+
 // belief record of one landmark: [eta 3 | Lambda 9 | mean 3 | pad]; shift != 0 keeps the
 // mean the last PrepMessageVertex pass used as the "old mu" (Copy(mu, oldmu), ba/ba.cpp:898)
 GBP_DEV void lmk_store_belief(const DeviceGraph& g, const uint32_t l, const float (&b)[12], const int shift) {
@@ -823,10 +838,15 @@ GBP_DEV void lmk_store_belief(const DeviceGraph& g, const uint32_t l, const floa
   for (int i = 0; i < 9; ++i) lam[i] = b[3 + i];
   inf2mean3(eta, lam, mean);
   float4* o = g.lmk_b + (size_t)l * GBP_LMKB_QUADS;
+  float4 prev;
   if (shift) {
     const float4 oldq = o[3];
-    g.lmk_mean_prev[l] = make_float4(oldq.x, oldq.y, oldq.z, 0.f);
+    prev = make_float4(oldq.x, oldq.y, oldq.z, 0.f);
+    g.lmk_mean_prev[l] = prev;
+  } else {
+    prev = g.lmk_mean_prev[l];
   }
+  g.lmk_sq[l] = lmk_sq_terms(prev, mean);
   o[0] = make_float4(b[0], b[1], b[2], b[3]);
   o[1] = make_float4(b[4], b[5], b[6], b[7]);
   o[2] = make_float4(b[8], b[9], b[10], b[11]);
@@ -892,6 +912,7 @@ GBP_DEV void update_camera(const DeviceGraph& g, const int shift, const uint32_t
     float R[9], num[9], den;
     cam_lin_consts(w, R, num, den);
     float* rec = reinterpret_cast<float*>(g.cam_rec + (size_t)c * 16);
+    float acc6 = 0.f;  // the camera's six terms of dmu (gbp_codelets.cpp:268-277), hoisted out of the factors
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
       const float prev = shift ? g.cam_mean[c * 6 + i] : g.cam_mean_prev[c * 6 + i];
@@ -899,7 +920,10 @@ GBP_DEV void update_camera(const DeviceGraph& g, const int shift, const uint32_t
       g.cam_mean[c * 6 + i] = mean[i];
       rec[42 + i] = mean[i];
       rec[48 + i] = prev;
+      const float d = fs(prev, mean[i]);
+      acc6 = fa(acc6, fm(d, d));
     }
+    rec[54] = acc6;
     float* lin = reinterpret_cast<float*>(g.cam_lin + (size_t)c * 5);
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
@@ -960,10 +984,15 @@ GBP_DEV void lmk_finish_quads(const DeviceGraph& g, const uint32_t l, const uint
 #pragma unroll
     for (int i = 0; i < 9; ++i) lam[i] = b[3 + i];
     inf2mean3(eta, lam, mean);
+    float4 prev;
     if (shift) {  // Copy(mu, oldmu), ba/ba.cpp:898
       const float4 oldq = o[3];
-      g.lmk_mean_prev[l] = make_float4(oldq.x, oldq.y, oldq.z, 0.f);
+      prev = make_float4(oldq.x, oldq.y, oldq.z, 0.f);
+      g.lmk_mean_prev[l] = prev;
+    } else {
+      prev = g.lmk_mean_prev[l];
     }
+    g.lmk_sq[l] = lmk_sq_terms(prev, mean);
     o[3] = make_float4(mean[0], mean[1], mean[2], 0.f);
   }
   if (q < 3) o[q] = acc;
@@ -1023,17 +1052,22 @@ GBP_DEV void boundary_push(const DeviceGraph& g, const uint32_t step, const uint
 }
 
 GBP_DEV void boundary_finish(const DeviceGraph& g, const int shift, const uint32_t step, const uint32_t block) {
+  __shared__ uint32_t s_timed_out;
+  if (threadIdx.x == 0) s_timed_out = 0u;
+  __syncthreads();
   if (threadIdx.x < g.world) {
     const long long t0 = clock64();
     while ((int32_t)(ld_acquire_sys(g.p2p_flag + threadIdx.x) - step) < 0) {
-      if (clock64() - t0 > 20000000000ll) {  // ~10 s: a peer died; do not hang the GPU
-        *g.p2p_error = 1u;
+      if (clock64() - t0 > g.p2p_timeout) {  // a peer died or never made the matching call: do not hang the GPU
+        *g.p2p_error = 1u;                   // (host-mapped, sticky: every later call on the handle fails)
+        s_timed_out = 1u;
         break;
       }
       __nanosleep(100);
     }
   }
   __syncthreads();
+  if (s_timed_out) return;  // nothing is stored from a receive buffer that is not complete
   const uint32_t k = block * GBP_LMK_PER_BLOCK + (threadIdx.x >> 2), q = threadIdx.x & 3;
   const bool mine = k < g.n_bnd_local;
   const uint32_t l = mine ? g.bnd_local[k] : 0u;
@@ -1391,9 +1425,22 @@ struct DeviceStats {  // == gbp_iter_stats
 // Fixed-order reduction of the per-block partials in double by ONE block of NT threads, then the result.
 // raw != nullptr (multi-GPU): the five sums are written as doubles for k_metric_combine instead.
 // cursor != nullptr (CUDA-graph replay): the result goes to out[*cursor] and the cursor advances.
+struct MetricPeers {  // the peer mappings the metric exchange needs (all null on a single-GPU / NCCL handle)
+  double** peer_metric;
+  uint32_t** peer_mflag;
+  const uint32_t* metric_step;
+  uint32_t world, rank;
+};
+GBP_DEV MetricPeers metric_peers(const DeviceGraph& g) {
+  MetricPeers px;
+  px.peer_metric = g.peer_metric; px.peer_mflag = g.peer_mflag; px.metric_step = g.metric_step;
+  px.world = g.world; px.rank = g.rank;
+  return px;
+}
+
 template <int NT>
 GBP_DEV void metric_finish(const MetricPartial* parts, const uint32_t n_parts, DeviceStats* __restrict__ out,
-                           double* __restrict__ raw, uint32_t* __restrict__ cursor) {
+                           double* __restrict__ raw, uint32_t* __restrict__ cursor, const MetricPeers px) {
   __shared__ double s_d[2][NT];
   __shared__ uint32_t s_u[3][NT];
   const uint32_t tid = threadIdx.x;
@@ -1419,6 +1466,16 @@ GBP_DEV void metric_finish(const MetricPartial* parts, const uint32_t n_parts, D
     raw[0] = s_d[0][0]; raw[1] = s_d[1][0];
     raw[2] = (double)s_u[0][0]; raw[3] = (double)s_u[1][0]; raw[4] = (double)s_u[2][0];
     raw[5] = raw[6] = raw[7] = 0.0;
+    if (px.peer_metric) {
+      // the five sums of this rank go straight into every rank's receive buffer (parity of the exchange step),
+      // then the step is published in every rank's arrival flag -- the protocol of boundary_push
+      const uint32_t mstep = *px.metric_step + 1u;
+      const size_t off = ((size_t)(mstep & 1u) * px.world + px.rank) * 8;
+      for (uint32_t r = 0; r < px.world; ++r)
+        for (int i = 0; i < 8; ++i) px.peer_metric[r][off + i] = raw[i];
+      __threadfence_system();
+      for (uint32_t r = 0; r < px.world; ++r) st_release_sys(px.peer_mflag[r] + px.rank, mstep);
+    }
   } else if (tid == 0) {
     DeviceStats s;
     s.n_active = s_u[2][0];
@@ -1509,24 +1566,51 @@ __global__ void __launch_bounds__(GBP_TILE) k_metric(const DeviceGraph g, const 
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  metric_finish<GBP_TILE>(out, gridDim.x, stats_out, raw, cursor);
+  metric_finish<GBP_TILE>(out, gridDim.x, stats_out, raw, cursor, metric_peers(g));
   if (tid == 0) *ticket = 0u;
 }
 
 
 // The empty graph (no k_metric launch): zero sums through the same finishing code.
-__global__ void __launch_bounds__(GBP_TILE) k_metric_finish(const MetricPartial* __restrict__ parts, const uint32_t n_parts,
-                                                           DeviceStats* __restrict__ out, double* __restrict__ raw,
-                                                           uint32_t* __restrict__ cursor) {
-  metric_finish<GBP_TILE>(parts, n_parts, out, raw, cursor);
+__global__ void __launch_bounds__(GBP_TILE) k_metric_finish(const DeviceGraph g, const MetricPartial* __restrict__ parts,
+                                                           const uint32_t n_parts, DeviceStats* __restrict__ out,
+                                                           double* __restrict__ raw, uint32_t* __restrict__ cursor) {
+  metric_finish<GBP_TILE>(parts, n_parts, out, raw, cursor, metric_peers(g));
 }
 
-// multi-GPU: sum the all-gathered per-rank metric sums [world][8] in rank order
-__global__ void k_metric_combine(const double* __restrict__ all, const uint32_t world, DeviceStats* __restrict__ out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// multi-GPU: sum the per-rank metric sums [world][8] in rank order.  all != nullptr: the NCCL all-gathered copy;
+// else the peer-to-peer receive buffer of the current exchange step, once every rank's flag has arrived.
+// cursor != nullptr (CUDA-graph replay): the result goes to out[*cursor] and the cursor advances.
+__global__ void k_metric_combine(const DeviceGraph g, const double* __restrict__ all, DeviceStats* __restrict__ out,
+                                 uint32_t* __restrict__ cursor) {
+  if (blockIdx.x != 0) return;
+  __shared__ uint32_t s_timed_out;
+  if (threadIdx.x == 0) s_timed_out = 0u;
+  __syncthreads();
+  const double* src = all;
+  uint32_t mstep = 0;
+  if (!all) {
+    mstep = *g.metric_step + 1u;
+    if (threadIdx.x < g.world) {
+      const long long t0 = clock64();
+      while ((int32_t)(ld_acquire_sys(g.metric_flag + threadIdx.x) - mstep) < 0) {
+        if (clock64() - t0 > g.p2p_timeout) {
+          *g.p2p_error = 1u;
+          s_timed_out = 1u;
+          break;
+        }
+        __nanosleep(100);
+      }
+    }
+    src = g.metric_recv + (size_t)(mstep & 1u) * g.world * 8;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  if (!all) *g.metric_step = mstep;
   double a[5] = {0, 0, 0, 0, 0};
-  for (uint32_t r = 0; r < world; ++r)
-    for (int i = 0; i < 5; ++i) a[i] += all[r * 8 + i];
+  if (!s_timed_out)
+    for (uint32_t r = 0; r < g.world; ++r)
+      for (int i = 0; i < 5; ++i) a[i] += __ldcg(src + r * 8 + i);
   DeviceStats s;
   s.n_active = (uint32_t)a[4];
   s.reproj_mean = (float)(a[0] / a[4]);
@@ -1534,7 +1618,12 @@ __global__ void k_metric_combine(const double* __restrict__ all, const uint32_t 
   s.n_relins = (uint32_t)a[2];
   s.n_robust = (uint32_t)a[3];
   s.reserved = 0;
-  *out = s;
+  if (cursor) {
+    out[*cursor] = s;
+    *cursor += 1;
+  } else {
+    *out = s;
+  }
 }
 
 // READ_PROG helpers: gather per-edge scalars back into the reference's edge order
@@ -1598,13 +1687,18 @@ __global__ void k_means_from_beliefs(const DeviceGraph g) {
     float R[9], num[9], den;
     cam_lin_consts(w, R, num, den);
     float* rec = reinterpret_cast<float*>(g.cam_rec + (size_t)i * 16);
+    float acc6 = 0.f;
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
       g.cam_mean[i * 6 + k] = mean[k];
       rec[k] = eta[k];
       rec[42 + k] = mean[k];
-      rec[48 + k] = g.cam_mean_prev[i * 6 + k];
+      const float prev = g.cam_mean_prev[i * 6 + k];
+      rec[48 + k] = prev;
+      const float d = fs(prev, mean[k]);
+      acc6 = fa(acc6, fm(d, d));
     }
+    rec[54] = acc6;
 #pragma unroll
     for (int k = 0; k < 36; ++k) rec[6 + k] = g.cam_b_lam[i * 36 + k];
     float* lin = reinterpret_cast<float*>(g.cam_lin + (size_t)i * 5);
@@ -1623,7 +1717,10 @@ __global__ void k_means_from_beliefs(const DeviceGraph g) {
     float mean[3];
     inf2mean3(eta, lam, mean);
     o[3] = make_float4(mean[0], mean[1], mean[2], 0.f);
+    g.lmk_sq[l] = lmk_sq_terms(g.lmk_mean_prev[l], mean);
   }
 }
 
 }  // namespace gbp
+
+#include "gbp_sweep_tma.cuh"

@@ -1,0 +1,448 @@
+// k_sweep_tma: the GBP sweep of every factor with the per-factor records staged by the Blackwell
+// copy engines (included by gbp_kernels.cuh; same arithmetic, bit for bit, as k_sweep).
+//
+// What changed against the cp.async kernel (k_sweep, kept as the reference implementation of the staging):
+//   * The 22 contiguous 512-byte rows a warp-tile needs -- factor potential 14, previous camera-bound message 7,
+//     edge state 1 -- plus its camera record arrive through TMA: ONE elected lane issues two
+//     cp.async.bulk.tensor.2d copies (a [14 x 512 B] and a [7 x 512 B] box of the quad-SoA arrays, tensor maps
+//     built at init) and two cp.async.bulk copies, all completing on an mbarrier the warp then waits on.
+//     The 26 per-lane LDGSTS with their 64-bit address arithmetic, the wait_group and the register-held
+//     landmark records of k_sweep are gone from the instruction stream.
+//   * Only the per-factor GATHERS stay per-lane cp.async: the previous landmark-bound message (3 quads at the
+//     factor's position in landmark order) and the landmark's belief record (3 quads + the quad of squared
+//     mean differences, below).  They live in a single-buffered 7-row region that is consumed at the TOP of a
+//     tile (3x3 inverse and the belief-minus-message vectors of the camera-bound message: 15 live registers)
+//     and refilled for the next tile right away, a whole tile of arithmetic before it is needed.
+//   * dmu (gbp_codelets.cpp:268-277) no longer needs the two variables' previous means per factor: the belief
+//     kernel leaves  acc6 = sum over the camera's 6 dofs of (old - new)^2  (sequential from +0, in the camera
+//     record) and  sq[i] = (old_i - new_i)^2  of the landmark (lmk_sq), so  dmu = sqrt(((acc6 + sq0) + sq1) + sq2)
+//     -- the very same fp32 operations in the same order, nine of them hoisted per variable.
+//   * Warp-tiles are handed out by a device-side queue (one atomicAdd per tile, fetched two tiles ahead) after
+//     the first two static rounds, so the makespan of a shard does not jump by a whole round when it holds a
+//     few tiles more than a multiple of the resident warps.
+#pragma once
+
+#include <cuda.h>  // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
+
+namespace gbp {
+
+#ifndef GBP_TW
+#define GBP_TW 8  // warps per block of k_sweep_tma (one block per SM)
+#endif
+#define GBP_T_ROWS 22        // TMA rows per buffer: potential 0..13 | camera-bound message 14..20 | edge state 21
+#define GBP_T_FAC 0
+#define GBP_T_MCAM 14
+#define GBP_T_RECA 21
+#define GBP_G_ROWS 7         // gathered rows: landmark-bound message 0..2 | landmark belief 3..5 | squared mean differences 6
+#define GBP_G_MLMK 0
+#define GBP_G_LB 3
+#define GBP_G_SQ 6
+#define GBP_T_SCAM_QUADS 14  // camera record: belief eta 0..5 | lambda 6..41 | mean 42..47 | previous mean 48..53 | acc6 54 | pad
+#define GBP_T_TX_BYTES ((GBP_T_ROWS * 32 + GBP_T_SCAM_QUADS) * 16)
+// per warp: [2 buffers x 22 rows x 32 quads | 7 gathered rows x 32 quads | 2 camera records | 2 mbarriers]
+#define GBP_T_WARP_QUADS (2 * GBP_T_ROWS * 32 + GBP_G_ROWS * 32 + 2 * GBP_T_SCAM_QUADS + 1)
+#define GBP_T_SMEM (GBP_TW * GBP_T_WARP_QUADS * 16)
+
+GBP_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+GBP_DEV void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+GBP_DEV void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+GBP_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// generic-proxy accesses of this thread to shared memory are ordered before later async-proxy (TMA) writes
+GBP_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// rows [row0, row0 + box rows) x 512 bytes of a quad-SoA array, for warp-tile wt -> dst
+GBP_DEV void tma_load_rows(void* dst, const CUtensorMap* map, uint32_t wt, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"((int)(wt * 128u)), "r"(0), "r"(smem_u32(bar))
+      : "memory");
+}
+GBP_DEV void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+struct SweepMaps {  // TMA descriptors of the two big quad-SoA arrays (box = [rows x 128 floats])
+  CUtensorMap fac;   // [14][E_pad * 4] floats, box 14 x 128
+  CUtensorMap mcam;  // [7][E_pad * 4] floats, box 7 x 128
+};
+
+template <int Q0, int N>
+GBP_DEV void rows_read(const float4* rows, uint32_t lane, float (&out)[N * 4]) {
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    const float4 v = rows[(Q0 + q) * 32 + lane];
+    out[q * 4] = v.x; out[q * 4 + 1] = v.y; out[q * 4 + 2] = v.z; out[q * 4 + 3] = v.w;
+  }
+}
+
+// one elected lane: everything of warp-tile wt that is contiguous -> buffer `tb` / camera record `sc`
+GBP_DEV void tma_issue_tile(const DeviceGraph& g, const SweepMaps& maps, float4* tb, float4* sc, uint64_t* bar, const uint32_t wt,
+                            const uint32_t cam) {
+  mbar_expect_tx(bar, GBP_T_TX_BYTES);
+  tma_load_rows(tb + GBP_T_FAC * 32, &maps.fac, wt, bar);
+  tma_load_rows(tb + GBP_T_MCAM * 32, &maps.mcam, wt, bar);
+  bulk_load(tb + GBP_T_RECA * 32, g.recA + (size_t)wt * 32, 512u, bar);
+  bulk_load(sc, g.cam_rec + (size_t)cam * 16, GBP_T_SCAM_QUADS * 16u, bar);
+}
+
+// every lane: the gathered records of ITS factor of the next warp-tile (landmark l, message position lpos)
+GBP_DEV void gather_issue(const DeviceGraph& g, float4* gat, const uint32_t l, const uint32_t lpos, const uint32_t lane) {
+#pragma unroll
+  for (int q = 0; q < GBP_MLMK_QUADS; ++q) cp_async16(gat + (GBP_G_MLMK + q) * 32 + lane, g.mlmk + (size_t)lpos * GBP_MLMK_QUADS + q);
+#pragma unroll
+  for (int q = 0; q < 3; ++q) cp_async16(gat + (GBP_G_LB + q) * 32 + lane, g.lmk_b + (size_t)l * GBP_LMKB_QUADS + q);
+  cp_async16(gat + GBP_G_SQ * 32 + lane, g.lmk_sq + l);
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+
+// staged factor record: rows 0..8 = eta 0..8 | ll(lower) 9..14 | cl 15..32 | cc(lower) 0..2 at 33..35, rows 9..13 = cc(lower) 3..20 | pad
+#define GBP_LLF(i, j) head[GBP_FAC_LL + gbp_sym(i, j)]
+#define GBP_CCF(i, j) ((gbp_sym(i, j) < 3) ? head[GBP_FAC_CC + gbp_sym(i, j)] : tail[gbp_sym(i, j) - 3])
+
+// Front half of the camera-bound message (gbp_codelets.cpp:446-462): everything that reads the landmark belief and
+// the previous landmark-bound message -- the 3x3 inverse of (Lambda_ll + belief - message) and eta_l + belief - message.
+// Afterwards the gathered rows are dead.  ple = previous f->lmk eta (needed again by the landmark-bound damping).
+GBP_DEV void cam_msg_front(const float4* tb, const float4* gat, const uint32_t lane, float (&Li)[9], float (&ed)[3], float (&ple)[3]) {
+  float pl[12], lb[12];
+  rows_read<GBP_G_MLMK, 3>(gat, lane, pl);
+  rows_read<GBP_G_LB, 3>(gat, lane, lb);
+  float head[16];  // eta 0..8 | ll(lower) 9..14
+  rows_read<GBP_T_FAC, 4>(tb, lane, head);
+  float Ld[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) Ld[i * 3 + j] = fs(fa(GBP_LLF(i, j), lb[3 + i * 3 + j]), pl[3 + i * 3 + j]);
+  inv3(Ld, Li);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    ed[i] = fs(fa(head[GBP_FAC_ETA + 6 + i], lb[i]), pl[i]);
+    ple[i] = pl[i];
+  }
+}
+
+// Back half (gbp_codelets.cpp:446-462, 619-627): Schur complement over the landmark block with the inverse from
+// cam_msg_front.  nc: eta 0..5 | lower lambda 6..26 | pad; ncu: the strict upper triangle (row-major, i<j).
+template <bool UPPER>
+GBP_DEV void cam_msg_back(const float4* tb, const uint32_t lane, const float (&Li)[9], const float (&ed)[3], const float damping,
+                          float (&nc)[28], float (&ncu)[16]) {
+  const float omd = fs(1.0f, damping);
+  float head[36], tail[20];
+  rows_read<GBP_T_FAC, 9>(tb, lane, head);
+  rows_read<GBP_T_FAC + 9, 5>(tb, lane, tail);
+  const float* eta = head + GBP_FAC_ETA;
+  const float* cl = head + GBP_FAC_CL;
+  float pc[8];  // previous f->cam eta 0..5
+  rows_read<GBP_T_MCAM, 2>(tb, lane, pc);
+  float P[18];  // Lambda_cl * inv (6x3)
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      P[i * 3 + j] = fa(fa(fm(cl[i * 3], Li[j]), fm(cl[i * 3 + 1], Li[3 + j])), fm(cl[i * 3 + 2], Li[6 + j]));
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const float acc = fa(fa(fm(P[i * 3], ed[0]), fm(P[i * 3 + 1], ed[1])), fm(P[i * 3 + 2], ed[2]));
+    const float h = fs(eta[i], acc);
+    nc[i] = fa(fm(h, omd), fm(pc[i], damping));
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      if (i >= j || UPPER) {
+        const float acc = fa(fa(fm(P[i * 3], cl[j * 3]), fm(P[i * 3 + 1], cl[j * 3 + 1])), fm(P[i * 3 + 2], cl[j * 3 + 2]));
+        const float v = fs(GBP_CCF(i, j), acc);
+        if (i >= j) nc[GBP_MCAM_LOWER + lt(i, j)] = v;
+        else ncu[gbp_upper(i, j)] = v;
+      } else {
+        ncu[gbp_upper(i, j)] = 0.f;
+      }
+    }
+  nc[27] = 0.f;
+  ncu[15] = 0.f;
+}
+
+// Landmark-bound message (gbp_codelets.cpp:536-552, 691-699): Schur complement over the camera block, one inv6x6.
+// sc: camera belief eta 0..5 | lambda 6..41.  ple: previous f->lmk eta.
+GBP_DEV void lmk_msg(const float4* tb, const float* sc, const uint32_t lane, const float damping, const float (&ple)[3],
+                     float (&nl)[12]) {
+  const float omd = fs(1.0f, damping);
+  float head[36], tail[20];
+  rows_read<GBP_T_FAC, 9>(tb, lane, head);
+  rows_read<GBP_T_FAC + 9, 5>(tb, lane, tail);
+  const float* eta = head + GBP_FAC_ETA;
+  const float* cl = head + GBP_FAC_CL;
+  float pc[28];  // previous f->cam message: eta 0..5, lower lambda 6..26
+  rows_read<GBP_T_MCAM, 7>(tb, lane, pc);
+  float Ai[36];
+  {
+    float Ld[21];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = 0; j <= i; ++j) Ld[lt(i, j)] = fs(fa(GBP_CCF(i, j), sc[6 + i * 6 + j]), pc[GBP_MCAM_LOWER + lt(i, j)]);
+    inv6(Ld, Ai);
+  }
+  float P[18];  // Lambda_lc * inv  (3x6), Lambda_lc(i,k) = Lambda_cl(k,i)
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      float acc = fm(cl[i], Ai[j]);
+#pragma unroll
+      for (int k = 1; k < 6; ++k) acc = fa(acc, fm(cl[k * 3 + i], Ai[k * 6 + j]));
+      P[i * 6 + j] = acc;
+    }
+  float ed[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) ed[i] = fs(fa(eta[i], sc[i]), pc[i]);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float acc = fm(P[i * 6], ed[0]);
+#pragma unroll
+    for (int k = 1; k < 6; ++k) acc = fa(acc, fm(P[i * 6 + k], ed[k]));
+    const float h = fs(eta[6 + i], acc);
+    nl[i] = fa(fm(h, omd), fm(ple[i], damping));
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float acc = fm(P[i * 6], cl[j]);
+#pragma unroll
+      for (int k = 1; k < 6; ++k) acc = fa(acc, fm(P[i * 6 + k], cl[k * 3 + j]));
+      nl[3 + i * 3 + j] = fs(GBP_LLF(i, j), acc);
+    }
+}
+#undef GBP_LLF
+#undef GBP_CCF
+
+// PrepMessageVertex (gbp_codelets.cpp:241-378) from the hoisted per-variable sums.  Out of line on the paths that
+// need more than them: an edge whose oldmu is still the streamed one (first sweep after init / set_tensor) and the
+// accumulating relinearisation itself.
+__device__ __noinline__ float dmu_from_edge_oldmu(const DeviceGraph g, const size_t e, const uint32_t l, const float c0, const float c1,
+                                                  const float c2, const float c3, const float c4, const float c5) {
+  const float x[9] = {c0, c1, c2, c3, c4, c5, 0.f, 0.f, 0.f};
+  const float4 m = g.lmk_b[(size_t)l * GBP_LMKB_QUADS + 3];
+  const float xl[3] = {m.x, m.y, m.z};
+  float acc = 0.f;  // gbp_codelets.cpp:268-277
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    const float old = g.oldmu_edge ? g.oldmu_edge[(size_t)i * g.E_pad + e] : 0.f;
+    const float d = fs(old, i < 6 ? x[i] : xl[i - 6]);
+    acc = fa(acc, fm(d, d));
+  }
+  return acc;
+}
+
+GBP_DEV void prep_factor_tma(const DeviceGraph& g, float4* tb, const float* sc, const float4 sq, const uint32_t cam, const uint32_t l,
+                             const size_t e, const uint32_t lane, float& damping, int& dcount, uint32_t& flags, float& dmu) {
+  if (dcount == 0) damping = g.hp.maxeta_damping;  // gbp_codelets.cpp:245-248
+  dcount += 1;
+  float acc;
+  if (flags & GBP_FLAG_MUVALID) {
+    acc = fa(fa(fa(sc[54], sq.x), sq.y), sq.z);
+  } else {
+    acc = dmu_from_edge_oldmu(g, e, l, sc[42], sc[43], sc[44], sc[45], sc[46], sc[47]);
+  }
+  dmu = __fsqrt_rn(acc);
+  flags |= GBP_FLAG_MUVALID;
+  if (dmu < g.hp.dmu_threshold && dcount > g.hp.min_linear_iters - g.hp.num_undamped_iters) {
+    damping = 0.0f;  // gbp_codelets.cpp:280-283
+    dcount = -g.hp.num_undamped_iters;
+    // the staged record is the current potential: accumulate onto it (quirk Q1), write it back
+    const float4 m = g.lmk_b[(size_t)l * GBP_LMKB_QUADS + 3];
+    const float4 rb = g.recB[e];
+    const uint32_t robust = relinearise_record(tb + lane, 32, g.fac + e, g.E_pad, tb + lane, g.cam_lin + (size_t)cam * 5,
+                                               make_float4(g.K[0], g.K[1], g.K[2], g.K[3]), g.hp.Nstds, rb.x, rb.y, g.var[e],
+                                               sc[42], sc[43], sc[44], sc[45], sc[46], sc[47], m.x, m.y, m.z);
+    flags = (flags & ~GBP_FLAG_ROBUST) | (robust ? GBP_FLAG_ROBUST : 0u);
+    const uint32_t m_act = __activemask();
+    if (lane == (uint32_t)__ffs(m_act) - 1u) atomicAdd(g.relin_ring + (g.relin_ring[GBP_RELIN_RING] % GBP_RELIN_RING), __popc(m_act));
+  }
+}
+
+// One warp-tile from a landed buffer.  lid = {landmark, message position} of this lane's factor; lid_n the same for
+// the warp's next tile (gather issued here once the gathered rows are consumed).
+template <bool PREP, bool MSG, bool UPPER>
+GBP_DEV void sweep_tile_tma(const DeviceGraph& g, float4* tb, const float* sc, float4* gat, const uint32_t wt, const uint2 ti,
+                            const uint2 lid, const bool has_next, const uint2 lid_n, const uint32_t lane) {
+  const size_t e = (size_t)wt * 32 + lane;
+  const bool valid = lane < ti.y;  // padding slots hold no factor
+  const float4 ra = tb[GBP_T_RECA * 32 + lane];
+  float damping = ra.x;
+  int dcount = __float_as_int(ra.y);
+  uint32_t flags = __float_as_uint(ra.z);
+  float dmu = ra.w;
+  const bool active = valid && (flags & GBP_FLAG_ACTIVE) != 0;
+  const size_t lpos = lid.y;
+
+  if (PREP && active) prep_factor_tma(g, tb, sc, gat[GBP_G_SQ * 32 + lane], ti.x, lid.x, e, lane, damping, dcount, flags, dmu);
+
+  float Li[9], ed3[3], ple[3];
+  if (MSG) cam_msg_front(tb, gat, lane, Li, ed3, ple);
+  // the gathered rows of this tile are consumed (every lane reads and refills only its own column)
+  if (has_next) gather_issue(g, gat, lid_n.x, lid_n.y, lane);
+
+  float nc[28];   // new f->cam message record: eta 0..5 | lower lambda 6..26 | pad
+  float ncu[16];  // its strict upper triangle (row-major, i<j): only summed into the camera partial
+  if (MSG) {
+    if (active) {
+      float nl[12];
+      lmk_msg(tb, sc, lane, damping, ple, nl);
+      float4* p = g.mlmk + lpos * GBP_MLMK_QUADS;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) p[q] = make_float4(nl[q * 4], nl[q * 4 + 1], nl[q * 4 + 2], nl[q * 4 + 3]);
+      cam_msg_back<UPPER>(tb, lane, Li, ed3, damping, nc, ncu);
+      store_cam_message(g, e, nc, ncu);
+      flags |= GBP_FLAG_HASMSG;
+    } else {
+      // inactive (or padding) slot: its messages are zero (gbp_codelets.cpp:464-468 etc.)
+#pragma unroll
+      for (int k = 0; k < 28; ++k) nc[k] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) ncu[k] = 0.f;
+      if (valid && (flags & GBP_FLAG_HASMSG)) {
+        store_cam_message(g, e, nc, ncu);
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) g.mlmk[lpos * GBP_MLMK_QUADS + q] = z4;
+        flags &= ~GBP_FLAG_HASMSG;
+      }
+    }
+  }
+  // the state record only changes in this kernel when prep ran here or the has-message flag toggled
+  if (valid && (PREP ? (active || MSG) : flags != __float_as_uint(ra.z)))
+    g.recA[e] = make_float4(damping, __int_as_float(dcount), __uint_as_float(flags), dmu);
+
+  if (MSG) {
+    // lane-ordered reduction through the warp's own (now consumed) buffer
+    float* red = reinterpret_cast<float*>(tb);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 6; ++i) red[i * GBP_RED_STRIDE + lane] = nc[i];
+    if (UPPER) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j)
+          red[(6 + i * 6 + j) * GBP_RED_STRIDE + lane] = (i >= j) ? nc[GBP_MCAM_LOWER + lt(i, j)] : ncu[gbp_upper(i, j)];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 21; ++k) red[(6 + k) * GBP_RED_STRIDE + lane] = nc[GBP_MCAM_LOWER + k];
+    }
+    __syncwarp();
+    warp_cam_reduce<UPPER>(red, lane, g.cam_partial + (size_t)wt * GBP_CAMPART);
+  }
+  // this buffer is rewritten by the copy engine two tiles from now: order the generic accesses before that
+  fence_proxy_async();
+  __syncwarp();
+}
+
+// next warp-tile of this warp: the first two rounds are static (their ids are already in flight), the rest comes
+// from the queue.  tile_queue = {tiles handed out beyond the two static rounds, warps that have finished}; the last
+// warp of the launch to finish rewinds both, so every launch starts from an empty queue without a memset node.
+GBP_DEV uint32_t next_tile(const DeviceGraph& g, const uint32_t lane, const uint32_t n_wt, const uint32_t n_static) {
+  uint32_t t = 0;
+  if (lane == 0) t = atomicAdd(g.tile_queue, 1u) + 2u * n_static;
+  t = __shfl_sync(0xffffffffu, t, 0);
+  return t < n_wt ? t : 0xffffffffu;
+}
+GBP_DEV void tile_queue_done(const DeviceGraph& g, const uint32_t lane, const uint32_t n_wt, const uint32_t n_static) {
+  if (lane != 0) return;
+  const uint32_t n_warps = n_static < n_wt ? n_static : n_wt;  // warps of this launch that had a first tile
+  __threadfence();
+  if (atomicAdd(g.tile_queue + 1, 1u) == n_warps - 1u) {
+    g.tile_queue[0] = 0u;
+    g.tile_queue[1] = 0u;
+  }
+}
+
+template <bool PREP, bool MSG, bool UPPER>
+__global__ void __launch_bounds__(GBP_TW * 32, 1) k_sweep_tma(const DeviceGraph g, const __grid_constant__ SweepMaps maps) {
+  extern __shared__ __align__(1024) float4 smem4[];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4* wbase = smem4 + (size_t)warp * GBP_T_WARP_QUADS;
+  float4* tbuf = wbase;                                   // [2][22 rows][32]
+  float4* gat = wbase + 2 * GBP_T_ROWS * 32;              // [7 rows][32]
+  float4* scam = gat + GBP_G_ROWS * 32;                   // [2][14]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(scam + 2 * GBP_T_SCAM_QUADS);  // [2]
+  const uint32_t n_wt = g.E_pad / 32;
+  const uint32_t n_static = gridDim.x * GBP_TW;           // tiles of the first (static) round
+  // consecutive warp-tiles go to different SMs, so small graphs spread over the whole chip
+  uint32_t wt = warp * gridDim.x + blockIdx.x;
+  if (wt >= n_wt) return;
+  if (lane == 0) {
+    mbar_init(bars + 0, 1);
+    mbar_init(bars + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  fence_proxy_async();
+  __syncwarp();
+
+  // prologue: everything of the first warp-tile, ids of the second
+  uint2 ti = __ldg(g.wt_info + wt);
+  // {landmark id, message position} of a lane's factor = the second half of its recB record
+  const uint2* lrec = reinterpret_cast<const uint2*>(g.recB) + 1;
+  uint2 lid = __ldg(lrec + 2 * ((size_t)wt * 32 + lane));
+  if (lane == 0) tma_issue_tile(g, maps, tbuf, scam, bars, wt, ti.x);
+  gather_issue(g, gat, lid.x, lid.y, lane);
+  uint32_t wt_n = wt + n_static;  // second round is static too: the queue starts at 2 * n_static
+  if (wt_n >= n_wt) wt_n = 0xffffffffu;
+  uint2 ti_n = make_uint2(0u, 0u), lid_n = make_uint2(0u, 0u);
+  if (wt_n != 0xffffffffu) {
+    ti_n = __ldg(g.wt_info + wt_n);
+    lid_n = __ldg(lrec + 2 * ((size_t)wt_n * 32 + lane));
+  }
+  uint32_t buf = 0, phase0 = 0, phase1 = 0;
+  for (;;) {
+    const bool has_next = wt_n != 0xffffffffu;
+    uint32_t wt_nn = 0xffffffffu;
+    uint2 ti_nn = make_uint2(0u, 0u), lid_nn = make_uint2(0u, 0u);
+    if (has_next) {
+      // the other buffer was released at the end of the previous tile (fence + __syncwarp in sweep_tile_tma)
+      if (lane == 0) tma_issue_tile(g, maps, tbuf + (buf ^ 1) * GBP_T_ROWS * 32, scam + (buf ^ 1) * GBP_T_SCAM_QUADS, bars + (buf ^ 1), wt_n, ti_n.x);
+      wt_nn = next_tile(g, lane, n_wt, n_static);
+      if (wt_nn != 0xffffffffu) {
+        ti_nn = __ldg(g.wt_info + wt_nn);
+        lid_nn = __ldg(lrec + 2 * ((size_t)wt_nn * 32 + lane));
+      }
+    }
+    // this tile: the bulk copies complete on the buffer's mbarrier, the gathers on the lane's cp.async group
+    mbar_wait(bars + buf, buf ? phase1 : phase0);
+    if (buf) phase1 ^= 1u; else phase0 ^= 1u;
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    sweep_tile_tma<PREP, MSG, UPPER>(g, tbuf + buf * GBP_T_ROWS * 32, reinterpret_cast<const float*>(scam + buf * GBP_T_SCAM_QUADS), gat, wt,
+                                     ti, lid, has_next, lid_n, lane);
+    if (!has_next) break;
+    wt = wt_n; wt_n = wt_nn;
+    ti = ti_n; ti_n = ti_nn;
+    lid = lid_n; lid_n = lid_nn;
+    buf ^= 1;
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  tile_queue_done(g, lane, n_wt, n_static);
+}
+
+}  // namespace gbp

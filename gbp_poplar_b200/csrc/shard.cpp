@@ -273,6 +273,33 @@ int gbp_shard_build_view(const gbp_problem* p, uint32_t world, uint32_t rank, gb
   return shard_build_impl(p, world, rank, true, out);
 }
 
+// After gbp_shard_build_view: drop every member of the local problem that points INTO the caller's arrays (the
+// per-edge / per-camera runs that were not copied).  What stays is owned by the shard: the index maps, the plan,
+// the boundary lists and whatever had to be gathered.  gbp_cuda_init_shard / gbp_cuda_init_group call this once the
+// device copy exists, so the shard they retain (gbp_cuda_shard_info) never dangles.
+void gbp_shard_detach_views(gbp_shard* s) {
+  if (!s) return;
+  gbp_problem& q = s->prob;
+  auto own = [](const void* ptr, const void* vec_data) { return ptr != nullptr && ptr == vec_data; };
+#define GBP_DETACH(member, vec) if (!own(q.member, s->vec.data())) q.member = nullptr
+  GBP_DETACH(measurements, z);
+  GBP_DETACH(meas_variances, var);
+  GBP_DETACH(active_flag, active);
+  GBP_DETACH(damping, damping);
+  GBP_DETACH(damping_count, dcount);
+  GBP_DETACH(mu, mu);
+  GBP_DETACH(oldmu, oldmu);
+  GBP_DETACH(cam_priors_eta, cam_pe);
+  GBP_DETACH(cam_priors_lambda, cam_pl);
+  GBP_DETACH(cam_scaling, cam_sc);
+  GBP_DETACH(cam_weaken_flag, cam_wflag);
+  GBP_DETACH(lmk_priors_eta, lmk_pe);
+  GBP_DETACH(lmk_priors_lambda, lmk_pl);
+  GBP_DETACH(lmk_scaling, lmk_sc);
+  GBP_DETACH(lmk_weaken_flag, lmk_wflag);
+#undef GBP_DETACH
+}
+
 void gbp_shard_free(gbp_shard* s) { delete s; }
 const gbp_problem* gbp_shard_problem(const gbp_shard* s) { return s ? &s->prob : nullptr; }
 const gbp_shard_plan* gbp_shard_get_plan(const gbp_shard* s) { return s ? &s->plan : nullptr; }

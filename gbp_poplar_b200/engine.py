@@ -39,15 +39,10 @@ TENSOR_NAMES = [
 
 
 def default_opts(**kw):
-    """gbp_opts with the hyper-parameters of ba/gbp_codelets.cpp:11-16."""
+    """gbp_opts with the hyper-parameters of ba/gbp_codelets.cpp:11-16 (gbp_opts_default: the library's own
+    defaults, including its environment overrides)."""
     o = GbpOpts()
-    o.device = 0
-    o.maxeta_damping = 0.4
-    o.num_undamped_iters = 8
-    o.dmu_threshold = 3e-3
-    o.min_linear_iters = 10
-    o.Nstds = 2.5
-    o.use_cuda_graph = 1
+    _capi.load_library().gbp_opts_default(C.byref(o))
     for k, v in kw.items():
         if not hasattr(o, k):
             raise TypeError(f"unknown option {k}")
@@ -63,10 +58,11 @@ def stats_to_dict(s):
 class GBPEngine:
     _uid_cache = {}
 
-    def __init__(self, problem, opts=None, lib=None, prefix="gbp_cuda_", keepalive=None, shard=None):
+    def __init__(self, problem, opts=None, lib=None, prefix="gbp_cuda_", keepalive=None, shard=None, adopt=None):
         """shard = (world, rank, nccl_unique_id bytes): this rank's part of the GLOBAL `problem`
         (gbp_cuda_init_shard); every program then includes the boundary-landmark exchange and is
-        collective over the ranks.  See GBPEngine.sharded()."""
+        collective over the ranks.  See GBPEngine.sharded().  adopt = (handle, world, rank): wrap a handle
+        that gbp_cuda_init_group built (GBPGroup owns it)."""
         if lib is None:
             lib = _capi.load_library()
         self._lib = lib
@@ -76,7 +72,14 @@ class GBPEngine:
         self.opts = opts if opts is not None else default_opts()
         self._h = C.c_void_p()
         self.shard = None
-        if shard is None:
+        self._borrowed = adopt is not None
+        if adopt is not None:
+            handle, world, rank = adopt
+            self._h = C.c_void_p(handle)
+            if world > 1:
+                from .host import Shard
+                self.shard = Shard(None, world, rank, owner=self, handle=C.c_void_p(lib.gbp_cuda_shard_info(self._h)))
+        elif shard is None:
             self._check(self._f["init"](C.byref(problem), C.byref(self.opts), C.byref(self._h)))
         else:
             world, rank, uid = shard
@@ -132,9 +135,9 @@ class GBPEngine:
         return self._h
 
     def close(self):
-        if self._h:
+        if self._h and not self._borrowed:
             self._f["free"](self._h)
-            self._h = C.c_void_p()
+        self._h = C.c_void_p()
 
     def __del__(self):
         try:
@@ -281,3 +284,63 @@ class GBPEngine:
 
     def synchronize(self):
         self._check(self._lib.gbp_cuda_synchronize(self._h))
+
+
+class GBPGroup:
+    """All ranks of a multi-GPU run in ONE process (gbp_cuda_init_group) -- the shape of the reference's own
+    multi-chip mode, one host program driving 2^k IPUs (--ipus, ba/ba.cpp:617-631).  `devices[r]` is the CUDA
+    device of rank r; ordinals may repeat (shards sharing one GPU: the multi-rank protocol on a one-GPU box).
+    Programs that exchange boundary partials go through the group; `ranks[r]` is a GBPEngine view of rank r's
+    handle for the per-rank read-backs (get_tensor, get_beliefs, shard maps)."""
+
+    def __init__(self, problem, world, devices=None, opts=None):
+        self._lib = _capi.load_library()
+        self.opts = opts if opts is not None else default_opts()
+        self.world = int(world)
+        dev = None
+        if devices is not None:
+            assert len(devices) == self.world
+            dev = (C.c_int * self.world)(*[int(d) for d in devices])
+        self._hs = (C.c_void_p * self.world)()
+        rc = self._lib.gbp_cuda_init_group(C.byref(problem), C.byref(self.opts), self.world, dev, self._hs)
+        if rc != 0:
+            raise RuntimeError(f"gbp_cuda_init_group failed with code {rc}: {self._lib.gbp_cuda_last_error().decode()}")
+        self.ranks = [GBPEngine(None, self.opts, adopt=(self._hs[r], self.world, r)) for r in range(self.world)]
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError(f"gbp_cuda_group_* failed with code {rc}: {self._lib.gbp_cuda_last_error().decode()}")
+
+    def iterate(self, n_sweeps=1, stats=False):
+        if stats:
+            arr = (GbpIterStats * n_sweeps)()
+            self._check(self._lib.gbp_cuda_group_iterate(self._hs, self.world, n_sweeps, arr))
+            return [stats_to_dict(s) for s in arr]
+        self._check(self._lib.gbp_cuda_group_iterate(self._hs, self.world, n_sweeps, None))
+        return None
+
+    def weaken_priors(self):
+        self._check(self._lib.gbp_cuda_group_weaken_priors(self._hs, self.world))
+
+    def eval(self):
+        s = GbpIterStats()
+        self._check(self._lib.gbp_cuda_group_eval(self._hs, self.world, C.byref(s)))
+        return stats_to_dict(s)
+
+    def last_timing(self):
+        """(max over ranks of the device time of the last iterate, kernels launched by all ranks)."""
+        t = [r.last_timing() for r in self.ranks]
+        return max(x[0] for x in t), sum(x[1] for x in t)
+
+    def close(self):
+        if self._hs is not None:
+            for r in self.ranks:
+                r.close()
+            self._lib.gbp_cuda_group_free(self._hs, self.world)
+            self._hs = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -294,15 +294,40 @@ const uint32_t* gbp_shard_cam_bounds(const gbp_shard* s);
 /* 128-byte NCCL unique id (rank 0 creates it, the caller's plumbing -- e.g.
  * torch.distributed -- broadcasts it). */
 int gbp_cuda_nccl_unique_id(void* id128);
-/* Build the handle for this rank's shard of the GLOBAL problem `p` and join the
- * NCCL communicator.  Afterwards every entry point works on the LOCAL shard
+/* Build the handle for this rank's shard of the GLOBAL problem `p` (its arrays are
+ * only read during the call) and join the NCCL communicator.  Afterwards every entry point works on the LOCAL shard
  * (sizes via gbp_cuda_dims, index maps via gbp_cuda_shard_info); iterate /
  * weaken_priors / update_beliefs include the boundary exchange and are
  * collective: every rank must make the same sequence of calls.  add_keyframe
  * is single-GPU only. */
 int gbp_cuda_init_shard(const gbp_problem* p, const gbp_opts* o, uint32_t world, uint32_t rank,
                         const void* nccl_unique_id, gbp_handle** out);
-/* The shard a handle was built from (NULL for a single-GPU handle). */
+/* ---- multi-GPU in ONE process (the reference's own multi-chip mode is one host process driving 2^k IPUs,
+ * --ipus, ba/ba.cpp:617-631) ------------------------------------------------------------------------------
+ * Builds all `world` shard handles of the GLOBAL problem `p` in this process: out[r] is rank r's handle on
+ * CUDA device devices[r] (NULL: device r modulo the device count).  The boundary exchange is the same fused
+ * peer-to-peer protocol as between processes, over directly addressed peer memory
+ * (cudaDeviceEnablePeerAccess); no NCCL, no IPC.  Device ordinals may repeat: shards that share a GPU are the
+ * way the whole multi-rank protocol is exercised on a one-GPU box (refused when their boundary is large
+ * enough for the waiting blocks to starve the peer's kernels).
+ * Programs that contain an exchange must be driven through the group calls below -- they enqueue on every
+ * rank before they wait on any; per-handle read-backs (get_beliefs, get_tensor, ...) work on each out[r]. */
+int gbp_cuda_init_group(const gbp_problem* p, const gbp_opts* o, uint32_t world, const int* devices, gbp_handle** out);
+/* GBP_PROG x n_sweeps on every rank (gbp_cuda_iterate semantics); stats (may be NULL) = the metric of the
+ * WHOLE graph after every sweep, identical on all ranks. */
+int gbp_cuda_group_iterate(gbp_handle** hs, uint32_t world, int n_sweeps, gbp_iter_stats* stats);
+int gbp_cuda_group_weaken_priors(gbp_handle** hs, uint32_t world);
+int gbp_cuda_group_eval(gbp_handle** hs, uint32_t world, gbp_iter_stats* out);
+/* Synchronises every rank, then frees all handles (hs[r] = NULL afterwards). */
+int gbp_cuda_group_free(gbp_handle** hs, uint32_t world);
+
+/* Device memory of freed handles is kept in a pool private to this library (one per device) for the next
+ * gbp_cuda_init of the process; this returns it to the driver. */
+int gbp_cuda_release_cached_memory(void);
+
+/* The shard a handle was built from (NULL for a single-GPU handle).  Its index maps, plan and boundary lists
+ * are owned by the handle; the array members of gbp_shard_problem() that were views of the caller's problem
+ * are NULL (the caller may free its arrays after init). */
 const gbp_shard* gbp_cuda_shard_info(gbp_handle* h);
 /* How this handle exchanges boundary partials: 0 = no exchange (single GPU or no boundary
  * landmarks), 1 = NCCL all-gather, 2 = peer-to-peer stores over NVLink. */

@@ -14,6 +14,29 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "slow: long-running trajectory test")
 
 
+def cuda_device_count():
+    """Number of CUDA devices, asked of the driver directly (no torch import)."""
+    import ctypes
+    try:
+        cu = ctypes.CDLL("libcuda.so.1")
+        n = ctypes.c_int(0)
+        if cu.cuInit(0) != 0 or cu.cuDeviceGetCount(ctypes.byref(n)) != 0:
+            return 0
+        return n.value
+    except OSError:
+        return 0
+
+
+def pytest_collection_modifyitems(config, items):
+    """Tests marked `gpu` are skipped (not failed) on a box without a CUDA device."""
+    if cuda_device_count() > 0:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session", autouse=True)
 def _built_libraries():
     """Make sure the C-ABI library and the port oracle exist (builds are seconds)."""

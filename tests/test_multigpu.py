@@ -44,6 +44,25 @@ def test_two_gpus_bit_identical_to_oracle_in_sharded_order(tmp_path, spec, n, ex
         assert (int(s[2]), int(s[3]), int(s[4])) == (o["n_relins"], o["n_robust"], o["n_active"])
 
 
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs at least 2 GPUs")
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_block_calls_between_processes_bit_identical_to_oracle(tmp_path, world, monkeypatch):
+    """One process per GPU, CUDA IPC peer mappings, the call pattern bench.py --gpus N times: blocks of sweeps
+    without per-sweep metrics (see tests/test_group_gpu.py for the single-process twin that runs on one GPU)."""
+    if _n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    spec, n = "synth:96:9000:9:5", 63
+    monkeypatch.setenv("GBP_TEST_EXCHANGE", "p2p")
+    monkeypatch.setenv("GBP_TEST_MODE", "blocks")
+    ranks = run_ranks("nccl", world, spec, n, tmp_path)
+    st = shard_worker.make_problem(spec)
+    ora = oracle_lib.OracleEngine(st.problem, kind=KIND)
+    ora.set_shard_bounds(ranks[0]["cam_bounds"])
+    common.run_ba(ora, 12)
+    ora.iterate(n - 12)
+    check_against_global(ranks, ora, st, exact=True)
+
+
 @pytest.mark.skipif(_n_gpus() < 4, reason="needs at least 4 GPUs")
 def test_four_gpus_bit_identical_to_oracle_in_sharded_order(tmp_path):
     spec, n = "synth:96:9000:9:5", 24
