@@ -271,7 +271,8 @@ int download(T* dst, const T* src, size_t n, cudaStream_t s) {
 }
 
 inline uint32_t metric_grid(const gbp_handle* h) { return std::min<uint32_t>(h->n_tiles, 8u * (uint32_t)h->num_sms); }
-inline uint32_t lmks_grid(const gbp_handle* h) { return (h->L + GBP_LMK_PER_BLOCK - 1) / GBP_LMK_PER_BLOCK; }
+inline uint32_t lmks_grid(const gbp_handle* h) { return h->g.n_lmk_blocks; }
+inline uint32_t cams_grid(const gbp_handle* h) { return (h->C + GBP_CAM_PER_BLOCK - 1) / GBP_CAM_PER_BLOCK; }
 
 int priors_about_to_change(gbp_handle* h) {
   if (!h->p_in_sync) return GBP_OK;
@@ -317,7 +318,7 @@ int launch_update_vars(gbp_handle* h, bool lower_only = false) {
     // one launch: the first blocks form the partial sums and push them into every rank's receive buffer
     // over NVLink, the last blocks finish the boundary landmarks once every rank's flag has arrived
     const uint32_t n_x = std::max((h->g.n_bnd_local + GBP_LMK_PER_BLOCK - 1) / GBP_LMK_PER_BLOCK, 1u);
-    gbp::k_update_vars<<<n_x + h->C + grid + n_x, GBP_TILE, 0, h->stream>>>(h->g, shift, n_x, lower_only ? 1 : 0);
+    gbp::k_update_vars<<<n_x + cams_grid(h) + grid + n_x, GBP_TILE, 0, h->stream>>>(h->g, shift, n_x, lower_only ? 1 : 0);
     h->kernels_launched++;
     h->exchanges++;
   } else {
@@ -333,8 +334,8 @@ int launch_update_vars(gbp_handle* h, bool lower_only = false) {
       GBP_CUDA_TRY(cudaEventRecord(h->ev_recv, h->comm_stream));
       h->exchanges++;
     }
-    if (grid + h->C) {
-      gbp::k_update_vars<<<grid + h->C, GBP_TILE, 0, h->stream>>>(h->g, shift, 0u, lower_only ? 1 : 0);
+    if (grid + cams_grid(h)) {
+      gbp::k_update_vars<<<grid + cams_grid(h), GBP_TILE, 0, h->stream>>>(h->g, shift, 0u, lower_only ? 1 : 0);
       h->kernels_launched++;
     }
     if (exchange) {
@@ -870,6 +871,15 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   std::vector<uint32_t>& lmk_ptr = h->lmk_ptr;
   lmk_ptr.assign(L + 1, 0);
   for (uint32_t l = 0; l < L; ++l) lmk_ptr[l + 1] = lmk_ptr[l] + deg_l[l];
+  // belief-update blocks of the landmarks: consecutive landmarks, at most GBP_LMK_PER_BLOCK of them and at most
+  // GBP_LMK_CAP messages (what a block stages in shared memory); a landmark above the cap stands alone
+  std::vector<uint32_t> lmk_blk(1, 0u);
+  for (uint32_t l = 0; l < L;) {
+    uint32_t n = 0, msgs = 0;
+    while (l + n < L && n < GBP_LMK_PER_BLOCK && (n == 0 || msgs + deg_l[l + n] <= GBP_LMK_CAP)) msgs += deg_l[l + n++];
+    l += n;
+    lmk_blk.push_back(l);
+  }
   std::vector<float> var(EP, 1.f);
   pt.lap("index maps");
   // per-edge state records (built by a few host threads: this is the largest part of gbp_cuda_init)
@@ -929,6 +939,7 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   DeviceGraph& g = h->g;
   std::memset(&g, 0, sizeof(g));
   g.C = C; g.L = L; g.E = E; g.E_pad = h->E_pad;
+  g.n_lmk_blocks = (uint32_t)lmk_blk.size() - 1;
   g.K[0] = p->K[0]; g.K[1] = p->K[4]; g.K[2] = p->K[2]; g.K[3] = p->K[5];
   g.hp.maxeta_damping = o->maxeta_damping;
   g.hp.num_undamped_iters = o->num_undamped_iters;
@@ -979,6 +990,7 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   A_(g.lmk_scaling, L);
   A_(g.lmk_wflag, L);
   A_(g.lmk_ptr, L + 1);
+  A_(g.lmk_blk, lmk_blk.size());
   A_(h->d_pos_of_orig, E);
   A_(h->d_lmk_first_cam, L);
   A_(h->d_kf_scratch, 4);
@@ -1088,6 +1100,7 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   U_(g.lmk_scaling, p->lmk_scaling, L);
   U_(g.lmk_wflag, p->lmk_weaken_flag, L);
   U_(g.lmk_ptr, lmk_ptr.data(), L + 1);
+  U_(g.lmk_blk, lmk_blk.data(), lmk_blk.size());
   U_(g.var, var.data(), EP);
   U_(h->d_pos_of_orig, h->pos_of_orig.data(), E);
   {

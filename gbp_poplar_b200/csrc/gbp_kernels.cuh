@@ -18,6 +18,7 @@
 
 #include "gbp_layout.h"
 #include "gbp_math.cuh"
+#include "gbp_tma.cuh"
 
 #define GBP_RELIN_RING 32  // sweeps of relinearisation history kept on the device
 
@@ -59,6 +60,8 @@ struct DeviceGraph {
   float* lmk_scaling;     // [L]
   uint32_t* lmk_wflag;    // [L]
   uint32_t* lmk_ptr;      // [L+1] first message of every landmark in mlmk (messages in original edge order)
+  uint32_t* lmk_blk;      // [n_lmk_blocks+1] first landmark of every belief-update block (<= 32 landmarks, <= GBP_LMK_CAP messages)
+  uint32_t n_lmk_blocks;
   // multi-GPU shard (all null / 0 on a single-GPU handle): boundary landmarks = landmarks
   // that other ranks observe too; their beliefs are formed from all-gathered partials
   uint32_t* lmk_bslot;    // [L] position in the global boundary list, 0xffffffff = interior
@@ -868,38 +871,58 @@ GBP_DEV void lmk_load_prior(const DeviceGraph& g, const uint32_t l, float (&b)[1
 // last PrepMessageVertex pass used becomes the "old mu" (Copy(mu, oldmu),
 // ba/ba.cpp:898) before the new mean is stored.
 // Belief update of the cameras (prog_ub, ba/ba.cpp:104-139, camera half) + per-camera mean and
-// rotation.  One block per camera: 42 threads add the per-warp-tile partials of k_sweep to the
-// prior in warp-tile order, one thread inverts the 6x6 belief (latency bound: a serial LDL^T).
-GBP_DEV void update_camera(const DeviceGraph& g, const int shift, const uint32_t c, const int lower_only) {
-  __shared__ float s_b[GBP_CAMPART];
-  const uint32_t tid = threadIdx.x;
-  // entry tid of [eta 6 | Lambda 36 row-major]; after a sweep that skipped the strict upper triangle of the
-  // camera messages (k_sweep<.., UPPER = false>) the upper entries of the belief mirror the lower ones
-  const uint32_t bi = (tid >= 6 && tid < GBP_CAMPART) ? (tid - 6) / 6 : 0u, bj = (tid >= 6 && tid < GBP_CAMPART) ? (tid - 6) % 6 : 0u;
-  const bool skip = lower_only && tid >= 6 && bi < bj;
-  if (tid < GBP_CAMPART && !skip) {
-    // the sum starts from +0 like a zero-initialised accumulator: 0 + prior (turns a -0 prior into +0)
-    float acc = fa(0.0f, (tid < 6) ? g.cam_prior_eta[c * 6 + tid] : g.cam_prior_lam[c * 36 + (tid - 6)]);
-    const uint32_t t0 = g.cam_wt_begin[c], t1 = g.cam_wt_begin[c + 1];
-    // sixteen partials are fetched together; the additions stay in warp-tile order
-    for (uint32_t t = t0; t < t1; t += 16) {
-      float v[16];
+// rotation.  One WARP per camera (four cameras per block, so the camera blocks leave the block slots of an SM to the
+// bandwidth-bound landmark blocks): the lanes add the per-warp-tile partials of k_sweep to the prior in warp-tile
+// order, entry `lane` and entry `lane + 32` of [eta 6 | Lambda 36], lane 0 inverts the 6x6 belief (latency bound: a
+// serial LDL^T).
+#define GBP_CAM_PER_BLOCK (GBP_TILE / 32)
+GBP_DEV float cam_entry_sum(const DeviceGraph& g, const uint32_t c, const uint32_t ent, const uint32_t t0, const uint32_t t1) {
+  // the sum starts from +0 like a zero-initialised accumulator: 0 + prior (turns a -0 prior into +0)
+  float acc = fa(0.0f, (ent < 6) ? g.cam_prior_eta[c * 6 + ent] : g.cam_prior_lam[c * 36 + (ent - 6)]);
+  // sixteen partials are fetched together; the additions stay in warp-tile order
+  for (uint32_t t = t0; t < t1; t += 16) {
+    float v[16];
 #pragma unroll
-      for (int u = 0; u < 16; ++u) v[u] = (t + u < t1) ? g.cam_partial[(size_t)(t + u) * GBP_CAMPART + tid] : 0.f;
+    for (int u = 0; u < 16; ++u) v[u] = (t + u < t1) ? g.cam_partial[(size_t)(t + u) * GBP_CAMPART + ent] : 0.f;
 #pragma unroll
-      for (int u = 0; u < 16; ++u)
-        if (t + u < t1) acc = fa(acc, v[u]);
+    for (int u = 0; u < 16; ++u)
+      if (t + u < t1) acc = fa(acc, v[u]);
+  }
+  return acc;
+}
+
+GBP_DEV void update_cameras(const DeviceGraph& g, const int shift, const uint32_t block, const int lower_only) {
+  __shared__ float s_ball[GBP_CAM_PER_BLOCK][GBP_CAMPART + 2];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t c = block * GBP_CAM_PER_BLOCK + warp;
+  if (c >= g.C) return;  // whole warp
+  float* s_b = s_ball[warp];
+  const uint32_t t0 = g.cam_wt_begin[c], t1 = g.cam_wt_begin[c + 1];
+  // entries `lane` and `lane + 32` of [eta 6 | Lambda 36 row-major]; after a sweep that skipped the strict upper triangle of
+  // the camera messages (k_sweep<.., UPPER = false>) the upper entries of the belief mirror the lower ones
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const uint32_t ent = lane + 32u * half;
+    if (ent < GBP_CAMPART) {
+      const uint32_t bi = ent >= 6 ? (ent - 6) / 6 : 0u, bj = ent >= 6 ? (ent - 6) % 6 : 0u;
+      const bool skip = lower_only && ent >= 6 && bi < bj;
+      if (!skip) s_b[ent] = cam_entry_sum(g, c, ent, t0, t1);
     }
-    s_b[tid] = acc;
   }
-  __syncthreads();
-  if (tid < GBP_CAMPART) {
-    const float v = skip ? s_b[6 + bj * 6 + bi] : s_b[tid];
-    if (tid < 6) g.cam_b_eta[c * 6 + tid] = v;
-    else g.cam_b_lam[c * 36 + (tid - 6)] = v;
-    reinterpret_cast<float*>(g.cam_rec + (size_t)c * 16)[tid] = v;
+  __syncwarp();
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const uint32_t ent = lane + 32u * half;
+    if (ent < GBP_CAMPART) {
+      const uint32_t bi = ent >= 6 ? (ent - 6) / 6 : 0u, bj = ent >= 6 ? (ent - 6) % 6 : 0u;
+      const bool skip = lower_only && ent >= 6 && bi < bj;
+      const float v = skip ? s_b[6 + bj * 6 + bi] : s_b[ent];
+      if (ent < 6) g.cam_b_eta[c * 6 + ent] = v;
+      else g.cam_b_lam[c * 36 + (ent - 6)] = v;
+      reinterpret_cast<float*>(g.cam_rec + (size_t)c * 16)[ent] = v;
+    }
   }
-  if (tid == 0) {
+  if (lane == 0) {
     float eta[6], lamL[21], mean[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) eta[i] = s_b[i];
@@ -998,12 +1021,51 @@ GBP_DEV void lmk_finish_quads(const DeviceGraph& g, const uint32_t l, const uint
   if (q < 3) o[q] = acc;
 }
 
+// A block updates the landmarks [lmk_blk[b], lmk_blk[b+1]) -- at most 32, four lanes each.  Their messages are ONE
+// contiguous run of mlmk (landmark order), so a single cp.async.bulk brings the whole run into shared memory (one
+// elected thread, completion on an mbarrier) instead of every lane chasing its landmark's messages through
+// dependent 16-byte loads; the sums then read shared memory, strictly in slot order as before.  A landmark with more
+// than GBP_LMK_CAP messages has a block of its own and takes the direct path.
+#define GBP_LMK_CAP 448  // messages a block stages (21 KB)
 GBP_DEV void update_landmarks(const DeviceGraph& g, const int shift, const uint32_t block) {
-  const uint32_t l = block * GBP_LMK_PER_BLOCK + (threadIdx.x >> 2), q = threadIdx.x & 3;
+  __shared__ __align__(128) float4 s_msg[GBP_LMK_CAP * GBP_MLMK_QUADS];
+  __shared__ __align__(8) uint64_t s_bar;
+  const uint32_t l0 = g.lmk_blk[block], l1 = g.lmk_blk[block + 1];
+  const uint32_t k0 = g.lmk_ptr[l0], k1 = g.lmk_ptr[l1];
+  const bool staged = k1 - k0 <= GBP_LMK_CAP && k1 > k0;
+  if (staged) {
+    if (threadIdx.x == 0) {
+      mbar_init(&s_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+      fence_proxy_async();
+      const uint32_t bytes = (k1 - k0) * (uint32_t)(GBP_MLMK_QUADS * sizeof(float4));
+      mbar_expect_tx(&s_bar, bytes);
+      bulk_load(s_msg, g.mlmk + (size_t)k0 * GBP_MLMK_QUADS, bytes, &s_bar);
+    }
+    __syncthreads();  // the barrier is initialised before anyone waits on it
+  }
+  const uint32_t l = l0 + (threadIdx.x >> 2), q = threadIdx.x & 3;
   // boundary landmarks of a multi-GPU shard are finished by the exchange blocks / kernels
-  const bool mine = l < g.L && !(g.lmk_bslot && g.lmk_bslot[l] != 0xffffffffu);
+  const bool mine = l < l1 && !(g.lmk_bslot && g.lmk_bslot[l] != 0xffffffffu);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (mine && q < 3) acc = lmk_sum_quad(g, l, q, lmk_prior_quad(g, l, q));
+  uint32_t a0 = 0, a1 = 0;
+  if (mine && q < 3) {
+    acc = lmk_prior_quad(g, l, q);
+    a0 = g.lmk_ptr[l];
+    a1 = g.lmk_ptr[l + 1];
+  }
+  if (staged) {
+    mbar_wait(&s_bar, 0);
+    if (mine && q < 3) {
+      const float4* m = s_msg + (size_t)(a0 - k0) * GBP_MLMK_QUADS + q;
+      for (uint32_t k = a0; k < a1; ++k, m += GBP_MLMK_QUADS) {
+        const float4 v = *m;
+        acc.x = fa(acc.x, v.x); acc.y = fa(acc.y, v.y); acc.z = fa(acc.z, v.z); acc.w = fa(acc.w, v.w);
+      }
+    }
+  } else if (mine && q < 3) {
+    acc = lmk_sum_quad(g, l, q, acc);
+  }
   lmk_finish_quads(g, l, q, acc, mine, shift);
 }
 
@@ -1085,9 +1147,9 @@ GBP_DEV void boundary_finish(const DeviceGraph& g, const int shift, const uint32
 
 // prog_ub in one launch.  Block roles, in dispatch order:
 //   [multi-GPU, peer-to-peer] boundary_push blocks  -- first, so the partials travel while the rest runs
-//   camera blocks     -- few, long-running (a serial 6x6 inverse + Rodrigues per camera), nearly idle:
+//   camera blocks     -- few, long-running (a serial 6x6 inverse + Rodrigues per camera, one warp each), nearly idle:
 //                        they overlap with the bandwidth-bound landmark blocks that fill the chip
-//   landmark blocks   -- GBP_LMK_PER_BLOCK landmarks each
+//   landmark blocks   -- up to GBP_LMK_PER_BLOCK landmarks each, their messages staged by one bulk copy
 //   [multi-GPU, peer-to-peer] boundary_finish blocks -- last; every block they wait for was dispatched before them
 // The register budget (10 blocks per SM) fits all paths.  n_push == 0: no fused exchange.
 #ifndef GBP_UV_BLOCKS
@@ -1095,7 +1157,8 @@ GBP_DEV void boundary_finish(const DeviceGraph& g, const int shift, const uint32
 #endif
 __global__ void __launch_bounds__(GBP_TILE, GBP_UV_BLOCKS) k_update_vars(const DeviceGraph g, const int shift, const uint32_t n_push,
                                                                          const int lower_only) {
-  const uint32_t nb_lmk = (g.L + GBP_LMK_PER_BLOCK - 1) / GBP_LMK_PER_BLOCK;
+  const uint32_t nb_lmk = g.n_lmk_blocks;
+  const uint32_t nb_cam = (g.C + GBP_CAM_PER_BLOCK - 1) / GBP_CAM_PER_BLOCK;
   if (shift && blockIdx.x == 0 && threadIdx.x == 0) {  // a sweep ended: open the next slot of the relinearisation ring
     const uint32_t next = g.relin_ring[GBP_RELIN_RING] + 1;
     g.relin_ring[next % GBP_RELIN_RING] = 0;
@@ -1108,9 +1171,9 @@ __global__ void __launch_bounds__(GBP_TILE, GBP_UV_BLOCKS) k_update_vars(const D
   uint32_t b = blockIdx.x;
   if (b < n_push) {
     boundary_push(g, step, b, n_push);
-  } else if ((b -= n_push) < g.C) {
-    update_camera(g, shift, b, lower_only);
-  } else if ((b -= g.C) < nb_lmk) {
+  } else if ((b -= n_push) < nb_cam) {
+    update_cameras(g, shift, b, lower_only);
+  } else if ((b -= nb_cam) < nb_lmk) {
     update_landmarks(g, shift, b);
   } else {
     boundary_finish(g, shift, step, b - nb_lmk);
