@@ -1026,6 +1026,7 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
     A_(g.bnd_send, 3 * (size_t)g.n_bnd_global);
     reserve((void**)&g.bnd_recv, 3 * (size_t)g.n_bnd_global * h->world * sizeof(float4));
     A_(g.p2p_step, 2);
+    A_(g.metric_step, 1);
     A_(h->d_metric_raw, 8);
     A_(h->d_metric_all, 8 * (size_t)h->world);
   }
@@ -1146,6 +1147,8 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   GBP_CUDA_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
   rc = setup_tma(h);
   if (rc) return rc;
+  if (const char* env = std::getenv("GBP_TILE_QUEUE"))
+    if (std::atoi(env) == 0) g.tile_queue = nullptr;  // static round-robin over the warp-tiles (diagnostics)
   pt.lap("uploads");
   return GBP_OK;
 }

@@ -386,7 +386,12 @@ __global__ void __launch_bounds__(GBP_TW * 32, 1) k_sweep_tma(const DeviceGraph 
     if (has_next) {
       // the other buffer was released at the end of the previous tile (fence + __syncwarp in sweep_tile_tma)
       if (lane == 0) tma_issue_tile(g, maps, tbuf + (buf ^ 1) * GBP_T_ROWS * 32, scam + (buf ^ 1) * GBP_T_SCAM_QUADS, bars + (buf ^ 1), wt_n, ti_n.x);
-      wt_nn = next_tile(g, lane, n_wt, n_static);
+      if (g.tile_queue) {
+        wt_nn = next_tile(g, lane, n_wt, n_static);
+      } else {  // static round-robin (GBP_TILE_QUEUE=0)
+        wt_nn = wt_n + n_static;
+        if (wt_nn >= n_wt) wt_nn = 0xffffffffu;
+      }
       if (wt_nn != 0xffffffffu) {
         ti_nn = __ldg(g.wt_info + wt_nn);
         lid_nn = __ldg(lrec + 2 * ((size_t)wt_nn * 32 + lane));
@@ -405,7 +410,7 @@ __global__ void __launch_bounds__(GBP_TW * 32, 1) k_sweep_tma(const DeviceGraph 
     buf ^= 1;
   }
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-  tile_queue_done(g, lane, n_wt, n_static);
+  if (g.tile_queue) tile_queue_done(g, lane, n_wt, n_static);
 }
 
 }  // namespace gbp
