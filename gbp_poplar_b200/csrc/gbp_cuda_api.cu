@@ -136,6 +136,7 @@ struct gbp_handle {
   int profile = 0;
   std::vector<cudaEvent_t> prof_events;
   float last_ms_factor = 0.f, last_ms_variable = 0.f;
+  std::vector<float> sweep_ms_factor, sweep_ms_variable;  // per sweep of the last profiled gbp_cuda_iterate
   float last_ms = 0.f;
   uint64_t kernels_launched = 0;
   uint64_t last_kernels = 0;
@@ -1241,7 +1242,9 @@ int sweep_graph(gbp_handle* h, bool with_stats, bool upper, cudaGraphExec_t* out
       }
       cudaGetLastError();
     }
+    PhaseTimer pti;
     const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+    pti.lap("  cudaGraphInstantiate");
     cudaGraphDestroy(graph);
     if (ie != cudaSuccess) {
       exec = nullptr;
@@ -1451,9 +1454,11 @@ int iterate_begin(gbp_handle* h, int n_sweeps, bool stats) {
   int rc = set_device(h);
   if (!rc) rc = check_peer_error(h);
   if (rc) return rc;
+  PhaseTimer pt;
   if (stats) {
     rc = ensure_stats(h, (size_t)n_sweeps);
     if (rc) return rc;
+    pt.lap("iterate: stats buffers");
   }
   h->it_k0 = h->kernels_launched;
   h->it_prof = h->profile != 0;
@@ -1477,6 +1482,7 @@ int iterate_begin(gbp_handle* h, int n_sweeps, bool stats) {
     // (not when per-sweep metrics are requested: the metric inverts the FULL camera belief, like the reference's)
     if (!rc && n_sweeps > 1 && !stats && can_skip_upper(h)) rc = sweep_graph(h, false, false, &h->it_exec_lower);
     if (rc) return rc;
+    pt.lap("iterate: sweep graphs");
   }
   return GBP_OK;
 }
@@ -1536,12 +1542,16 @@ int iterate_finish(gbp_handle* h, int n_sweeps, gbp_iter_stats* stats) {
   h->last_ms_factor = h->last_ms_variable = 0.f;
   if (h->it_prof) {
     double a = 0, b = 0;
+    h->sweep_ms_factor.assign((size_t)n_sweeps, 0.f);
+    h->sweep_ms_variable.assign((size_t)n_sweeps, 0.f);
     for (int i = 0; i < n_sweeps; ++i) {
       float t;
       GBP_CUDA_TRY(cudaEventElapsedTime(&t, h->prof_events[3 * i], h->prof_events[3 * i + 1]));
       a += t;
+      h->sweep_ms_factor[(size_t)i] = t;
       GBP_CUDA_TRY(cudaEventElapsedTime(&t, h->prof_events[3 * i + 1], h->prof_events[3 * i + 2]));
       b += t;
+      h->sweep_ms_variable[(size_t)i] = t;
     }
     h->last_ms_factor = (float)a;
     h->last_ms_variable = (float)b;
@@ -1620,6 +1630,17 @@ int gbp_cuda_last_kernel_times(gbp_handle* h, float* ms_factor, float* ms_variab
   if (!h) return GBP_ERR_ARG;
   if (ms_factor) *ms_factor = h->last_ms_factor;
   if (ms_variable) *ms_variable = h->last_ms_variable;
+  return GBP_OK;
+}
+
+int gbp_cuda_last_sweep_times(gbp_handle* h, float* ms_factor_kernel, float* ms_variable_kernel, int capacity, int* n_sweeps) {
+  if (!h || capacity < 0) return GBP_ERR_ARG;
+  const int n = (int)std::min<size_t>(h->sweep_ms_factor.size(), (size_t)capacity);
+  for (int i = 0; i < n; ++i) {
+    if (ms_factor_kernel) ms_factor_kernel[i] = h->sweep_ms_factor[(size_t)i];
+    if (ms_variable_kernel) ms_variable_kernel[i] = h->sweep_ms_variable[(size_t)i];
+  }
+  if (n_sweeps) *n_sweeps = (int)h->sweep_ms_factor.size();
   return GBP_OK;
 }
 

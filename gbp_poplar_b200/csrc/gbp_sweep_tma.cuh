@@ -39,9 +39,13 @@ namespace gbp {
 #define GBP_G_SQ 6
 #define GBP_T_SCAM_QUADS 14  // camera record: belief eta 0..5 | lambda 6..41 | mean 42..47 | previous mean 48..53 | acc6 54 | pad
 #define GBP_T_TX_BYTES ((GBP_T_ROWS * 32 + GBP_T_SCAM_QUADS) * 16)
-// per warp: [2 buffers x 22 rows x 32 quads | 7 gathered rows x 32 quads | 2 camera records | 2 mbarriers]
+// GBP_TW = 8: two buffers per warp (the reduction runs through the consumed one);
+// GBP_TW = 12: one buffer per warp + a reduction scratch of its own (27 rows of GBP_RED_STRIDE floats).
+#define GBP_T_NBUF (GBP_TW <= 8 ? 2 : 1)
+#define GBP_T_RED_QUADS (GBP_T_NBUF == 1 ? (27 * GBP_RED_STRIDE / 4) : 0)
+// per warp: [NBUF buffers x 22 rows x 32 quads | 7 gathered rows x 32 quads | NBUF camera records | mbarriers | scratch]
 // (rounded up to whole 128-byte lines: the destination of a tensor copy must be 128-byte aligned)
-#define GBP_T_WARP_QUADS ((2 * GBP_T_ROWS * 32 + GBP_G_ROWS * 32 + 2 * GBP_T_SCAM_QUADS + 1 + 7) / 8 * 8)
+#define GBP_T_WARP_QUADS ((GBP_T_NBUF * GBP_T_ROWS * 32 + GBP_G_ROWS * 32 + GBP_T_NBUF * GBP_T_SCAM_QUADS + 1 + GBP_T_RED_QUADS + 7) / 8 * 8)
 #define GBP_T_SMEM (GBP_TW * GBP_T_WARP_QUADS * 16)
 
 struct SweepMaps {  // TMA descriptors of the two big quad-SoA arrays (box = [rows x 128 floats])
@@ -246,11 +250,37 @@ GBP_DEV void prep_factor_tma(const DeviceGraph& g, float4* tb, const float* sc, 
   }
 }
 
+// Lane-ordered sums of the 32 camera-bound messages through `red` (rows of GBP_RED_STRIDE floats, one row per message
+// entry): one pass over [eta 6 | lower 21]; with UPPER a second pass over the 15 strictly upper entries.  Every entry is
+// summed over the lanes in lane order by ONE lane (row_sum_lane_order), so the result does not depend on the split.
+template <bool UPPER>
+GBP_DEV void reduce_cam_messages(float* red, const uint32_t lane, const float (&nc)[28], const float (&ncu)[16], float* __restrict__ out42) {
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 27; ++k) red[k * GBP_RED_STRIDE + lane] = nc[k];
+  __syncwarp();
+  warp_cam_reduce<false>(red, lane, out42);
+  if (UPPER) {
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 15; ++k) red[k * GBP_RED_STRIDE + lane] = ncu[k];
+    __syncwarp();
+    if (lane < 15) {
+      const float acc = row_sum_lane_order(red + lane * GBP_RED_STRIDE);
+      // entry `lane` of the row-major strict upper triangle (i < j) inside [eta 6 | Lambda 36 row-major]
+      const uint32_t i = (lane >= 14) ? 4u : (lane >= 12) ? 3u : (lane >= 9) ? 2u : (lane >= 5) ? 1u : 0u;
+      const uint32_t j = lane - (5u * i - i * (i - 1u) / 2u) + i + 1u;
+      out42[6 + i * 6 + j] = acc;
+    }
+  }
+}
+
 // One warp-tile from a landed buffer.  lid = {landmark, message position} of this lane's factor; lid_n the same for
-// the warp's next tile (gather issued here once the gathered rows are consumed).
-template <bool PREP, bool MSG, bool UPPER>
-GBP_DEV void sweep_tile_tma(const DeviceGraph& g, float4* tb, const float* sc, float4* gat, const uint32_t wt, const uint2 ti,
-                            const uint2 lid, const bool has_next, const uint2 lid_n, const uint32_t lane) {
+// the warp's next tile (gather issued here once the gathered rows are consumed).  refill(): called once every lane has
+// read the last staged value (single-buffered configuration: the copy engine may overwrite the buffer from here on).
+template <bool PREP, bool MSG, bool UPPER, class Refill>
+GBP_DEV void sweep_tile_tma(const DeviceGraph& g, float4* tb, const float* sc, float4* gat, float* red, const uint32_t wt, const uint2 ti,
+                            const uint2 lid, const bool has_next, const uint2 lid_n, const uint32_t lane, Refill&& refill) {
   const size_t e = (size_t)wt * 32 + lane;
   const bool valid = lane < ti.y;  // padding slots hold no factor
   const float4 ra = tb[GBP_T_RECA * 32 + lane];
@@ -270,66 +300,52 @@ GBP_DEV void sweep_tile_tma(const DeviceGraph& g, float4* tb, const float* sc, f
 
   float nc[28];   // new f->cam message record: eta 0..5 | lower lambda 6..26 | pad
   float ncu[16];  // its strict upper triangle (row-major, i<j): only summed into the camera partial
+  float nl[12];   // new f->lmk message
   if (MSG) {
     if (active) {
-      float nl[12];
       lmk_msg(tb, sc, lane, damping, ple, nl);
-      float4* p = g.mlmk + lpos * GBP_MLMK_QUADS;
-#pragma unroll
-      for (int q = 0; q < 3; ++q) p[q] = make_float4(nl[q * 4], nl[q * 4 + 1], nl[q * 4 + 2], nl[q * 4 + 3]);
       cam_msg_back<UPPER>(tb, lane, Li, ed3, damping, nc, ncu);
-      store_cam_message(g, e, nc, ncu);
-      flags |= GBP_FLAG_HASMSG;
     } else {
       // inactive (or padding) slot: its messages are zero (gbp_codelets.cpp:464-468 etc.)
 #pragma unroll
       for (int k = 0; k < 28; ++k) nc[k] = 0.f;
 #pragma unroll
       for (int k = 0; k < 16; ++k) ncu[k] = 0.f;
-      if (valid && (flags & GBP_FLAG_HASMSG)) {
-        store_cam_message(g, e, nc, ncu);
-        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int q = 0; q < 3; ++q) g.mlmk[lpos * GBP_MLMK_QUADS + q] = z4;
-        flags &= ~GBP_FLAG_HASMSG;
-      }
+      for (int k = 0; k < 12; ++k) nl[k] = 0.f;
+    }
+  }
+  // generic accesses to the staged rows end here (a relinearising lane also WROTE its potential into them)
+  fence_proxy_async();
+  __syncwarp();
+  refill();
+  if (MSG) {
+    if (active || (valid && (flags & GBP_FLAG_HASMSG))) {
+      float4* p = g.mlmk + lpos * GBP_MLMK_QUADS;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) p[q] = make_float4(nl[q * 4], nl[q * 4 + 1], nl[q * 4 + 2], nl[q * 4 + 3]);
+      store_cam_message(g, e, nc, ncu);
+      flags = active ? (flags | GBP_FLAG_HASMSG) : (flags & ~GBP_FLAG_HASMSG);
     }
   }
   // the state record only changes in this kernel when prep ran here or the has-message flag toggled
   if (valid && (PREP ? (active || MSG) : flags != __float_as_uint(ra.z)))
     g.recA[e] = make_float4(damping, __int_as_float(dcount), __uint_as_float(flags), dmu);
-
-  if (MSG) {
-    // lane-ordered reduction through the warp's own (now consumed) buffer
-    float* red = reinterpret_cast<float*>(tb);
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 6; ++i) red[i * GBP_RED_STRIDE + lane] = nc[i];
-    if (UPPER) {
-#pragma unroll
-      for (int i = 0; i < 6; ++i)
-#pragma unroll
-        for (int j = 0; j < 6; ++j)
-          red[(6 + i * 6 + j) * GBP_RED_STRIDE + lane] = (i >= j) ? nc[GBP_MCAM_LOWER + lt(i, j)] : ncu[gbp_upper(i, j)];
-    } else {
-#pragma unroll
-      for (int k = 0; k < 21; ++k) red[(6 + k) * GBP_RED_STRIDE + lane] = nc[GBP_MCAM_LOWER + k];
-    }
-    __syncwarp();
-    warp_cam_reduce<UPPER>(red, lane, g.cam_partial + (size_t)wt * GBP_CAMPART);
-  }
-  // this buffer is rewritten by the copy engine two tiles from now: order the generic accesses before that
-  fence_proxy_async();
-  __syncwarp();
+  if (MSG) reduce_cam_messages<UPPER>(red, lane, nc, ncu, g.cam_partial + (size_t)wt * GBP_CAMPART);
 }
 
-// next warp-tile of this warp: the first two rounds are static (their ids are already in flight), the rest comes
-// from the queue.  tile_queue = {tiles handed out beyond the two static rounds, warps that have finished}; the last
-// warp of the launch to finish rewinds both, so every launch starts from an empty queue without a memset node.
-GBP_DEV uint32_t next_tile(const DeviceGraph& g, const uint32_t lane, const uint32_t n_wt, const uint32_t n_static) {
+// Warp-tiles beyond the first two (static) rounds come from a device-side queue.  tile_queue = {tickets handed out,
+// warps that have finished}; the last warp of the launch to finish rewinds both, so every launch starts from an empty
+// queue without a memset node.  A ticket is DRAWN one tile before it is needed (the atomic's round trip is hidden
+// behind a tile of arithmetic) and a warp only draws again while its last ticket was valid, so no valid ticket is
+// ever dropped.
+GBP_DEV uint32_t queue_draw(const DeviceGraph& g, const uint32_t lane) {
   uint32_t t = 0;
-  if (lane == 0) t = atomicAdd(g.tile_queue, 1u) + 2u * n_static;
-  t = __shfl_sync(0xffffffffu, t, 0);
+  if (lane == 0) t = atomicAdd(g.tile_queue, 1u);
+  return t;
+}
+GBP_DEV uint32_t queue_resolve(const uint32_t ticket, const uint32_t n_wt, const uint32_t n_static) {
+  const uint32_t t = __shfl_sync(0xffffffffu, ticket, 0) + 2u * n_static;
   return t < n_wt ? t : 0xffffffffu;
 }
 GBP_DEV void tile_queue_done(const DeviceGraph& g, const uint32_t lane, const uint32_t n_wt, const uint32_t n_static) {
@@ -342,52 +358,66 @@ GBP_DEV void tile_queue_done(const DeviceGraph& g, const uint32_t lane, const ui
   }
 }
 
+// NBUF = 2: the next tile's rows are requested at the top of a tile into the other buffer (a whole tile of arithmetic
+// ahead); the lane-ordered reduction runs through the consumed buffer.  8 warps per SM.
+// NBUF = 1: ONE buffer per warp, refilled as soon as the message functions have read it -- while the warp stores its
+// results and reduces them through a scratch of its own; the latency of the refill is covered by the other warps of
+// the scheduler, of which there are three instead of two: 12 warps per SM at <= 168 registers.
 template <bool PREP, bool MSG, bool UPPER>
 __global__ void __launch_bounds__(GBP_TW * 32, 1) k_sweep_tma(const DeviceGraph g, const __grid_constant__ SweepMaps maps) {
   extern __shared__ __align__(1024) float4 smem4[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float4* wbase = smem4 + (size_t)warp * GBP_T_WARP_QUADS;
-  float4* tbuf = wbase;                                   // [2][22 rows][32]
-  float4* gat = wbase + 2 * GBP_T_ROWS * 32;              // [7 rows][32]
-  float4* scam = gat + GBP_G_ROWS * 32;                   // [2][14]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(scam + 2 * GBP_T_SCAM_QUADS);  // [2]
+  float4* tbuf = wbase;                                           // [NBUF][22 rows][32]
+  float4* gat = wbase + GBP_T_NBUF * GBP_T_ROWS * 32;             // [7 rows][32]
+  float4* scam = gat + GBP_G_ROWS * 32;                           // [NBUF][14]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(scam + GBP_T_NBUF * GBP_T_SCAM_QUADS);  // [NBUF]
+  float* red_own = reinterpret_cast<float*>(scam + GBP_T_NBUF * GBP_T_SCAM_QUADS + 1);  // [27 rows][36] (NBUF == 1 only)
   const uint32_t n_wt = g.E_pad / 32;
-  const uint32_t n_static = gridDim.x * GBP_TW;           // tiles of the first (static) round
+  const uint32_t n_static = gridDim.x * GBP_TW;           // tiles of one static round
   // consecutive warp-tiles go to different SMs, so small graphs spread over the whole chip
   uint32_t wt = warp * gridDim.x + blockIdx.x;
   if (wt >= n_wt) return;
   if (lane == 0) {
-    mbar_init(bars + 0, 1);
-    mbar_init(bars + 1, 1);
+#pragma unroll
+    for (int b = 0; b < GBP_T_NBUF; ++b) mbar_init(bars + b, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   fence_proxy_async();
   __syncwarp();
 
-  // prologue: everything of the first warp-tile, ids of the second
+  // prologue: everything of the first warp-tile, ids of the second, a ticket for the third
   uint2 ti = __ldg(g.wt_info + wt);
   // {landmark id, message position} of a lane's factor = the second half of its recB record
   const uint2* lrec = reinterpret_cast<const uint2*>(g.recB) + 1;
   uint2 lid = __ldg(lrec + 2 * ((size_t)wt * 32 + lane));
   if (lane == 0) tma_issue_tile(g, maps, tbuf, scam, bars, wt, ti.x);
   gather_issue(g, gat, lid.x, lid.y, lane);
-  uint32_t wt_n = wt + n_static;  // second round is static too: the queue starts at 2 * n_static
+  uint32_t wt_n = wt + n_static;  // the second round is static too
   if (wt_n >= n_wt) wt_n = 0xffffffffu;
   uint2 ti_n = make_uint2(0u, 0u), lid_n = make_uint2(0u, 0u);
+  uint32_t ticket = 0;
+  bool drawn = false;
   if (wt_n != 0xffffffffu) {
     ti_n = __ldg(g.wt_info + wt_n);
     lid_n = __ldg(lrec + 2 * ((size_t)wt_n * 32 + lane));
+    if (g.tile_queue) {
+      ticket = queue_draw(g, lane);
+      drawn = true;
+    }
   }
-  uint32_t buf = 0, phase0 = 0, phase1 = 0;
+  uint32_t buf = 0, phase = 0;  // phase: bit b = parity the next wait on buffer b expects
   for (;;) {
     const bool has_next = wt_n != 0xffffffffu;
     uint32_t wt_nn = 0xffffffffu;
     uint2 ti_nn = make_uint2(0u, 0u), lid_nn = make_uint2(0u, 0u);
     if (has_next) {
-      // the other buffer was released at the end of the previous tile (fence + __syncwarp in sweep_tile_tma)
-      if (lane == 0) tma_issue_tile(g, maps, tbuf + (buf ^ 1) * GBP_T_ROWS * 32, scam + (buf ^ 1) * GBP_T_SCAM_QUADS, bars + (buf ^ 1), wt_n, ti_n.x);
+      if (GBP_T_NBUF == 2 && lane == 0)  // the other buffer was released at the end of the previous tile
+        tma_issue_tile(g, maps, tbuf + (buf ^ 1) * GBP_T_ROWS * 32, scam + (buf ^ 1) * GBP_T_SCAM_QUADS, bars + (buf ^ 1), wt_n, ti_n.x);
       if (g.tile_queue) {
-        wt_nn = next_tile(g, lane, n_wt, n_static);
+        if (drawn) wt_nn = queue_resolve(ticket, n_wt, n_static);   // drawn one tile ago
+        drawn = wt_nn != 0xffffffffu;
+        if (drawn) ticket = queue_draw(g, lane);
       } else {  // static round-robin (GBP_TILE_QUEUE=0)
         wt_nn = wt_n + n_static;
         if (wt_nn >= n_wt) wt_nn = 0xffffffffu;
@@ -398,16 +428,25 @@ __global__ void __launch_bounds__(GBP_TW * 32, 1) k_sweep_tma(const DeviceGraph 
       }
     }
     // this tile: the bulk copies complete on the buffer's mbarrier, the gathers on the lane's cp.async group
-    mbar_wait(bars + buf, buf ? phase1 : phase0);
-    if (buf) phase1 ^= 1u; else phase0 ^= 1u;
+    mbar_wait(bars + buf, (phase >> buf) & 1u);
+    phase ^= 1u << buf;
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-    sweep_tile_tma<PREP, MSG, UPPER>(g, tbuf + buf * GBP_T_ROWS * 32, reinterpret_cast<const float*>(scam + buf * GBP_T_SCAM_QUADS), gat, wt,
-                                     ti, lid, has_next, lid_n, lane);
+    float4* tb = tbuf + buf * GBP_T_ROWS * 32;
+    float4* sc4 = scam + buf * GBP_T_SCAM_QUADS;
+    sweep_tile_tma<PREP, MSG, UPPER>(g, tb, reinterpret_cast<const float*>(sc4), gat,
+                                     GBP_T_NBUF == 1 ? red_own : reinterpret_cast<float*>(tb), wt, ti, lid, has_next, lid_n, lane, [&]() {
+                                       if (GBP_T_NBUF == 1 && has_next && lane == 0) tma_issue_tile(g, maps, tb, sc4, bars + buf, wt_n, ti_n.x);
+                                     });
+    if (GBP_T_NBUF == 2) {
+      // the reduction wrote through this buffer; the copy engine rewrites it two tiles from now
+      fence_proxy_async();
+      __syncwarp();
+    }
     if (!has_next) break;
     wt = wt_n; wt_n = wt_nn;
     ti = ti_n; ti_n = ti_nn;
     lid = lid_n; lid_n = lid_nn;
-    buf ^= 1;
+    if (GBP_T_NBUF == 2) buf ^= 1;
   }
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
   if (g.tile_queue) tile_queue_done(g, lane, n_wt, n_static);

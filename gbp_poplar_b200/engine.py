@@ -275,6 +275,15 @@ class GBPEngine:
         self._check(self._lib.gbp_cuda_last_kernel_times(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def last_sweep_times(self):
+        """Per sweep of the last iterate() under set_profile(True): (factor-kernel ms array, variable-kernel ms array)."""
+        n = C.c_int()
+        self._check(self._lib.gbp_cuda_last_sweep_times(self._h, None, None, 0, C.byref(n)))
+        a, b = np.empty(n.value, _F32), np.empty(n.value, _F32)
+        self._check(self._lib.gbp_cuda_last_sweep_times(self._h, a.ctypes.data_as(_capi.c_f32p), b.ctypes.data_as(_capi.c_f32p),
+                                                        n.value, C.byref(n)))
+        return a, b
+
     def exchange_mode(self):
         """'none' | 'nccl' | 'p2p': how a sharded engine exchanges boundary-landmark partials."""
         return ("none", "nccl", "p2p")[self._lib.gbp_cuda_exchange_mode(self._h)]

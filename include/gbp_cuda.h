@@ -241,6 +241,10 @@ int gbp_cuda_last_timing(gbp_handle* h, float* ms_total, uint64_t* kernels_launc
  * (k_update_vars) over the last gbp_cuda_iterate call. */
 int gbp_cuda_set_profile(gbp_handle* h, int enabled);
 int gbp_cuda_last_kernel_times(gbp_handle* h, float* ms_factor_kernel, float* ms_variable_kernel);
+/* The same per sweep of the last profiled call (arrays of `capacity` entries, either may be NULL); *n_sweeps = sweeps
+ * on record.  A sweep in which the factors relinearise is a different kernel workload than one in which they do not:
+ * the roofline is reported per class (bench.py). */
+int gbp_cuda_last_sweep_times(gbp_handle* h, float* ms_factor_kernel, float* ms_variable_kernel, int capacity, int* n_sweeps);
 
 /* ---- asynchronous / resident use (bench, multi-GPU) ------------------- */
 /* Enqueue n sweeps on the handle's stream without synchronising. */
