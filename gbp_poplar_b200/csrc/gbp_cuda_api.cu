@@ -129,9 +129,12 @@ struct gbp_handle {
   size_t d_stats_cap = 0;
   // pinned staging for the small per-call read-backs (per-sweep metrics, relinearisation ring): one
   // asynchronous copy each and ONE stream synchronisation per gbp_cuda_iterate call
+  void* pin_block = nullptr;   // page-locked staging block (pinned_get): error word | ring | stats
+  size_t pin_block_bytes = 0;
   gbp_iter_stats* pin_stats = nullptr;
   size_t pin_stats_cap = 0;
   uint32_t* pin_ring = nullptr;
+  bool d_stats_in_arena = false;
   // timing
   int profile = 0;
   std::vector<cudaEvent_t> prof_events;
@@ -251,6 +254,47 @@ L2State& l2_state(int device) {
   return l2_states().back();
 }
 
+// Page-locked host memory is expensive to get and to give back on some boxes (cudaHostAlloc / cudaFreeHost of a few
+// KB: 10-150 ms measured), so the small staging blocks of the handles are recycled process-wide: a freed handle's
+// block is handed to the next gbp_cuda_init.  All blocks are mapped + portable, so any of them can serve as the
+// device-visible error word of a sharded handle.  gbp_cuda_release_cached_memory() frees them.
+struct PinnedBlock {
+  void* p;
+  size_t bytes;
+};
+std::vector<PinnedBlock>& pinned_free_list() {
+  static std::vector<PinnedBlock> v;
+  return v;
+}
+void* pinned_get(size_t bytes, size_t* got) {
+  {
+    std::lock_guard<std::mutex> lk(pools_mutex());
+    std::vector<PinnedBlock>& fl = pinned_free_list();
+    for (size_t i = 0; i < fl.size(); ++i)
+      if (fl[i].bytes >= bytes) {
+        PinnedBlock b = fl[i];
+        fl.erase(fl.begin() + (long)i);
+        *got = b.bytes;
+        return b.p;
+      }
+  }
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  *got = bytes;
+  return p;
+}
+void pinned_put(void* p, size_t bytes) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(pools_mutex());
+  pinned_free_list().push_back({p, bytes});
+}
+// layout of a handle's staging block: [error word + padding 64 B | relinearisation ring 192 B | per-sweep stats ...]
+constexpr size_t PIN_OFF_RING = 64, PIN_OFF_STATS = 256;
+constexpr size_t STATS_PREALLOC = 4096;  // sweeps of per-sweep metrics a handle can return without growing its buffers
+
 template <class T>
 int h_alloc(gbp_handle* h, T** p, size_t n, bool zero = true) {
   int rc = dev_alloc(p, n, zero);
@@ -310,7 +354,9 @@ std::vector<CommEntry>& comm_cache() {
 // prog_ub (ba/ba.cpp:104-139).  On a shard the boundary landmarks go first: their partial
 // sums are all-gathered on the communication stream while the main stream updates the
 // interior landmarks and the cameras; k_boundary_finish then waits for the gather.
-int launch_update_vars(gbp_handle* h, bool lower_only = false) {
+int launch_update_vars(gbp_handle* h, bool lower_only_in = false) {
+  static const int uv_debug = std::getenv("GBP_UV_DEBUG") ? std::atoi(std::getenv("GBP_UV_DEBUG")) : 0;  // timing diagnostics: 1 skips the cameras, 2 the landmarks (results are then WRONG)
+  const int lower_only = (lower_only_in ? 1 : 0) | (uv_debug << 1);
   const int shift = h->pending_shift ? 1 : 0;
   const uint32_t grid = lmks_grid(h);
   const bool exchange = h->shard && h->g.n_bnd_global > 0;
@@ -319,7 +365,7 @@ int launch_update_vars(gbp_handle* h, bool lower_only = false) {
     // one launch: the first blocks form the partial sums and push them into every rank's receive buffer
     // over NVLink, the last blocks finish the boundary landmarks once every rank's flag has arrived
     const uint32_t n_x = std::max((h->g.n_bnd_local + GBP_LMK_PER_BLOCK - 1) / GBP_LMK_PER_BLOCK, 1u);
-    gbp::k_update_vars<<<n_x + cams_grid(h) + grid + n_x, GBP_TILE, 0, h->stream>>>(h->g, shift, n_x, lower_only ? 1 : 0);
+    gbp::k_update_vars<<<n_x + cams_grid(h) + grid + n_x, GBP_TILE, 0, h->stream>>>(h->g, shift, n_x, lower_only);
     h->kernels_launched++;
     h->exchanges++;
   } else {
@@ -336,7 +382,7 @@ int launch_update_vars(gbp_handle* h, bool lower_only = false) {
       h->exchanges++;
     }
     if (grid + cams_grid(h)) {
-      gbp::k_update_vars<<<grid + cams_grid(h), GBP_TILE, 0, h->stream>>>(h->g, shift, 0u, lower_only ? 1 : 0);
+      gbp::k_update_vars<<<grid + cams_grid(h), GBP_TILE, 0, h->stream>>>(h->g, shift, 0u, lower_only);
       h->kernels_launched++;
     }
     if (exchange) {
@@ -445,17 +491,41 @@ int check_peer_error(gbp_handle* h) {
   return GBP_OK;
 }
 
+// (re)binds the handle's page-locked staging block with room for `n` per-sweep stats
+int pin_block_bind(gbp_handle* h, size_t n) {
+  size_t got = 0;
+  void* p = pinned_get(PIN_OFF_STATS + n * sizeof(gbp_iter_stats), &got);
+  if (!p) {
+    gbp_set_error("cudaHostAlloc of the staging block failed");
+    return GBP_ERR_CUDA;
+  }
+  if (h->pin_block) {
+    std::memcpy(p, h->pin_block, PIN_OFF_STATS);  // error word + ring keep their values
+    pinned_put(h->pin_block, h->pin_block_bytes);
+  } else {
+    std::memset(p, 0, PIN_OFF_STATS);
+  }
+  h->pin_block = p;
+  h->pin_block_bytes = got;
+  h->pin_ring = (uint32_t*)((char*)p + PIN_OFF_RING);
+  h->pin_stats = (gbp_iter_stats*)((char*)p + PIN_OFF_STATS);
+  h->pin_stats_cap = (got - PIN_OFF_STATS) / sizeof(gbp_iter_stats);
+  return GBP_OK;
+}
+
 int ensure_stats(gbp_handle* h, size_t n) {
   if (n > h->pin_stats_cap) {
-    if (h->pin_stats) cudaFreeHost(h->pin_stats);
-    h->pin_stats = nullptr;
-    h->pin_stats_cap = 0;
-    GBP_CUDA_TRY(cudaHostAlloc((void**)&h->pin_stats, std::max<size_t>(n, 64) * sizeof(gbp_iter_stats), cudaHostAllocDefault));
-    h->pin_stats_cap = std::max<size_t>(n, 64);
+    if (h->p2p_err_host) {  // the error word of a sharded handle is baked into its kernels' arguments: it cannot move
+      gbp_set_error("per-sweep metrics of more than 4096 sweeps per call are not supported on a sharded handle");
+      return GBP_ERR_ARG;
+    }
+    int rc = pin_block_bind(h, std::max<size_t>(n, STATS_PREALLOC));
+    if (rc) return rc;
   }
   if (n <= h->d_stats_cap) return GBP_OK;
-  if (h->d_stats) cudaFree(h->d_stats);
+  if (h->d_stats && !h->d_stats_in_arena) cudaFree(h->d_stats);
   h->d_stats = nullptr;
+  h->d_stats_in_arena = false;
   GBP_CUDA_TRY(cudaMalloc((void**)&h->d_stats, n * sizeof(gbp::DeviceStats)));
   h->d_stats_cap = n;
   return GBP_OK;
@@ -662,7 +732,7 @@ int p2p_wire(gbp_handle* h, const std::vector<void*>& bases) {
   g.metric_recv = (const double*)(own + P2P_OFF_METRIC);
   g.p2p_recv = (const float4*)(own + P2P_OFF_RECV);
   // the error word lives in mapped host memory: a timed-out kernel sets it, every synchronising entry point reads it
-  GBP_CUDA_TRY(cudaHostAlloc((void**)&h->p2p_err_host, sizeof(uint32_t), cudaHostAllocMapped));
+  h->p2p_err_host = (uint32_t*)h->pin_block;
   *h->p2p_err_host = 0u;
   GBP_CUDA_TRY(cudaHostGetDevicePointer((void**)&g.p2p_error, h->p2p_err_host, 0));
   // how long a block waits for its peers: generous (a peer may be instantiating a graph or sit in a debugger),
@@ -998,6 +1068,7 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   A_(h->d_metric_parts, h->n_tiles);
   A_(h->d_metric_ticket, 1);
   A_(h->d_stat_cursor, 1);
+  A_(h->d_stats, STATS_PREALLOC);
   A_(g.relin_list, E);
   A_(g.relin_count, 1);
   A_(g.relin_ring, GBP_RELIN_RING + 1);
@@ -1038,6 +1109,10 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
     if (rc) return rc;
     GBP_CUDA_TRY(cudaMemsetAsync(base, 0, arena_bytes, h->stream));  // ordered before the uploads below
     for (auto& r : arena) *r.first = base + r.second;
+    h->d_stats_cap = STATS_PREALLOC;
+    h->d_stats_in_arena = true;
+    rc = pin_block_bind(h, STATS_PREALLOC);
+    if (rc) return rc;
     // L2 residency of the re-used buffers (B200: 126 MB L2, at most 79 MB of it can be set aside).
     // GBP_L2_PERSIST: 0 off, 1 (default) the landmark-bound messages, 2 all re-used buffers.  Measured on
     // config 4 (profiles/): 161.9 us per sweep without, 155.1 us with the 48 MB of landmark-bound messages
@@ -1327,6 +1402,8 @@ int gbp_cuda_release_cached_memory(void) {
   std::lock_guard<std::mutex> lk(pools_mutex());
   for (const DevicePool& d : pools())
     if (d.pool) cudaMemPoolTrimTo(d.pool, 0);
+  for (const PinnedBlock& b : pinned_free_list()) cudaFreeHost(b.p);
+  pinned_free_list().clear();
   cudaGetLastError();
   return GBP_OK;
 }
@@ -1349,9 +1426,8 @@ int gbp_cuda_free(gbp_handle* h) {
   for (void* p : h->allocs) cudaFree(p);
   for (void* p : h->pool_allocs) cudaFreeAsync(p, h->stream);  // stays in the pool for the next handle
   if (h->stream && !h->pool_allocs.empty()) cudaStreamSynchronize(h->stream);
-  if (h->d_stats) cudaFree(h->d_stats);
-  if (h->pin_stats) cudaFreeHost(h->pin_stats);
-  if (h->pin_ring) cudaFreeHost(h->pin_ring);
+  if (h->d_stats && !h->d_stats_in_arena) cudaFree(h->d_stats);
+  pinned_put(h->pin_block, h->pin_block_bytes);  // recycled by the next handle
   for (cudaEvent_t ev : h->prof_events) cudaEventDestroy(ev);
   drop_graphs(h);
   if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);  // the communicator itself stays cached
@@ -1376,7 +1452,6 @@ int gbp_cuda_free(gbp_handle* h) {
     cudaSetDevice(h->device);
     delete h->group;
   }
-  if (h->p2p_err_host) cudaFreeHost(h->p2p_err_host);
   if (h->ev_send) cudaEventDestroy(h->ev_send);
   if (h->ev_recv) cudaEventDestroy(h->ev_recv);
   if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
@@ -1518,7 +1593,6 @@ int iterate_end(gbp_handle* h, int n_sweeps, bool stats) {
   // every 16 sweeps the relinearisation ring (132 bytes) rides along with the same synchronisation
   h->sweeps_since_choice += (uint32_t)n_sweeps;
   if (h->sweeps_since_choice >= 16 && h->E && h->relin_mode == 0) {
-    if (!h->pin_ring) GBP_CUDA_TRY(cudaHostAlloc((void**)&h->pin_ring, (GBP_RELIN_RING + 1) * sizeof(uint32_t), cudaHostAllocDefault));
     GBP_CUDA_TRY(cudaMemcpyAsync(h->pin_ring, h->g.relin_ring, (GBP_RELIN_RING + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                                  h->stream));
   }

@@ -1172,9 +1172,9 @@ __global__ void __launch_bounds__(GBP_TILE, GBP_UV_BLOCKS) k_update_vars(const D
   if (b < n_push) {
     boundary_push(g, step, b, n_push);
   } else if ((b -= n_push) < nb_cam) {
-    update_cameras(g, shift, b, lower_only);
+    if (!(lower_only & 2)) update_cameras(g, shift, b, lower_only & 1);   // bits 1, 2: timing diagnostics (GBP_UV_DEBUG)
   } else if ((b -= nb_cam) < nb_lmk) {
-    update_landmarks(g, shift, b);
+    if (!(lower_only & 4)) update_landmarks(g, shift, b);
   } else {
     boundary_finish(g, shift, step, b - nb_lmk);
   }
