@@ -408,16 +408,19 @@ int launch_sweep(gbp_handle* h, bool upper = true) {
     const uint32_t grid = std::min<uint32_t>((uint32_t)h->num_sms, n_wt);
     const bool full = upper || !MSG || h->g.mcam_up;
     if constexpr (MSG) {
-      if (h->use_tma) {
+      if (h->use_tma == 2) {  // GBP_SWEEP=tma2: the restructured kernel (gbp_sweep_tma.cuh)
         if (full) gbp::k_sweep_tma<PREP, true, true><<<grid, GBP_TW * 32, GBP_T_SMEM, h->stream>>>(h->g, h->maps);
         else gbp::k_sweep_tma<PREP, true, false><<<grid, GBP_TW * 32, GBP_T_SMEM, h->stream>>>(h->g, h->maps);
+      } else if (h->use_tma) {
+        if (full) gbp::k_sweep<PREP, true, true, true><<<grid, GBP_SW_WARPS * 32, GBP_SWEEP_SMEM, h->stream>>>(h->g, h->maps);
+        else gbp::k_sweep<PREP, true, false, true><<<grid, GBP_SW_WARPS * 32, GBP_SWEEP_SMEM, h->stream>>>(h->g, h->maps);
       } else if (full) {
-        gbp::k_sweep<PREP, true, true><<<grid, GBP_SW_WARPS * 32, GBP_SWEEP_SMEM, h->stream>>>(h->g);
+        gbp::k_sweep<PREP, true, true, false><<<grid, GBP_SW_WARPS * 32, GBP_SWEEP_SMEM, h->stream>>>(h->g, h->maps);
       } else {
-        gbp::k_sweep<PREP, true, false><<<grid, GBP_SW_WARPS * 32, GBP_SWEEP_SMEM, h->stream>>>(h->g);
+        gbp::k_sweep<PREP, true, false, false><<<grid, GBP_SW_WARPS * 32, GBP_SWEEP_SMEM, h->stream>>>(h->g, h->maps);
       }
     } else {
-      gbp::k_sweep<PREP, MSG, true><<<grid, GBP_SW_WARPS * 32, GBP_SWEEP_SMEM, h->stream>>>(h->g);
+      gbp::k_sweep<PREP, MSG, true, false><<<grid, GBP_SW_WARPS * 32, GBP_SWEEP_SMEM, h->stream>>>(h->g, h->maps);
     }
     h->kernels_launched++;
   }
@@ -814,10 +817,10 @@ int setup_p2p(gbp_handle* h, int mode) {
 
 // TMA descriptors for k_sweep_tma: the factor potentials and the camera-bound messages seen as 2-D fp32 tensors
 // [rows][E_pad * 4] whose box is one warp-tile: [rows] x [128 floats = the 32 lanes' quads of one row].
-// GBP_SWEEP=cpasync selects the cp.async kernel (k_sweep) instead.
+// GBP_SWEEP=cpasync selects per-lane cp.async staging instead, GBP_SWEEP=tma2 the restructured kernel of gbp_sweep_tma.cuh.
 int setup_tma(gbp_handle* h) {
   h->use_tma = 1;
-  if (const char* env = std::getenv("GBP_SWEEP")) h->use_tma = std::strcmp(env, "cpasync") != 0;
+  if (const char* env = std::getenv("GBP_SWEEP")) h->use_tma = !std::strcmp(env, "cpasync") ? 0 : !std::strcmp(env, "tma2") ? 2 : 1;
   if (!h->use_tma || !h->n_tiles) return GBP_OK;
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -869,8 +872,10 @@ void preload(K kernel) {
   cudaFuncGetAttributes(&a, kernel);
 }
 void preload_kernels() {
-  preload(gbp::k_sweep<true, true, true>); preload(gbp::k_sweep<true, true, false>);
-  preload(gbp::k_sweep<false, true, true>); preload(gbp::k_sweep<false, true, false>);
+  preload(gbp::k_sweep<true, true, true, false>); preload(gbp::k_sweep<true, true, false, false>);
+  preload(gbp::k_sweep<false, true, true, false>); preload(gbp::k_sweep<false, true, false, false>);
+  preload(gbp::k_sweep<true, true, true, true>); preload(gbp::k_sweep<true, true, false, true>);
+  preload(gbp::k_sweep<false, true, true, true>); preload(gbp::k_sweep<false, true, false, true>);
   preload(gbp::k_sweep_tma<true, true, true>); preload(gbp::k_sweep_tma<true, true, false>);
   preload(gbp::k_sweep_tma<false, true, true>); preload(gbp::k_sweep_tma<false, true, false>);
   preload(gbp::k_prep_pass); preload(gbp::k_relin_list); preload(gbp::k_cam_partials); preload(gbp::k_update_vars);
@@ -1215,11 +1220,13 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
 #undef U_
   if (rc) return rc;
   GBP_CUDA_TRY(cudaStreamSynchronize(s));
-  GBP_CUDA_TRY(cudaFuncSetAttribute(gbp::k_sweep<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GBP_SWEEP_SMEM));
-  GBP_CUDA_TRY(cudaFuncSetAttribute(gbp::k_sweep<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GBP_SWEEP_SMEM));
-  GBP_CUDA_TRY(cudaFuncSetAttribute(gbp::k_sweep<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GBP_SWEEP_SMEM));
-  GBP_CUDA_TRY(cudaFuncSetAttribute(gbp::k_sweep<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GBP_SWEEP_SMEM));
-  GBP_CUDA_TRY(cudaFuncSetAttribute(gbp::k_sweep<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GBP_SWEEP_SMEM));
+#define GBP_SMEM_ATTR(k) GBP_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, GBP_SWEEP_SMEM))
+  GBP_SMEM_ATTR((gbp::k_sweep<true, true, true, false>)); GBP_SMEM_ATTR((gbp::k_sweep<true, true, false, false>));
+  GBP_SMEM_ATTR((gbp::k_sweep<false, true, true, false>)); GBP_SMEM_ATTR((gbp::k_sweep<false, true, false, false>));
+  GBP_SMEM_ATTR((gbp::k_sweep<true, true, true, true>)); GBP_SMEM_ATTR((gbp::k_sweep<true, true, false, true>));
+  GBP_SMEM_ATTR((gbp::k_sweep<false, true, true, true>)); GBP_SMEM_ATTR((gbp::k_sweep<false, true, false, true>));
+  GBP_SMEM_ATTR((gbp::k_sweep<true, false, true, false>));
+#undef GBP_SMEM_ATTR
   GBP_CUDA_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
   rc = setup_tma(h);
   if (rc) return rc;

@@ -287,7 +287,7 @@ __device__ __noinline__ uint32_t relinearise_record(const float4* src, size_t sr
 #define GBP_STAGE_QUADS (GBP_SQ * 32)
 #define GBP_SCAM 56  // per-warp copy of: belief eta 6 | belief lambda 36 | mean 6 | previous mean 6
 #define GBP_RED_STRIDE 36  // floats per row of the reduction scratch: 32 lanes + 4 pad, rows 16-byte aligned for LDS.128
-#define GBP_SWEEP_SMEM (GBP_SW_WARPS * GBP_NBUF * (GBP_STAGE_QUADS * 16 + GBP_SCAM * 4))
+#define GBP_SWEEP_SMEM (GBP_SW_WARPS * GBP_NBUF * (GBP_STAGE_QUADS * 16 + GBP_SCAM * 4) + GBP_SW_WARPS * GBP_NBUF * 8)
 
 GBP_DEV void cp_async16(void* smem, const void* gmem) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -316,6 +316,25 @@ GBP_DEV void issue_stage(const DeviceGraph& g, float4* stage, float* s_cam, cons
   for (int q = 0; q < GBP_MCAM_QUADS; ++q) cp_async16(stage + (GBP_SQ_MCAM + q) * 32 + lane, g.mcam + (size_t)q * g.E_pad + e);
 #pragma unroll
   for (int q = 0; q < GBP_FAC_QUADS; ++q) cp_async16(stage + (GBP_SQ_FAC + q) * 32 + lane, g.fac + (size_t)q * g.E_pad + e);
+}
+
+// The same stage filled by the copy engines: ONE elected lane issues two tensor copies (the [14 x 512 B] box of the
+// potentials, the [7 x 512 B] box of the camera-bound messages) and three bulk copies (the two edge-state rows, the
+// camera record), all completing on the buffer's mbarrier; only the gathered landmark-bound messages stay per-lane
+// cp.async.  23 of the 26 per-lane LDGSTS and their 64-bit address arithmetic leave the instruction stream.
+#define GBP_STAGE_TX_BYTES ((GBP_FAC_QUADS + GBP_MCAM_QUADS + 2) * 512 + GBP_SCAM * 4)
+GBP_DEV void issue_stage_tma(const DeviceGraph& g, const SweepMaps& maps, float4* stage, float* s_cam, uint64_t* bar, const uint32_t wt,
+                             const uint32_t cam, const uint32_t lpos, const uint32_t lane) {
+  if (lane == 0) {
+    mbar_expect_tx(bar, GBP_STAGE_TX_BYTES);
+    tma_load_rows(stage + GBP_SQ_FAC * 32, &maps.fac, wt, bar);
+    tma_load_rows(stage + GBP_SQ_MCAM * 32, &maps.mcam, wt, bar);
+    bulk_load(stage + GBP_SQ_RECA * 32, g.recA + (size_t)wt * 32, 512u, bar);
+    bulk_load(stage + GBP_SQ_RECB * 32, g.recB + (size_t)wt * 32, 512u, bar);
+    bulk_load(s_cam, g.cam_rec + (size_t)cam * 16, GBP_SCAM * 4u, bar);
+  }
+#pragma unroll
+  for (int q = 0; q < GBP_MLMK_QUADS; ++q) cp_async16(stage + (GBP_SQ_MLMK + q) * 32 + lane, g.mlmk + (size_t)lpos * GBP_MLMK_QUADS + q);
 }
 
 // landmark record of one factor: belief eta 0..2 | lambda 3..11 | mean 12..14 | - | previous mean 16..18 | -
@@ -619,76 +638,118 @@ GBP_DEV void sweep_tile(const DeviceGraph& g, float4* stage, const float* s_cam,
 // every sweep of a call without per-sweep metrics but the LAST in this mode (k_update_vars mirrors the lower triangle meanwhile): the
 // belief of a camera is the sum of the messages of the latest sweep alone, so after the call every tensor is
 // what the all-UPPER sequence would have produced, bit for bit.
-template <bool PREP, bool MSG, bool UPPER>
-__global__ void __launch_bounds__(GBP_SW_WARPS * 32, 1) k_sweep(const DeviceGraph g) {
-  extern __shared__ float4 smem4[];
+// Warp-tiles beyond the first two (static) rounds come from a device-side queue.  tile_queue = {tickets handed out,
+// warps that have finished}; the last warp of the launch to finish rewinds both, so every launch starts from an empty
+// queue without a memset node.  A ticket is DRAWN one tile before it is needed (the atomic's round trip is hidden
+// behind a tile of arithmetic) and a warp only draws again while its last ticket was valid, so no valid ticket is
+// ever dropped.  The makespan of a launch then no longer jumps by a whole round when the graph (or a shard) holds a
+// few warp-tiles more than a multiple of the resident warps.
+GBP_DEV uint32_t queue_draw(const DeviceGraph& g, const uint32_t lane) {
+  uint32_t t = 0;
+  if (lane == 0) t = atomicAdd(g.tile_queue, 1u);
+  return t;
+}
+GBP_DEV uint32_t queue_resolve(const uint32_t ticket, const uint32_t n_wt, const uint32_t n_static) {
+  const uint32_t t = __shfl_sync(0xffffffffu, ticket, 0) + 2u * n_static;
+  return t < n_wt ? t : 0xffffffffu;
+}
+GBP_DEV void tile_queue_done(const DeviceGraph& g, const uint32_t lane, const uint32_t n_wt, const uint32_t n_static) {
+  if (lane != 0) return;
+  const uint32_t n_warps = n_static < n_wt ? n_static : n_wt;  // warps of this launch that had a first tile
+  __threadfence();
+  if (atomicAdd(g.tile_queue + 1, 1u) == n_warps - 1u) {
+    g.tile_queue[0] = 0u;
+    g.tile_queue[1] = 0u;
+  }
+}
+
+// TMA = true: the stage is filled by the copy engines (issue_stage_tma), completion on one mbarrier per buffer;
+// TMA = false: per-lane cp.async (issue_stage).  Same stage layout, same arithmetic.
+template <bool PREP, bool MSG, bool UPPER, bool TMA>
+__global__ void __launch_bounds__(GBP_SW_WARPS * 32, 1) k_sweep(const DeviceGraph g, const __grid_constant__ SweepMaps maps) {
+  extern __shared__ __align__(1024) float4 smem4[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float4* stage_base = smem4 + warp * (GBP_NBUF * GBP_STAGE_QUADS);
   float* scam_base = reinterpret_cast<float*>(smem4 + GBP_SW_WARPS * GBP_NBUF * GBP_STAGE_QUADS) + warp * (GBP_NBUF * GBP_SCAM);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(smem4 + GBP_SW_WARPS * GBP_NBUF * GBP_STAGE_QUADS) +
+                                               GBP_SW_WARPS * GBP_NBUF * GBP_SCAM) + warp * GBP_NBUF;
   const uint32_t n_wt = g.E_pad / 32;
-  const uint32_t stride = gridDim.x * GBP_SW_WARPS;
+  const uint32_t n_static = gridDim.x * GBP_SW_WARPS;  // warp-tiles of one static round
   // consecutive warp-tiles go to different SMs, so small graphs spread over the whole chip
   uint32_t wt = warp * gridDim.x + blockIdx.x;
   if (wt >= n_wt) return;
+  if (TMA) {
+    if (lane == 0) {
+      mbar_init(bars + 0, 1);
+      mbar_init(bars + 1, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    fence_proxy_async();
+    __syncwarp();
+  }
 
-  // prologue: everything of the first warp-tile, ids of the second
+  // prologue: everything of the first warp-tile, ids of the second, a ticket for the third
   uint2 ti = __ldg(g.wt_info + wt);
-  uint32_t buf = 0;
+  uint32_t buf = 0, phase = 0;  // phase: bit b = parity the next wait on buffer b expects
   // {landmark id, message position} of a lane's factor = the second half of its recB record
   const uint2* lrec = reinterpret_cast<const uint2*>(g.recB) + 1;
   uint2 lid = __ldg(lrec + 2 * ((size_t)wt * 32 + lane));
-  issue_stage(g, stage_base, scam_base, wt, ti.x, lid.y, lane);
+  if (TMA) issue_stage_tma(g, maps, stage_base, scam_base, bars, wt, ti.x, lid.y, lane);
+  else issue_stage(g, stage_base, scam_base, wt, ti.x, lid.y, lane);
   asm volatile("cp.async.commit_group;\n" ::: "memory");
   float lb[20];
   load_lmk_belief(g, lid.x, lb);
-  uint32_t wt_n = wt + stride;
+  uint32_t wt_n = wt + n_static;  // the second round is static too
+  if (wt_n >= n_wt) wt_n = 0xffffffffu;
   uint2 ti_n = make_uint2(0u, 0u);
   uint2 lid_n = make_uint2(0u, 0u);
-  if (wt_n < n_wt) {
+  uint32_t ticket = 0;
+  bool drawn = false;
+  if (wt_n != 0xffffffffu) {
     ti_n = __ldg(g.wt_info + wt_n);
     lid_n = __ldg(lrec + 2 * ((size_t)wt_n * 32 + lane));
+    if (g.tile_queue) {
+      ticket = queue_draw(g, lane);
+      drawn = true;
+    }
   }
   for (;;) {
-    const bool has_next = wt_n < n_wt;
+    const bool has_next = wt_n != 0xffffffffu;
     float lb_n[20];
     uint2 ti_nn = make_uint2(0u, 0u);
     uint2 lid_nn = make_uint2(0u, 0u);
-    const uint32_t wt_nn = wt_n + stride;
+    uint32_t wt_nn = 0xffffffffu;
     if (has_next) {
-      issue_stage(g, stage_base + (buf ^ 1) * GBP_STAGE_QUADS, scam_base + (buf ^ 1) * GBP_SCAM, wt_n, ti_n.x, lid_n.y, lane);
+      if (TMA) issue_stage_tma(g, maps, stage_base + (buf ^ 1) * GBP_STAGE_QUADS, scam_base + (buf ^ 1) * GBP_SCAM, bars + (buf ^ 1), wt_n, ti_n.x, lid_n.y, lane);
+      else issue_stage(g, stage_base + (buf ^ 1) * GBP_STAGE_QUADS, scam_base + (buf ^ 1) * GBP_SCAM, wt_n, ti_n.x, lid_n.y, lane);
       load_lmk_belief(g, lid_n.x, lb_n);
-      if (wt_nn < n_wt) {
+      if (g.tile_queue) {
+        if (drawn) wt_nn = queue_resolve(ticket, n_wt, n_static);  // drawn one tile ago
+        drawn = wt_nn != 0xffffffffu;
+        if (drawn) ticket = queue_draw(g, lane);
+      } else {  // static round-robin (GBP_TILE_QUEUE=0)
+        wt_nn = wt_n + n_static;
+        if (wt_nn >= n_wt) wt_nn = 0xffffffffu;
+      }
+      if (wt_nn != 0xffffffffu) {
         ti_nn = __ldg(g.wt_info + wt_nn);
         lid_nn = __ldg(lrec + 2 * ((size_t)wt_nn * 32 + lane));
-#if GBP_L2_PREFETCH == 1
-        // warp-tile t+2: pull its 23 contiguous 512-byte rows (potential 14, camera message 7, the two
-        // edge-state records) into L2 now, one bulk prefetch per lane, so that the cp.async copies issued
-        // at the top of the next iteration are served from L2 instead of queueing behind DRAM
-        const float4* row = nullptr;
-        if (lane < GBP_FAC_QUADS) row = g.fac + (size_t)lane * g.E_pad;
-        else if (lane < GBP_FAC_QUADS + GBP_MCAM_QUADS) row = g.mcam + (size_t)(lane - GBP_FAC_QUADS) * g.E_pad;
-        else if (lane == GBP_FAC_QUADS + GBP_MCAM_QUADS) row = g.recA;
-        else if (lane == GBP_FAC_QUADS + GBP_MCAM_QUADS + 1) row = g.recB;
-        if (row) asm volatile("cp.async.bulk.prefetch.L2.global [%0], 512;\n" ::"l"(row + (size_t)wt_nn * 32) : "memory");
-#elif GBP_L2_PREFETCH == 2
-        // the same 23 rows x 4 lines of 128 B, one prefetch.global.L2 per line, three per lane
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const uint32_t i = lane + 32u * k, r = i >> 2;
-          if (r < GBP_FAC_QUADS + GBP_MCAM_QUADS + 2) {
-            const float4* row = (r < GBP_FAC_QUADS) ? g.fac + (size_t)r * g.E_pad
-                                : (r < GBP_FAC_QUADS + GBP_MCAM_QUADS) ? g.mcam + (size_t)(r - GBP_FAC_QUADS) * g.E_pad
-                                : (r == GBP_FAC_QUADS + GBP_MCAM_QUADS) ? g.recA : g.recB;
-            asm volatile("prefetch.global.L2 [%0];\n" ::"l"(row + (size_t)wt_nn * 32 + (i & 3u) * 8) : "memory");
-          }
-        }
-#endif
       }
     }
     // the copies of THIS warp-tile were committed one iteration ago: leave the newest group in flight
     asm volatile("cp.async.commit_group;\n cp.async.wait_group 1;\n" ::: "memory");
+    if (TMA) {
+      mbar_wait(bars + buf, (phase >> buf) & 1u);
+      phase ^= 1u << buf;
+    }
     __syncwarp();
     sweep_tile<PREP, MSG, UPPER>(g, stage_base + buf * GBP_STAGE_QUADS, scam_base + buf * GBP_SCAM, wt, ti, lb, lane);
+    if (TMA) {
+      // the copy engine rewrites this buffer two tiles from now: order the generic accesses (stage reads, the
+      // relinearised record, the reduction scratch) before that
+      fence_proxy_async();
+      __syncwarp();
+    }
     if (!has_next) break;
     wt = wt_n; wt_n = wt_nn;
     ti = ti_n; ti_n = ti_nn;
@@ -698,6 +759,7 @@ __global__ void __launch_bounds__(GBP_SW_WARPS * 32, 1) k_sweep(const DeviceGrap
     buf ^= 1;
   }
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  if (g.tile_queue) tile_queue_done(g, lane, n_wt, n_static);
 }
 
 // ---- PrepMessageVertex as its own pass, relinearisation by compaction ---------------------------

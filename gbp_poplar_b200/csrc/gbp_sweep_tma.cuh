@@ -48,11 +48,6 @@ namespace gbp {
 #define GBP_T_WARP_QUADS ((GBP_T_NBUF * GBP_T_ROWS * 32 + GBP_G_ROWS * 32 + GBP_T_NBUF * GBP_T_SCAM_QUADS + 1 + GBP_T_RED_QUADS + 7) / 8 * 8)
 #define GBP_T_SMEM (GBP_TW * GBP_T_WARP_QUADS * 16)
 
-struct SweepMaps {  // TMA descriptors of the two big quad-SoA arrays (box = [rows x 128 floats])
-  CUtensorMap fac;   // [14][E_pad * 4] floats, box 14 x 128
-  CUtensorMap mcam;  // [7][E_pad * 4] floats, box 7 x 128
-};
-
 template <int Q0, int N>
 GBP_DEV void rows_read(const float4* rows, uint32_t lane, float (&out)[N * 4]) {
 #pragma unroll
@@ -332,30 +327,6 @@ GBP_DEV void sweep_tile_tma(const DeviceGraph& g, float4* tb, const float* sc, f
   if (valid && (PREP ? (active || MSG) : flags != __float_as_uint(ra.z)))
     g.recA[e] = make_float4(damping, __int_as_float(dcount), __uint_as_float(flags), dmu);
   if (MSG) reduce_cam_messages<UPPER>(red, lane, nc, ncu, g.cam_partial + (size_t)wt * GBP_CAMPART);
-}
-
-// Warp-tiles beyond the first two (static) rounds come from a device-side queue.  tile_queue = {tickets handed out,
-// warps that have finished}; the last warp of the launch to finish rewinds both, so every launch starts from an empty
-// queue without a memset node.  A ticket is DRAWN one tile before it is needed (the atomic's round trip is hidden
-// behind a tile of arithmetic) and a warp only draws again while its last ticket was valid, so no valid ticket is
-// ever dropped.
-GBP_DEV uint32_t queue_draw(const DeviceGraph& g, const uint32_t lane) {
-  uint32_t t = 0;
-  if (lane == 0) t = atomicAdd(g.tile_queue, 1u);
-  return t;
-}
-GBP_DEV uint32_t queue_resolve(const uint32_t ticket, const uint32_t n_wt, const uint32_t n_static) {
-  const uint32_t t = __shfl_sync(0xffffffffu, ticket, 0) + 2u * n_static;
-  return t < n_wt ? t : 0xffffffffu;
-}
-GBP_DEV void tile_queue_done(const DeviceGraph& g, const uint32_t lane, const uint32_t n_wt, const uint32_t n_static) {
-  if (lane != 0) return;
-  const uint32_t n_warps = n_static < n_wt ? n_static : n_wt;  // warps of this launch that had a first tile
-  __threadfence();
-  if (atomicAdd(g.tile_queue + 1, 1u) == n_warps - 1u) {
-    g.tile_queue[0] = 0u;
-    g.tile_queue[1] = 0u;
-  }
 }
 
 // NBUF = 2: the next tile's rows are requested at the top of a tile into the other buffer (a whole tile of arithmetic

@@ -46,4 +46,9 @@ GBP_DEV void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar
                : "memory");
 }
 
+struct SweepMaps {  // TMA descriptors of the two big quad-SoA arrays (box = [rows x 128 floats])
+  CUtensorMap fac;   // [14][E_pad * 4] floats, box 14 x 128
+  CUtensorMap mcam;  // [7][E_pad * 4] floats, box 7 x 128
+};
+
 }  // namespace gbp
