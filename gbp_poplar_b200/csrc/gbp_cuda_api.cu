@@ -354,9 +354,10 @@ std::vector<CommEntry>& comm_cache() {
 // prog_ub (ba/ba.cpp:104-139).  On a shard the boundary landmarks go first: their partial
 // sums are all-gathered on the communication stream while the main stream updates the
 // interior landmarks and the cameras; k_boundary_finish then waits for the gather.
-int launch_update_vars(gbp_handle* h, bool lower_only_in = false) {
+int launch_update_vars(gbp_handle* h, bool lower_only_in = false, bool skip_cams = false) {
   static const int uv_debug = std::getenv("GBP_UV_DEBUG") ? std::atoi(std::getenv("GBP_UV_DEBUG")) : 0;  // timing diagnostics: 1 skips the cameras, 2 the landmarks (results are then WRONG)
-  const int lower_only = (lower_only_in ? 1 : 0) | (uv_debug << 1);
+  // bit 0: mirror the lower triangle of the camera beliefs; bit 1: the cameras are already done (fused into the sweep)
+  const int lower_only = (lower_only_in ? 1 : 0) | (skip_cams ? 2 : 0) | (uv_debug << 1);
   const int shift = h->pending_shift ? 1 : 0;
   const uint32_t grid = lmks_grid(h);
   const bool exchange = h->shard && h->g.n_bnd_global > 0;
@@ -400,27 +401,26 @@ int launch_update_vars(gbp_handle* h, bool lower_only_in = false) {
 
 // upper == false: the strict upper triangle of the camera messages is skipped (see k_sweep); only valid when the
 // following belief update runs with lower_only and another, complete sweep follows before anything is read
+// fuse_cam: the camera half of the belief update runs inside the sweep kernel (camera tickets); the caller then launches
+// the belief update with skip_cams
 template <bool PREP, bool MSG>
-int launch_sweep(gbp_handle* h, bool upper = true) {
+int launch_sweep(gbp_handle* h, bool upper = true, bool fuse_cam = false) {
   if (h->n_tiles) {
     // persistent: one block per SM (fewer when the graph has fewer warp-tiles than that)
     const uint32_t n_wt = h->E_pad / 32;
     const uint32_t grid = std::min<uint32_t>((uint32_t)h->num_sms, n_wt);
     const bool full = upper || !MSG || h->g.mcam_up;
     if constexpr (MSG) {
-      if (h->use_tma == 2) {  // GBP_SWEEP=tma2: the restructured kernel (gbp_sweep_tma.cuh)
-        if (full) gbp::k_sweep_tma<PREP, true, true><<<grid, GBP_TW * 32, GBP_T_SMEM, h->stream>>>(h->g, h->maps);
-        else gbp::k_sweep_tma<PREP, true, false><<<grid, GBP_TW * 32, GBP_T_SMEM, h->stream>>>(h->g, h->maps);
-      } else if (h->use_tma) {
-        if (full) gbp::k_sweep<PREP, true, true, true><<<grid, GBP_SW_WARPS * 32, GBP_SWEEP_SMEM, h->stream>>>(h->g, h->maps);
-        else gbp::k_sweep<PREP, true, false, true><<<grid, GBP_SW_WARPS * 32, GBP_SWEEP_SMEM, h->stream>>>(h->g, h->maps);
-      } else if (full) {
-        gbp::k_sweep<PREP, true, true, false><<<grid, GBP_SW_WARPS * 32, GBP_SWEEP_SMEM, h->stream>>>(h->g, h->maps);
+      if (h->use_tma) {
+        if (full) gbp::k_sweep_tma<PREP, true, true><<<grid, GBP_TW * 32, GBP_T_SMEM, h->stream>>>(h->g, h->maps, fuse_cam);
+        else gbp::k_sweep_tma<PREP, true, false><<<grid, GBP_TW * 32, GBP_T_SMEM, h->stream>>>(h->g, h->maps, fuse_cam);
+      } else if (full) {  // GBP_SWEEP=cpasync: the round-1 kernel (per-lane cp.async staging, static tile order), kept as the reference
+        gbp::k_sweep<PREP, true, true><<<grid, GBP_SW_WARPS * 32, GBP_SWEEP_SMEM, h->stream>>>(h->g);
       } else {
-        gbp::k_sweep<PREP, true, false, false><<<grid, GBP_SW_WARPS * 32, GBP_SWEEP_SMEM, h->stream>>>(h->g, h->maps);
+        gbp::k_sweep<PREP, true, false><<<grid, GBP_SW_WARPS * 32, GBP_SWEEP_SMEM, h->stream>>>(h->g);
       }
     } else {
-      gbp::k_sweep<PREP, MSG, true, false><<<grid, GBP_SW_WARPS * 32, GBP_SWEEP_SMEM, h->stream>>>(h->g, h->maps);
+      gbp::k_sweep<PREP, MSG, true><<<grid, GBP_SW_WARPS * 32, GBP_SWEEP_SMEM, h->stream>>>(h->g);
     }
     h->kernels_launched++;
   }
@@ -443,11 +443,17 @@ int launch_prep(gbp_handle* h) {
   return GBP_OK;
 }
 
-// one full sweep of the factors (prep + messages)
+// can the camera beliefs be finished inside the sweep kernel?  (GBP_FUSE_CAM=0 keeps them in k_update_vars)
+inline bool fuse_cams(const gbp_handle* h) {
+  static const int on = std::getenv("GBP_FUSE_CAM") ? std::atoi(std::getenv("GBP_FUSE_CAM")) : 1;
+  return on && h->use_tma && h->n_tiles;
+}
+// one full sweep of the factors (prep + messages); with fuse_cams(h) the camera beliefs are updated too and the
+// following launch_update_vars must be told to skip them
 int launch_full_sweep(gbp_handle* h, bool upper = true) {
-  if (!h->two_pass) return launch_sweep<true, true>(h, upper);
+  if (!h->two_pass) return launch_sweep<true, true>(h, upper, fuse_cams(h));
   int rc = launch_prep(h);
-  if (!rc) rc = launch_sweep<false, true>(h, upper);
+  if (!rc) rc = launch_sweep<false, true>(h, upper, fuse_cams(h));
   return rc;
 }
 // may the sweeps of a call other than the last skip the upper triangle of the camera messages?
@@ -817,10 +823,10 @@ int setup_p2p(gbp_handle* h, int mode) {
 
 // TMA descriptors for k_sweep_tma: the factor potentials and the camera-bound messages seen as 2-D fp32 tensors
 // [rows][E_pad * 4] whose box is one warp-tile: [rows] x [128 floats = the 32 lanes' quads of one row].
-// GBP_SWEEP=cpasync selects per-lane cp.async staging instead, GBP_SWEEP=tma2 the restructured kernel of gbp_sweep_tma.cuh.
+// GBP_SWEEP=cpasync selects the round-1 kernel (k_sweep: per-lane cp.async staging) instead.
 int setup_tma(gbp_handle* h) {
   h->use_tma = 1;
-  if (const char* env = std::getenv("GBP_SWEEP")) h->use_tma = !std::strcmp(env, "cpasync") ? 0 : !std::strcmp(env, "tma2") ? 2 : 1;
+  if (const char* env = std::getenv("GBP_SWEEP")) h->use_tma = std::strcmp(env, "cpasync") != 0;
   if (!h->use_tma || !h->n_tiles) return GBP_OK;
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -872,10 +878,8 @@ void preload(K kernel) {
   cudaFuncGetAttributes(&a, kernel);
 }
 void preload_kernels() {
-  preload(gbp::k_sweep<true, true, true, false>); preload(gbp::k_sweep<true, true, false, false>);
-  preload(gbp::k_sweep<false, true, true, false>); preload(gbp::k_sweep<false, true, false, false>);
-  preload(gbp::k_sweep<true, true, true, true>); preload(gbp::k_sweep<true, true, false, true>);
-  preload(gbp::k_sweep<false, true, true, true>); preload(gbp::k_sweep<false, true, false, true>);
+  preload(gbp::k_sweep<true, true, true>); preload(gbp::k_sweep<true, true, false>);
+  preload(gbp::k_sweep<false, true, true>); preload(gbp::k_sweep<false, true, false>);
   preload(gbp::k_sweep_tma<true, true, true>); preload(gbp::k_sweep_tma<true, true, false>);
   preload(gbp::k_sweep_tma<false, true, true>); preload(gbp::k_sweep_tma<false, true, false>);
   preload(gbp::k_prep_pass); preload(gbp::k_relin_list); preload(gbp::k_cam_partials); preload(gbp::k_update_vars);
@@ -935,7 +939,8 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   std::vector<uint2> wt_info(n_wt, make_uint2(0u, 0u));
   for (uint32_t c = 0; c < C; ++c)
     for (uint32_t t = cam_wt_begin[c]; t < cam_wt_begin[c + 1]; ++t)
-      wt_info[t] = make_uint2(c, std::min<uint32_t>(32u, deg_c[c] - (t - cam_wt_begin[c]) * 32));
+      wt_info[t] = make_uint2(c, std::min<uint32_t>(32u, deg_c[c] - (t - cam_wt_begin[c]) * 32) |
+                                     ((cam_wt_begin[c + 1] - cam_wt_begin[c]) << 8));  // .y: factors in the tile | warp-tiles of the camera << 8
   h->pos_of_orig.resize(E);
   std::vector<uint32_t> edge_orig(EP, 0xffffffffu);
   for (uint32_t e = 0; e < E; ++e) {
@@ -1078,6 +1083,7 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   A_(g.relin_count, 1);
   A_(g.relin_ring, GBP_RELIN_RING + 1);
   A_(g.tile_queue, 2);
+  A_(g.cam_ticket, C);
   A_(h->d_exp_lmk_eta, 3 * (size_t)L);   // READ_PROG staging (unpacked landmark beliefs, per-edge scalars in edge order)
   A_(h->d_exp_lmk_lam, 9 * (size_t)L);
   A_(h->d_exp_damping, E);
@@ -1221,11 +1227,9 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   if (rc) return rc;
   GBP_CUDA_TRY(cudaStreamSynchronize(s));
 #define GBP_SMEM_ATTR(k) GBP_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, GBP_SWEEP_SMEM))
-  GBP_SMEM_ATTR((gbp::k_sweep<true, true, true, false>)); GBP_SMEM_ATTR((gbp::k_sweep<true, true, false, false>));
-  GBP_SMEM_ATTR((gbp::k_sweep<false, true, true, false>)); GBP_SMEM_ATTR((gbp::k_sweep<false, true, false, false>));
-  GBP_SMEM_ATTR((gbp::k_sweep<true, true, true, true>)); GBP_SMEM_ATTR((gbp::k_sweep<true, true, false, true>));
-  GBP_SMEM_ATTR((gbp::k_sweep<false, true, true, true>)); GBP_SMEM_ATTR((gbp::k_sweep<false, true, false, true>));
-  GBP_SMEM_ATTR((gbp::k_sweep<true, false, true, false>));
+  GBP_SMEM_ATTR((gbp::k_sweep<true, true, true>)); GBP_SMEM_ATTR((gbp::k_sweep<true, true, false>));
+  GBP_SMEM_ATTR((gbp::k_sweep<false, true, true>)); GBP_SMEM_ATTR((gbp::k_sweep<false, true, false>));
+  GBP_SMEM_ATTR((gbp::k_sweep<true, false, true>));
 #undef GBP_SMEM_ATTR
   GBP_CUDA_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
   rc = setup_tma(h);
@@ -1299,7 +1303,7 @@ int sweep_graph(gbp_handle* h, bool with_stats, bool upper, cudaGraphExec_t* out
     GBP_CUDA_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
     h->capturing = true;
     int rc = launch_full_sweep(h, upper);
-    if (!rc) rc = launch_update_vars(h, !upper);
+    if (!rc) rc = launch_update_vars(h, !upper, fuse_cams(h));
     if (!rc && with_stats) rc = launch_metric(h, h->d_stats);
     h->capturing = false;
     const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
@@ -1517,7 +1521,7 @@ int gbp_cuda_iterate_async(gbp_handle* h, int n_sweeps) {
   for (int i = 0; i < n_sweeps && !rc; ++i) {
     const bool upper = i == n_sweeps - 1 || !can_skip_upper(h);
     rc = launch_full_sweep(h, upper);
-    if (!rc) rc = launch_update_vars(h, !upper);
+    if (!rc) rc = launch_update_vars(h, !upper, fuse_cams(h));
   }
   return rc;
 }
@@ -1584,7 +1588,7 @@ int iterate_enqueue(gbp_handle* h, int i, int n_sweeps, bool stats) {
   if (prof) GBP_CUDA_TRY(cudaEventRecord(h->prof_events[3 * i], h->stream));
   rc = launch_full_sweep(h, upper);
   if (prof) GBP_CUDA_TRY(cudaEventRecord(h->prof_events[3 * i + 1], h->stream));
-  if (!rc) rc = launch_update_vars(h, !upper);
+  if (!rc) rc = launch_update_vars(h, !upper, fuse_cams(h));
   if (prof) GBP_CUDA_TRY(cudaEventRecord(h->prof_events[3 * i + 2], h->stream));
   if (!rc && stats) rc = launch_metric(h, h->d_stats + i);
   return rc;

@@ -89,7 +89,8 @@ struct DeviceGraph {
   uint32_t* relin_list;   // [E] edge slots that relinearise this sweep (compacted by k_prep_pass)
   uint32_t* relin_count;  // [1]
   uint32_t* relin_ring;   // [GBP_RELIN_RING + 1] relinearisations of the last sweeps; [GBP_RELIN_RING] = sweep counter
-  uint32_t* tile_queue;   // [1] next warp-tile k_sweep_tma hands out (reset by k_update_vars)
+  uint32_t* tile_queue;   // [2] {tickets handed out, warps done}: warp-tile queue of the sweep kernels
+  uint32_t* cam_ticket;   // [C] finished warp-tiles of every camera in the running sweep (camera_ticket)
   float K[4];             // fx fy cx cy
   Hyper hp;
 };
@@ -287,7 +288,7 @@ __device__ __noinline__ uint32_t relinearise_record(const float4* src, size_t sr
 #define GBP_STAGE_QUADS (GBP_SQ * 32)
 #define GBP_SCAM 56  // per-warp copy of: belief eta 6 | belief lambda 36 | mean 6 | previous mean 6
 #define GBP_RED_STRIDE 36  // floats per row of the reduction scratch: 32 lanes + 4 pad, rows 16-byte aligned for LDS.128
-#define GBP_SWEEP_SMEM (GBP_SW_WARPS * GBP_NBUF * (GBP_STAGE_QUADS * 16 + GBP_SCAM * 4) + GBP_SW_WARPS * GBP_NBUF * 8)
+#define GBP_SWEEP_SMEM (GBP_SW_WARPS * GBP_NBUF * (GBP_STAGE_QUADS * 16 + GBP_SCAM * 4))
 
 GBP_DEV void cp_async16(void* smem, const void* gmem) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -316,25 +317,6 @@ GBP_DEV void issue_stage(const DeviceGraph& g, float4* stage, float* s_cam, cons
   for (int q = 0; q < GBP_MCAM_QUADS; ++q) cp_async16(stage + (GBP_SQ_MCAM + q) * 32 + lane, g.mcam + (size_t)q * g.E_pad + e);
 #pragma unroll
   for (int q = 0; q < GBP_FAC_QUADS; ++q) cp_async16(stage + (GBP_SQ_FAC + q) * 32 + lane, g.fac + (size_t)q * g.E_pad + e);
-}
-
-// The same stage filled by the copy engines: ONE elected lane issues two tensor copies (the [14 x 512 B] box of the
-// potentials, the [7 x 512 B] box of the camera-bound messages) and three bulk copies (the two edge-state rows, the
-// camera record), all completing on the buffer's mbarrier; only the gathered landmark-bound messages stay per-lane
-// cp.async.  23 of the 26 per-lane LDGSTS and their 64-bit address arithmetic leave the instruction stream.
-#define GBP_STAGE_TX_BYTES ((GBP_FAC_QUADS + GBP_MCAM_QUADS + 2) * 512 + GBP_SCAM * 4)
-GBP_DEV void issue_stage_tma(const DeviceGraph& g, const SweepMaps& maps, float4* stage, float* s_cam, uint64_t* bar, const uint32_t wt,
-                             const uint32_t cam, const uint32_t lpos, const uint32_t lane) {
-  if (lane == 0) {
-    mbar_expect_tx(bar, GBP_STAGE_TX_BYTES);
-    tma_load_rows(stage + GBP_SQ_FAC * 32, &maps.fac, wt, bar);
-    tma_load_rows(stage + GBP_SQ_MCAM * 32, &maps.mcam, wt, bar);
-    bulk_load(stage + GBP_SQ_RECA * 32, g.recA + (size_t)wt * 32, 512u, bar);
-    bulk_load(stage + GBP_SQ_RECB * 32, g.recB + (size_t)wt * 32, 512u, bar);
-    bulk_load(s_cam, g.cam_rec + (size_t)cam * 16, GBP_SCAM * 4u, bar);
-  }
-#pragma unroll
-  for (int q = 0; q < GBP_MLMK_QUADS; ++q) cp_async16(stage + (GBP_SQ_MLMK + q) * 32 + lane, g.mlmk + (size_t)lpos * GBP_MLMK_QUADS + q);
 }
 
 // landmark record of one factor: belief eta 0..2 | lambda 3..11 | mean 12..14 | - | previous mean 16..18 | -
@@ -566,7 +548,7 @@ template <bool PREP, bool MSG, bool UPPER>
 GBP_DEV void sweep_tile(const DeviceGraph& g, float4* stage, const float* s_cam, const uint32_t wt, const uint2 ti,
                         const float (&lb)[20], const uint32_t lane) {
   const size_t e = (size_t)wt * 32 + lane;
-  const bool valid = lane < ti.y;  // padding slots hold no factor
+  const bool valid = lane < (ti.y & 0xffu);  // padding slots hold no factor (upper bits of ti.y: warp-tiles of the camera)
   const float4 ra = stage[GBP_SQ_RECA * 32 + lane];
   const float4 rb = stage[GBP_SQ_RECB * 32 + lane];
   float damping = ra.x;
@@ -638,6 +620,198 @@ GBP_DEV void sweep_tile(const DeviceGraph& g, float4* stage, const float* s_cam,
 // every sweep of a call without per-sweep metrics but the LAST in this mode (k_update_vars mirrors the lower triangle meanwhile): the
 // belief of a camera is the sum of the messages of the latest sweep alone, so after the call every tensor is
 // what the all-UPPER sequence would have produced, bit for bit.
+template <bool PREP, bool MSG, bool UPPER>
+__global__ void __launch_bounds__(GBP_SW_WARPS * 32, 1) k_sweep(const DeviceGraph g) {
+  extern __shared__ float4 smem4[];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4* stage_base = smem4 + warp * (GBP_NBUF * GBP_STAGE_QUADS);
+  float* scam_base = reinterpret_cast<float*>(smem4 + GBP_SW_WARPS * GBP_NBUF * GBP_STAGE_QUADS) + warp * (GBP_NBUF * GBP_SCAM);
+  const uint32_t n_wt = g.E_pad / 32;
+  const uint32_t stride = gridDim.x * GBP_SW_WARPS;
+  // consecutive warp-tiles go to different SMs, so small graphs spread over the whole chip
+  uint32_t wt = warp * gridDim.x + blockIdx.x;
+  if (wt >= n_wt) return;
+
+  // prologue: everything of the first warp-tile, ids of the second
+  uint2 ti = __ldg(g.wt_info + wt);
+  uint32_t buf = 0;
+  // {landmark id, message position} of a lane's factor = the second half of its recB record
+  const uint2* lrec = reinterpret_cast<const uint2*>(g.recB) + 1;
+  uint2 lid = __ldg(lrec + 2 * ((size_t)wt * 32 + lane));
+  issue_stage(g, stage_base, scam_base, wt, ti.x, lid.y, lane);
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  float lb[20];
+  load_lmk_belief(g, lid.x, lb);
+  uint32_t wt_n = wt + stride;
+  uint2 ti_n = make_uint2(0u, 0u);
+  uint2 lid_n = make_uint2(0u, 0u);
+  if (wt_n < n_wt) {
+    ti_n = __ldg(g.wt_info + wt_n);
+    lid_n = __ldg(lrec + 2 * ((size_t)wt_n * 32 + lane));
+  }
+  for (;;) {
+    const bool has_next = wt_n < n_wt;
+    float lb_n[20];
+    uint2 ti_nn = make_uint2(0u, 0u);
+    uint2 lid_nn = make_uint2(0u, 0u);
+    const uint32_t wt_nn = wt_n + stride;
+    if (has_next) {
+      issue_stage(g, stage_base + (buf ^ 1) * GBP_STAGE_QUADS, scam_base + (buf ^ 1) * GBP_SCAM, wt_n, ti_n.x, lid_n.y, lane);
+      load_lmk_belief(g, lid_n.x, lb_n);
+      if (wt_nn < n_wt) {
+        ti_nn = __ldg(g.wt_info + wt_nn);
+        lid_nn = __ldg(lrec + 2 * ((size_t)wt_nn * 32 + lane));
+#if GBP_L2_PREFETCH == 1
+        // warp-tile t+2: pull its 23 contiguous 512-byte rows (potential 14, camera message 7, the two
+        // edge-state records) into L2 now, one bulk prefetch per lane, so that the cp.async copies issued
+        // at the top of the next iteration are served from L2 instead of queueing behind DRAM
+        const float4* row = nullptr;
+        if (lane < GBP_FAC_QUADS) row = g.fac + (size_t)lane * g.E_pad;
+        else if (lane < GBP_FAC_QUADS + GBP_MCAM_QUADS) row = g.mcam + (size_t)(lane - GBP_FAC_QUADS) * g.E_pad;
+        else if (lane == GBP_FAC_QUADS + GBP_MCAM_QUADS) row = g.recA;
+        else if (lane == GBP_FAC_QUADS + GBP_MCAM_QUADS + 1) row = g.recB;
+        if (row) asm volatile("cp.async.bulk.prefetch.L2.global [%0], 512;\n" ::"l"(row + (size_t)wt_nn * 32) : "memory");
+#elif GBP_L2_PREFETCH == 2
+        // the same 23 rows x 4 lines of 128 B, one prefetch.global.L2 per line, three per lane
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const uint32_t i = lane + 32u * k, r = i >> 2;
+          if (r < GBP_FAC_QUADS + GBP_MCAM_QUADS + 2) {
+            const float4* row = (r < GBP_FAC_QUADS) ? g.fac + (size_t)r * g.E_pad
+                                : (r < GBP_FAC_QUADS + GBP_MCAM_QUADS) ? g.mcam + (size_t)(r - GBP_FAC_QUADS) * g.E_pad
+                                : (r == GBP_FAC_QUADS + GBP_MCAM_QUADS) ? g.recA : g.recB;
+            asm volatile("prefetch.global.L2 [%0];\n" ::"l"(row + (size_t)wt_nn * 32 + (i & 3u) * 8) : "memory");
+          }
+        }
+#endif
+      }
+    }
+    // the copies of THIS warp-tile were committed one iteration ago: leave the newest group in flight
+    asm volatile("cp.async.commit_group;\n cp.async.wait_group 1;\n" ::: "memory");
+    __syncwarp();
+    sweep_tile<PREP, MSG, UPPER>(g, stage_base + buf * GBP_STAGE_QUADS, scam_base + buf * GBP_SCAM, wt, ti, lb, lane);
+    if (!has_next) break;
+    wt = wt_n; wt_n = wt_nn;
+    ti = ti_n; ti_n = ti_nn;
+    lid_n = lid_nn;
+#pragma unroll
+    for (int i = 0; i < 20; ++i) lb[i] = lb_n[i];
+    buf ^= 1;
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+
+// ---- camera belief update inside the sweep kernel ------------------------------------------------------------
+// The camera half of prog_ub is a latency chain (partials -> 6x6 LDL^T inverse -> Rodrigues in double), ~15 us when it
+// runs as blocks of k_update_vars after the sweep.  Inside the sweep it costs nothing visible: every warp-tile takes
+// a TICKET of its camera once its partial sum is stored; the warp that draws the last ticket of a camera owns the
+// complete set of partials and finishes the camera -- sums them in warp-tile order onto the prior, inverts, forms
+// the linearisation constants, rewrites the camera record (all warp-tiles of that camera are done with it).  The
+// other warps of the SM keep the pipes busy meanwhile.  The ticket of tile t is taken in the MIDDLE of tile t+1
+// (sweep_tile's mid hook): the fence that publishes the partial then finds the warp's stores already drained.
+struct CamFinish {  // what finish_camera touches, by value (the kernel parameter block never has its address taken)
+  const uint32_t* cam_wt_begin;
+  const float* cam_partial;
+  const float* prior_eta;
+  const float* prior_lam;
+  float* b_eta;
+  float* b_lam;
+  float4* rec;
+  float* mean;
+  float* mean_prev;
+  float4* lin;
+};
+__device__ __noinline__ void finish_camera(const CamFinish f, const uint32_t c, const int lower_only) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t t0 = f.cam_wt_begin[c], t1 = f.cam_wt_begin[c + 1];
+  float v[2] = {0.f, 0.f};  // entries `lane` and `lane + 32` of [eta 6 | Lambda 36 row-major]
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const uint32_t ent = lane + 32u * half;
+    if (ent < GBP_CAMPART) {
+      const uint32_t bi = ent >= 6 ? (ent - 6) / 6 : 0u, bj = ent >= 6 ? (ent - 6) % 6 : 0u;
+      if (!(lower_only && ent >= 6 && bi < bj)) {
+        // the sum starts from +0 like a zero-initialised accumulator: 0 + prior (turns a -0 prior into +0)
+        float acc = fa(0.0f, (ent < 6) ? f.prior_eta[c * 6 + ent] : f.prior_lam[c * 36 + (ent - 6)]);
+        for (uint32_t t = t0; t < t1; t += 16) {  // sixteen partials in flight; the additions stay in warp-tile order
+          float p[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) p[u] = (t + u < t1) ? __ldcg(f.cam_partial + (size_t)(t + u) * GBP_CAMPART + ent) : 0.f;
+#pragma unroll
+          for (int u = 0; u < 16; ++u)
+            if (t + u < t1) acc = fa(acc, p[u]);
+        }
+        v[half] = acc;
+      }
+    }
+  }
+  // after a sweep that skipped the strict upper triangle of the camera messages the upper entries mirror the lower ones
+  float s_b[GBP_CAMPART];
+#pragma unroll
+  for (int k = 0; k < GBP_CAMPART; ++k) s_b[k] = __shfl_sync(0xffffffffu, k < 32 ? v[0] : v[1], k & 31);
+  if (lower_only) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = i + 1; j < 6; ++j) s_b[6 + i * 6 + j] = s_b[6 + j * 6 + i];
+  }
+  float* rec = reinterpret_cast<float*>(f.rec + (size_t)c * 16);
+#pragma unroll
+  for (int k = 0; k < GBP_CAMPART; ++k)
+    if (lane == (uint32_t)(k & 31)) {
+      if (k < 6) f.b_eta[c * 6 + k] = s_b[k];
+      else f.b_lam[c * 36 + (k - 6)] = s_b[k];
+      rec[k] = s_b[k];
+    }
+  if (lane == 0) {
+    float eta[6], lamL[21], mean[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) eta[i] = s_b[i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = 0; j <= i; ++j) lamL[lt(i, j)] = s_b[6 + i * 6 + j];
+    inf2mean6(eta, lamL, mean);
+    const float w[3] = {mean[3], mean[4], mean[5]};
+    float R[9], num[9], den;
+    cam_lin_consts(w, R, num, den);
+    float acc6 = 0.f;  // the camera's six terms of dmu (gbp_codelets.cpp:268-277)
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const float prev = f.mean[c * 6 + i];  // Copy(mu, oldmu), ba/ba.cpp:898: a prep ran in this sweep
+      f.mean_prev[c * 6 + i] = prev;
+      f.mean[c * 6 + i] = mean[i];
+      rec[42 + i] = mean[i];
+      rec[48 + i] = prev;
+      const float d = fs(prev, mean[i]);
+      acc6 = fa(acc6, fm(d, d));
+    }
+    rec[54] = acc6;
+    float* lin = reinterpret_cast<float*>(f.lin + (size_t)c * 5);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      lin[i] = R[i];
+      lin[9 + i] = num[i];
+    }
+    lin[18] = den;
+  }
+}
+// the ticket of one finished warp-tile of camera `cam` (n_tiles warp-tiles in all); converged warp
+GBP_DEV void camera_ticket(const DeviceGraph& g, const uint32_t cam, const uint32_t n_tiles, const int lower_only, const uint32_t lane) {
+  __threadfence();  // this warp's partial sums (stored by many lanes) are visible before the ticket is
+  __syncwarp();
+  uint32_t last = 0;
+  if (lane == 0) last = (atomicAdd(g.cam_ticket + cam, 1u) == n_tiles - 1u) ? 1u : 0u;
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (!last) return;
+  if (lane == 0) g.cam_ticket[cam] = 0u;  // rewound for the next sweep
+  __threadfence();                         // the other warps' partials are visible after their tickets
+  CamFinish f;
+  f.cam_wt_begin = g.cam_wt_begin; f.cam_partial = g.cam_partial; f.prior_eta = g.cam_prior_eta; f.prior_lam = g.cam_prior_lam;
+  f.b_eta = g.cam_b_eta; f.b_lam = g.cam_b_lam; f.rec = g.cam_rec; f.mean = g.cam_mean; f.mean_prev = g.cam_mean_prev; f.lin = g.cam_lin;
+  finish_camera(f, cam, lower_only);
+}
+
 // Warp-tiles beyond the first two (static) rounds come from a device-side queue.  tile_queue = {tickets handed out,
 // warps that have finished}; the last warp of the launch to finish rewinds both, so every launch starts from an empty
 // queue without a memset node.  A ticket is DRAWN one tile before it is needed (the atomic's round trip is hidden
@@ -661,105 +835,6 @@ GBP_DEV void tile_queue_done(const DeviceGraph& g, const uint32_t lane, const ui
     g.tile_queue[0] = 0u;
     g.tile_queue[1] = 0u;
   }
-}
-
-// TMA = true: the stage is filled by the copy engines (issue_stage_tma), completion on one mbarrier per buffer;
-// TMA = false: per-lane cp.async (issue_stage).  Same stage layout, same arithmetic.
-template <bool PREP, bool MSG, bool UPPER, bool TMA>
-__global__ void __launch_bounds__(GBP_SW_WARPS * 32, 1) k_sweep(const DeviceGraph g, const __grid_constant__ SweepMaps maps) {
-  extern __shared__ __align__(1024) float4 smem4[];
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4* stage_base = smem4 + warp * (GBP_NBUF * GBP_STAGE_QUADS);
-  float* scam_base = reinterpret_cast<float*>(smem4 + GBP_SW_WARPS * GBP_NBUF * GBP_STAGE_QUADS) + warp * (GBP_NBUF * GBP_SCAM);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(smem4 + GBP_SW_WARPS * GBP_NBUF * GBP_STAGE_QUADS) +
-                                               GBP_SW_WARPS * GBP_NBUF * GBP_SCAM) + warp * GBP_NBUF;
-  const uint32_t n_wt = g.E_pad / 32;
-  const uint32_t n_static = gridDim.x * GBP_SW_WARPS;  // warp-tiles of one static round
-  // consecutive warp-tiles go to different SMs, so small graphs spread over the whole chip
-  uint32_t wt = warp * gridDim.x + blockIdx.x;
-  if (wt >= n_wt) return;
-  if (TMA) {
-    if (lane == 0) {
-      mbar_init(bars + 0, 1);
-      mbar_init(bars + 1, 1);
-      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    }
-    fence_proxy_async();
-    __syncwarp();
-  }
-
-  // prologue: everything of the first warp-tile, ids of the second, a ticket for the third
-  uint2 ti = __ldg(g.wt_info + wt);
-  uint32_t buf = 0, phase = 0;  // phase: bit b = parity the next wait on buffer b expects
-  // {landmark id, message position} of a lane's factor = the second half of its recB record
-  const uint2* lrec = reinterpret_cast<const uint2*>(g.recB) + 1;
-  uint2 lid = __ldg(lrec + 2 * ((size_t)wt * 32 + lane));
-  if (TMA) issue_stage_tma(g, maps, stage_base, scam_base, bars, wt, ti.x, lid.y, lane);
-  else issue_stage(g, stage_base, scam_base, wt, ti.x, lid.y, lane);
-  asm volatile("cp.async.commit_group;\n" ::: "memory");
-  float lb[20];
-  load_lmk_belief(g, lid.x, lb);
-  uint32_t wt_n = wt + n_static;  // the second round is static too
-  if (wt_n >= n_wt) wt_n = 0xffffffffu;
-  uint2 ti_n = make_uint2(0u, 0u);
-  uint2 lid_n = make_uint2(0u, 0u);
-  uint32_t ticket = 0;
-  bool drawn = false;
-  if (wt_n != 0xffffffffu) {
-    ti_n = __ldg(g.wt_info + wt_n);
-    lid_n = __ldg(lrec + 2 * ((size_t)wt_n * 32 + lane));
-    if (g.tile_queue) {
-      ticket = queue_draw(g, lane);
-      drawn = true;
-    }
-  }
-  for (;;) {
-    const bool has_next = wt_n != 0xffffffffu;
-    float lb_n[20];
-    uint2 ti_nn = make_uint2(0u, 0u);
-    uint2 lid_nn = make_uint2(0u, 0u);
-    uint32_t wt_nn = 0xffffffffu;
-    if (has_next) {
-      if (TMA) issue_stage_tma(g, maps, stage_base + (buf ^ 1) * GBP_STAGE_QUADS, scam_base + (buf ^ 1) * GBP_SCAM, bars + (buf ^ 1), wt_n, ti_n.x, lid_n.y, lane);
-      else issue_stage(g, stage_base + (buf ^ 1) * GBP_STAGE_QUADS, scam_base + (buf ^ 1) * GBP_SCAM, wt_n, ti_n.x, lid_n.y, lane);
-      load_lmk_belief(g, lid_n.x, lb_n);
-      if (g.tile_queue) {
-        if (drawn) wt_nn = queue_resolve(ticket, n_wt, n_static);  // drawn one tile ago
-        drawn = wt_nn != 0xffffffffu;
-        if (drawn) ticket = queue_draw(g, lane);
-      } else {  // static round-robin (GBP_TILE_QUEUE=0)
-        wt_nn = wt_n + n_static;
-        if (wt_nn >= n_wt) wt_nn = 0xffffffffu;
-      }
-      if (wt_nn != 0xffffffffu) {
-        ti_nn = __ldg(g.wt_info + wt_nn);
-        lid_nn = __ldg(lrec + 2 * ((size_t)wt_nn * 32 + lane));
-      }
-    }
-    // the copies of THIS warp-tile were committed one iteration ago: leave the newest group in flight
-    asm volatile("cp.async.commit_group;\n cp.async.wait_group 1;\n" ::: "memory");
-    if (TMA) {
-      mbar_wait(bars + buf, (phase >> buf) & 1u);
-      phase ^= 1u << buf;
-    }
-    __syncwarp();
-    sweep_tile<PREP, MSG, UPPER>(g, stage_base + buf * GBP_STAGE_QUADS, scam_base + buf * GBP_SCAM, wt, ti, lb, lane);
-    if (TMA) {
-      // the copy engine rewrites this buffer two tiles from now: order the generic accesses (stage reads, the
-      // relinearised record, the reduction scratch) before that
-      fence_proxy_async();
-      __syncwarp();
-    }
-    if (!has_next) break;
-    wt = wt_n; wt_n = wt_nn;
-    ti = ti_n; ti_n = ti_nn;
-    lid_n = lid_nn;
-#pragma unroll
-    for (int i = 0; i < 20; ++i) lb[i] = lb_n[i];
-    buf ^= 1;
-  }
-  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-  if (g.tile_queue) tile_queue_done(g, lane, n_wt, n_static);
 }
 
 // ---- PrepMessageVertex as its own pass, relinearisation by compaction ---------------------------
