@@ -401,10 +401,8 @@ int launch_update_vars(gbp_handle* h, bool lower_only_in = false, bool skip_cams
 
 // upper == false: the strict upper triangle of the camera messages is skipped (see k_sweep); only valid when the
 // following belief update runs with lower_only and another, complete sweep follows before anything is read
-// fuse_cam: the camera half of the belief update runs inside the sweep kernel (camera tickets); the caller then launches
-// the belief update with skip_cams
 template <bool PREP, bool MSG>
-int launch_sweep(gbp_handle* h, bool upper = true, bool fuse_cam = false) {
+int launch_sweep(gbp_handle* h, bool upper = true) {
   if (h->n_tiles) {
     // persistent: one block per SM (fewer when the graph has fewer warp-tiles than that)
     const uint32_t n_wt = h->E_pad / 32;
@@ -412,8 +410,8 @@ int launch_sweep(gbp_handle* h, bool upper = true, bool fuse_cam = false) {
     const bool full = upper || !MSG || h->g.mcam_up;
     if constexpr (MSG) {
       if (h->use_tma) {
-        if (full) gbp::k_sweep_tma<PREP, true, true><<<grid, GBP_TW * 32, GBP_T_SMEM, h->stream>>>(h->g, h->maps, fuse_cam);
-        else gbp::k_sweep_tma<PREP, true, false><<<grid, GBP_TW * 32, GBP_T_SMEM, h->stream>>>(h->g, h->maps, fuse_cam);
+        if (full) gbp::k_sweep_tma<PREP, true, true><<<grid, GBP_TW * 32, GBP_T_SMEM, h->stream>>>(h->g, h->maps);
+        else gbp::k_sweep_tma<PREP, true, false><<<grid, GBP_TW * 32, GBP_T_SMEM, h->stream>>>(h->g, h->maps);
       } else if (full) {  // GBP_SWEEP=cpasync: the round-1 kernel (per-lane cp.async staging, static tile order), kept as the reference
         gbp::k_sweep<PREP, true, true><<<grid, GBP_SW_WARPS * 32, GBP_SWEEP_SMEM, h->stream>>>(h->g);
       } else {
@@ -443,17 +441,11 @@ int launch_prep(gbp_handle* h) {
   return GBP_OK;
 }
 
-// can the camera beliefs be finished inside the sweep kernel?  (GBP_FUSE_CAM=0 keeps them in k_update_vars)
-inline bool fuse_cams(const gbp_handle* h) {
-  static const int on = std::getenv("GBP_FUSE_CAM") ? std::atoi(std::getenv("GBP_FUSE_CAM")) : 1;
-  return on && h->use_tma && h->n_tiles;
-}
-// one full sweep of the factors (prep + messages); with fuse_cams(h) the camera beliefs are updated too and the
-// following launch_update_vars must be told to skip them
+// one full sweep of the factors (prep + messages)
 int launch_full_sweep(gbp_handle* h, bool upper = true) {
-  if (!h->two_pass) return launch_sweep<true, true>(h, upper, fuse_cams(h));
+  if (!h->two_pass) return launch_sweep<true, true>(h, upper);
   int rc = launch_prep(h);
-  if (!rc) rc = launch_sweep<false, true>(h, upper, fuse_cams(h));
+  if (!rc) rc = launch_sweep<false, true>(h, upper);
   return rc;
 }
 // may the sweeps of a call other than the last skip the upper triangle of the camera messages?
@@ -954,12 +946,13 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   for (uint32_t l = 0; l < L; ++l) lmk_ptr[l + 1] = lmk_ptr[l] + deg_l[l];
   // belief-update blocks of the landmarks: consecutive landmarks, at most GBP_LMK_PER_BLOCK of them and at most
   // GBP_LMK_CAP messages (what a block stages in shared memory); a landmark above the cap stands alone
-  std::vector<uint32_t> lmk_blk(1, 0u);
-  for (uint32_t l = 0; l < L;) {
+  std::vector<uint4> lmk_blk;
+  for (uint32_t l = 0, k = 0; l < L;) {
     uint32_t n = 0, msgs = 0;
     while (l + n < L && n < GBP_LMK_PER_BLOCK && (n == 0 || msgs + deg_l[l + n] <= GBP_LMK_CAP)) msgs += deg_l[l + n++];
+    lmk_blk.push_back(make_uint4(l, l + n, k, k + msgs));
     l += n;
-    lmk_blk.push_back(l);
+    k += msgs;
   }
   std::vector<float> var(EP, 1.f);
   pt.lap("index maps");
@@ -1020,7 +1013,7 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   DeviceGraph& g = h->g;
   std::memset(&g, 0, sizeof(g));
   g.C = C; g.L = L; g.E = E; g.E_pad = h->E_pad;
-  g.n_lmk_blocks = (uint32_t)lmk_blk.size() - 1;
+  g.n_lmk_blocks = (uint32_t)lmk_blk.size();
   g.K[0] = p->K[0]; g.K[1] = p->K[4]; g.K[2] = p->K[2]; g.K[3] = p->K[5];
   g.hp.maxeta_damping = o->maxeta_damping;
   g.hp.num_undamped_iters = o->num_undamped_iters;
@@ -1047,7 +1040,7 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   A_(g.mlmk, GBP_MLMK_QUADS * (size_t)E);
   const size_t reuse_mlmk_end = arena_bytes;
   A_(g.recA, EP);
-  A_(g.cam_partial, (size_t)n_wt * GBP_CAMPART);
+  A_(g.cam_partial, (size_t)n_wt * GBP_CAMPART_STRIDE);
   A_(g.lmk_b, GBP_LMKB_QUADS * (size_t)L);
   A_(g.lmk_mean_prev, L);
   A_(g.lmk_sq, L);
@@ -1083,7 +1076,6 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   A_(g.relin_count, 1);
   A_(g.relin_ring, GBP_RELIN_RING + 1);
   A_(g.tile_queue, 2);
-  A_(g.cam_ticket, C);
   A_(h->d_exp_lmk_eta, 3 * (size_t)L);   // READ_PROG staging (unpacked landmark beliefs, per-edge scalars in edge order)
   A_(h->d_exp_lmk_lam, 9 * (size_t)L);
   A_(h->d_exp_damping, E);
@@ -1303,7 +1295,7 @@ int sweep_graph(gbp_handle* h, bool with_stats, bool upper, cudaGraphExec_t* out
     GBP_CUDA_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
     h->capturing = true;
     int rc = launch_full_sweep(h, upper);
-    if (!rc) rc = launch_update_vars(h, !upper, fuse_cams(h));
+    if (!rc) rc = launch_update_vars(h, !upper);
     if (!rc && with_stats) rc = launch_metric(h, h->d_stats);
     h->capturing = false;
     const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
@@ -1521,7 +1513,7 @@ int gbp_cuda_iterate_async(gbp_handle* h, int n_sweeps) {
   for (int i = 0; i < n_sweeps && !rc; ++i) {
     const bool upper = i == n_sweeps - 1 || !can_skip_upper(h);
     rc = launch_full_sweep(h, upper);
-    if (!rc) rc = launch_update_vars(h, !upper, fuse_cams(h));
+    if (!rc) rc = launch_update_vars(h, !upper);
   }
   return rc;
 }
@@ -1588,7 +1580,7 @@ int iterate_enqueue(gbp_handle* h, int i, int n_sweeps, bool stats) {
   if (prof) GBP_CUDA_TRY(cudaEventRecord(h->prof_events[3 * i], h->stream));
   rc = launch_full_sweep(h, upper);
   if (prof) GBP_CUDA_TRY(cudaEventRecord(h->prof_events[3 * i + 1], h->stream));
-  if (!rc) rc = launch_update_vars(h, !upper, fuse_cams(h));
+  if (!rc) rc = launch_update_vars(h, !upper);
   if (prof) GBP_CUDA_TRY(cudaEventRecord(h->prof_events[3 * i + 2], h->stream));
   if (!rc && stats) rc = launch_metric(h, h->d_stats + i);
   return rc;

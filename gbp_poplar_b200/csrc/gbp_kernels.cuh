@@ -60,7 +60,7 @@ struct DeviceGraph {
   float* lmk_scaling;     // [L]
   uint32_t* lmk_wflag;    // [L]
   uint32_t* lmk_ptr;      // [L+1] first message of every landmark in mlmk (messages in original edge order)
-  uint32_t* lmk_blk;      // [n_lmk_blocks+1] first landmark of every belief-update block (<= 32 landmarks, <= GBP_LMK_CAP messages)
+  uint4* lmk_blk;         // [n_lmk_blocks] {first landmark, one past the last, first message, one past the last} of every belief-update block (<= 32 landmarks, <= GBP_LMK_CAP messages)
   uint32_t n_lmk_blocks;
   // multi-GPU shard (all null / 0 on a single-GPU handle): boundary landmarks = landmarks
   // that other ranks observe too; their beliefs are formed from all-gathered partials
@@ -90,7 +90,6 @@ struct DeviceGraph {
   uint32_t* relin_count;  // [1]
   uint32_t* relin_ring;   // [GBP_RELIN_RING + 1] relinearisations of the last sweeps; [GBP_RELIN_RING] = sweep counter
   uint32_t* tile_queue;   // [2] {tickets handed out, warps done}: warp-tile queue of the sweep kernels
-  uint32_t* cam_ticket;   // [C] finished warp-tiles of every camera in the running sweep (camera_ticket)
   float K[4];             // fx fy cx cy
   Hyper hp;
 };
@@ -609,7 +608,7 @@ GBP_DEV void sweep_tile(const DeviceGraph& g, float4* stage, const float* s_cam,
       for (int k = 0; k < 21; ++k) red[(6 + k) * GBP_RED_STRIDE + lane] = nc[GBP_MCAM_LOWER + k];
     }
     __syncwarp();
-    warp_cam_reduce<UPPER>(red, lane, g.cam_partial + (size_t)wt * GBP_CAMPART);
+    warp_cam_reduce<UPPER>(red, lane, g.cam_partial + (size_t)wt * GBP_CAMPART_STRIDE);
     __syncwarp();
   }
 }
@@ -699,117 +698,6 @@ __global__ void __launch_bounds__(GBP_SW_WARPS * 32, 1) k_sweep(const DeviceGrap
     buf ^= 1;
   }
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-}
-
-// ---- camera belief update inside the sweep kernel ------------------------------------------------------------
-// The camera half of prog_ub is a latency chain (partials -> 6x6 LDL^T inverse -> Rodrigues in double), ~15 us when it
-// runs as blocks of k_update_vars after the sweep.  Inside the sweep it costs nothing visible: every warp-tile takes
-// a TICKET of its camera once its partial sum is stored; the warp that draws the last ticket of a camera owns the
-// complete set of partials and finishes the camera -- sums them in warp-tile order onto the prior, inverts, forms
-// the linearisation constants, rewrites the camera record (all warp-tiles of that camera are done with it).  The
-// other warps of the SM keep the pipes busy meanwhile.  The ticket of tile t is taken in the MIDDLE of tile t+1
-// (sweep_tile's mid hook): the fence that publishes the partial then finds the warp's stores already drained.
-struct CamFinish {  // what finish_camera touches, by value (the kernel parameter block never has its address taken)
-  const uint32_t* cam_wt_begin;
-  const float* cam_partial;
-  const float* prior_eta;
-  const float* prior_lam;
-  float* b_eta;
-  float* b_lam;
-  float4* rec;
-  float* mean;
-  float* mean_prev;
-  float4* lin;
-};
-__device__ __noinline__ void finish_camera(const CamFinish f, const uint32_t c, const int lower_only) {
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t t0 = f.cam_wt_begin[c], t1 = f.cam_wt_begin[c + 1];
-  float v[2] = {0.f, 0.f};  // entries `lane` and `lane + 32` of [eta 6 | Lambda 36 row-major]
-#pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    const uint32_t ent = lane + 32u * half;
-    if (ent < GBP_CAMPART) {
-      const uint32_t bi = ent >= 6 ? (ent - 6) / 6 : 0u, bj = ent >= 6 ? (ent - 6) % 6 : 0u;
-      if (!(lower_only && ent >= 6 && bi < bj)) {
-        // the sum starts from +0 like a zero-initialised accumulator: 0 + prior (turns a -0 prior into +0)
-        float acc = fa(0.0f, (ent < 6) ? f.prior_eta[c * 6 + ent] : f.prior_lam[c * 36 + (ent - 6)]);
-        for (uint32_t t = t0; t < t1; t += 16) {  // sixteen partials in flight; the additions stay in warp-tile order
-          float p[16];
-#pragma unroll
-          for (int u = 0; u < 16; ++u) p[u] = (t + u < t1) ? __ldcg(f.cam_partial + (size_t)(t + u) * GBP_CAMPART + ent) : 0.f;
-#pragma unroll
-          for (int u = 0; u < 16; ++u)
-            if (t + u < t1) acc = fa(acc, p[u]);
-        }
-        v[half] = acc;
-      }
-    }
-  }
-  // after a sweep that skipped the strict upper triangle of the camera messages the upper entries mirror the lower ones
-  float s_b[GBP_CAMPART];
-#pragma unroll
-  for (int k = 0; k < GBP_CAMPART; ++k) s_b[k] = __shfl_sync(0xffffffffu, k < 32 ? v[0] : v[1], k & 31);
-  if (lower_only) {
-#pragma unroll
-    for (int i = 0; i < 6; ++i)
-#pragma unroll
-      for (int j = i + 1; j < 6; ++j) s_b[6 + i * 6 + j] = s_b[6 + j * 6 + i];
-  }
-  float* rec = reinterpret_cast<float*>(f.rec + (size_t)c * 16);
-#pragma unroll
-  for (int k = 0; k < GBP_CAMPART; ++k)
-    if (lane == (uint32_t)(k & 31)) {
-      if (k < 6) f.b_eta[c * 6 + k] = s_b[k];
-      else f.b_lam[c * 36 + (k - 6)] = s_b[k];
-      rec[k] = s_b[k];
-    }
-  if (lane == 0) {
-    float eta[6], lamL[21], mean[6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) eta[i] = s_b[i];
-#pragma unroll
-    for (int i = 0; i < 6; ++i)
-#pragma unroll
-      for (int j = 0; j <= i; ++j) lamL[lt(i, j)] = s_b[6 + i * 6 + j];
-    inf2mean6(eta, lamL, mean);
-    const float w[3] = {mean[3], mean[4], mean[5]};
-    float R[9], num[9], den;
-    cam_lin_consts(w, R, num, den);
-    float acc6 = 0.f;  // the camera's six terms of dmu (gbp_codelets.cpp:268-277)
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      const float prev = f.mean[c * 6 + i];  // Copy(mu, oldmu), ba/ba.cpp:898: a prep ran in this sweep
-      f.mean_prev[c * 6 + i] = prev;
-      f.mean[c * 6 + i] = mean[i];
-      rec[42 + i] = mean[i];
-      rec[48 + i] = prev;
-      const float d = fs(prev, mean[i]);
-      acc6 = fa(acc6, fm(d, d));
-    }
-    rec[54] = acc6;
-    float* lin = reinterpret_cast<float*>(f.lin + (size_t)c * 5);
-#pragma unroll
-    for (int i = 0; i < 9; ++i) {
-      lin[i] = R[i];
-      lin[9 + i] = num[i];
-    }
-    lin[18] = den;
-  }
-}
-// the ticket of one finished warp-tile of camera `cam` (n_tiles warp-tiles in all); converged warp
-GBP_DEV void camera_ticket(const DeviceGraph& g, const uint32_t cam, const uint32_t n_tiles, const int lower_only, const uint32_t lane) {
-  __threadfence();  // this warp's partial sums (stored by many lanes) are visible before the ticket is
-  __syncwarp();
-  uint32_t last = 0;
-  if (lane == 0) last = (atomicAdd(g.cam_ticket + cam, 1u) == n_tiles - 1u) ? 1u : 0u;
-  last = __shfl_sync(0xffffffffu, last, 0);
-  if (!last) return;
-  if (lane == 0) g.cam_ticket[cam] = 0u;  // rewound for the next sweep
-  __threadfence();                         // the other warps' partials are visible after their tickets
-  CamFinish f;
-  f.cam_wt_begin = g.cam_wt_begin; f.cam_partial = g.cam_partial; f.prior_eta = g.cam_prior_eta; f.prior_lam = g.cam_prior_lam;
-  f.b_eta = g.cam_b_eta; f.b_lam = g.cam_b_lam; f.rec = g.cam_rec; f.mean = g.cam_mean; f.mean_prev = g.cam_mean_prev; f.lin = g.cam_lin;
-  finish_camera(f, cam, lower_only);
 }
 
 // Warp-tiles beyond the first two (static) rounds come from a device-side queue.  tile_queue = {tickets handed out,
@@ -947,7 +835,7 @@ __global__ void __launch_bounds__(GBP_TILE) k_cam_partials(const DeviceGraph g) 
       for (int j = i + 1; j < 6; ++j) red[(6 + i * 6 + j) * GBP_RED_STRIDE + lane] = u[gbp_upper(i, j)];
   }
   __syncwarp();
-  warp_cam_reduce<true>(red, lane, g.cam_partial + ((size_t)tile * (GBP_TILE / 32) + warp) * GBP_CAMPART);
+  warp_cam_reduce<true>(red, lane, g.cam_partial + ((size_t)tile * (GBP_TILE / 32) + warp) * GBP_CAMPART_STRIDE);
 }
 
 // b += the factor->landmark messages of landmark l, strictly in slot order (= original
@@ -1007,58 +895,84 @@ GBP_DEV void lmk_load_prior(const DeviceGraph& g, const uint32_t l, float (&b)[1
 // Belief update + per-variable mean (inf2mean hoisted out of PrepMessageVertex).  shift != 0: the mean that the
 // last PrepMessageVertex pass used becomes the "old mu" (Copy(mu, oldmu),
 // ba/ba.cpp:898) before the new mean is stored.
-// Belief update of the cameras (prog_ub, ba/ba.cpp:104-139, camera half) + per-camera mean and
-// rotation.  One WARP per camera (four cameras per block, so the camera blocks leave the block slots of an SM to the
-// bandwidth-bound landmark blocks): the lanes add the per-warp-tile partials of k_sweep to the prior in warp-tile
-// order, entry `lane` and entry `lane + 32` of [eta 6 | Lambda 36], lane 0 inverts the 6x6 belief (latency bound: a
-// serial LDL^T).
-#define GBP_CAM_PER_BLOCK (GBP_TILE / 32)
-GBP_DEV float cam_entry_sum(const DeviceGraph& g, const uint32_t c, const uint32_t ent, const uint32_t t0, const uint32_t t1) {
-  // the sum starts from +0 like a zero-initialised accumulator: 0 + prior (turns a -0 prior into +0)
-  float acc = fa(0.0f, (ent < 6) ? g.cam_prior_eta[c * 6 + ent] : g.cam_prior_lam[c * 36 + (ent - 6)]);
-  // sixteen partials are fetched together; the additions stay in warp-tile order
-  for (uint32_t t = t0; t < t1; t += 16) {
-    float v[16];
-#pragma unroll
-    for (int u = 0; u < 16; ++u) v[u] = (t + u < t1) ? g.cam_partial[(size_t)(t + u) * GBP_CAMPART + ent] : 0.f;
-#pragma unroll
-    for (int u = 0; u < 16; ++u)
-      if (t + u < t1) acc = fa(acc, v[u]);
-  }
-  return acc;
-}
-
-GBP_DEV void update_cameras(const DeviceGraph& g, const int shift, const uint32_t block, const int lower_only) {
-  __shared__ float s_ball[GBP_CAM_PER_BLOCK][GBP_CAMPART + 2];
+// Belief update of the cameras (prog_ub, ba/ba.cpp:104-139, camera half) + per-camera mean and rotation.
+// One WARP per camera, two cameras per block.  The per-warp-tile partial sums k_sweep left for the camera are one
+// contiguous run of cam_partial: lane 0 stages it with ONE bulk copy (completion on the warp's mbarrier) while the
+// lanes fetch the prior entries and the old mean, so a camera is two memory round trips deep (its tile range, then
+// everything else) before the arithmetic starts: the lanes add the partials to the prior in warp-tile order -- entry
+// `lane` and entry `lane + 32` of [eta 6 | Lambda 36] -- and lane 0 inverts the 6x6 belief (a serial LDL^T) and
+// forms the linearisation constants.
+#define GBP_CAM_PER_BLOCK 2
+#define GBP_CAM_STAGE_TILES 60  // warp-tiles of one camera a warp stages (60 x 176 B); longer runs finish through direct loads
+GBP_DEV void update_cameras(const DeviceGraph& g, float* s_buf, uint64_t* s_bars, const int shift, const uint32_t block, const int lower_only) {
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t c = block * GBP_CAM_PER_BLOCK + warp;
-  if (c >= g.C) return;  // whole warp
-  float* s_b = s_ball[warp];
+  if (warp >= GBP_CAM_PER_BLOCK || c >= g.C) return;  // whole warp
+  float* s_part = s_buf + warp * (GBP_CAM_STAGE_TILES * GBP_CAMPART_STRIDE);
+  uint64_t* bar = s_bars + warp;
   const uint32_t t0 = g.cam_wt_begin[c], t1 = g.cam_wt_begin[c + 1];
+  const uint32_t n_st = (t1 - t0 < GBP_CAM_STAGE_TILES) ? t1 - t0 : GBP_CAM_STAGE_TILES;
+  if (lane == 0 && n_st) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    fence_proxy_async();
+    const uint32_t bytes = n_st * (uint32_t)(GBP_CAMPART_STRIDE * sizeof(float));
+    mbar_expect_tx(bar, bytes);
+    bulk_load(s_part, g.cam_partial + (size_t)t0 * GBP_CAMPART_STRIDE, bytes, bar);
+  }
   // entries `lane` and `lane + 32` of [eta 6 | Lambda 36 row-major]; after a sweep that skipped the strict upper triangle of
   // the camera messages (k_sweep<.., UPPER = false>) the upper entries of the belief mirror the lower ones
+  float acc[2] = {0.f, 0.f};
+  bool skip[2] = {true, true};
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const uint32_t ent = lane + 32u * half;
     if (ent < GBP_CAMPART) {
       const uint32_t bi = ent >= 6 ? (ent - 6) / 6 : 0u, bj = ent >= 6 ? (ent - 6) % 6 : 0u;
-      const bool skip = lower_only && ent >= 6 && bi < bj;
-      if (!skip) s_b[ent] = cam_entry_sum(g, c, ent, t0, t1);
+      skip[half] = lower_only && ent >= 6 && bi < bj;
+      // the sum starts from +0 like a zero-initialised accumulator: 0 + prior (turns a -0 prior into +0)
+      if (!skip[half]) acc[half] = fa(0.0f, (ent < 6) ? g.cam_prior_eta[c * 6 + ent] : g.cam_prior_lam[c * 36 + (ent - 6)]);
     }
+  }
+  float prev6 = 0.f;  // lanes 0..5: the mean the last PrepMessageVertex pass used (Copy(mu, oldmu), ba/ba.cpp:898)
+  if (lane < 6) prev6 = shift ? g.cam_mean[c * 6 + lane] : g.cam_mean_prev[c * 6 + lane];
+  __syncwarp();
+  if (n_st) mbar_wait(bar, 0);
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const uint32_t ent = lane + 32u * half;
+    if (ent < GBP_CAMPART && !skip[half]) {
+      float a = acc[half];
+      for (uint32_t t = 0; t < n_st; ++t) a = fa(a, s_part[t * GBP_CAMPART_STRIDE + ent]);  // warp-tile order
+      for (uint32_t t = t0 + n_st; t < t1; ++t) a = fa(a, g.cam_partial[(size_t)t * GBP_CAMPART_STRIDE + ent]);
+      acc[half] = a;
+    }
+  }
+  // the 42 sums go through the (consumed) staging buffer: lane 0 needs all of them for the inverse, the mirrored entries
+  // come from their transposes
+  __syncwarp();
+  float* s_b = s_part;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const uint32_t ent = lane + 32u * half;
+    if (ent < GBP_CAMPART && !skip[half]) s_b[ent] = acc[half];
   }
   __syncwarp();
+  float* rec = reinterpret_cast<float*>(g.cam_rec + (size_t)c * 16);
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const uint32_t ent = lane + 32u * half;
     if (ent < GBP_CAMPART) {
       const uint32_t bi = ent >= 6 ? (ent - 6) / 6 : 0u, bj = ent >= 6 ? (ent - 6) % 6 : 0u;
-      const bool skip = lower_only && ent >= 6 && bi < bj;
-      const float v = skip ? s_b[6 + bj * 6 + bi] : s_b[ent];
+      const float v = skip[half] ? s_b[6 + bj * 6 + bi] : s_b[ent];
       if (ent < 6) g.cam_b_eta[c * 6 + ent] = v;
       else g.cam_b_lam[c * 36 + (ent - 6)] = v;
-      reinterpret_cast<float*>(g.cam_rec + (size_t)c * 16)[ent] = v;
+      rec[ent] = v;
     }
   }
+  float prev[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) prev[i] = __shfl_sync(0xffffffffu, prev6, i);
   if (lane == 0) {
     float eta[6], lamL[21], mean[6];
 #pragma unroll
@@ -1071,16 +985,14 @@ GBP_DEV void update_cameras(const DeviceGraph& g, const int shift, const uint32_
     const float w[3] = {mean[3], mean[4], mean[5]};
     float R[9], num[9], den;
     cam_lin_consts(w, R, num, den);
-    float* rec = reinterpret_cast<float*>(g.cam_rec + (size_t)c * 16);
     float acc6 = 0.f;  // the camera's six terms of dmu (gbp_codelets.cpp:268-277), hoisted out of the factors
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
-      const float prev = shift ? g.cam_mean[c * 6 + i] : g.cam_mean_prev[c * 6 + i];
-      g.cam_mean_prev[c * 6 + i] = prev;
+      g.cam_mean_prev[c * 6 + i] = prev[i];
       g.cam_mean[c * 6 + i] = mean[i];
       rec[42 + i] = mean[i];
-      rec[48 + i] = prev;
-      const float d = fs(prev, mean[i]);
+      rec[48 + i] = prev[i];
+      const float d = fs(prev[i], mean[i]);
       acc6 = fa(acc6, fm(d, d));
     }
     rec[54] = acc6;
@@ -1125,8 +1037,10 @@ GBP_DEV float4 lmk_prior_quad(const DeviceGraph& g, const uint32_t l, const uint
 }
 // The landmark's first lane collects the 12 sums, forms the mean and stores the belief record
 // [eta 3 | Lambda 9 | mean 3 | pad].  Must be reached by all 32 lanes of the warp.
+// prev_in (have_prev): the landmark's previous mean fetched by the caller ahead of time -- the old mean (shift) or
+// lmk_mean_prev -- so that the load does not sit at the end of the block's dependency chain
 GBP_DEV void lmk_finish_quads(const DeviceGraph& g, const uint32_t l, const uint32_t q, const float4 acc, const bool mine,
-                              const int shift) {
+                              const int shift, const bool have_prev = false, const float4 prev_in = make_float4(0.f, 0.f, 0.f, 0.f)) {
   float b[12];
   const uint32_t base = (threadIdx.x & 31) & ~3u;
 #pragma unroll
@@ -1146,11 +1060,11 @@ GBP_DEV void lmk_finish_quads(const DeviceGraph& g, const uint32_t l, const uint
     inf2mean3(eta, lam, mean);
     float4 prev;
     if (shift) {  // Copy(mu, oldmu), ba/ba.cpp:898
-      const float4 oldq = o[3];
+      const float4 oldq = have_prev ? prev_in : o[3];
       prev = make_float4(oldq.x, oldq.y, oldq.z, 0.f);
       g.lmk_mean_prev[l] = prev;
     } else {
-      prev = g.lmk_mean_prev[l];
+      prev = have_prev ? prev_in : g.lmk_mean_prev[l];
     }
     g.lmk_sq[l] = lmk_sq_terms(prev, mean);
     o[3] = make_float4(mean[0], mean[1], mean[2], 0.f);
@@ -1158,40 +1072,40 @@ GBP_DEV void lmk_finish_quads(const DeviceGraph& g, const uint32_t l, const uint
   if (q < 3) o[q] = acc;
 }
 
-// A block updates the landmarks [lmk_blk[b], lmk_blk[b+1]) -- at most 32, four lanes each.  Their messages are ONE
-// contiguous run of mlmk (landmark order), so a single cp.async.bulk brings the whole run into shared memory (one
-// elected thread, completion on an mbarrier) instead of every lane chasing its landmark's messages through
-// dependent 16-byte loads; the sums then read shared memory, strictly in slot order as before.  A landmark with more
-// than GBP_LMK_CAP messages has a block of its own and takes the direct path.
+// A block updates the landmarks [l0, l1) of its record lmk_blk[b] = {l0, l1, k0, k1} -- at most 32, four lanes each.
+// Their messages are ONE contiguous run [k0, k1) of mlmk (landmark order), so a single cp.async.bulk brings the whole
+// run into shared memory (one elected thread, completion on an mbarrier) instead of every lane chasing its landmark's
+// messages through dependent 16-byte loads; the sums then read shared memory, strictly in slot order as before.
+// Everything a lane needs besides (its message range, its prior quad, the landmark's previous mean) is requested in
+// the same breath, so a block is two memory round trips deep: the record, then all of the rest.  A landmark with
+// more than GBP_LMK_CAP messages has a block of its own and takes the direct path.
 #define GBP_LMK_CAP 448  // messages a block stages (21 KB)
-GBP_DEV void update_landmarks(const DeviceGraph& g, const int shift, const uint32_t block) {
-  __shared__ __align__(128) float4 s_msg[GBP_LMK_CAP * GBP_MLMK_QUADS];
-  __shared__ __align__(8) uint64_t s_bar;
-  const uint32_t l0 = g.lmk_blk[block], l1 = g.lmk_blk[block + 1];
-  const uint32_t k0 = g.lmk_ptr[l0], k1 = g.lmk_ptr[l1];
+GBP_DEV void update_landmarks(const DeviceGraph& g, float4* s_msg, uint64_t* s_bars, const int shift, const uint32_t block) {
+  uint64_t& s_bar = s_bars[0];
+  const uint4 rec = __ldg(g.lmk_blk + block);
+  const uint32_t l0 = rec.x, l1 = rec.y, k0 = rec.z, k1 = rec.w;
   const bool staged = k1 - k0 <= GBP_LMK_CAP && k1 > k0;
-  if (staged) {
-    if (threadIdx.x == 0) {
-      mbar_init(&s_bar, 1);
-      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-      fence_proxy_async();
-      const uint32_t bytes = (k1 - k0) * (uint32_t)(GBP_MLMK_QUADS * sizeof(float4));
-      mbar_expect_tx(&s_bar, bytes);
-      bulk_load(s_msg, g.mlmk + (size_t)k0 * GBP_MLMK_QUADS, bytes, &s_bar);
-    }
-    __syncthreads();  // the barrier is initialised before anyone waits on it
+  if (staged && threadIdx.x == 0) {
+    mbar_init(&s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    fence_proxy_async();
+    const uint32_t bytes = (k1 - k0) * (uint32_t)(GBP_MLMK_QUADS * sizeof(float4));
+    mbar_expect_tx(&s_bar, bytes);
+    bulk_load(s_msg, g.mlmk + (size_t)k0 * GBP_MLMK_QUADS, bytes, &s_bar);
   }
   const uint32_t l = l0 + (threadIdx.x >> 2), q = threadIdx.x & 3;
   // boundary landmarks of a multi-GPU shard are finished by the exchange blocks / kernels
   const bool mine = l < l1 && !(g.lmk_bslot && g.lmk_bslot[l] != 0xffffffffu);
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), prev = make_float4(0.f, 0.f, 0.f, 0.f);
   uint32_t a0 = 0, a1 = 0;
   if (mine && q < 3) {
     acc = lmk_prior_quad(g, l, q);
     a0 = g.lmk_ptr[l];
     a1 = g.lmk_ptr[l + 1];
   }
+  if (mine && q == 0) prev = shift ? g.lmk_b[(size_t)l * GBP_LMKB_QUADS + 3] : g.lmk_mean_prev[l];
   if (staged) {
+    __syncthreads();  // the barrier is initialised before anyone waits on it
     mbar_wait(&s_bar, 0);
     if (mine && q < 3) {
       const float4* m = s_msg + (size_t)(a0 - k0) * GBP_MLMK_QUADS + q;
@@ -1203,7 +1117,7 @@ GBP_DEV void update_landmarks(const DeviceGraph& g, const int shift, const uint3
   } else if (mine && q < 3) {
     acc = lmk_sum_quad(g, l, q, acc);
   }
-  lmk_finish_quads(g, l, q, acc, mine, shift);
+  lmk_finish_quads(g, l, q, acc, mine, shift, true, prev);
 }
 
 // ---- multi-GPU: partial sums fused with their exchange over peer memory ----------------
@@ -1287,13 +1201,19 @@ GBP_DEV void boundary_finish(const DeviceGraph& g, const int shift, const uint32
 //   camera blocks     -- few, long-running (a serial 6x6 inverse + Rodrigues per camera, one warp each), nearly idle:
 //                        they overlap with the bandwidth-bound landmark blocks that fill the chip
 //   landmark blocks   -- up to GBP_LMK_PER_BLOCK landmarks each, their messages staged by one bulk copy
-//   [multi-GPU, peer-to-peer] boundary_finish blocks -- last; every block they wait for was dispatched before them
+//   [multi-GPU, peer-to-peer] boundary_finish blocks -- BEFORE the landmark blocks: they wait for the peers' flags (every block
+//                        they wait for on this rank was dispatched before them) while the landmark blocks stream, instead of
+//                        forming a serial tail after them
 // The register budget (10 blocks per SM) fits all paths.  n_push == 0: no fused exchange.
 #ifndef GBP_UV_BLOCKS
-#define GBP_UV_BLOCKS 10
+#define GBP_UV_BLOCKS 9
 #endif
 __global__ void __launch_bounds__(GBP_TILE, GBP_UV_BLOCKS) k_update_vars(const DeviceGraph g, const int shift, const uint32_t n_push,
                                                                          const int lower_only) {
+  // one staging buffer per block, used by whichever role the block plays (landmark message run / camera partial runs)
+  __shared__ __align__(128) float4 s_stage[GBP_LMK_CAP * GBP_MLMK_QUADS];
+  __shared__ __align__(8) uint64_t s_bars[GBP_CAM_PER_BLOCK];
+  static_assert(GBP_CAM_PER_BLOCK * GBP_CAM_STAGE_TILES * GBP_CAMPART_STRIDE * 4 <= GBP_LMK_CAP * GBP_MLMK_QUADS * 16, "camera staging fits");
   const uint32_t nb_lmk = g.n_lmk_blocks;
   const uint32_t nb_cam = (g.C + GBP_CAM_PER_BLOCK - 1) / GBP_CAM_PER_BLOCK;
   if (shift && blockIdx.x == 0 && threadIdx.x == 0) {  // a sweep ended: open the next slot of the relinearisation ring
@@ -1309,11 +1229,11 @@ __global__ void __launch_bounds__(GBP_TILE, GBP_UV_BLOCKS) k_update_vars(const D
   if (b < n_push) {
     boundary_push(g, step, b, n_push);
   } else if ((b -= n_push) < nb_cam) {
-    if (!(lower_only & 2)) update_cameras(g, shift, b, lower_only & 1);   // bits 1, 2: timing diagnostics (GBP_UV_DEBUG)
-  } else if ((b -= nb_cam) < nb_lmk) {
-    if (!(lower_only & 4)) update_landmarks(g, shift, b);
-  } else {
-    boundary_finish(g, shift, step, b - nb_lmk);
+    if (!(lower_only & 2)) update_cameras(g, reinterpret_cast<float*>(s_stage), s_bars, shift, b, lower_only & 1);   // bits 1, 2: timing diagnostics (GBP_UV_DEBUG)
+  } else if ((b -= nb_cam) < n_push) {
+    boundary_finish(g, shift, step, b);
+  } else if ((b -= n_push) < nb_lmk) {
+    if (!(lower_only & 4)) update_landmarks(g, s_stage, s_bars, shift, b);
   }
   if (n_push) {
     __syncthreads();

@@ -63,6 +63,8 @@
 
 // ---- per-tile camera partial: 42 floats [eta 6 | Lambda 36 row-major] -----------
 #define GBP_CAMPART 42
+#define GBP_CAMPART_STRIDE 44  // floats between the partials of consecutive warp-tiles: 176 bytes, so that a camera's run of
+                               // partials is 16-byte aligned and sized (one bulk copy stages it in the belief update)
 
 #ifdef __CUDACC__
 #define GBP_HD __host__ __device__

@@ -276,8 +276,6 @@ GBP_DEV void reduce_cam_messages(float* red, const uint32_t lane, const float (&
 template <bool PREP, bool MSG, bool UPPER, class Refill>
 GBP_DEV void sweep_tile_tma(const DeviceGraph& g, float4* tb, const float* sc, float4* gat, float* red, const uint32_t wt, const uint2 ti,
                             const uint2 lid, const bool has_next, const uint2 lid_n, const uint32_t lane, Refill&& refill) {
-  // refill() also is the point where the camera ticket of the warp's PREVIOUS tile is taken: between the arithmetic of
-  // a tile and its stores, when the previous tile's stores have long drained (see camera_ticket)
   const size_t e = (size_t)wt * 32 + lane;
   const bool valid = lane < (ti.y & 0xffu);  // padding slots hold no factor (upper bits: warp-tiles of the camera)
   const float4 ra = tb[GBP_T_RECA * 32 + lane];
@@ -337,7 +335,7 @@ GBP_DEV void sweep_tile_tma(const DeviceGraph& g, float4* tb, const float* sc, f
 // results and reduces them through a scratch of its own; the latency of the refill is covered by the other warps of
 // the scheduler, of which there are three instead of two: 12 warps per SM at <= 168 registers.
 template <bool PREP, bool MSG, bool UPPER>
-__global__ void __launch_bounds__(GBP_TW * 32, 1) k_sweep_tma(const DeviceGraph g, const __grid_constant__ SweepMaps maps, const int fuse_cam) {
+__global__ void __launch_bounds__(GBP_TW * 32, 1) k_sweep_tma(const DeviceGraph g, const __grid_constant__ SweepMaps maps) {
   extern __shared__ __align__(1024) float4 smem4[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float4* wbase = smem4 + (size_t)warp * GBP_T_WARP_QUADS;
@@ -380,7 +378,6 @@ __global__ void __launch_bounds__(GBP_TW * 32, 1) k_sweep_tma(const DeviceGraph 
     }
   }
   uint32_t buf = 0, phase = 0;  // phase: bit b = parity the next wait on buffer b expects
-  uint32_t pend_cam = 0xffffffffu, pend_tiles = 0;  // camera ticket of the previous warp-tile, not yet taken
   for (;;) {
     const bool has_next = wt_n != 0xffffffffu;
     uint32_t wt_nn = 0xffffffffu;
@@ -410,10 +407,7 @@ __global__ void __launch_bounds__(GBP_TW * 32, 1) k_sweep_tma(const DeviceGraph 
     sweep_tile_tma<PREP, MSG, UPPER>(g, tb, reinterpret_cast<const float*>(sc4), gat,
                                      GBP_T_NBUF == 1 ? red_own : reinterpret_cast<float*>(tb), wt, ti, lid, has_next, lid_n, lane, [&]() {
                                        if (GBP_T_NBUF == 1 && has_next && lane == 0) tma_issue_tile(g, maps, tb, sc4, bars + buf, wt_n, ti_n.x);
-                                       if (pend_cam != 0xffffffffu) camera_ticket(g, pend_cam, pend_tiles, UPPER ? 0 : 1, lane);
                                      });
-    pend_cam = (MSG && fuse_cam) ? ti.x : 0xffffffffu;
-    pend_tiles = ti.y >> 8;
     if (GBP_T_NBUF == 2) {
       // the reduction wrote through this buffer; the copy engine rewrites it two tiles from now
       fence_proxy_async();
@@ -426,7 +420,6 @@ __global__ void __launch_bounds__(GBP_TW * 32, 1) k_sweep_tma(const DeviceGraph 
     if (GBP_T_NBUF == 2) buf ^= 1;
   }
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-  if (pend_cam != 0xffffffffu) camera_ticket(g, pend_cam, pend_tiles, UPPER ? 0 : 1, lane);  // of the warp's last tile
   if (g.tile_queue) tile_queue_done(g, lane, n_wt, n_static);
 }
 

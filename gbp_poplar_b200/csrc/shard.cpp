@@ -1,5 +1,5 @@
 // Host-side graph partitioning for the multi-GPU path (pure host code, no CUDA):
-// contiguous camera ranges balanced by edge count, the rank-local sub-problem and
+// contiguous camera ranges balanced by warp-tile count, the rank-local sub-problem and
 // the boundary-landmark lists of include/gbp_cuda.h.
 //
 // Replaces the reference's static placement of cameras / landmarks / factors on the
@@ -31,7 +31,7 @@ struct gbp_shard {
 
 namespace {
 
-// rank r owns the cameras whose cumulative edge count first reaches r/world of the total
+// rank r owns the cameras whose cumulative warp-tile count first reaches r/world of the total
 int camera_bounds(const gbp_problem* p, uint32_t world, std::vector<uint32_t>& bounds) {
   const uint32_t C = p->n_keyframes, L = p->n_points, E = p->n_edges;
   std::vector<uint64_t> deg(C, 0);
@@ -50,13 +50,18 @@ int camera_bounds(const gbp_problem* p, uint32_t world, std::vector<uint32_t>& b
     }
     deg[c] += e - e0;
   }
+  // Balanced by WARP-TILES (a camera's factors are padded to whole 32-slot tiles and a tile is the unit of work of the
+  // sweep kernel), not by edges: the ranks advance in lock step, so the job runs at the pace of the rank with the
+  // most tiles.
   bounds.assign(world + 1, C);
   bounds[0] = 0;
+  uint64_t total = 0;
+  for (uint32_t c = 0; c < C; ++c) total += (deg[c] + 31) / 32;
   uint64_t cum = 0;
   uint32_t r = 1;
   for (uint32_t c = 0; c < C && r < world; ++c) {
-    cum += deg[c];
-    while (r < world && cum * world >= (uint64_t)r * E && cum > 0) bounds[r++] = c + 1;
+    cum += (deg[c] + 31) / 32;
+    while (r < world && cum * world >= (uint64_t)r * total && cum > 0) bounds[r++] = c + 1;
   }
   for (uint32_t i = 1; i <= world; ++i) bounds[i] = std::max(bounds[i], bounds[i - 1]);
   bounds[world] = C;
