@@ -326,7 +326,7 @@ GBP_DEV void sweep_tile_tma(const DeviceGraph& g, float4* tb, const float* sc, f
   // the state record only changes in this kernel when prep ran here or the has-message flag toggled
   if (valid && (PREP ? (active || MSG) : flags != __float_as_uint(ra.z)))
     g.recA[e] = make_float4(damping, __int_as_float(dcount), __uint_as_float(flags), dmu);
-  if (MSG) reduce_cam_messages<UPPER>(red, lane, nc, ncu, g.cam_partial + (size_t)wt * GBP_CAMPART);
+  if (MSG) reduce_cam_messages<UPPER>(red, lane, nc, ncu, g.cam_partial + (size_t)wt * GBP_CAMPART_STRIDE);
 }
 
 // NBUF = 2: the next tile's rows are requested at the top of a tile into the other buffer (a whole tile of arithmetic
