@@ -27,7 +27,7 @@
 namespace gbp {
 
 #ifndef GBP_TW
-#define GBP_TW 8  // warps per block of k_sweep_tma (one block per SM)
+#define GBP_TW 10  // warps per block of k_sweep_tma (one block per SM); measured on config 4: 8 warps (two buffers) 129.6 us, 10 warps (one buffer) 123.9 us, 12 warps 131.5 us
 #endif
 #define GBP_T_ROWS 22        // TMA rows per buffer: potential 0..13 | camera-bound message 14..20 | edge state 21
 #define GBP_T_FAC 0
