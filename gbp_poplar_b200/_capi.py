@@ -164,6 +164,9 @@ CUDA_ONLY_API = {
     "gbp_cuda_group_eval": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32, C.POINTER(GbpIterStats)]),
     "gbp_cuda_group_free": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32]),
     "gbp_cuda_release_cached_memory": (C.c_int, []),
+    "gbp_cuda_test_inv6x6": (C.c_int, [c_f32p, c_f32p, C.c_int]),
+    "gbp_cuda_test_inv3x3": (C.c_int, [c_f32p, c_f32p, C.c_int]),
+    "gbp_cuda_test_project": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int]),
     "gbp_cuda_shard_info": (C.c_void_p, [C.c_void_p]),
     "gbp_cuda_exchange_mode": (C.c_int, [C.c_void_p]),
     # pure host: the rank-local sub-problem of a camera-range partition

@@ -20,6 +20,7 @@
 
 #include "../../include/gbp_cuda.h"
 #include "gbp_kernels.cuh"
+#include "gbp_setup.h"
 #include "nccl_dyn.h"
 
 
@@ -48,20 +49,10 @@ int dev_alloc(T** p, size_t n, bool zero = true) {
   return GBP_OK;
 }
 
-inline float u2f(uint32_t u) {
-  float f;
-  std::memcpy(&f, &u, 4);
-  return f;
-}
 inline uint32_t f2u(float f) {
   uint32_t u;
   std::memcpy(&u, &f, 4);
   return u;
-}
-inline float i2f(int32_t i) {
-  float f;
-  std::memcpy(&f, &i, 4);
-  return f;
 }
 inline int32_t f2i(float f) {
   int32_t i;
@@ -109,6 +100,9 @@ struct gbp_handle {
   int num_sms = 148;
   // staging for READ_PROG
   uint32_t* d_pos_of_orig = nullptr;
+  uint32_t* d_cam_ids = nullptr;   // [E] | [E] the caller's camera / landmark ids, kept for ensure_host_maps
+  uint32_t* d_lmk_ids = nullptr;
+  bool host_maps_ready = false;
   // device-side keyframe insertion (gbp_cuda_add_keyframe_device)
   uint32_t* d_lmk_first_cam = nullptr;      // [L] lowest camera index observing the landmark (0xffffffff: none)
   float* d_kf_scratch = nullptr;            // [4] see k_kf_pose
@@ -893,32 +887,156 @@ struct PhaseTimer {  // GBP_INIT_TIMING=1: wall time of the phases of gbp_cuda_i
   }
 };
 
-int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t* edge_global = nullptr) {
-  PhaseTimer pt;
-  const uint32_t C = p->n_keyframes, L = p->n_points, E = p->n_edges;
-  h->C = C; h->L = L; h->E = E;
-  h->cam_ids.assign(p->cam_ids, p->cam_ids + E);
-  h->lmk_ids.assign(p->lmk_ids, p->lmk_ids + E);
-  // degree counts and slots in O(E) (the reference's are O(V*E) / O(E^2): ba.cpp:267-279,514-521)
+// Host-side copies of the index maps (reference edge order <-> edge slots, message slots): only get_tensor / set_tensor
+// and the SLAM bookkeeping need them, so they are rebuilt from the device arrays the first time such a call is made --
+// gbp_cuda_init itself does no O(E) work on the host (the maps are built by the kernels of gbp_setup.cu).
+int ensure_host_maps(gbp_handle* h) {
+  if (h->host_maps_ready) return GBP_OK;
+  const uint32_t C = h->C, L = h->L, E = h->E;
+  h->cam_ids.resize(E);
+  h->lmk_ids.resize(E);
+  h->pos_of_orig.resize(E);
+  h->lmk_ptr.assign(L + 1, 0);
+  std::vector<uint32_t> first_cam(L, 0xffffffffu);
+  int rc = download(h->cam_ids.data(), h->d_cam_ids, E, h->stream);
+  if (!rc) rc = download(h->lmk_ids.data(), h->d_lmk_ids, E, h->stream);
+  if (!rc) rc = download(h->pos_of_orig.data(), h->d_pos_of_orig, E, h->stream);
+  if (!rc) rc = download(h->lmk_ptr.data(), h->g.lmk_ptr, (size_t)L + 1, h->stream);
+  if (!rc) rc = download(first_cam.data(), h->d_lmk_first_cam, L, h->stream);
+  if (rc) return rc;
+  GBP_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  // message slots = number of earlier edges of the same variable (ba/ba.cpp:267-279), in O(E)
   std::vector<uint32_t> deg_c(C, 0), deg_l(L, 0);
   h->slot_c.resize(E);
   h->slot_l.resize(E);
   for (uint32_t e = 0; e < E; ++e) {
-    if (h->cam_ids[e] >= C || h->lmk_ids[e] >= L) {
-      gbp_set_error("edge index out of range");
-      return GBP_ERR_ARG;
-    }
     h->slot_c[e] = deg_c[h->cam_ids[e]]++;
     h->slot_l[e] = deg_l[h->lmk_ids[e]]++;
   }
-  h->SK = (C ? *std::max_element(deg_c.begin(), deg_c.end()) : 0) + 1;
-  h->SL = (L ? *std::max_element(deg_l.begin(), deg_l.end()) : 0) + 1;
+  if (h->active_host.empty()) h->active_host.assign(E, 1u);
+  // SLAM bookkeeping: landmarks first observed by each camera, the factors of every camera
+  h->new_lmks_at_cam.assign(C, 0u);
+  for (uint32_t l = 0; l < L; ++l)
+    if (first_cam[l] != 0xffffffffu) h->new_lmks_at_cam[first_cam[l]]++;
+  h->cam_edge_ptr.assign(C + 1, 0u);
+  for (uint32_t c = 0; c < C; ++c) h->cam_edge_ptr[c + 1] = h->cam_edge_ptr[c] + deg_c[c];
+  h->cam_edge_ids.resize(E);
+  for (uint32_t e = 0; e < E; ++e) h->cam_edge_ids[h->cam_edge_ptr[h->cam_ids[e]] + h->slot_c[e]] = e;
+  h->host_maps_ready = true;
+  return GBP_OK;
+}
+
+// a block from the library's stream-ordered pool that is given back as soon as the stream has passed this point
+struct ScopedPoolBlock {
+  gbp_handle* h;
+  char* p = nullptr;
+  bool from_pool = false;
+  explicit ScopedPoolBlock(gbp_handle* hh) : h(hh) {}
+  int alloc(size_t bytes) {
+    if (cudaMemPool_t pool = private_pool(h->device)) {
+      if (cudaMallocFromPoolAsync((void**)&p, std::max<size_t>(bytes, 16), pool, h->stream) == cudaSuccess) {
+        from_pool = true;
+        return GBP_OK;
+      }
+      cudaGetLastError();
+    }
+    GBP_CUDA_TRY(cudaMalloc((void**)&p, std::max<size_t>(bytes, 16)));
+    return GBP_OK;
+  }
+  ~ScopedPoolBlock() {
+    if (!p) return;
+    if (from_pool) {
+      cudaFreeAsync(p, h->stream);
+    } else {
+      cudaStreamSynchronize(h->stream);
+      cudaFree(p);
+    }
+  }
+};
+
+int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t* edge_global = nullptr) {
+  PhaseTimer pt;
+  const uint32_t C = p->n_keyframes, L = p->n_points, E = p->n_edges;
+  h->C = C; h->L = L; h->E = E;
+  cudaStream_t s = h->stream;
+  int rc = GBP_OK;
+  // ---- stage A: raw arrays to the device, degrees + warp-tile count back (gbp_setup.cu)
+  // the two id arrays stay resident (the lazily built host maps come from them); everything else of this block is scratch
+  GBP_CUDA_TRY(cudaMalloc((void**)&h->d_cam_ids, std::max<size_t>((size_t)E * 8, 16)));
+  h->allocs.push_back((void*)h->d_cam_ids);
+  h->d_lmk_ids = h->d_cam_ids + E;
+  auto up256 = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t raw_bytes = up256((size_t)E * 8) + up256((size_t)E * 4) * 5 + up256((size_t)L * 12) + up256((size_t)L * 36);
+  ScopedPoolBlock tmp(h);
+  rc = tmp.alloc(raw_bytes + gbp::setup_temp_bytes(E, C, L));
+  if (rc) return rc;
+  char* cur = tmp.p;
+  auto take = [&](size_t bytes) {
+    char* q = cur;
+    cur += up256(bytes);
+    return q;
+  };
+  float* d_z = (float*)take((size_t)E * 8);
+  float* d_var = (float*)take((size_t)E * 4);
+  uint32_t* d_active = (uint32_t*)take((size_t)E * 4);
+  float* d_damping = (float*)take((size_t)E * 4);
+  int32_t* d_dcount = (int32_t*)take((size_t)E * 4);
+  uint32_t* d_eglobal = (uint32_t*)take((size_t)E * 4);
+  float* d_lpe = (float*)take((size_t)L * 12);
+  float* d_lpl = (float*)take((size_t)L * 36);
+  char* d_setup_tmp = cur;
+#define U_(dst, src, n) if (!rc) rc = upload(dst, src, (size_t)(n), s)
+  U_(h->d_cam_ids, p->cam_ids, E);
+  U_(h->d_lmk_ids, p->lmk_ids, E);
+  gbp::SetupInputs in{};
+  in.E = E; in.C = C; in.L = L;
+  in.cam_ids = h->d_cam_ids;
+  in.lmk_ids = h->d_lmk_ids;
+  gbp::SetupTemp st{};
+  if (!rc && gbp::setup_stage_a(s, in, d_setup_tmp, &st) != 0) {
+    gbp_set_error(std::string("device setup (stage A): ") + cudaGetErrorString(cudaGetLastError()));
+    rc = GBP_ERR_CUDA;
+  }
+  uint32_t info[4] = {0, 0, 0, 0};
+  if (!rc) rc = download(info, st.info, 4, s);
+  // the rest of the raw arrays travels while the host waits for those 16 bytes
+  U_(d_z, p->measurements, 2 * (size_t)E);
+  U_(d_var, p->meas_variances, E);
+  if (p->active_flag) U_(d_active, p->active_flag, E);
+  if (p->damping) U_(d_damping, p->damping, E);
+  if (p->damping_count) U_(d_dcount, p->damping_count, E);
+  if (edge_global) U_(d_eglobal, edge_global, E);
+  U_(d_lpe, p->lmk_priors_eta, 3 * (size_t)L);
+  U_(d_lpl, p->lmk_priors_lambda, 9 * (size_t)L);
+  if (rc) return rc;
+  // host work that overlaps the transfers: active-edge count, the streamed mu / oldmu (normally null or zero)
+  h->n_active = E;
+  if (p->active_flag) {
+    h->active_host.assign(p->active_flag, p->active_flag + E);
+    h->n_active = 0;
+    for (uint32_t e = 0; e < E; ++e) h->n_active += (p->active_flag[e] == 1u) ? 1u : 0u;
+  }
+  if (h->shard) h->n_active = gbp_shard_n_active_global(h->shard);
+  auto any_nonzero = [&](const float* a) {
+    if (!a) return false;
+    const size_t n = (size_t)9 * E;
+    for (size_t i = 0; i < n; ++i)
+      if (a[i] != 0.f) return true;
+    return false;
+  };
+  if (any_nonzero(p->mu)) h->mu_init.assign(p->mu, p->mu + (size_t)9 * E);
+  if (any_nonzero(p->oldmu)) h->oldmu_init.assign(p->oldmu, p->oldmu + (size_t)9 * E);
+  GBP_CUDA_TRY(cudaStreamSynchronize(s));
+  if (info[3]) {
+    gbp_set_error("edge index out of range");
+    return GBP_ERR_ARG;
+  }
+  h->SK = info[1] + 1;
+  h->SL = info[2] + 1;
   // warp-tiles: each camera's factors are padded to a multiple of 32 edge slots (one thread per
   // factor, one camera per warp); the slot count is rounded up to whole GBP_TILE blocks for the
   // helper kernels (trailing warp-tiles hold no factor)
-  std::vector<uint32_t> cam_wt_begin(C + 1, 0);
-  for (uint32_t c = 0; c < C; ++c) cam_wt_begin[c + 1] = cam_wt_begin[c] + (deg_c[c] + 31) / 32;
-  const uint64_t n_wt64 = ((uint64_t)cam_wt_begin[C] + GBP_WARPS - 1) / GBP_WARPS * GBP_WARPS;
+  const uint64_t n_wt64 = ((uint64_t)info[0] + GBP_WARPS - 1) / GBP_WARPS * GBP_WARPS;
   const uint64_t epad64 = n_wt64 * 32;
   if (epad64 >= 0xffffffffull) {
     gbp_set_error("problem too large for 32-bit edge slots");
@@ -928,99 +1046,19 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   h->n_tiles = h->E_pad / GBP_TILE;
   const uint32_t n_wt = h->E_pad / 32;
   const size_t EP = h->E_pad;
-  std::vector<uint2> wt_info(n_wt, make_uint2(0u, 0u));
-  for (uint32_t c = 0; c < C; ++c)
-    for (uint32_t t = cam_wt_begin[c]; t < cam_wt_begin[c + 1]; ++t)
-      wt_info[t] = make_uint2(c, std::min<uint32_t>(32u, deg_c[c] - (t - cam_wt_begin[c]) * 32) |
-                                     ((cam_wt_begin[c + 1] - cam_wt_begin[c]) << 8));  // .y: factors in the tile | warp-tiles of the camera << 8
-  h->pos_of_orig.resize(E);
-  std::vector<uint32_t> edge_orig(EP, 0xffffffffu);
-  for (uint32_t e = 0; e < E; ++e) {
-    const uint32_t pos = cam_wt_begin[h->cam_ids[e]] * 32 + h->slot_c[e];
-    h->pos_of_orig[e] = pos;
-    edge_orig[pos] = edge_global ? edge_global[e] : e;  // quirk Q7 compares GLOBAL edge ids
-  }
-  // landmark-bound messages live in LANDMARK order: message of edge e at lmk_ptr[l] + slot_l(e)
-  std::vector<uint32_t>& lmk_ptr = h->lmk_ptr;
-  lmk_ptr.assign(L + 1, 0);
-  for (uint32_t l = 0; l < L; ++l) lmk_ptr[l + 1] = lmk_ptr[l] + deg_l[l];
-  // belief-update blocks of the landmarks: consecutive landmarks, at most GBP_LMK_PER_BLOCK of them and at most
-  // GBP_LMK_CAP messages (what a block stages in shared memory); a landmark above the cap stands alone
-  std::vector<uint4> lmk_blk;
-  for (uint32_t l = 0, k = 0; l < L;) {
-    uint32_t n = 0, msgs = 0;
-    while (l + n < L && n < GBP_LMK_PER_BLOCK && (n == 0 || msgs + deg_l[l + n] <= GBP_LMK_CAP)) msgs += deg_l[l + n++];
-    lmk_blk.push_back(make_uint4(l, l + n, k, k + msgs));
-    l += n;
-    k += msgs;
-  }
-  std::vector<float> var(EP, 1.f);
-  pt.lap("index maps");
-  // per-edge state records (built by a few host threads: this is the largest part of gbp_cuda_init)
-  std::vector<float4> recA(EP), recB(EP);
-  h->active_host.assign(E, 1u);
-  if (p->active_flag) h->active_host.assign(p->active_flag, p->active_flag + E);
-  const unsigned n_thr = (E > (1u << 16)) ? std::max(1u, std::min(8u, std::thread::hardware_concurrency())) : 1u;
-  std::vector<uint32_t> act_count(n_thr, 0);
-  std::vector<uint8_t> nz_mu(n_thr, 0), nz_oldmu(n_thr, 0);
-  auto worker = [&](unsigned t) {
-    for (size_t s = (size_t)EP * t / n_thr, s1 = (size_t)EP * (t + 1) / n_thr; s < s1; ++s) {
-      recA[s] = make_float4(0.f, i2f(0), u2f(GBP_FLAG_PAD), 0.f);
-      recB[s] = make_float4(0.f, 0.f, u2f(0), u2f(0));
-    }
-  };
-  auto worker2 = [&](unsigned t) {
-    uint32_t n_act = 0;
-    const size_t e0 = (size_t)E * t / n_thr, e1 = (size_t)E * (t + 1) / n_thr;
-    for (size_t e = e0; e < e1; ++e) {
-      const size_t s = h->pos_of_orig[e];
-      const uint32_t act = (h->active_host[e] == 1u) ? 1u : 0u;
-      n_act += act;
-      recA[s] = make_float4(p->damping ? p->damping[e] : 0.f, i2f(p->damping_count ? p->damping_count[e] : -15),
-                            u2f(act ? GBP_FLAG_ACTIVE : 0u), 0.f);
-      recB[s] = make_float4(p->measurements[2 * e], p->measurements[2 * e + 1], u2f(h->lmk_ids[e]),
-                            u2f(lmk_ptr[h->lmk_ids[e]] + h->slot_l[e]));
-      var[s] = p->meas_variances[e];
-    }
-    act_count[t] = n_act;
-    auto any_nonzero = [&](const float* a) -> uint8_t {
-      if (!a) return 0;
-      for (size_t i = 9 * e0; i < 9 * e1; ++i)
-        if (a[i] != 0.f) return 1;
-      return 0;
-    };
-    nz_mu[t] = any_nonzero(p->mu);
-    nz_oldmu[t] = any_nonzero(p->oldmu);
-  };
-  auto run_parallel = [&](auto&& fn) {
-    std::vector<std::thread> th;
-    for (unsigned t = 1; t < n_thr; ++t) th.emplace_back(fn, t);
-    fn(0u);
-    for (std::thread& x : th) x.join();
-  };
-  run_parallel(worker);   // padding defaults first (edge slots of different threads interleave)
-  run_parallel(worker2);
-  h->n_active = 0;
-  for (unsigned t = 0; t < n_thr; ++t) h->n_active += act_count[t];
-  if (h->shard) h->n_active = gbp_shard_n_active_global(h->shard);
-  bool any_mu = false, any_oldmu = false;
-  for (unsigned t = 0; t < n_thr; ++t) { any_mu |= nz_mu[t] != 0; any_oldmu |= nz_oldmu[t] != 0; }
-  if (any_mu) h->mu_init.assign(p->mu, p->mu + (size_t)9 * E);
-  if (any_oldmu) h->oldmu_init.assign(p->oldmu, p->oldmu + (size_t)9 * E);
-
-  pt.lap("edge records (host)");
+  const uint32_t n_lmk_blocks = (L + GBP_LMK_PER_BLOCK - 1) / GBP_LMK_PER_BLOCK;
+  pt.lap("raw uploads + degrees (device)");
   // ---- device allocation (everything the reference relies on being zero IS zeroed, quirk Q4)
   DeviceGraph& g = h->g;
   std::memset(&g, 0, sizeof(g));
   g.C = C; g.L = L; g.E = E; g.E_pad = h->E_pad;
-  g.n_lmk_blocks = (uint32_t)lmk_blk.size();
+  g.n_lmk_blocks = n_lmk_blocks;
   g.K[0] = p->K[0]; g.K[1] = p->K[4]; g.K[2] = p->K[2]; g.K[3] = p->K[5];
   g.hp.maxeta_damping = o->maxeta_damping;
   g.hp.num_undamped_iters = o->num_undamped_iters;
   g.hp.dmu_threshold = o->dmu_threshold;
   g.hp.min_linear_iters = o->min_linear_iters;
   g.hp.Nstds = o->Nstds;
-  int rc = GBP_OK;
   // one device arena for all per-handle buffers: a single cudaMalloc + cudaMemset instead of ~40
   // (everything the reference relies on being zero IS zeroed, quirk Q4)
   std::vector<std::pair<void**, size_t>> arena;
@@ -1064,7 +1102,7 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   A_(g.lmk_scaling, L);
   A_(g.lmk_wflag, L);
   A_(g.lmk_ptr, L + 1);
-  A_(g.lmk_blk, lmk_blk.size());
+  A_(g.lmk_blk, n_lmk_blocks);
   A_(h->d_pos_of_orig, E);
   A_(h->d_lmk_first_cam, L);
   A_(h->d_kf_scratch, 4);
@@ -1166,52 +1204,41 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
     }
   }
   pt.lap("cudaMalloc + memset");
-  cudaStream_t s = h->stream;
-#define U_(dst, src, n) if (!rc) rc = upload(dst, src, (size_t)(n), s)
-  U_(g.recA, recA.data(), EP);
-  U_(g.recB, recB.data(), EP);
-  U_(g.edge_orig, edge_orig.data(), EP);
-  U_(g.wt_info, wt_info.data(), n_wt);
-  U_(g.cam_wt_begin, cam_wt_begin.data(), C + 1);
+  // ---- stage B: scans, stable sorts, edge records, warp-tile table, packed priors -- all into the arena
+  in.measurements = d_z;
+  in.meas_variances = d_var;
+  in.active_flag = p->active_flag ? d_active : nullptr;
+  in.damping = p->damping ? d_damping : nullptr;
+  in.damping_count = p->damping_count ? d_dcount : nullptr;
+  in.edge_global = edge_global ? d_eglobal : nullptr;
+  in.lmk_priors_eta = d_lpe;
+  in.lmk_priors_lambda = d_lpl;
+  gbp::SetupOutputs so{};
+  so.E_pad = h->E_pad; so.lmk_per_block = GBP_LMK_PER_BLOCK;
+  so.recA = g.recA; so.recB = g.recB; so.var = g.var; so.edge_orig = g.edge_orig; so.wt_info = g.wt_info;
+  so.cam_wt_begin = g.cam_wt_begin; so.lmk_ptr = g.lmk_ptr; so.pos_of_orig = h->d_pos_of_orig;
+  so.lmk_first_cam = h->d_lmk_first_cam; so.lmk_prior = g.lmk_prior; so.lmk_blk = g.lmk_blk;
+  if (gbp::setup_stage_b(s, in, st, so) != 0) {
+    gbp_set_error(std::string("device setup (stage B): ") + cudaGetErrorString(cudaGetLastError()));
+    return GBP_ERR_CUDA;
+  }
   U_(g.cam_prior_eta, p->cam_priors_eta, 6 * (size_t)C);
   U_(g.cam_prior_lam, p->cam_priors_lambda, 36 * (size_t)C);
   U_(g.cam_scaling, p->cam_scaling, C);
   U_(g.cam_wflag, p->cam_weaken_flag, C);
   U_(g.lmk_scaling, p->lmk_scaling, L);
   U_(g.lmk_wflag, p->lmk_weaken_flag, L);
-  U_(g.lmk_ptr, lmk_ptr.data(), L + 1);
-  U_(g.lmk_blk, lmk_blk.data(), lmk_blk.size());
-  U_(g.var, var.data(), EP);
-  U_(h->d_pos_of_orig, h->pos_of_orig.data(), E);
-  {
-    std::vector<uint32_t> first_cam(L, 0xffffffffu);
-    for (uint32_t e = 0; e < E; ++e) first_cam[h->lmk_ids[e]] = std::min(first_cam[h->lmk_ids[e]], h->cam_ids[e]);
-    h->new_lmks_at_cam.assign(C, 0u);
-    for (uint32_t l = 0; l < L; ++l)
-      if (first_cam[l] != 0xffffffffu) h->new_lmks_at_cam[first_cam[l]]++;
-    h->cam_edge_ptr.assign(C + 1, 0u);
-    for (uint32_t c = 0; c < C; ++c) h->cam_edge_ptr[c + 1] = h->cam_edge_ptr[c] + deg_c[c];
-    h->cam_edge_ids.resize(E);
-    for (uint32_t e = 0; e < E; ++e) h->cam_edge_ids[h->cam_edge_ptr[h->cam_ids[e]] + h->slot_c[e]] = e;
-    U_(h->d_lmk_first_cam, first_cam.data(), L);
-  }
   if (h->shard) {
     U_(g.lmk_bslot, lmk_bslot.data(), L);
     U_(g.bnd_local, gbp_shard_boundary_local(h->shard), g.n_bnd_local);
     U_(g.bnd_slot, gbp_shard_boundary_slot(h->shard), g.n_bnd_local);
   }
-  std::vector<float4> lpr((size_t)L * 3);
-  for (size_t l = 0; l < L; ++l) {
-    float* r = &lpr[l * 3].x;
-    for (int i = 0; i < 3; ++i) r[i] = p->lmk_priors_eta[l * 3 + i];
-    for (int i = 0; i < 9; ++i) r[3 + i] = p->lmk_priors_lambda[l * 9 + i];
-  }
-  U_(g.lmk_prior, lpr.data(), lpr.size());
   std::vector<float> oldmu_t;
-  if (!h->oldmu_init.empty()) {
+  if (!rc && !h->oldmu_init.empty()) {  // a streamed per-edge oldmu (rare): transposed into edge-slot order
+    rc = ensure_host_maps(h);
     if (!rc) rc = h_alloc(h, &g.oldmu_edge, 9 * EP);
     oldmu_t.assign(9 * EP, 0.f);
-    for (uint32_t e = 0; e < E; ++e)
+    for (uint32_t e = 0; e < E && !rc; ++e)
       for (int i = 0; i < 9; ++i) oldmu_t[(size_t)i * EP + h->pos_of_orig[e]] = h->oldmu_init[(size_t)9 * e + i];
     U_(g.oldmu_edge, oldmu_t.data(), oldmu_t.size());
   }
@@ -1849,6 +1876,8 @@ int gbp_cuda_add_keyframe_device(gbp_handle* h, uint32_t new_cam, uint32_t steps
     return GBP_ERR_ARG;
   }
   // host mirrors of the flags (get_tensor("active_flag"), the metric's active-edge count)
+  rc = ensure_host_maps(h);
+  if (rc) return rc;
   uint32_t newly = 0;
   for (uint32_t k = h->cam_edge_ptr[new_cam]; k < h->cam_edge_ptr[new_cam + 1]; ++k) {
     const uint32_t e = h->cam_edge_ids[k];
@@ -1918,6 +1947,7 @@ int gbp_cuda_get_tensor(gbp_handle* h, const char* name, void* dst, size_t nbyte
     return GBP_ERR_SIZE;
   }
   int rc = set_device(h);
+  if (!rc) rc = ensure_host_maps(h);
   if (rc) return rc;
   cudaStream_t s = h->stream;
   float* out = (float*)dst;
@@ -2082,6 +2112,7 @@ int gbp_cuda_set_tensor(gbp_handle* h, const char* name, const void* src, size_t
     return GBP_ERR_SIZE;
   }
   int rc = set_device(h);
+  if (!rc) rc = ensure_host_maps(h);
   if (rc) return rc;
   cudaStream_t s = h->stream;
   const float* in = (const float*)src;

@@ -219,12 +219,11 @@ GBP_DEV void cam_lin_consts(const float (&w)[3], float (&R)[9], float (&num)[9],
   den = fa(fa(fm(w[0], w[0]), fm(w[1], w[1])), fm(w[2], w[2]));
 }
 
-GBP_DEV uint32_t linearise_accumulate(const float z0, const float z1, const float var,
-                                      const float (&K)[4] /* fx fy cx cy */,
-                                      const float (&x_kf)[6], const float (&x_l)[3],
-                                      const float (&R)[9], const float (&num)[9], const float den,
-                                      const float Nstds, float (&eta)[9], float (&ll)[9],
-                                      float (&cl)[18], float (&cc)[36]) {
+// Projection of the landmark into the camera and its Jacobians at (x_kf, x_l): hfunc (bafuncs.cpp:83-103) and Jac
+// (bafuncs.cpp:107-213) given the camera-only constants of cam_lin_consts.  Jk: 2x6 row-major (d h / d pose),
+// Jl: 2x3 (d h / d landmark), (h0, h1) = h(x0).
+GBP_DEV void project_jac(const float (&K)[4] /* fx fy cx cy */, const float (&x_kf)[6], const float (&x_l)[3], const float (&R)[9],
+                         const float (&num)[9], const float den, float (&Jk)[12], float (&Jl)[6], float& h0, float& h1) {
   const float fx = K[0], fy = K[1], cx = K[2], cy = K[3];
   float y[3];
 #pragma unroll
@@ -235,7 +234,6 @@ GBP_DEV uint32_t linearise_accumulate(const float z0, const float z1, const floa
   const float jb = fd(-fm(fx, y[0]), fm(y[2], y[2]));
   const float jc = fd(fy, y[2]);
   const float jd = fd(-fm(fy, y[1]), fm(y[2], y[2]));
-  float Jk[12], Jl[6];
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     Jl[j] = fa(fm(ja, R[j]), fm(jb, R[6 + j]));
@@ -258,6 +256,18 @@ GBP_DEV uint32_t linearise_accumulate(const float z0, const float z1, const floa
     Jk[3 + j] = fa(fm(ja, dR[j]), fm(jb, dR[6 + j]));
     Jk[9 + j] = fa(fm(jc, dR[3 + j]), fm(jd, dR[6 + j]));
   }
+  h0 = fa(fm(fx, fd(y[0], y[2])), cx);
+  h1 = fa(fm(fy, fd(y[1], y[2])), cy);
+}
+
+GBP_DEV uint32_t linearise_accumulate(const float z0, const float z1, const float var,
+                                      const float (&K)[4] /* fx fy cx cy */,
+                                      const float (&x_kf)[6], const float (&x_l)[3],
+                                      const float (&R)[9], const float (&num)[9], const float den,
+                                      const float Nstds, float (&eta)[9], float (&ll)[9],
+                                      float (&cl)[18], float (&cc)[36]) {
+  float Jk[12], Jl[6], h0, h1;
+  project_jac(K, x_kf, x_l, R, num, den, Jk, Jl, h0, h1);
   // J^T J accumulated onto the blocks (matMul(.., true, false), matlib.cpp:60-68)
 #pragma unroll
   for (int i = 0; i < 6; ++i)
@@ -271,9 +281,6 @@ GBP_DEV uint32_t linearise_accumulate(const float z0, const float z1, const floa
   for (int i = 0; i < 6; ++i)
 #pragma unroll
     for (int j = 0; j < 3; ++j) cl[i * 3 + j] = fa(fa(cl[i * 3 + j], fm(Jk[i], Jl[j])), fm(Jk[6 + i], Jl[3 + j]));
-  // h(x0)
-  const float h0 = fa(fm(fx, fd(y[0], y[2])), cx);
-  const float h1 = fa(fm(fy, fd(y[1], y[2])), cy);
   // eb = J x0 + z - h ; eta += J^T eb
   float eb[2];
 #pragma unroll

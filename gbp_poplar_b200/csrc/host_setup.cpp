@@ -507,8 +507,6 @@ int gbp_setup_create(const gbp_bal* b, const gbp_cli_options* opt_in, int mode, 
   // damping state (ba/ba.cpp:580-584)
   s->damping.assign(E, 0.f);
   s->damping_count.assign(E, -o.iters_before_damping);
-  s->mu.assign((size_t)9 * E, 0.f);
-  s->oldmu.assign((size_t)9 * E, 0.f);
   if (mode == GBP_MODE_BA) {  // ba/ba.cpp:588-590
     s->active.assign(E, 1u);
     s->cam_wflag.assign(C, (uint32_t)o.steps);
@@ -546,8 +544,10 @@ int gbp_setup_create(const gbp_bal* b, const gbp_cli_options* opt_in, int mode, 
   p.active_flag = s->active.data();
   p.damping = s->damping.data();
   p.damping_count = s->damping_count.data();
-  p.mu = s->mu.data();
-  p.oldmu = s->oldmu.data();
+  // mu / oldmu: the reference streams zeros (ba/ba.cpp:582-583); NULL means exactly that (include/gbp_cuda.h) and
+  // spares the engine two 9E-float arrays it would only scan for a non-zero
+  p.mu = nullptr;
+  p.oldmu = nullptr;
   *out = s;
   return GBP_OK;
 }

@@ -163,7 +163,10 @@ class Setup:
             "damping_count": (E_, np.int32), "mu": (9 * E_, np.float32), "oldmu": (9 * E_, np.float32),
         }
         n, dt = sizes[field]
-        return _view(getattr(p, field), n, dt, self)
+        ptr = getattr(p, field)
+        if not ptr:  # an optional array the setup leaves NULL (mu / oldmu: the reference streams zeros)
+            return np.zeros(n, dtype=dt)
+        return _view(ptr, n, dt, self)
 
     @property
     def K(self):

@@ -246,6 +246,15 @@ int gbp_cuda_last_kernel_times(gbp_handle* h, float* ms_factor_kernel, float* ms
  * the roofline is reported per class (bench.py). */
 int gbp_cuda_last_sweep_times(gbp_handle* h, float* ms_factor_kernel, float* ms_variable_kernel, int capacity, int* n_sweeps);
 
+/* ---- device-side unit checks of the math helpers (test support) -------- */
+/* The __device__ helpers the sweep kernels inline, run on caller-supplied inputs (one thread per item): inv6x6 /
+ * inv3x3 (ba/matlib.cpp:143-222; A, out: [n][36] / [n][9] row-major) and so3exp + hfunc + Jac
+ * (ba/bafuncs.cpp:32-213; X [n][6] poses, P [n][3] points, K9 the 3x3 intrinsics; hx [n][2], Jkf [n][12] = 2x6,
+ * Jlmk [n][6] = 2x3).  tests/test_device_helpers.py pins them to the reference's own functions. */
+int gbp_cuda_test_inv6x6(const float* A, float* out, int n);
+int gbp_cuda_test_inv3x3(const float* A, float* out, int n);
+int gbp_cuda_test_project(const float* X, const float* P, const float* K9, float* hx, float* Jkf, float* Jlmk, int n);
+
 /* ---- asynchronous / resident use (bench, multi-GPU) ------------------- */
 /* Enqueue n sweeps on the handle's stream without synchronising. */
 int gbp_cuda_iterate_async(gbp_handle* h, int n_sweeps);

@@ -186,8 +186,14 @@ def test_shard_view_equals_owning_shard(world, sorted_by_camera):
         st = Setup(shuffled)
         p = st.problem
         keep += [shuffled, st]
-    mu = np.ctypeslib.as_array(p.mu, shape=(9 * E,))
-    mu[:] = np.random.default_rng(1).normal(size=9 * E).astype(np.float32)     # oldmu stays all zero
+    # the setup leaves mu / oldmu NULL (= the zeros the reference streams): give a copy of the problem a non-zero mu
+    import ctypes as C
+    from gbp_poplar_b200 import _capi
+    p = _capi.GbpProblem.from_buffer_copy(p)
+    mu = np.random.default_rng(1).normal(size=9 * E).astype(np.float32)
+    oldmu = np.zeros(9 * E, np.float32)                                         # oldmu stays all zero
+    p.mu, p.oldmu = mu.ctypes.data_as(_capi.c_f32p), oldmu.ctypes.data_as(_capi.c_f32p)
+    keep += [mu, oldmu]
     for r in range(world):
         own, view = Shard(p, world, r, owner=st), Shard(p, world, r, owner=st, view=True)
         a, b = _problem_arrays(own.problem), _problem_arrays(view.problem)
@@ -203,7 +209,6 @@ def test_shard_view_equals_owning_shard(world, sorted_by_camera):
         for f in ("edge_global", "lmk_global", "boundary_local", "boundary_slot", "cam_bounds"):
             assert np.array_equal(np.array(getattr(own, f)), np.array(getattr(view, f))), f
         assert (own.n_boundary_points, own.n_active_global) == (view.n_boundary_points, view.n_active_global)
-    mu[:] = 0
 
 
 def _plan(p, world, rank):
