@@ -1124,7 +1124,7 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   A_(h->d_pprior_cam_eta, 6 * (size_t)C);
   A_(h->d_pprior_cam_lam, 36 * (size_t)C);
   A_(h->d_pprior_lmk, 3 * (size_t)L);
-  std::vector<uint32_t> lmk_bslot;
+  std::vector<uint32_t> lmk_bslot, bnd_wait;
   if (h->shard) {
     const uint32_t nbl = gbp_shard_n_boundary_local(h->shard);
     g.n_bnd_local = nbl;
@@ -1136,6 +1136,8 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
     A_(g.lmk_bslot, L);
     A_(g.bnd_local, nbl);
     A_(g.bnd_slot, nbl);
+    A_(g.bnd_span, nbl);
+    A_(g.bnd_wait, h->world);
     A_(g.bnd_send, 3 * (size_t)g.n_bnd_global);
     reserve((void**)&g.bnd_recv, 3 * (size_t)g.n_bnd_global * h->world * sizeof(float4));
     A_(g.p2p_step, 2);
@@ -1232,6 +1234,13 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
     U_(g.lmk_bslot, lmk_bslot.data(), L);
     U_(g.bnd_local, gbp_shard_boundary_local(h->shard), g.n_bnd_local);
     U_(g.bnd_slot, gbp_shard_boundary_slot(h->shard), g.n_bnd_local);
+    U_(g.bnd_span, gbp_shard_boundary_span(h->shard), g.n_bnd_local);
+    bnd_wait.assign(h->world, 0u);
+    for (uint32_t k = 0; k < g.n_bnd_local; ++k) {
+      const uint32_t span = gbp_shard_boundary_span(h->shard)[k];
+      for (uint32_t r = span & 0xffffu; r <= (span >> 16) && r < h->world; ++r) bnd_wait[r] = 1u;
+    }
+    U_(g.bnd_wait, bnd_wait.data(), h->world);
   }
   std::vector<float> oldmu_t;
   if (!rc && !h->oldmu_init.empty()) {  // a streamed per-edge oldmu (rare): transposed into edge-slot order

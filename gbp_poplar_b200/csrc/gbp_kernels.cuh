@@ -67,6 +67,8 @@ struct DeviceGraph {
   uint32_t* lmk_bslot;    // [L] position in the global boundary list, 0xffffffff = interior
   uint32_t* bnd_local;    // [n_bnd_local] local landmark id
   uint32_t* bnd_slot;     // [n_bnd_local] position in the global boundary list
+  uint32_t* bnd_span;     // [n_bnd_local] first | last << 16 rank observing the landmark: the ranks its partials go to / come from
+  uint32_t* bnd_wait;     // [world] 1 = this rank receives partials from that rank (it waits for its flag), 0 = never
   float4* bnd_send;       // [n_bnd_global][3]  this rank's partial sums (zero where it has no factor)
   const float4* bnd_recv; // [world][n_bnd_global][3]  all ranks' partial sums
   uint32_t n_bnd_local, n_bnd_global, world, rank;
@@ -1148,7 +1150,9 @@ GBP_DEV void boundary_push(const DeviceGraph& g, const uint32_t step, const uint
   if (k < g.n_bnd_local && q < 3) {
     const float4 acc = lmk_sum_quad(g, g.bnd_local[k], q, make_float4(0.f, 0.f, 0.f, 0.f));
     const size_t off = ((size_t)((step & 1u) * g.world + g.rank) * g.n_bnd_global + g.bnd_slot[k]) * 3 + q;
-    for (uint32_t r = 0; r < g.world; ++r) g.peer_recv[r][off] = acc;
+    // only the ranks that observe this landmark (its rank span) ever read the partial
+    const uint32_t span = g.bnd_span[k];
+    for (uint32_t r = span & 0xffffu; r <= (span >> 16); ++r) g.peer_recv[r][off] = acc;
   }
   // threadFenceReduction pattern at system scope: every block fences its peer stores, the last
   // one to arrive publishes the step to all ranks
@@ -1168,7 +1172,7 @@ GBP_DEV void boundary_finish(const DeviceGraph& g, const int shift, const uint32
   __shared__ uint32_t s_timed_out;
   if (threadIdx.x == 0) s_timed_out = 0u;
   __syncthreads();
-  if (threadIdx.x < g.world) {
+  if (threadIdx.x < g.world && g.bnd_wait[threadIdx.x]) {  // only the ranks this rank shares a landmark with
     const long long t0 = clock64();
     while ((int32_t)(ld_acquire_sys(g.p2p_flag + threadIdx.x) - step) < 0) {
       if (clock64() - t0 > g.p2p_timeout) {  // a peer died or never made the matching call: do not hang the GPU
@@ -1188,7 +1192,10 @@ GBP_DEV void boundary_finish(const DeviceGraph& g, const int shift, const uint32
   if (mine && q < 3) {
     acc = lmk_prior_quad(g, l, q);
     const float4* base = g.p2p_recv + (size_t)(step & 1u) * g.world * g.n_bnd_global * 3 + (size_t)g.bnd_slot[k] * 3 + q;
-    for (uint32_t r = 0; r < g.world; ++r) {
+    // rank order over the landmark's rank span.  The ranks outside it contribute +0 to the sum over ALL ranks that
+    // defines the belief, and acc + (+0) == acc bit for bit (acc starts as 0 + prior, so it is never -0): skipped.
+    const uint32_t span = g.bnd_span[k];
+    for (uint32_t r = span & 0xffffu; r <= (span >> 16); ++r) {
       const float4 v = __ldcg(base + (size_t)r * g.n_bnd_global * 3);
       acc.x = fa(acc.x, v.x); acc.y = fa(acc.y, v.y); acc.z = fa(acc.z, v.z); acc.w = fa(acc.w, v.w);
     }

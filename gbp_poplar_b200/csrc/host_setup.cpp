@@ -541,9 +541,11 @@ int gbp_setup_create(const gbp_bal* b, const gbp_cli_options* opt_in, int mode, 
   p.lmk_scaling = s->lmk_scaling.data();
   p.cam_weaken_flag = s->cam_wflag.data();
   p.lmk_weaken_flag = s->lmk_wflag.data();
-  p.active_flag = s->active.data();
-  p.damping = s->damping.data();
-  p.damping_count = s->damping_count.data();
+  // optional arrays that hold nothing but the defaults of include/gbp_cuda.h are passed as NULL: the engine then
+  // neither copies nor uploads them (12 bytes per factor at init)
+  p.active_flag = (mode == GBP_MODE_BA) ? nullptr : s->active.data();         // BA: every factor active (ba/ba.cpp:588)
+  p.damping = nullptr;                                                          // all zero (ba/ba.cpp:580)
+  p.damping_count = (o.iters_before_damping == 15) ? nullptr : s->damping_count.data();  // -15 unless --iters_before_damping says otherwise
   // mu / oldmu: the reference streams zeros (ba/ba.cpp:582-583); NULL means exactly that (include/gbp_cuda.h) and
   // spares the engine two 9E-float arrays it would only scan for a non-zero
   p.mu = nullptr;

@@ -25,7 +25,7 @@ struct gbp_shard {
   std::vector<uint32_t> cam_ids, lmk_ids, active, cam_wflag, lmk_wflag;
   std::vector<float> z, var, cam_pe, cam_pl, lmk_pe, lmk_pl, cam_sc, lmk_sc, damping, mu, oldmu;
   std::vector<int32_t> dcount;
-  std::vector<uint32_t> lmk_global, edge_global, bnd_local, bnd_slot;
+  std::vector<uint32_t> lmk_global, edge_global, bnd_local, bnd_slot, bnd_span;
   uint32_t n_active_global = 0;
 };
 
@@ -174,6 +174,10 @@ static int shard_build_impl(const gbp_problem* p, uint32_t world, uint32_t rank,
     gbp_set_error("gbp_problem has a null required array");
     return GBP_ERR_ARG;
   }
+  if (world > 0xffffu) {
+    gbp_set_error("too many ranks");
+    return GBP_ERR_ARG;
+  }
   gbp_shard* s = new gbp_shard();
   const bool timing = std::getenv("GBP_INIT_TIMING") != nullptr;
   auto t_last = std::chrono::steady_clock::now();
@@ -218,6 +222,7 @@ static int shard_build_impl(const gbp_problem* p, uint32_t world, uint32_t rank,
       if (boundary) {
         s->bnd_local.push_back(lmk_local[l]);
         s->bnd_slot.push_back(n_boundary);
+        s->bnd_span.push_back(lo[l] | (hi[l] << 16));  // first | last rank observing it: every contributor lies in between
       }
     }
     if (boundary) n_boundary++;
@@ -313,6 +318,7 @@ const uint32_t* gbp_shard_edge_global(const gbp_shard* s) { return s ? s->edge_g
 uint32_t gbp_shard_n_boundary_local(const gbp_shard* s) { return s ? (uint32_t)s->bnd_local.size() : 0; }
 const uint32_t* gbp_shard_boundary_local(const gbp_shard* s) { return s ? s->bnd_local.data() : nullptr; }
 const uint32_t* gbp_shard_boundary_slot(const gbp_shard* s) { return s ? s->bnd_slot.data() : nullptr; }
+const uint32_t* gbp_shard_boundary_span(const gbp_shard* s) { return s ? s->bnd_span.data() : nullptr; }
 uint32_t gbp_shard_n_active_global(const gbp_shard* s) { return s ? s->n_active_global : 0; }
 const uint32_t* gbp_shard_cam_bounds(const gbp_shard* s) { return s ? s->cam_bounds.data() : nullptr; }
 

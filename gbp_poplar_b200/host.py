@@ -164,8 +164,9 @@ class Setup:
         }
         n, dt = sizes[field]
         ptr = getattr(p, field)
-        if not ptr:  # an optional array the setup leaves NULL (mu / oldmu: the reference streams zeros)
-            return np.zeros(n, dtype=dt)
+        if not ptr:  # an optional array the setup leaves NULL because it only holds the default (include/gbp_cuda.h)
+            default = {"active_flag": 1, "damping_count": -15}.get(field, 0)
+            return np.full(n, default, dtype=dt)
         return _view(ptr, n, dt, self)
 
     @property
@@ -251,6 +252,11 @@ class Shard:
     @property
     def boundary_slot(self):
         return _view(self._lib.gbp_shard_boundary_slot(self._h), self.n_boundary_local, np.uint32, self)
+
+    @property
+    def boundary_span(self):
+        """[n_boundary_local] first rank | last rank << 16 observing each boundary landmark."""
+        return _view(self._lib.gbp_shard_boundary_span(self._h), self.n_boundary_local, np.uint32, self)
 
     @property
     def cam_bounds(self):

@@ -299,6 +299,9 @@ const uint32_t* gbp_shard_edge_global(const gbp_shard* s);   /* [n_local_edges] 
 uint32_t gbp_shard_n_boundary_local(const gbp_shard* s);
 const uint32_t* gbp_shard_boundary_local(const gbp_shard* s);
 const uint32_t* gbp_shard_boundary_slot(const gbp_shard* s);
+/* [n_boundary_local] first rank | last rank << 16 observing the landmark: all ranks that contribute a partial sum to
+ * it lie in that span (camera ranges are contiguous), so the exchange only involves those. */
+const uint32_t* gbp_shard_boundary_span(const gbp_shard* s);
 /* Number of active edges of the GLOBAL problem (quirk Q7: the metric covers global edges [0, n_active)). */
 uint32_t gbp_shard_n_active_global(const gbp_shard* s);
 /* camera-range bounds of all ranks: [world+1] */

@@ -141,12 +141,17 @@ def test_shard_build_partitions_the_graph(world):
         assert np.array_equal(boundary_global[bs], lg[bl])
         assert set(lg[bl]) == set(boundary_global) & set(lg)
         assert s.n_active_global == E
+        # rank span of every boundary landmark: exactly [first observing rank, last observing rank]
+        span = np.array(s.boundary_span)
+        for g_l, sp in zip(lg[bl], span):
+            ranks = rank_of_cam[cam_ids[lmk_ids == g_l]]
+            assert (sp & 0xffff, sp >> 16) == (ranks.min(), ranks.max()) and sp & 0xffff <= r <= sp >> 16
         loads.append(eg.size)
         plan = _plan(p, world, r)
         assert (plan.cam_begin, plan.cam_end, plan.n_local_edges, plan.n_local_points, plan.n_boundary_points) == \
                (bounds[r], bounds[r + 1], eg.size, lg.size, boundary_global.size)
     if world > 1:
-        assert max(loads) < 1.35 * E / world   # balanced by edge count (camera granularity)
+        assert max(loads) < 1.35 * E / world   # balanced by warp-tile count (camera granularity)
 
 
 _FIELDS = [  # (member of gbp_problem, elements per local edge / camera / landmark, which count)
