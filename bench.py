@@ -416,6 +416,36 @@ def main():
     roofline["frac_moved_what"] = ("sum over launch classes of (launches x measured DRAM bytes per launch) / total k_sweep time / peak; "
                                    "per-class figures in `classes`" + ("" if ss else " (no ncu traffic on record for this shard size: layout model)"))
 
+    # ---- the opt-in contracted-FMA build of the sweep kernel (gbp_opts.fast_math), reported BESIDE the bit-faithful
+    # default above, never instead of it: same workload, same call pattern, same timing
+    fma = None
+    try:
+        opts_f = default_opts(device=local_rank, fast_math=1)
+        eng_f = GBPEngine.sharded(setup.problem, opts_f) if world > 1 else GBPEngine(setup.problem, opts_f)
+        ba_preroll(eng_f)
+        eng_f.iterate(args.warmup)
+        barrier()
+        eng_f.iterate(args.steps)
+        ms_f, _ = eng_f.last_timing()
+        barrier()
+        if world > 1:
+            t = torch.tensor([ms_f], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_f = float(t.item())
+        eng_f.set_profile(True)
+        eng_f.iterate(args.steps)
+        ms_factor_f, ms_var_f = eng_f.last_kernel_times()
+        eng_f.set_profile(False)
+        stats_f = eng_f.eval()
+        eng_f.close()
+        fma = {"value": E * args.steps / (ms_f / 1e3), "unit": "factor-updates/s", "ms_per_step": ms_f / args.steps,
+               "k_sweep_avg_us": ms_factor_f / args.steps * 1e3, "final_reproj_px": stats_f["reproj_mean"],
+               "final_reproj_px_bit_faithful": stats["reproj_mean"],
+               "what": "gbp_opts.fast_math = 1: multiply-adds contracted (one rounding instead of two); NOT bit-comparable with "
+                       "the reference, validated at the north-star tolerance (tests/test_fast_math_gpu.py)"}
+    except Exception as e:  # the default measurement never depends on the optional build
+        fma = {"error": repr(e)}
+
     # ---- e2e: a whole ba-style job through the C ABI with host buffers (rank-local problem)
     e2e = None
     eng.close()                                        # the e2e job below is a fresh one: nothing of the timed engine is kept
@@ -432,7 +462,9 @@ def main():
         t_loop = time.time() - t0 - t_init
         beliefs = eng2.get_beliefs()                   # READ_PROG: D2H beliefs + damping state
         wall = time.time() - t0
-        h2d = 4 * (2 * E_loc + 2 * E_loc + E_loc + 42 * C_loc + 12 * L_loc + C_loc + L_loc + C_loc + L_loc + 3 * E_loc)
+        # what gbp_cuda_init copies to the device: camera / landmark ids, measurements, variances (the optional per-edge
+        # arrays are NULL = defaults here), the priors, scalings and weaken flags of both variable kinds
+        h2d = 4 * (2 * E_loc + 2 * E_loc + E_loc + 42 * C_loc + 12 * L_loc + 2 * C_loc + 2 * L_loc)
         d2h = 24 * args.steps + sum(v.nbytes for v in beliefs.values())
         if world > 1:
             t = torch.tensor([float(h2d), float(d2h)], device="cuda")
@@ -471,7 +503,7 @@ def main():
                        "cache": "per-sweep working set ~0.65 GB per GPU >> 126 MB L2 (no flush needed)",
                        "preroll": f"{BA_PREROLL} sweeps of the ba.cpp schedule incl. prior weakening, untimed",
                        "init_s": init_s},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "fma_mode": fma,
             "parity_n": {"status": "ok" if all(parity_flags) and (parity_small or {}).get("status") in ("ok", "oracle not run (--no-cpu-baseline)")
                          else "MISMATCH",
                          "full_size": {"ranks_identical": parity_flags,

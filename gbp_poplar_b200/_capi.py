@@ -59,7 +59,8 @@ class GbpOpts(C.Structure):
         ("store_full_messages", C.c_int),
         ("exchange", C.c_int),
         ("relin_mode", C.c_int),
-        ("reserved", C.c_int * 4),
+        ("fast_math", C.c_int),
+        ("reserved", C.c_int * 3),
     ]
 
 

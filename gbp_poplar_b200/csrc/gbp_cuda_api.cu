@@ -21,6 +21,7 @@
 #include "../../include/gbp_cuda.h"
 #include "gbp_kernels.cuh"
 #include "gbp_setup.h"
+#include "gbp_fast.h"
 #include "nccl_dyn.h"
 
 
@@ -162,6 +163,7 @@ struct gbp_handle {
   // TMA-staged sweep kernel (k_sweep_tma): descriptors of the two big quad-SoA arrays
   gbp::SweepMaps maps;
   int use_tma = 0;
+  int fast_math = 0;  // gbp_opts.fast_math: the contracted-FMA build of the sweep kernel (gbp_fast.cu)
 };
 
 // A single-process group of shard handles: the exchange blocks of all ranks live (and die) together, so that
@@ -403,7 +405,12 @@ int launch_sweep(gbp_handle* h, bool upper = true) {
     const uint32_t grid = std::min<uint32_t>((uint32_t)h->num_sms, n_wt);
     const bool full = upper || !MSG || h->g.mcam_up;
     if constexpr (MSG) {
-      if (h->use_tma) {
+      if (h->use_tma && h->fast_math) {
+        if (gbp_fast_launch_sweep(&h->g, &h->maps, PREP ? 1 : 0, full ? 1 : 0, grid, h->stream) != 0) {
+          gbp_set_error(std::string("fast-math sweep launch: ") + cudaGetErrorString(cudaGetLastError()));
+          return GBP_ERR_CUDA;
+        }
+      } else if (h->use_tma) {
         if (full) gbp::k_sweep_tma<PREP, true, true><<<grid, GBP_TW * 32, GBP_T_SMEM, h->stream>>>(h->g, h->maps);
         else gbp::k_sweep_tma<PREP, true, false><<<grid, GBP_TW * 32, GBP_T_SMEM, h->stream>>>(h->g, h->maps);
       } else if (full) {  // GBP_SWEEP=cpasync: the round-1 kernel (per-lane cp.async staging, static tile order), kept as the reference
@@ -844,6 +851,10 @@ int setup_tma(gbp_handle* h) {
     }
     return GBP_OK;
   };
+  if (h->fast_math && gbp_fast_graph_bytes() != sizeof(DeviceGraph)) {
+    gbp_set_error("fast-math build out of sync with the default build (DeviceGraph layout)");
+    return GBP_ERR_CUDA;
+  }
   int rc = make(&h->maps.fac, h->g.fac, GBP_FAC_QUADS);
   if (!rc) rc = make(&h->maps.mcam, h->g.mcam, GBP_MCAM_QUADS);
   if (rc) return rc;
@@ -1417,6 +1428,7 @@ int gbp_cuda_init(const gbp_problem* p, const gbp_opts* o_in, gbp_handle** out) 
   gbp_handle* h = new gbp_handle();
   h->device = o.device;
   h->use_graph = o.use_cuda_graph;
+  h->fast_math = o.fast_math ? 1 : 0;
   if (const char* env = std::getenv("GBP_SKIP_UPPER")) h->skip_upper = std::atoi(env) != 0;
   h->relin_mode = o.relin_mode;
   h->two_pass = (o.relin_mode == 2) ? 1 : 0;
@@ -2321,6 +2333,7 @@ int gbp_cuda_init_shard(const gbp_problem* p, const gbp_opts* o_in, uint32_t wor
   gbp_handle* h = new gbp_handle();
   h->device = o.device;
   h->use_graph = o.use_cuda_graph;
+  h->fast_math = o.fast_math ? 1 : 0;
   if (const char* env = std::getenv("GBP_SKIP_UPPER")) h->skip_upper = std::atoi(env) != 0;
   h->relin_mode = o.relin_mode;
   h->two_pass = (o.relin_mode == 2) ? 1 : 0;
@@ -2438,6 +2451,7 @@ int gbp_cuda_init_group(const gbp_problem* p, const gbp_opts* o_in, uint32_t wor
     out[r] = h;
     h->device = dev[r];
     h->use_graph = o.use_cuda_graph;
+    h->fast_math = o.fast_math ? 1 : 0;
     if (const char* env = std::getenv("GBP_SKIP_UPPER")) h->skip_upper = std::atoi(env) != 0;
     h->relin_mode = o.relin_mode;
     h->two_pass = (o.relin_mode == 2) ? 1 : 0;

@@ -24,10 +24,18 @@ namespace gbp {
 
 #define GBP_DEV __device__ __forceinline__
 
+#ifndef GBP_FAST_MATH
 GBP_DEV float fm(float a, float b) { return __fmul_rn(a, b); }
 GBP_DEV float fa(float a, float b) { return __fadd_rn(a, b); }
 GBP_DEV float fs(float a, float b) { return __fsub_rn(a, b); }
 GBP_DEV float fd(float a, float b) { return __fdiv_rn(a, b); }
+#else
+// gbp_fast.cu (opt-in, gbp_opts.fast_math): plain operators, which nvcc may contract into FMAs; the division stays IEEE
+GBP_DEV float fm(float a, float b) { return a * b; }
+GBP_DEV float fa(float a, float b) { return a + b; }
+GBP_DEV float fs(float a, float b) { return a - b; }
+GBP_DEV float fd(float a, float b) { return __fdiv_rn(a, b); }
+#endif
 
 // index of (i,j), i>=j, in a row-major packed lower triangle
 __host__ __device__ constexpr int lt(int i, int j) { return i * (i + 1) / 2 + j; }

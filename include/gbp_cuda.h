@@ -93,7 +93,13 @@ typedef struct gbp_opts {
                                  1 = one fused kernel; 2 = state-machine pass + compacted relinearisation +
                                  message-only kernel; 0 (default) = chosen from the pattern of the last sweeps
                                  (fused while relinearisations come in lock step, two-pass once they are spread) */
-  int reserved[4];
+  int fast_math;              /* 0 (default): every fp32 operation of the sweep is the reference's, in its order, never
+                                 contracted -- results are bit-identical to the reference's codelets.
+                                 1: the sweep kernel built with contracted multiply-adds (one rounding instead of two
+                                 per a*b+c; ~25 % fewer instructions).  NOT bit-comparable: GBP amplifies the rounding
+                                 difference over the sweeps; validated at the north-star tolerance (one sweep <= 1e-4
+                                 per block, plateau reprojection error within 1 %).  Single-GPU and sharded handles. */
+  int reserved[3];
 } gbp_opts;
 
 /* Per-sweep metrics = what the reference's host computes after READ_PROG
