@@ -880,7 +880,7 @@ void preload_kernels() {
   preload(gbp::k_sweep_tma<true, true, true>); preload(gbp::k_sweep_tma<true, true, false>);
   preload(gbp::k_sweep_tma<false, true, true>); preload(gbp::k_sweep_tma<false, true, false>);
   preload(gbp::k_prep_pass); preload(gbp::k_relin_list); preload(gbp::k_cam_partials); preload(gbp::k_update_vars);
-  preload(gbp::k_boundary_partial); preload(gbp::k_boundary_finish); preload(gbp::k_relinearise_all); preload(gbp::k_weaken);
+  preload(gbp::k_boundary_partial); preload(gbp::k_boundary_records); preload(gbp::k_boundary_finish); preload(gbp::k_relinearise_all); preload(gbp::k_weaken);
   preload(gbp::k_kf_pose); preload(gbp::k_kf_apply); preload(gbp::k_metric_prep); preload(gbp::k_metric);
   preload(gbp::k_metric_finish); preload(gbp::k_metric_combine); preload(gbp::k_export_edges);
   preload(gbp::k_export_lmk_beliefs); preload(gbp::k_import_edges); preload(gbp::k_means_from_beliefs);
@@ -1148,6 +1148,7 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
     A_(g.bnd_local, nbl);
     A_(g.bnd_slot, nbl);
     A_(g.bnd_span, nbl);
+    A_(g.bnd_rec, nbl);
     A_(g.bnd_wait, h->world);
     A_(g.bnd_send, 3 * (size_t)g.n_bnd_global);
     reserve((void**)&g.bnd_recv, 3 * (size_t)g.n_bnd_global * h->world * sizeof(float4));
@@ -1252,6 +1253,10 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
       for (uint32_t r = span & 0xffffu; r <= (span >> 16) && r < h->world; ++r) bnd_wait[r] = 1u;
     }
     U_(g.bnd_wait, bnd_wait.data(), h->world);
+    if (!rc && g.n_bnd_local) {
+      gbp::k_boundary_records<<<(g.n_bnd_local + 255) / 256, 256, 0, s>>>(g);  // after stage B: it reads lmk_ptr
+      h->kernels_launched++;
+    }
   }
   std::vector<float> oldmu_t;
   if (!rc && !h->oldmu_init.empty()) {  // a streamed per-edge oldmu (rare): transposed into edge-slot order

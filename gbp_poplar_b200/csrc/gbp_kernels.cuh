@@ -68,6 +68,7 @@ struct DeviceGraph {
   uint32_t* bnd_local;    // [n_bnd_local] local landmark id
   uint32_t* bnd_slot;     // [n_bnd_local] position in the global boundary list
   uint32_t* bnd_span;     // [n_bnd_local] first | last << 16 rank observing the landmark: the ranks its partials go to / come from
+  uint4* bnd_rec;         // [n_bnd_local] {local landmark, its first message, one past its last, position in the global boundary list}
   uint32_t* bnd_wait;     // [world] 1 = this rank receives partials from that rank (it waits for its flag), 0 = never
   float4* bnd_send;       // [n_bnd_global][3]  this rank's partial sums (zero where it has no factor)
   const float4* bnd_recv; // [world][n_bnd_global][3]  all ranks' partial sums
@@ -1148,10 +1149,24 @@ GBP_DEV uint32_t ld_acquire_sys(const uint32_t* p) {
 GBP_DEV void boundary_push(const DeviceGraph& g, const uint32_t step, const uint32_t block, const uint32_t n_blocks) {
   const uint32_t k = block * GBP_LMK_PER_BLOCK + (threadIdx.x >> 2), q = threadIdx.x & 3;
   if (k < g.n_bnd_local && q < 3) {
-    const float4 acc = lmk_sum_quad(g, g.bnd_local[k], q, make_float4(0.f, 0.f, 0.f, 0.f));
-    const size_t off = ((size_t)((step & 1u) * g.world + g.rank) * g.n_bnd_global + g.bnd_slot[k]) * 3 + q;
+    // one record per boundary landmark (k_boundary_records): the partial sum is two memory round trips deep --
+    // the record, then up to eight of its messages at a time, added strictly in slot order from +0
+    const uint4 rec = __ldg(g.bnd_rec + k);
+    const uint32_t span = __ldg(g.bnd_span + k);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (uint32_t m = rec.y; m < rec.z; m += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (m + u < rec.z) v[u] = g.mlmk[(size_t)(m + u) * GBP_MLMK_QUADS + q];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (m + u < rec.z) {
+          acc.x = fa(acc.x, v[u].x); acc.y = fa(acc.y, v[u].y); acc.z = fa(acc.z, v[u].z); acc.w = fa(acc.w, v[u].w);
+        }
+    }
+    const size_t off = ((size_t)((step & 1u) * g.world + g.rank) * g.n_bnd_global + rec.w) * 3 + q;
     // only the ranks that observe this landmark (its rank span) ever read the partial
-    const uint32_t span = g.bnd_span[k];
     for (uint32_t r = span & 0xffffu; r <= (span >> 16); ++r) g.peer_recv[r][off] = acc;
   }
   // threadFenceReduction pattern at system scope: every block fences its peer stores, the last
@@ -1171,6 +1186,18 @@ GBP_DEV void boundary_push(const DeviceGraph& g, const uint32_t step, const uint
 GBP_DEV void boundary_finish(const DeviceGraph& g, const int shift, const uint32_t step, const uint32_t block) {
   __shared__ uint32_t s_timed_out;
   if (threadIdx.x == 0) s_timed_out = 0u;
+  // everything that does not depend on the peers is fetched BEFORE the wait: the record, the prior, the previous mean
+  const uint32_t k = block * GBP_LMK_PER_BLOCK + (threadIdx.x >> 2), q = threadIdx.x & 3;
+  const bool mine = k < g.n_bnd_local;
+  uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+  uint32_t span = 0;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), prev = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (mine) {
+    rec = __ldg(g.bnd_rec + k);
+    span = __ldg(g.bnd_span + k);
+    if (q < 3) acc = lmk_prior_quad(g, rec.x, q);
+    if (q == 0) prev = shift ? g.lmk_b[(size_t)rec.x * GBP_LMKB_QUADS + 3] : g.lmk_mean_prev[rec.x];
+  }
   __syncthreads();
   if (threadIdx.x < g.world && g.bnd_wait[threadIdx.x]) {  // only the ranks this rank shares a landmark with
     const long long t0 = clock64();
@@ -1180,27 +1207,43 @@ GBP_DEV void boundary_finish(const DeviceGraph& g, const int shift, const uint32
         s_timed_out = 1u;
         break;
       }
-      __nanosleep(100);
+      __nanosleep(40);
     }
   }
   __syncthreads();
   if (s_timed_out) return;  // nothing is stored from a receive buffer that is not complete
-  const uint32_t k = block * GBP_LMK_PER_BLOCK + (threadIdx.x >> 2), q = threadIdx.x & 3;
-  const bool mine = k < g.n_bnd_local;
-  const uint32_t l = mine ? g.bnd_local[k] : 0u;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (mine && q < 3) {
-    acc = lmk_prior_quad(g, l, q);
-    const float4* base = g.p2p_recv + (size_t)(step & 1u) * g.world * g.n_bnd_global * 3 + (size_t)g.bnd_slot[k] * 3 + q;
+    const float4* base = g.p2p_recv + (size_t)(step & 1u) * g.world * g.n_bnd_global * 3 + (size_t)rec.w * 3 + q;
     // rank order over the landmark's rank span.  The ranks outside it contribute +0 to the sum over ALL ranks that
     // defines the belief, and acc + (+0) == acc bit for bit (acc starts as 0 + prior, so it is never -0): skipped.
-    const uint32_t span = g.bnd_span[k];
-    for (uint32_t r = span & 0xffffu; r <= (span >> 16); ++r) {
-      const float4 v = __ldcg(base + (size_t)r * g.n_bnd_global * 3);
-      acc.x = fa(acc.x, v.x); acc.y = fa(acc.y, v.y); acc.z = fa(acc.z, v.z); acc.w = fa(acc.w, v.w);
+    const uint32_t r0 = span & 0xffffu, r1 = span >> 16;
+    if (r1 - r0 < 4) {  // the usual case (two or three ranks): all partials in flight together
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (r0 + u <= r1) v[u] = __ldcg(base + (size_t)(r0 + u) * g.n_bnd_global * 3);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (r0 + u <= r1) {
+          acc.x = fa(acc.x, v[u].x); acc.y = fa(acc.y, v[u].y); acc.z = fa(acc.z, v[u].z); acc.w = fa(acc.w, v[u].w);
+        }
+    } else {
+      for (uint32_t r = r0; r <= r1; ++r) {
+        const float4 v = __ldcg(base + (size_t)r * g.n_bnd_global * 3);
+        acc.x = fa(acc.x, v.x); acc.y = fa(acc.y, v.y); acc.z = fa(acc.z, v.z); acc.w = fa(acc.w, v.w);
+      }
     }
   }
-  lmk_finish_quads(g, l, q, acc, mine, shift);
+  lmk_finish_quads(g, rec.x, q, acc, mine, shift, true, prev);
+}
+
+// {local landmark, first message, one past the last message, position in the global boundary list} of every boundary
+// landmark this rank touches (built once at init from the device-side lmk_ptr)
+__global__ void k_boundary_records(const DeviceGraph g) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= g.n_bnd_local) return;
+  const uint32_t l = g.bnd_local[k];
+  g.bnd_rec[k] = make_uint4(l, g.lmk_ptr[l], g.lmk_ptr[l + 1], g.bnd_slot[k]);
 }
 
 // prog_ub in one launch.  Block roles, in dispatch order:

@@ -358,6 +358,34 @@ def test_config4_full_size_properties():
     assert e1["n_active"] == bal.n_edges and e1["reproj_mean"] < 0.25 * e0["reproj_mean"]
 
 
+@pytest.mark.slow
+def test_config4_full_size_block_calls_bit_exact():
+    """Config 4 at full size in the call pattern that is TIMED (bench.py): 12 single sweeps of the ba.cpp schedule, then
+    block calls without per-sweep metrics (CUDA-graph replay, lower-only sweeps) over 51 more sweeps -- four of them
+    (18, 29, 40, 51) relinearise every factor in lock step, the power-of-two reciprocal shortcut included.  Every belief,
+    message, potential and damping state bit-identical to the reference's codelets (~10 s of CPU on the box)."""
+    bal = BALProblem.synthetic(1000, 100000, 10.5, seed=1234)
+    st = Setup(bal)
+    gpu = GBPEngine(st.problem)
+    ora = oracle_lib.OracleEngine(st.problem, kind=KIND)
+    ora.set_reduce_order(1)
+    common.run_ba(gpu, 12)
+    common.run_ba(ora, 12)
+    relins = 0
+    for n in (7, 1, 13, 30):
+        gpu.iterate(n)
+        for _ in range(n):
+            ora.iterate(1)
+            relins += ora.eval()["n_relins"] > bal.n_edges // 2
+    assert relins >= 3, relins                      # the block calls really crossed lock-step relinearisations
+    for t in ("cam_beliefs_eta", "cam_beliefs_lambda", "lmk_beliefs_eta", "lmk_beliefs_lambda", "cam_messages_eta",
+              "cam_messages_lambda", "lmk_messages_eta", "lmk_messages_lambda", "factor_potentials_eta",
+              "factor_potentials_lambda", "damping", "damping_count", "robust_flag"):
+        assert common.canon(t, gpu.get_tensor(t)).tobytes() == common.canon(t, ora.get_tensor(t)).tobytes(), t
+    a, b = gpu.eval(), ora.eval()
+    assert a["reproj_mean"] == pytest.approx(b["reproj_mean"], rel=1e-4) and a["n_robust"] == b["n_robust"]
+
+
 # ---- BASELINE.json configs 1-3 at their full horizons, against series frozen from the reference codelets
 # (tests/golden/make_golden.py, CUDA summation order); no oracle run is needed on the GPU box -------------
 def _golden_long():
