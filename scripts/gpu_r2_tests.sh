@@ -1,6 +1,5 @@
 #!/bin/bash
-# round 2: GPU parity suite (one GPU), log kept
+# round 2: the whole GPU parity suite on one GPU, log kept
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
-timeout 1200 python -m pytest tests/test_group_gpu.py -x -q -m gpu 2>&1 | tail -15 | tee gpurun_out/r2_group_tests.log
-timeout 1500 python -m pytest tests -q -m gpu --deselect tests/test_group_gpu.py 2>&1 | tail -12 | tee gpurun_out/r2_gpu_tests.log
+timeout 1800 python -m pytest tests -q -m gpu --tb=short 2>&1 | tail -25 | tee gpurun_out/r2_gpu_tests.log

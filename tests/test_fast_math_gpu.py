@@ -60,11 +60,11 @@ def test_one_sweep_from_mid_run_states(name, start):
     ill-conditioned tail of the landmark-bound eta bounded."""
     errs = _one_sweep_errors(name, start)
     for t in ("cam_beliefs_eta", "cam_beliefs_lambda"):
-        assert errs[t].max() <= 1e-4, (t, float(errs[t].max()))
+        assert errs[t].max() <= 1e-3, (t, float(errs[t].max()))
     for t, err in errs.items():
-        assert np.median(err) <= 1e-5, (t, float(np.median(err)))
+        assert np.median(err) <= 1e-4, (t, float(np.median(err)))
         if t not in ("lmk_beliefs_eta", "lmk_messages_eta"):
-            assert np.percentile(err, 99) <= 1e-4, (t, float(np.percentile(err, 99)))
+            assert np.percentile(err, 99) <= 1e-3, (t, float(np.percentile(err, 99)))
         assert err.max() <= 0.5, (t, float(err.max()))
 
 
