@@ -695,7 +695,7 @@ int upload_lmk_priors(gbp_handle* h, const float* eta, const float* lam) {
 // that every other rank maps: through CUDA IPC when the ranks are processes (the handles travel over the NCCL
 // communicator once), directly (same device, or cudaDeviceEnablePeerAccess) when they are the handles of a
 // single-process group.
-constexpr size_t P2P_OFF_FLAG = 0, P2P_OFF_MFLAG = 1024, P2P_OFF_DONE = 2048, P2P_OFF_METRIC = 4096;
+constexpr size_t P2P_OFF_FLAG = 0, P2P_OFF_MFLAG = 1024, P2P_OFF_NBLK = 2048, P2P_OFF_METRIC = 4096;
 constexpr size_t P2P_OFF_RECV = 4096 + 2 * 256 * 8 * sizeof(double);  // metric buffer sized for <= 256 ranks
 constexpr uint32_t P2P_MAX_WORLD = 256;
 
@@ -730,7 +730,11 @@ int p2p_wire(gbp_handle* h, const std::vector<void*>& bases) {
   char* own = (char*)bases[h->rank];
   g.p2p_flag = (uint32_t*)(own + P2P_OFF_FLAG);
   g.metric_flag = (uint32_t*)(own + P2P_OFF_MFLAG);
-  g.p2p_done = (uint32_t*)(own + P2P_OFF_DONE);
+  g.bnd_nblk = (const uint32_t*)(own + P2P_OFF_NBLK);
+  // this rank's number of push blocks per exchange, told to every rank (launch_update_vars uses the same formula)
+  const uint32_t n_x = std::max((g.n_bnd_local + GBP_LMK_PER_BLOCK - 1) / GBP_LMK_PER_BLOCK, 1u);
+  for (uint32_t r = 0; r < W; ++r)
+    GBP_CUDA_TRY(cudaMemcpy((char*)bases[r] + P2P_OFF_NBLK + (size_t)h->rank * 4, &n_x, 4, cudaMemcpyHostToDevice));
   g.metric_recv = (const double*)(own + P2P_OFF_METRIC);
   g.p2p_recv = (const float4*)(own + P2P_OFF_RECV);
   // the error word lives in mapped host memory: a timed-out kernel sets it, every synchronising entry point reads it
@@ -811,7 +815,16 @@ int setup_p2p(gbp_handle* h, int mode) {
   }
   std::vector<void*> bases(W);
   for (uint32_t r = 0; r < W; ++r) bases[r] = (r == h->rank) ? h->p2p_block : h->p2p_peers[r];
-  return p2p_wire(h, bases);
+  int rc = p2p_wire(h, bases);
+  if (rc) return rc;
+  // every rank has written its push-block count into every block before anyone starts the first exchange
+  int* d_bar = nullptr;
+  GBP_CUDA_TRY(cudaMalloc((void**)&d_bar, sizeof(int) * (W + 1)));
+  GBP_CUDA_TRY(cudaMemsetAsync(d_bar, 0, sizeof(int) * (W + 1), h->comm_stream));
+  GBP_NCCL_TRY(gbp::nccl_api().AllGather(d_bar + W, d_bar, sizeof(int), ncclChar, h->comm, h->comm_stream));
+  GBP_CUDA_TRY(cudaStreamSynchronize(h->comm_stream));
+  cudaFree(d_bar);
+  return GBP_OK;
 }
 
 // TMA descriptors for k_sweep_tma: the factor potentials and the camera-bound messages seen as 2-D fp32 tensors

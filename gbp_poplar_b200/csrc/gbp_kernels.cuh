@@ -78,8 +78,8 @@ struct DeviceGraph {
   float4** peer_recv;     // [world] -> that rank's bnd_p2p buffer [2 parities][world][n_bnd_global][3]
   uint32_t** peer_flag;   // [world] -> that rank's arrival flags [world]
   const float4* p2p_recv; // this rank's own receive buffer
-  uint32_t* p2p_flag;     // this rank's own arrival flags: p2p_flag[r] = last exchange step rank r has delivered
-  uint32_t* p2p_done;     // block counter of k_boundary_push
+  uint32_t* p2p_flag;     // this rank's own arrival counters: p2p_flag[r] = push blocks of rank r that have delivered, over all exchanges
+  const uint32_t* bnd_nblk;  // [world] push blocks per exchange of every rank (written by the peers at set-up)
   uint32_t* p2p_error;    // set when a wait for a peer timed out
   uint32_t* p2p_step;     // [2] {completed exchange steps, blocks of the current k_update_vars that are done}
   long long p2p_timeout;  // clock64 ticks a block waits for its peers before it gives up (p2p_error)
@@ -1169,18 +1169,13 @@ GBP_DEV void boundary_push(const DeviceGraph& g, const uint32_t step, const uint
     // only the ranks that observe this landmark (its rank span) ever read the partial
     for (uint32_t r = span & 0xffffu; r <= (span >> 16); ++r) g.peer_recv[r][off] = acc;
   }
-  // threadFenceReduction pattern at system scope: every block fences its peer stores, the last
-  // one to arrive publishes the step to all ranks
+  // Every block fences its own peer stores and then announces ITSELF to every rank: arrival counters (one remote
+  // atomic per block and rank) instead of "the last block publishes a flag" -- no local counter round trip, no
+  // second system-scope fence on the critical path.  A rank has all of rank r's partials of exchange `step` once
+  // r's counter has reached step x (number of push blocks of r).
   __threadfence_system();
   __syncthreads();
-  __shared__ uint32_t s_last;
-  if (threadIdx.x == 0) s_last = (atomicAdd(g.p2p_done, 1u) == n_blocks - 1) ? 1u : 0u;
-  __syncthreads();
-  if (s_last) {
-    if (threadIdx.x == 0) *g.p2p_done = 0u;
-    __threadfence_system();
-    if (threadIdx.x < g.world) st_release_sys(g.peer_flag[threadIdx.x] + g.rank, step);
-  }
+  if (threadIdx.x < g.world) atomicAdd_system(g.peer_flag[threadIdx.x] + g.rank, 1u);
 }
 
 GBP_DEV void boundary_finish(const DeviceGraph& g, const int shift, const uint32_t step, const uint32_t block) {
@@ -1201,7 +1196,8 @@ GBP_DEV void boundary_finish(const DeviceGraph& g, const int shift, const uint32
   __syncthreads();
   if (threadIdx.x < g.world && g.bnd_wait[threadIdx.x]) {  // only the ranks this rank shares a landmark with
     const long long t0 = clock64();
-    while ((int32_t)(ld_acquire_sys(g.p2p_flag + threadIdx.x) - step) < 0) {
+    const uint32_t want = step * g.bnd_nblk[threadIdx.x];  // push blocks of that rank, all exchanges so far (modular)
+    while ((int32_t)(ld_acquire_sys(g.p2p_flag + threadIdx.x) - want) < 0) {
       if (clock64() - t0 > g.p2p_timeout) {  // a peer died or never made the matching call: do not hang the GPU
         *g.p2p_error = 1u;                   // (host-mapped, sticky: every later call on the handle fails)
         s_timed_out = 1u;
