@@ -1291,6 +1291,13 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   GBP_CUDA_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
   rc = setup_tma(h);
   if (rc) return rc;
+  if (std::getenv("GBP_DEBUG_TS")) {  // diagnostic builds (-DGBP_DEBUG_TS): per-exchange timestamps of k_update_vars
+    rc = h_alloc(h, &g.dbg_ts, 32 * 8);
+    if (rc) return rc;
+    std::vector<unsigned long long> init(32 * 8, 0ull);
+    for (int i = 0; i < 32; ++i) init[i * 8 + 0] = init[i * 8 + 2] = ~0ull;  // the two minima
+    GBP_CUDA_TRY(cudaMemcpy(g.dbg_ts, init.data(), init.size() * 8, cudaMemcpyHostToDevice));
+  }
   if (const char* env = std::getenv("GBP_TILE_QUEUE"))
     if (std::atoi(env) == 0) g.tile_queue = nullptr;  // static round-robin over the warp-tiles (diagnostics)
   pt.lap("uploads");
@@ -1785,6 +1792,20 @@ int gbp_cuda_last_sweep_times(gbp_handle* h, float* ms_factor_kernel, float* ms_
   }
   if (n_sweeps) *n_sweeps = (int)h->sweep_ms_factor.size();
   return GBP_OK;
+}
+
+int gbp_cuda_debug_timestamps(gbp_handle* h, uint64_t* out, int capacity) {
+  if (!h || !out || capacity < 0) return GBP_ERR_ARG;
+  if (!h->g.dbg_ts) return 0;
+  const int n = std::min(capacity, 32 * 8);
+  if (cudaSetDevice(h->device) != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess ||
+      cudaMemcpy(out, h->g.dbg_ts, (size_t)n * 8, cudaMemcpyDeviceToHost) != cudaSuccess)
+    return GBP_ERR_CUDA;
+  // re-arm the minima for the next window
+  std::vector<unsigned long long> init(32 * 8, 0ull);
+  for (int i = 0; i < 32; ++i) init[i * 8 + 0] = init[i * 8 + 2] = ~0ull;
+  cudaMemcpy(h->g.dbg_ts, init.data(), init.size() * 8, cudaMemcpyHostToDevice);
+  return n;
 }
 
 int gbp_cuda_last_timing(gbp_handle* h, float* ms_total, uint64_t* kernels) {

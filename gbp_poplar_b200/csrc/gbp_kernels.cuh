@@ -93,6 +93,7 @@ struct DeviceGraph {
   uint32_t* relin_count;  // [1]
   uint32_t* relin_ring;   // [GBP_RELIN_RING + 1] relinearisations of the last sweeps; [GBP_RELIN_RING] = sweep counter
   uint32_t* tile_queue;   // [2] {tickets handed out, warps done}: warp-tile queue of the sweep kernels
+  unsigned long long* dbg_ts;  // [32][8] per-exchange timestamps (diagnostic builds with -DGBP_DEBUG_TS, GBP_DEBUG_TS=1), else null
   float K[4];             // fx fy cx cy
   Hyper hp;
 };
@@ -1137,6 +1138,19 @@ GBP_DEV void update_landmarks(const DeviceGraph& g, float4* s_msg, uint64_t* s_b
 // finish the boundary landmarks from the receive buffer (read past L1).
 // Buffers are double-buffered by step parity: a peer may already push step s+1 while this
 // rank still reads step s, never s+2 (it needs this rank's step-s+1 flag first).
+#ifdef GBP_DEBUG_TS
+GBP_DEV unsigned long long dbg_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define GBP_TS_MAX(g, step, i) do { if ((g).dbg_ts && threadIdx.x == 0) atomicMax((g).dbg_ts + ((step) % 32u) * 8u + (i), dbg_now()); } while (0)
+#define GBP_TS_MIN(g, step, i) do { if ((g).dbg_ts && threadIdx.x == 0) atomicMin((g).dbg_ts + ((step) % 32u) * 8u + (i), dbg_now()); } while (0)
+#else
+#define GBP_TS_MAX(g, step, i) do { } while (0)
+#define GBP_TS_MIN(g, step, i) do { } while (0)
+#endif
+
 GBP_DEV void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
 }
@@ -1176,6 +1190,7 @@ GBP_DEV void boundary_push(const DeviceGraph& g, const uint32_t step, const uint
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x < g.world) atomicAdd_system(g.peer_flag[threadIdx.x] + g.rank, 1u);
+  GBP_TS_MAX(g, step, 1);  // last push block has announced itself
 }
 
 GBP_DEV void boundary_finish(const DeviceGraph& g, const int shift, const uint32_t step, const uint32_t block) {
@@ -1208,6 +1223,8 @@ GBP_DEV void boundary_finish(const DeviceGraph& g, const int shift, const uint32
   }
   __syncthreads();
   if (s_timed_out) return;  // nothing is stored from a receive buffer that is not complete
+  GBP_TS_MIN(g, step, 2);  // first / last finish block that has seen all its peers
+  GBP_TS_MAX(g, step, 3);
   if (mine && q < 3) {
     const float4* base = g.p2p_recv + (size_t)(step & 1u) * g.world * g.n_bnd_global * 3 + (size_t)rec.w * 3 + q;
     // rank order over the landmark's rank span.  The ranks outside it contribute +0 to the sum over ALL ranks that
@@ -1231,6 +1248,7 @@ GBP_DEV void boundary_finish(const DeviceGraph& g, const int shift, const uint32
     }
   }
   lmk_finish_quads(g, rec.x, q, acc, mine, shift, true, prev);
+  GBP_TS_MAX(g, step, 4);  // last finish block done
 }
 
 // {local landmark, first message, one past the last message, position in the global boundary list} of every boundary
@@ -1272,14 +1290,17 @@ __global__ void __launch_bounds__(GBP_TILE, GBP_UV_BLOCKS) k_update_vars(const D
   // of the grid to finish advances it.
   const uint32_t step = n_push ? g.p2p_step[0] + 1u : 0u;
   uint32_t b = blockIdx.x;
+  GBP_TS_MIN(g, step, 0);  // first block of the launch
   if (b < n_push) {
     boundary_push(g, step, b, n_push);
   } else if ((b -= n_push) < nb_cam) {
     if (!(lower_only & 2)) update_cameras(g, reinterpret_cast<float*>(s_stage), s_bars, shift, b, lower_only & 1);   // bits 1, 2: timing diagnostics (GBP_UV_DEBUG)
+    GBP_TS_MAX(g, step, 6);  // last camera block done
   } else if ((b -= nb_cam) < n_push) {
     boundary_finish(g, shift, step, b);
   } else if ((b -= n_push) < nb_lmk) {
     if (!(lower_only & 4)) update_landmarks(g, s_stage, s_bars, shift, b);
+    GBP_TS_MAX(g, step, 5);  // last landmark block done
   }
   if (n_push) {
     __syncthreads();

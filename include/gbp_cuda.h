@@ -261,6 +261,12 @@ int gbp_cuda_test_inv6x6(const float* A, float* out, int n);
 int gbp_cuda_test_inv3x3(const float* A, float* out, int n);
 int gbp_cuda_test_project(const float* X, const float* P, const float* K9, float* hx, float* Jkf, float* Jlmk, int n);
 
+/* Diagnostic builds only (-DGBP_DEBUG_TS and GBP_DEBUG_TS=1 in the environment): %globaltimer stamps of the phases of
+ * the last 32 belief updates, [32][8] = {first block, last push block, first / last finish block past its wait,
+ * last finish block done, last landmark block done, last camera block done, -}.  Returns the number of values
+ * copied (0 in a normal build). */
+int gbp_cuda_debug_timestamps(gbp_handle* h, uint64_t* out, int capacity);
+
 /* ---- asynchronous / resident use (bench, multi-GPU) ------------------- */
 /* Enqueue n sweeps on the handle's stream without synchronising. */
 int gbp_cuda_iterate_async(gbp_handle* h, int n_sweeps);
