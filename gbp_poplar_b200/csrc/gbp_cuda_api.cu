@@ -700,7 +700,7 @@ constexpr size_t P2P_OFF_RECV = 4096 + 2 * 256 * 8 * sizeof(double);  // metric 
 constexpr uint32_t P2P_MAX_WORLD = 256;
 
 size_t p2p_block_bytes(uint32_t W, uint32_t n_bnd_global) {
-  const size_t recv_bytes = (size_t)2 * W * n_bnd_global * 3 * sizeof(float4);
+  const size_t recv_bytes = (size_t)2 * W * n_bnd_global * 6 * sizeof(uint4);  // every float travels as {value, step}
   return ((P2P_OFF_RECV + recv_bytes + (2u << 20) - 1) >> 21) << 21;  // whole 2 MB pages
 }
 
@@ -708,7 +708,7 @@ size_t p2p_block_bytes(uint32_t W, uint32_t n_bnd_global) {
 int p2p_wire(gbp_handle* h, const std::vector<void*>& bases) {
   DeviceGraph& g = h->g;
   const uint32_t W = h->world;
-  std::vector<float4*> recv(W);
+  std::vector<uint4*> recv(W);
   std::vector<uint32_t*> flag(W), mflag(W);
   std::vector<double*> metric(W);
   for (uint32_t r = 0; r < W; ++r) {
@@ -716,14 +716,14 @@ int p2p_wire(gbp_handle* h, const std::vector<void*>& bases) {
     flag[r] = (uint32_t*)(base + P2P_OFF_FLAG);
     mflag[r] = (uint32_t*)(base + P2P_OFF_MFLAG);
     metric[r] = (double*)(base + P2P_OFF_METRIC);
-    recv[r] = (float4*)(base + P2P_OFF_RECV);
+    recv[r] = (uint4*)(base + P2P_OFF_RECV);
   }
   int rc = h_alloc(h, &g.peer_recv, W);
   if (!rc) rc = h_alloc(h, &g.peer_flag, W);
   if (!rc) rc = h_alloc(h, &g.peer_mflag, W);
   if (!rc) rc = h_alloc(h, &g.peer_metric, W);
   if (rc) return rc;
-  GBP_CUDA_TRY(cudaMemcpy(g.peer_recv, recv.data(), sizeof(float4*) * W, cudaMemcpyHostToDevice));
+  GBP_CUDA_TRY(cudaMemcpy(g.peer_recv, recv.data(), sizeof(uint4*) * W, cudaMemcpyHostToDevice));
   GBP_CUDA_TRY(cudaMemcpy(g.peer_flag, flag.data(), sizeof(uint32_t*) * W, cudaMemcpyHostToDevice));
   GBP_CUDA_TRY(cudaMemcpy(g.peer_mflag, mflag.data(), sizeof(uint32_t*) * W, cudaMemcpyHostToDevice));
   GBP_CUDA_TRY(cudaMemcpy(g.peer_metric, metric.data(), sizeof(double*) * W, cudaMemcpyHostToDevice));
@@ -736,7 +736,7 @@ int p2p_wire(gbp_handle* h, const std::vector<void*>& bases) {
   for (uint32_t r = 0; r < W; ++r)
     GBP_CUDA_TRY(cudaMemcpy((char*)bases[r] + P2P_OFF_NBLK + (size_t)h->rank * 4, &n_x, 4, cudaMemcpyHostToDevice));
   g.metric_recv = (const double*)(own + P2P_OFF_METRIC);
-  g.p2p_recv = (const float4*)(own + P2P_OFF_RECV);
+  g.p2p_recv = (const uint4*)(own + P2P_OFF_RECV);
   // the error word lives in mapped host memory: a timed-out kernel sets it, every synchronising entry point reads it
   h->p2p_err_host = (uint32_t*)h->pin_block;
   *h->p2p_err_host = 0u;

@@ -75,9 +75,9 @@ struct DeviceGraph {
   uint32_t n_bnd_local, n_bnd_global, world, rank;
   // peer-to-peer exchange over NVLink (null = the NCCL all-gather path): every rank maps the
   // receive buffers and arrival flags of all ranks (CUDA IPC)
-  float4** peer_recv;     // [world] -> that rank's bnd_p2p buffer [2 parities][world][n_bnd_global][3]
+  uint4** peer_recv;      // [world] -> that rank's receive buffer [2 parities][world][n_bnd_global][3 quads][2] of tagged pairs {a, step, b, step}
   uint32_t** peer_flag;   // [world] -> that rank's arrival flags [world]
-  const float4* p2p_recv; // this rank's own receive buffer
+  const uint4* p2p_recv;  // this rank's own receive buffer
   uint32_t* p2p_flag;     // this rank's own arrival counters: p2p_flag[r] = push blocks of rank r that have delivered, over all exchanges
   const uint32_t* bnd_nblk;  // [world] push blocks per exchange of every rank (written by the peers at set-up)
   uint32_t* p2p_error;    // set when a wait for a peer timed out
@@ -1098,16 +1098,20 @@ GBP_DEV void update_landmarks(const DeviceGraph& g, float4* s_msg, uint64_t* s_b
     bulk_load(s_msg, g.mlmk + (size_t)k0 * GBP_MLMK_QUADS, bytes, &s_bar);
   }
   const uint32_t l = l0 + (threadIdx.x >> 2), q = threadIdx.x & 3;
-  // boundary landmarks of a multi-GPU shard are finished by the exchange blocks / kernels
-  const bool mine = l < l1 && !(g.lmk_bslot && g.lmk_bslot[l] != 0xffffffffu);
+  const bool here = l < l1;
+  // boundary landmarks of a multi-GPU shard are finished by the exchange blocks / kernels; whether this one is a
+  // boundary landmark is fetched alongside everything else (not ahead of it: one round trip less per block)
+  uint32_t bslot = 0xffffffffu;
+  if (here && g.lmk_bslot) bslot = g.lmk_bslot[l];
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), prev = make_float4(0.f, 0.f, 0.f, 0.f);
   uint32_t a0 = 0, a1 = 0;
-  if (mine && q < 3) {
+  if (here && q < 3) {
     acc = lmk_prior_quad(g, l, q);
     a0 = g.lmk_ptr[l];
     a1 = g.lmk_ptr[l + 1];
   }
-  if (mine && q == 0) prev = shift ? g.lmk_b[(size_t)l * GBP_LMKB_QUADS + 3] : g.lmk_mean_prev[l];
+  if (here && q == 0) prev = shift ? g.lmk_b[(size_t)l * GBP_LMKB_QUADS + 3] : g.lmk_mean_prev[l];
+  const bool mine = here && bslot == 0xffffffffu;
   if (staged) {
     __syncthreads();  // the barrier is initialised before anyone waits on it
     mbar_wait(&s_bar, 0);
@@ -1160,6 +1164,21 @@ GBP_DEV uint32_t ld_acquire_sys(const uint32_t* p) {
   return v;
 }
 
+// Flag-in-data exchange (the scheme of NCCL's LL protocol): every float of a partial sum travels as an 8-byte word
+// {value bits, exchange step}; an aligned 8-byte store is indivisible on the way to a peer, so the receiver needs no
+// fence, no flag and no counter -- it polls the very words it is going to add until their tag is the step it is in.
+// The receive buffers start out zeroed and steps count from 1, so a stale word can never pass for a fresh one; two
+// parities because a peer may already push step s+1 while this rank still reads step s (never s+2: it needs this
+// rank's step-s+1 partials first).
+GBP_DEV void st_pair_sys(uint4* p, const float a, const float b, const uint32_t tag) {
+  asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "r"(__float_as_uint(a)), "r"(tag), "r"(__float_as_uint(b)), "r"(tag) : "memory");
+}
+GBP_DEV uint4 ld_pair_sys(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
 GBP_DEV void boundary_push(const DeviceGraph& g, const uint32_t step, const uint32_t block, const uint32_t n_blocks) {
   const uint32_t k = block * GBP_LMK_PER_BLOCK + (threadIdx.x >> 2), q = threadIdx.x & 3;
   if (k < g.n_bnd_local && q < 3) {
@@ -1179,24 +1198,20 @@ GBP_DEV void boundary_push(const DeviceGraph& g, const uint32_t step, const uint
           acc.x = fa(acc.x, v[u].x); acc.y = fa(acc.y, v[u].y); acc.z = fa(acc.z, v[u].z); acc.w = fa(acc.w, v[u].w);
         }
     }
-    const size_t off = ((size_t)((step & 1u) * g.world + g.rank) * g.n_bnd_global + rec.w) * 3 + q;
-    // only the ranks that observe this landmark (its rank span) ever read the partial
-    for (uint32_t r = span & 0xffffu; r <= (span >> 16); ++r) g.peer_recv[r][off] = acc;
+    // quad q of the landmark's slot in THIS rank's lane of the receive buffer = two 16-byte stores of tagged pairs;
+    // only the ranks that observe this landmark (its rank span) ever read it
+    const size_t off = (((size_t)((step & 1u) * g.world + g.rank) * g.n_bnd_global + rec.w) * 3 + q) * 2;
+    for (uint32_t r = span & 0xffffu; r <= (span >> 16); ++r) {
+      uint4* dst = g.peer_recv[r] + off;
+      st_pair_sys(dst, acc.x, acc.y, step);
+      st_pair_sys(dst + 1, acc.z, acc.w, step);
+    }
   }
-  // Every block fences its own peer stores and then announces ITSELF to every rank: arrival counters (one remote
-  // atomic per block and rank) instead of "the last block publishes a flag" -- no local counter round trip, no
-  // second system-scope fence on the critical path.  A rank has all of rank r's partials of exchange `step` once
-  // r's counter has reached step x (number of push blocks of r).
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x < g.world) atomicAdd_system(g.peer_flag[threadIdx.x] + g.rank, 1u);
-  GBP_TS_MAX(g, step, 1);  // last push block has announced itself
+  GBP_TS_MAX(g, step, 1);  // last push block has stored its partials
 }
 
 GBP_DEV void boundary_finish(const DeviceGraph& g, const int shift, const uint32_t step, const uint32_t block) {
-  __shared__ uint32_t s_timed_out;
-  if (threadIdx.x == 0) s_timed_out = 0u;
-  // everything that does not depend on the peers is fetched BEFORE the wait: the record, the prior, the previous mean
+  // everything that does not depend on the peers is fetched before the first poll: the record, the prior, the previous mean
   const uint32_t k = block * GBP_LMK_PER_BLOCK + (threadIdx.x >> 2), q = threadIdx.x & 3;
   const bool mine = k < g.n_bnd_local;
   uint4 rec = make_uint4(0u, 0u, 0u, 0u);
@@ -1208,46 +1223,34 @@ GBP_DEV void boundary_finish(const DeviceGraph& g, const int shift, const uint32
     if (q < 3) acc = lmk_prior_quad(g, rec.x, q);
     if (q == 0) prev = shift ? g.lmk_b[(size_t)rec.x * GBP_LMKB_QUADS + 3] : g.lmk_mean_prev[rec.x];
   }
-  __syncthreads();
-  if (threadIdx.x < g.world && g.bnd_wait[threadIdx.x]) {  // only the ranks this rank shares a landmark with
-    const long long t0 = clock64();
-    const uint32_t want = step * g.bnd_nblk[threadIdx.x];  // push blocks of that rank, all exchanges so far (modular)
-    while ((int32_t)(ld_acquire_sys(g.p2p_flag + threadIdx.x) - want) < 0) {
-      if (clock64() - t0 > g.p2p_timeout) {  // a peer died or never made the matching call: do not hang the GPU
-        *g.p2p_error = 1u;                   // (host-mapped, sticky: every later call on the handle fails)
-        s_timed_out = 1u;
-        break;
-      }
-      __nanosleep(40);
-    }
-  }
-  __syncthreads();
-  if (s_timed_out) return;  // nothing is stored from a receive buffer that is not complete
-  GBP_TS_MIN(g, step, 2);  // first / last finish block that has seen all its peers
-  GBP_TS_MAX(g, step, 3);
+  bool ok = true;
   if (mine && q < 3) {
-    const float4* base = g.p2p_recv + (size_t)(step & 1u) * g.world * g.n_bnd_global * 3 + (size_t)rec.w * 3 + q;
     // rank order over the landmark's rank span.  The ranks outside it contribute +0 to the sum over ALL ranks that
     // defines the belief, and acc + (+0) == acc bit for bit (acc starts as 0 + prior, so it is never -0): skipped.
-    const uint32_t r0 = span & 0xffffu, r1 = span >> 16;
-    if (r1 - r0 < 4) {  // the usual case (two or three ranks): all partials in flight together
-      float4 v[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (r0 + u <= r1) v[u] = __ldcg(base + (size_t)(r0 + u) * g.n_bnd_global * 3);
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (r0 + u <= r1) {
-          acc.x = fa(acc.x, v[u].x); acc.y = fa(acc.y, v[u].y); acc.z = fa(acc.z, v[u].z); acc.w = fa(acc.w, v[u].w);
+    const uint4* base = g.p2p_recv + ((size_t)(step & 1u) * g.world * g.n_bnd_global + rec.w) * 6 + (size_t)q * 2;
+    const long long t0 = clock64();
+    for (uint32_t r = span & 0xffffu; r <= (span >> 16) && ok; ++r) {
+      const uint4* src = base + (size_t)r * g.n_bnd_global * 6;
+      uint4 a = ld_pair_sys(src), b = ld_pair_sys(src + 1);
+      while (a.y != step || a.w != step || b.y != step || b.w != step) {  // that rank's partial has not landed yet
+        if (clock64() - t0 > g.p2p_timeout) {  // a peer died or never made the matching call: do not hang the GPU
+          *g.p2p_error = 1u;                   // (host-mapped, sticky: every later call on the handle fails)
+          ok = false;
+          break;
         }
-    } else {
-      for (uint32_t r = r0; r <= r1; ++r) {
-        const float4 v = __ldcg(base + (size_t)r * g.n_bnd_global * 3);
-        acc.x = fa(acc.x, v.x); acc.y = fa(acc.y, v.y); acc.z = fa(acc.z, v.z); acc.w = fa(acc.w, v.w);
+        __nanosleep(20);
+        a = ld_pair_sys(src);
+        b = ld_pair_sys(src + 1);
       }
+      acc.x = fa(acc.x, __uint_as_float(a.x)); acc.y = fa(acc.y, __uint_as_float(a.z));
+      acc.z = fa(acc.z, __uint_as_float(b.x)); acc.w = fa(acc.w, __uint_as_float(b.z));
     }
   }
-  lmk_finish_quads(g, rec.x, q, acc, mine, shift, true, prev);
+  GBP_TS_MIN(g, step, 2);  // first / last finish block that has all its partials
+  GBP_TS_MAX(g, step, 3);
+  // nothing is stored from a receive buffer that is not complete (the four lanes of a landmark decide together)
+  ok = __all_sync(0xffffffffu, ok);
+  lmk_finish_quads(g, rec.x, q, acc, mine && ok, shift, true, prev);
   GBP_TS_MAX(g, step, 4);  // last finish block done
 }
 
