@@ -182,7 +182,7 @@ CUDA_ONLY_API = {
     "gbp_shard_n_boundary_local": (C.c_uint32, [C.c_void_p]),
     "gbp_shard_boundary_local": (c_u32p, [C.c_void_p]),
     "gbp_shard_boundary_slot": (c_u32p, [C.c_void_p]),
-    "gbp_shard_boundary_span": (c_u32p, [C.c_void_p]),
+    "gbp_shard_boundary_ranks": (c_u32p, [C.c_void_p]),
     "gbp_shard_n_active_global": (C.c_uint32, [C.c_void_p]),
     "gbp_shard_cam_bounds": (c_u32p, [C.c_void_p]),
 }

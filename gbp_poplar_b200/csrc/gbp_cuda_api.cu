@@ -353,7 +353,8 @@ std::vector<CommEntry>& comm_cache() {
 int launch_update_vars(gbp_handle* h, bool lower_only_in = false, bool skip_cams = false) {
   static const int uv_debug = std::getenv("GBP_UV_DEBUG") ? std::atoi(std::getenv("GBP_UV_DEBUG")) : 0;  // timing diagnostics: 1 skips the cameras, 2 the landmarks (results are then WRONG)
   // bit 0: mirror the lower triangle of the camera beliefs; bit 1: the cameras are already done (fused into the sweep)
-  const int lower_only = (lower_only_in ? 1 : 0) | (skip_cams ? 2 : 0) | (uv_debug << 1);
+  static const int finish_last = std::getenv("GBP_FINISH_LAST") ? std::atoi(std::getenv("GBP_FINISH_LAST")) : 0;
+  const int lower_only = (lower_only_in ? 1 : 0) | (skip_cams ? 2 : 0) | (uv_debug << 1) | (finish_last ? 8 : 0);
   const int shift = h->pending_shift ? 1 : 0;
   const uint32_t grid = lmks_grid(h);
   const bool exchange = h->shard && h->g.n_bnd_global > 0;
@@ -759,6 +760,13 @@ int setup_p2p(gbp_handle* h, int mode) {
   const uint32_t W = h->world;
   h->p2p = 0;
   if (mode == 1 || g.n_bnd_global == 0) return GBP_OK;
+  if (W > 32) {  // the per-landmark rank masks of the peer-to-peer exchange are 32 bits wide
+    if (mode == 2) {
+      gbp_set_error("peer-to-peer exchange supports up to 32 ranks");
+      return GBP_ERR_ARG;
+    }
+    return GBP_OK;
+  }
   const size_t total = p2p_block_bytes(W, g.n_bnd_global);
   int ok = 1;
   cudaIpcMemHandle_t mine;
@@ -1259,11 +1267,12 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
     U_(g.lmk_bslot, lmk_bslot.data(), L);
     U_(g.bnd_local, gbp_shard_boundary_local(h->shard), g.n_bnd_local);
     U_(g.bnd_slot, gbp_shard_boundary_slot(h->shard), g.n_bnd_local);
-    U_(g.bnd_span, gbp_shard_boundary_span(h->shard), g.n_bnd_local);
+    U_(g.bnd_span, gbp_shard_boundary_ranks(h->shard), g.n_bnd_local);
     bnd_wait.assign(h->world, 0u);
     for (uint32_t k = 0; k < g.n_bnd_local; ++k) {
-      const uint32_t span = gbp_shard_boundary_span(h->shard)[k];
-      for (uint32_t r = span & 0xffffu; r <= (span >> 16) && r < h->world; ++r) bnd_wait[r] = 1u;
+      const uint32_t mask = gbp_shard_boundary_ranks(h->shard)[k];
+      for (uint32_t r = 0; r < h->world && r < 32; ++r)
+        if ((mask >> r) & 1u) bnd_wait[r] = 1u;
     }
     U_(g.bnd_wait, bnd_wait.data(), h->world);
     if (!rc && g.n_bnd_local) {
@@ -2423,7 +2432,7 @@ int gbp_cuda_init_shard(const gbp_problem* p, const gbp_opts* o_in, uint32_t wor
 
 // ---- single-process group: `world` shard handles of one problem driven by one host thread -------------------
 int gbp_cuda_init_group(const gbp_problem* p, const gbp_opts* o_in, uint32_t world, const int* devices, gbp_handle** out) {
-  if (!p || !out || world == 0 || world > P2P_MAX_WORLD) {
+  if (!p || !out || world == 0 || world > 32) {  // (the per-landmark rank masks of the exchange are 32 bits wide)
     gbp_set_error("bad gbp_cuda_init_group arguments");
     return GBP_ERR_ARG;
   }

@@ -67,7 +67,7 @@ struct DeviceGraph {
   uint32_t* lmk_bslot;    // [L] position in the global boundary list, 0xffffffff = interior
   uint32_t* bnd_local;    // [n_bnd_local] local landmark id
   uint32_t* bnd_slot;     // [n_bnd_local] position in the global boundary list
-  uint32_t* bnd_span;     // [n_bnd_local] first | last << 16 rank observing the landmark: the ranks its partials go to / come from
+  uint32_t* bnd_span;     // [n_bnd_local] bit r: rank r observes the landmark -- the ranks its partials go to / come from
   uint4* bnd_rec;         // [n_bnd_local] {local landmark, its first message, one past its last, position in the global boundary list}
   uint32_t* bnd_wait;     // [world] 1 = this rank receives partials from that rank (it waits for its flag), 0 = never
   float4* bnd_send;       // [n_bnd_global][3]  this rank's partial sums (zero where it has no factor)
@@ -1198,11 +1198,11 @@ GBP_DEV void boundary_push(const DeviceGraph& g, const uint32_t step, const uint
           acc.x = fa(acc.x, v[u].x); acc.y = fa(acc.y, v[u].y); acc.z = fa(acc.z, v[u].z); acc.w = fa(acc.w, v[u].w);
         }
     }
-    // quad q of the landmark's slot in THIS rank's lane of the receive buffer = two 16-byte stores of tagged pairs;
-    // only the ranks that observe this landmark (its rank span) ever read it
+    // quad q of the landmark's slot in THIS rank's lane of the receive buffer = two 16-byte stores of tagged pairs,
+    // to the ranks that observe this landmark (no other rank ever reads it)
     const size_t off = (((size_t)((step & 1u) * g.world + g.rank) * g.n_bnd_global + rec.w) * 3 + q) * 2;
-    for (uint32_t r = span & 0xffffu; r <= (span >> 16); ++r) {
-      uint4* dst = g.peer_recv[r] + off;
+    for (uint32_t m = span; m; m &= m - 1) {
+      uint4* dst = g.peer_recv[__ffs(m) - 1] + off;
       st_pair_sys(dst, acc.x, acc.y, step);
       st_pair_sys(dst + 1, acc.z, acc.w, step);
     }
@@ -1225,11 +1225,12 @@ GBP_DEV void boundary_finish(const DeviceGraph& g, const int shift, const uint32
   }
   bool ok = true;
   if (mine && q < 3) {
-    // rank order over the landmark's rank span.  The ranks outside it contribute +0 to the sum over ALL ranks that
+    // rank order over the ranks that observe the landmark.  The others contribute +0 to the sum over ALL ranks that
     // defines the belief, and acc + (+0) == acc bit for bit (acc starts as 0 + prior, so it is never -0): skipped.
     const uint4* base = g.p2p_recv + ((size_t)(step & 1u) * g.world * g.n_bnd_global + rec.w) * 6 + (size_t)q * 2;
     const long long t0 = clock64();
-    for (uint32_t r = span & 0xffffu; r <= (span >> 16) && ok; ++r) {
+    for (uint32_t m = span; m && ok; m &= m - 1) {  // ascending rank order
+      const uint32_t r = __ffs(m) - 1;
       const uint4* src = base + (size_t)r * g.n_bnd_global * 6;
       uint4 a = ld_pair_sys(src), b = ld_pair_sys(src + 1);
       while (a.y != step || a.w != step || b.y != step || b.w != step) {  // that rank's partial has not landed yet
@@ -1299,6 +1300,13 @@ __global__ void __launch_bounds__(GBP_TILE, GBP_UV_BLOCKS) k_update_vars(const D
   } else if ((b -= n_push) < nb_cam) {
     if (!(lower_only & 2)) update_cameras(g, reinterpret_cast<float*>(s_stage), s_bars, shift, b, lower_only & 1);   // bits 1, 2: timing diagnostics (GBP_UV_DEBUG)
     GBP_TS_MAX(g, step, 6);  // last camera block done
+  } else if (lower_only & 8) {  // GBP_FINISH_LAST=1 (diagnostics): the finish blocks after the landmark blocks
+    if ((b -= nb_cam) < nb_lmk) {
+      if (!(lower_only & 4)) update_landmarks(g, s_stage, s_bars, shift, b);
+      GBP_TS_MAX(g, step, 5);
+    } else {
+      boundary_finish(g, shift, step, b - nb_lmk);
+    }
   } else if ((b -= nb_cam) < n_push) {
     boundary_finish(g, shift, step, b);
   } else if ((b -= n_push) < nb_lmk) {

@@ -199,6 +199,7 @@ static int shard_build_impl(const gbp_problem* p, uint32_t world, uint32_t rank,
   // order) and landmarks, the active-edge count of the whole graph
   const std::vector<uint32_t> cam_rank = camera_ranks(s->cam_bounds, p->n_keyframes);
   std::vector<uint32_t> lo(L, 0xffffffffu), hi(L, 0u);
+  std::vector<uint32_t> rank_mask(world <= 32 ? L : 0, 0u);  // bit r: rank r observes the landmark (worlds of up to 32 ranks)
   std::vector<uint32_t> lmk_local(L, 0xffffffffu);
   s->edge_global.reserve((size_t)E / world + (size_t)E / (8 * world) + 64);
   for (uint32_t e = 0; e < E; ++e) {
@@ -206,6 +207,7 @@ static int shard_build_impl(const gbp_problem* p, uint32_t world, uint32_t rank,
     const uint32_t l = p->lmk_ids[e];
     lo[l] = std::min(lo[l], r);
     hi[l] = std::max(hi[l], r);
+    if (!rank_mask.empty()) rank_mask[l] |= 1u << r;
     if (r == rank) {
       s->edge_global.push_back(e);
       lmk_local[l] = 0;
@@ -222,7 +224,7 @@ static int shard_build_impl(const gbp_problem* p, uint32_t world, uint32_t rank,
       if (boundary) {
         s->bnd_local.push_back(lmk_local[l]);
         s->bnd_slot.push_back(n_boundary);
-        s->bnd_span.push_back(lo[l] | (hi[l] << 16));  // first | last rank observing it: every contributor lies in between
+        s->bnd_span.push_back(rank_mask.empty() ? 0u : rank_mask[l]);  // the ranks that contribute a partial sum to it
       }
     }
     if (boundary) n_boundary++;
@@ -318,7 +320,7 @@ const uint32_t* gbp_shard_edge_global(const gbp_shard* s) { return s ? s->edge_g
 uint32_t gbp_shard_n_boundary_local(const gbp_shard* s) { return s ? (uint32_t)s->bnd_local.size() : 0; }
 const uint32_t* gbp_shard_boundary_local(const gbp_shard* s) { return s ? s->bnd_local.data() : nullptr; }
 const uint32_t* gbp_shard_boundary_slot(const gbp_shard* s) { return s ? s->bnd_slot.data() : nullptr; }
-const uint32_t* gbp_shard_boundary_span(const gbp_shard* s) { return s ? s->bnd_span.data() : nullptr; }
+const uint32_t* gbp_shard_boundary_ranks(const gbp_shard* s) { return s ? s->bnd_span.data() : nullptr; }
 uint32_t gbp_shard_n_active_global(const gbp_shard* s) { return s ? s->n_active_global : 0; }
 const uint32_t* gbp_shard_cam_bounds(const gbp_shard* s) { return s ? s->cam_bounds.data() : nullptr; }
 

@@ -254,9 +254,9 @@ class Shard:
         return _view(self._lib.gbp_shard_boundary_slot(self._h), self.n_boundary_local, np.uint32, self)
 
     @property
-    def boundary_span(self):
-        """[n_boundary_local] first rank | last rank << 16 observing each boundary landmark."""
-        return _view(self._lib.gbp_shard_boundary_span(self._h), self.n_boundary_local, np.uint32, self)
+    def boundary_ranks(self):
+        """[n_boundary_local] bit r = rank r observes the boundary landmark (contributes a partial sum)."""
+        return _view(self._lib.gbp_shard_boundary_ranks(self._h), self.n_boundary_local, np.uint32, self)
 
     @property
     def cam_bounds(self):

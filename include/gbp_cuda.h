@@ -311,9 +311,10 @@ const uint32_t* gbp_shard_edge_global(const gbp_shard* s);   /* [n_local_edges] 
 uint32_t gbp_shard_n_boundary_local(const gbp_shard* s);
 const uint32_t* gbp_shard_boundary_local(const gbp_shard* s);
 const uint32_t* gbp_shard_boundary_slot(const gbp_shard* s);
-/* [n_boundary_local] first rank | last rank << 16 observing the landmark: all ranks that contribute a partial sum to
- * it lie in that span (camera ranges are contiguous), so the exchange only involves those. */
-const uint32_t* gbp_shard_boundary_span(const gbp_shard* s);
+/* [n_boundary_local] bit r set = rank r observes the landmark, i.e. contributes a partial sum to its belief (worlds of
+ * up to 32 ranks; all zero above that, where the engine uses the NCCL all-gather).  The peer-to-peer exchange sends a
+ * partial to exactly those ranks and waits for exactly those ranks' partials. */
+const uint32_t* gbp_shard_boundary_ranks(const gbp_shard* s);
 /* Number of active edges of the GLOBAL problem (quirk Q7: the metric covers global edges [0, n_active)). */
 uint32_t gbp_shard_n_active_global(const gbp_shard* s);
 /* camera-range bounds of all ranks: [world+1] */

@@ -16,7 +16,9 @@ from gbp_poplar_b200 import GBPGroup, _capi, default_opts  # noqa: E402
 
 world = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 bal, setup = bench.build_problem(world)
-grp = GBPGroup(setup.problem, world, devices=list(range(world)), opts=default_opts())
+import torch  # noqa: E402
+ndev = torch.cuda.device_count()
+grp = GBPGroup(setup.problem, world, devices=[r % ndev for r in range(world)], opts=default_opts())
 bench.ba_preroll(grp)
 grp.iterate(40)
 lib = _capi.load_library()
@@ -31,7 +33,8 @@ for rank, r in enumerate(grp.ranks):
     buf = (C.c_uint64 * 256)()
     n = lib.gbp_cuda_debug_timestamps(r.handle, buf, 256)
     t = np.array(buf[:n], dtype=np.uint64).reshape(-1, 8).astype(np.float64)
-    ok = (t[:, 0] < 1.8e19) & (t[:, 1] > 0)
+    ok = (t[:, 0] < 1.8e19) & (t[:, 5] > 0)
     d = (t[ok][:, 1:7] - t[ok][:, :1]) / 1e3
-    print(f"rank {rank} ({ok.sum()} exchanges), us after the first block:", ", ".join(f"{nm} {v:.1f}" for nm, v in zip(names, d.mean(axis=0))))
+    d[d < 0] = np.nan
+    print(f"rank {rank} ({ok.sum()} exchanges), us after the first block:", ", ".join(f"{nm} {v:.1f}" for nm, v in zip(names, np.nanmean(d, axis=0))))
 grp.close()

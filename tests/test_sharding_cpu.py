@@ -141,11 +141,11 @@ def test_shard_build_partitions_the_graph(world):
         assert np.array_equal(boundary_global[bs], lg[bl])
         assert set(lg[bl]) == set(boundary_global) & set(lg)
         assert s.n_active_global == E
-        # rank span of every boundary landmark: exactly [first observing rank, last observing rank]
-        span = np.array(s.boundary_span)
-        for g_l, sp in zip(lg[bl], span):
-            ranks = rank_of_cam[cam_ids[lmk_ids == g_l]]
-            assert (sp & 0xffff, sp >> 16) == (ranks.min(), ranks.max()) and sp & 0xffff <= r <= sp >> 16
+        # the ranks observing every boundary landmark (who sends a partial sum to whom)
+        masks = np.array(s.boundary_ranks)
+        for g_l, m in zip(lg[bl], masks):
+            ranks = set(int(x) for x in rank_of_cam[cam_ids[lmk_ids == g_l]])
+            assert m == sum(1 << x for x in ranks) and (m >> r) & 1 and len(ranks) > 1
         loads.append(eg.size)
         plan = _plan(p, world, r)
         assert (plan.cam_begin, plan.cam_end, plan.n_local_edges, plan.n_local_points, plan.n_boundary_points) == \
