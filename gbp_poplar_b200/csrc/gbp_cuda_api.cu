@@ -354,7 +354,9 @@ int launch_update_vars(gbp_handle* h, bool lower_only_in = false, bool skip_cams
   static const int uv_debug = std::getenv("GBP_UV_DEBUG") ? std::atoi(std::getenv("GBP_UV_DEBUG")) : 0;  // timing diagnostics: 1 skips the cameras, 2 the landmarks (results are then WRONG)
   // bit 0: mirror the lower triangle of the camera beliefs; bit 1: the cameras are already done (fused into the sweep)
   static const int finish_last = std::getenv("GBP_FINISH_LAST") ? std::atoi(std::getenv("GBP_FINISH_LAST")) : 0;
-  const int lower_only = (lower_only_in ? 1 : 0) | (skip_cams ? 2 : 0) | (uv_debug << 1) | (finish_last ? 8 : 0);
+  // timing diagnostics of the exchange (results are then WRONG): 1 = push blocks idle, 2 = finish blocks idle, 3 = both
+  static const int xchg_debug = std::getenv("GBP_XCHG_DEBUG") ? std::atoi(std::getenv("GBP_XCHG_DEBUG")) : 0;
+  const int lower_only = (lower_only_in ? 1 : 0) | (skip_cams ? 2 : 0) | (uv_debug << 1) | (finish_last ? 8 : 0) | ((xchg_debug & 3) << 4);
   const int shift = h->pending_shift ? 1 : 0;
   const uint32_t grid = lmks_grid(h);
   const bool exchange = h->shard && h->g.n_bnd_global > 0;

@@ -1296,7 +1296,7 @@ __global__ void __launch_bounds__(GBP_TILE, GBP_UV_BLOCKS) k_update_vars(const D
   uint32_t b = blockIdx.x;
   GBP_TS_MIN(g, step, 0);  // first block of the launch
   if (b < n_push) {
-    boundary_push(g, step, b, n_push);
+    if (!(lower_only & 16)) boundary_push(g, step, b, n_push);   // bits 4, 5: timing diagnostics (GBP_XCHG_DEBUG)
   } else if ((b -= n_push) < nb_cam) {
     if (!(lower_only & 2)) update_cameras(g, reinterpret_cast<float*>(s_stage), s_bars, shift, b, lower_only & 1);   // bits 1, 2: timing diagnostics (GBP_UV_DEBUG)
     GBP_TS_MAX(g, step, 6);  // last camera block done
@@ -1308,7 +1308,7 @@ __global__ void __launch_bounds__(GBP_TILE, GBP_UV_BLOCKS) k_update_vars(const D
       boundary_finish(g, shift, step, b - nb_lmk);
     }
   } else if ((b -= nb_cam) < n_push) {
-    boundary_finish(g, shift, step, b);
+    if (!(lower_only & 32)) boundary_finish(g, shift, step, b);
   } else if ((b -= n_push) < nb_lmk) {
     if (!(lower_only & 4)) update_landmarks(g, s_stage, s_bars, shift, b);
     GBP_TS_MAX(g, step, 5);  // last landmark block done
