@@ -81,7 +81,7 @@ struct DeviceGraph {
   uint32_t* p2p_flag;     // this rank's own arrival counters: p2p_flag[r] = push blocks of rank r that have delivered, over all exchanges
   const uint32_t* bnd_nblk;  // [world] push blocks per exchange of every rank (written by the peers at set-up)
   uint32_t* p2p_error;    // set when a wait for a peer timed out
-  uint32_t* p2p_step;     // [2] {completed exchange steps, blocks of the current k_update_vars that are done}
+  unsigned long long* p2p_step;  // [1] blocks of exchanging k_update_vars launches that have finished, over all launches
   long long p2p_timeout;  // clock64 ticks a block waits for its peers before it gives up (p2p_error)
   // metric exchange over the same peer mappings (no collective call in a sweep that asks for the metric)
   double** peer_metric;       // [world] -> that rank's metric receive buffer [2 parities][world][8]
@@ -1289,10 +1289,11 @@ __global__ void __launch_bounds__(GBP_TILE, GBP_UV_BLOCKS) k_update_vars(const D
     g.relin_ring[next % GBP_RELIN_RING] = 0;
     g.relin_ring[GBP_RELIN_RING] = next;
   }
-  // The exchange step lives on the device (the same sequence on every rank), so the launch has no
-  // per-sweep argument and can be replayed from a CUDA graph: every block reads it, the last block
-  // of the grid to finish advances it.
-  const uint32_t step = n_push ? g.p2p_step[0] + 1u : 0u;
+  // The exchange step lives on the device (the launch has no per-sweep argument and is replayed from a CUDA graph):
+  // every block of an exchanging launch bumps a cumulative counter when it is done -- a fire-and-forget reduction,
+  // nobody waits for its result -- and reads it when it starts.  All launches of a handle have the same grid, and
+  // while launch n runs the counter stays within [n G, (n + 1) G): every one of its blocks derives the same step.
+  const uint32_t step = n_push ? (uint32_t)(*(volatile unsigned long long*)g.p2p_step / gridDim.x) + 1u : 0u;
   uint32_t b = blockIdx.x;
   GBP_TS_MIN(g, step, 0);  // first block of the launch
   if (b < n_push) {
@@ -1315,10 +1316,7 @@ __global__ void __launch_bounds__(GBP_TILE, GBP_UV_BLOCKS) k_update_vars(const D
   }
   if (n_push) {
     __syncthreads();
-    if (threadIdx.x == 0 && atomicAdd(g.p2p_step + 1, 1u) == gridDim.x - 1) {
-      g.p2p_step[1] = 0u;
-      g.p2p_step[0] = step;
-    }
+    if (threadIdx.x == 0) atomicAdd(g.p2p_step, 1ull);  // (result unused: compiles to a reduction)
   }
 }
 
