@@ -1175,7 +1175,7 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
     A_(g.bnd_wait, h->world);
     A_(g.bnd_send, 3 * (size_t)g.n_bnd_global);
     reserve((void**)&g.bnd_recv, 3 * (size_t)g.n_bnd_global * h->world * sizeof(float4));
-    A_(g.p2p_step, 1);
+    A_(g.p2p_step, 2);
     A_(g.metric_step, 1);
     A_(h->d_metric_raw, 8);
     A_(h->d_metric_all, 8 * (size_t)h->world);

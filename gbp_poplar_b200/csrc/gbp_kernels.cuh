@@ -81,7 +81,7 @@ struct DeviceGraph {
   uint32_t* p2p_flag;     // this rank's own arrival counters: p2p_flag[r] = push blocks of rank r that have delivered, over all exchanges
   const uint32_t* bnd_nblk;  // [world] push blocks per exchange of every rank (written by the peers at set-up)
   uint32_t* p2p_error;    // set when a wait for a peer timed out
-  unsigned long long* p2p_step;  // [1] blocks of exchanging k_update_vars launches that have finished, over all launches
+  uint32_t* p2p_step;     // [2] {completed exchange steps, blocks of the current k_update_vars that have read it}
   long long p2p_timeout;  // clock64 ticks a block waits for its peers before it gives up (p2p_error)
   // metric exchange over the same peer mappings (no collective call in a sweep that asks for the metric)
   double** peer_metric;       // [world] -> that rank's metric receive buffer [2 parities][world][8]
@@ -1289,11 +1289,20 @@ __global__ void __launch_bounds__(GBP_TILE, GBP_UV_BLOCKS) k_update_vars(const D
     g.relin_ring[next % GBP_RELIN_RING] = 0;
     g.relin_ring[GBP_RELIN_RING] = next;
   }
-  // The exchange step lives on the device (the launch has no per-sweep argument and is replayed from a CUDA graph):
-  // every block of an exchanging launch bumps a cumulative counter when it is done -- a fire-and-forget reduction,
-  // nobody waits for its result -- and reads it when it starts.  All launches of a handle have the same grid, and
-  // while launch n runs the counter stays within [n G, (n + 1) G): every one of its blocks derives the same step.
-  const uint32_t step = n_push ? (uint32_t)(*(volatile unsigned long long*)g.p2p_step / gridDim.x) + 1u : 0u;
+  // The exchange step lives on the device (the same sequence on every rank), so the launch has no per-sweep argument
+  // and can be replayed from a CUDA graph.  Thread 0 of every block reads it and THEN takes a ticket; the block that
+  // draws the last ticket knows every other block has read the step and advances it for the next launch.  The ticket's
+  // round trip overlaps the block's work (its result is only looked at when the block is done).
+  __shared__ uint32_t s_step;
+  uint32_t ticket = 0;
+  if (n_push) {
+    if (threadIdx.x == 0) {
+      s_step = *(volatile uint32_t*)g.p2p_step + 1u;
+      ticket = atomicAdd(g.p2p_step + 1, 1u);
+    }
+    __syncthreads();
+  }
+  const uint32_t step = n_push ? s_step : 0u;
   uint32_t b = blockIdx.x;
   GBP_TS_MIN(g, step, 0);  // first block of the launch
   if (b < n_push) {
@@ -1314,9 +1323,9 @@ __global__ void __launch_bounds__(GBP_TILE, GBP_UV_BLOCKS) k_update_vars(const D
     if (!(lower_only & 4)) update_landmarks(g, s_stage, s_bars, shift, b);
     GBP_TS_MAX(g, step, 5);  // last landmark block done
   }
-  if (n_push) {
-    __syncthreads();
-    if (threadIdx.x == 0) atomicAdd(g.p2p_step, 1ull);  // (result unused: compiles to a reduction)
+  if (n_push && threadIdx.x == 0 && ticket == gridDim.x - 1) {
+    g.p2p_step[1] = 0u;
+    g.p2p_step[0] = step;
   }
 }
 
