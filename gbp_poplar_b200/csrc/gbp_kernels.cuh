@@ -900,14 +900,14 @@ GBP_DEV void lmk_load_prior(const DeviceGraph& g, const uint32_t l, float (&b)[1
 // last PrepMessageVertex pass used becomes the "old mu" (Copy(mu, oldmu),
 // ba/ba.cpp:898) before the new mean is stored.
 // Belief update of the cameras (prog_ub, ba/ba.cpp:104-139, camera half) + per-camera mean and rotation.
-// One WARP per camera, two cameras per block.  The per-warp-tile partial sums k_sweep left for the camera are one
+// One WARP per camera, four cameras per block.  The per-warp-tile partial sums k_sweep left for the camera are one
 // contiguous run of cam_partial: lane 0 stages it with ONE bulk copy (completion on the warp's mbarrier) while the
 // lanes fetch the prior entries and the old mean, so a camera is two memory round trips deep (its tile range, then
 // everything else) before the arithmetic starts: the lanes add the partials to the prior in warp-tile order -- entry
 // `lane` and entry `lane + 32` of [eta 6 | Lambda 36] -- and lane 0 inverts the 6x6 belief (a serial LDL^T) and
 // forms the linearisation constants.
-#define GBP_CAM_PER_BLOCK 2
-#define GBP_CAM_STAGE_TILES 60  // warp-tiles of one camera a warp stages (60 x 176 B); longer runs finish through direct loads
+#define GBP_CAM_PER_BLOCK 4
+#define GBP_CAM_STAGE_TILES 30  // warp-tiles of one camera a warp stages (30 x 176 B); longer runs finish through direct loads
 GBP_DEV void update_cameras(const DeviceGraph& g, float* s_buf, uint64_t* s_bars, const int shift, const uint32_t block, const int lower_only) {
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t c = block * GBP_CAM_PER_BLOCK + warp;
@@ -948,7 +948,14 @@ GBP_DEV void update_cameras(const DeviceGraph& g, float* s_buf, uint64_t* s_bars
     if (ent < GBP_CAMPART && !skip[half]) {
       float a = acc[half];
       for (uint32_t t = 0; t < n_st; ++t) a = fa(a, s_part[t * GBP_CAMPART_STRIDE + ent]);  // warp-tile order
-      for (uint32_t t = t0 + n_st; t < t1; ++t) a = fa(a, g.cam_partial[(size_t)t * GBP_CAMPART_STRIDE + ent]);
+      for (uint32_t t = t0 + n_st; t < t1; t += 8) {  // the rest of a long run: eight direct loads in flight
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (t + u < t1) ? g.cam_partial[(size_t)(t + u) * GBP_CAMPART_STRIDE + ent] : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (t + u < t1) a = fa(a, v[u]);
+      }
       acc[half] = a;
     }
   }
