@@ -693,12 +693,12 @@ int upload_lmk_priors(gbp_handle* h, const float* eta, const float* lam) {
 
 // ---- peer-to-peer exchange set-up ------------------------------------------------------------
 // Every rank owns one block
-//   [boundary arrival flags W | metric arrival flags W | counters | metric receive buffer 2 x W x 8 doubles |
-//    boundary receive buffer 2 parities x W x n_boundary x 3 quads]
+//   [- | metric arrival flags W | - | metric receive buffer 2 x W x 8 doubles |
+//    boundary receive buffer 2 parities x W x n_boundary x 12 tagged words {value, exchange step}]
 // that every other rank maps: through CUDA IPC when the ranks are processes (the handles travel over the NCCL
 // communicator once), directly (same device, or cudaDeviceEnablePeerAccess) when they are the handles of a
 // single-process group.
-constexpr size_t P2P_OFF_FLAG = 0, P2P_OFF_MFLAG = 1024, P2P_OFF_NBLK = 2048, P2P_OFF_METRIC = 4096;
+constexpr size_t P2P_OFF_MFLAG = 1024, P2P_OFF_METRIC = 4096;
 constexpr size_t P2P_OFF_RECV = 4096 + 2 * 256 * 8 * sizeof(double);  // metric buffer sized for <= 256 ranks
 constexpr uint32_t P2P_MAX_WORLD = 256;
 
@@ -712,32 +712,23 @@ int p2p_wire(gbp_handle* h, const std::vector<void*>& bases) {
   DeviceGraph& g = h->g;
   const uint32_t W = h->world;
   std::vector<uint4*> recv(W);
-  std::vector<uint32_t*> flag(W), mflag(W);
+  std::vector<uint32_t*> mflag(W);
   std::vector<double*> metric(W);
   for (uint32_t r = 0; r < W; ++r) {
     char* base = (char*)bases[r];
-    flag[r] = (uint32_t*)(base + P2P_OFF_FLAG);
     mflag[r] = (uint32_t*)(base + P2P_OFF_MFLAG);
     metric[r] = (double*)(base + P2P_OFF_METRIC);
     recv[r] = (uint4*)(base + P2P_OFF_RECV);
   }
   int rc = h_alloc(h, &g.peer_recv, W);
-  if (!rc) rc = h_alloc(h, &g.peer_flag, W);
   if (!rc) rc = h_alloc(h, &g.peer_mflag, W);
   if (!rc) rc = h_alloc(h, &g.peer_metric, W);
   if (rc) return rc;
   GBP_CUDA_TRY(cudaMemcpy(g.peer_recv, recv.data(), sizeof(uint4*) * W, cudaMemcpyHostToDevice));
-  GBP_CUDA_TRY(cudaMemcpy(g.peer_flag, flag.data(), sizeof(uint32_t*) * W, cudaMemcpyHostToDevice));
   GBP_CUDA_TRY(cudaMemcpy(g.peer_mflag, mflag.data(), sizeof(uint32_t*) * W, cudaMemcpyHostToDevice));
   GBP_CUDA_TRY(cudaMemcpy(g.peer_metric, metric.data(), sizeof(double*) * W, cudaMemcpyHostToDevice));
   char* own = (char*)bases[h->rank];
-  g.p2p_flag = (uint32_t*)(own + P2P_OFF_FLAG);
   g.metric_flag = (uint32_t*)(own + P2P_OFF_MFLAG);
-  g.bnd_nblk = (const uint32_t*)(own + P2P_OFF_NBLK);
-  // this rank's number of push blocks per exchange, told to every rank (launch_update_vars uses the same formula)
-  const uint32_t n_x = std::max((g.n_bnd_local + GBP_LMK_PER_BLOCK - 1) / GBP_LMK_PER_BLOCK, 1u);
-  for (uint32_t r = 0; r < W; ++r)
-    GBP_CUDA_TRY(cudaMemcpy((char*)bases[r] + P2P_OFF_NBLK + (size_t)h->rank * 4, &n_x, 4, cudaMemcpyHostToDevice));
   g.metric_recv = (const double*)(own + P2P_OFF_METRIC);
   g.p2p_recv = (const uint4*)(own + P2P_OFF_RECV);
   // the error word lives in mapped host memory: a timed-out kernel sets it, every synchronising entry point reads it
@@ -776,6 +767,7 @@ int setup_p2p(gbp_handle* h, int mode) {
   if (W > P2P_MAX_WORLD) ok = 0;
   if (ok && cudaMalloc(&h->p2p_block, total) != cudaSuccess) ok = 0;
   if (ok && cudaMemset(h->p2p_block, 0, total) != cudaSuccess) ok = 0;
+  if (ok && cudaDeviceSynchronize() != cudaSuccess) ok = 0;  // zeroed BEFORE any peer can learn the handle and push into it
   if (ok && cudaIpcGetMemHandle(&mine, h->p2p_block) != cudaSuccess) ok = 0;
   cudaGetLastError();
   // all-gather {ok, handle} over the communicator (also tells every rank whether ALL ranks can do it)
@@ -825,16 +817,7 @@ int setup_p2p(gbp_handle* h, int mode) {
   }
   std::vector<void*> bases(W);
   for (uint32_t r = 0; r < W; ++r) bases[r] = (r == h->rank) ? h->p2p_block : h->p2p_peers[r];
-  int rc = p2p_wire(h, bases);
-  if (rc) return rc;
-  // every rank has written its push-block count into every block before anyone starts the first exchange
-  int* d_bar = nullptr;
-  GBP_CUDA_TRY(cudaMalloc((void**)&d_bar, sizeof(int) * (W + 1)));
-  GBP_CUDA_TRY(cudaMemsetAsync(d_bar, 0, sizeof(int) * (W + 1), h->comm_stream));
-  GBP_NCCL_TRY(gbp::nccl_api().AllGather(d_bar + W, d_bar, sizeof(int), ncclChar, h->comm, h->comm_stream));
-  GBP_CUDA_TRY(cudaStreamSynchronize(h->comm_stream));
-  cudaFree(d_bar);
-  return GBP_OK;
+  return p2p_wire(h, bases);
 }
 
 // TMA descriptors for k_sweep_tma: the factor potentials and the camera-bound messages seen as 2-D fp32 tensors
@@ -1158,7 +1141,7 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   A_(h->d_pprior_cam_eta, 6 * (size_t)C);
   A_(h->d_pprior_cam_lam, 36 * (size_t)C);
   A_(h->d_pprior_lmk, 3 * (size_t)L);
-  std::vector<uint32_t> lmk_bslot, bnd_wait;
+  std::vector<uint32_t> lmk_bslot;
   if (h->shard) {
     const uint32_t nbl = gbp_shard_n_boundary_local(h->shard);
     g.n_bnd_local = nbl;
@@ -1172,7 +1155,6 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
     A_(g.bnd_slot, nbl);
     A_(g.bnd_span, nbl);
     A_(g.bnd_rec, nbl);
-    A_(g.bnd_wait, h->world);
     A_(g.bnd_send, 3 * (size_t)g.n_bnd_global);
     reserve((void**)&g.bnd_recv, 3 * (size_t)g.n_bnd_global * h->world * sizeof(float4));
     A_(g.p2p_step, 2);
@@ -1270,13 +1252,6 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
     U_(g.bnd_local, gbp_shard_boundary_local(h->shard), g.n_bnd_local);
     U_(g.bnd_slot, gbp_shard_boundary_slot(h->shard), g.n_bnd_local);
     U_(g.bnd_span, gbp_shard_boundary_ranks(h->shard), g.n_bnd_local);
-    bnd_wait.assign(h->world, 0u);
-    for (uint32_t k = 0; k < g.n_bnd_local; ++k) {
-      const uint32_t mask = gbp_shard_boundary_ranks(h->shard)[k];
-      for (uint32_t r = 0; r < h->world && r < 32; ++r)
-        if ((mask >> r) & 1u) bnd_wait[r] = 1u;
-    }
-    U_(g.bnd_wait, bnd_wait.data(), h->world);
     if (!rc && g.n_bnd_local) {
       gbp::k_boundary_records<<<(g.n_bnd_local + 255) / 256, 256, 0, s>>>(g);  // after stage B: it reads lmk_ptr
       h->kernels_launched++;
@@ -2540,7 +2515,9 @@ int gbp_cuda_init_group(const gbp_problem* p, const gbp_opts* o_in, uint32_t wor
   const size_t total = p2p_block_bytes(world, out[0]->g.n_bnd_global);
   for (uint32_t r = 0; r < world && !rc; ++r) {
     cudaSetDevice(dev[r]);
-    if (cudaMalloc(&gs->blocks[r], total) != cudaSuccess || cudaMemset(gs->blocks[r], 0, total) != cudaSuccess) rc = GBP_ERR_CUDA;
+    if (cudaMalloc(&gs->blocks[r], total) != cudaSuccess || cudaMemset(gs->blocks[r], 0, total) != cudaSuccess ||
+        cudaDeviceSynchronize() != cudaSuccess)
+      rc = GBP_ERR_CUDA;
   }
   if (rc) {
     for (uint32_t r = 0; r < world; ++r)

@@ -69,17 +69,13 @@ struct DeviceGraph {
   uint32_t* bnd_slot;     // [n_bnd_local] position in the global boundary list
   uint32_t* bnd_span;     // [n_bnd_local] bit r: rank r observes the landmark -- the ranks its partials go to / come from
   uint4* bnd_rec;         // [n_bnd_local] {local landmark, its first message, one past its last, position in the global boundary list}
-  uint32_t* bnd_wait;     // [world] 1 = this rank receives partials from that rank (it waits for its flag), 0 = never
   float4* bnd_send;       // [n_bnd_global][3]  this rank's partial sums (zero where it has no factor)
   const float4* bnd_recv; // [world][n_bnd_global][3]  all ranks' partial sums
   uint32_t n_bnd_local, n_bnd_global, world, rank;
   // peer-to-peer exchange over NVLink (null = the NCCL all-gather path): every rank maps the
   // receive buffers and arrival flags of all ranks (CUDA IPC)
   uint4** peer_recv;      // [world] -> that rank's receive buffer [2 parities][world][n_bnd_global][3 quads][2] of tagged pairs {a, step, b, step}
-  uint32_t** peer_flag;   // [world] -> that rank's arrival flags [world]
   const uint4* p2p_recv;  // this rank's own receive buffer
-  uint32_t* p2p_flag;     // this rank's own arrival counters: p2p_flag[r] = push blocks of rank r that have delivered, over all exchanges
-  const uint32_t* bnd_nblk;  // [world] push blocks per exchange of every rank (written by the peers at set-up)
   uint32_t* p2p_error;    // set when a wait for a peer timed out
   uint32_t* p2p_step;     // [2] {completed exchange steps, blocks of the current k_update_vars that have read it}
   long long p2p_timeout;  // clock64 ticks a block waits for its peers before it gives up (p2p_error)
@@ -1186,7 +1182,7 @@ GBP_DEV uint4 ld_pair_sys(const uint4* p) {
   return v;
 }
 
-GBP_DEV void boundary_push(const DeviceGraph& g, const uint32_t step, const uint32_t block, const uint32_t n_blocks) {
+GBP_DEV void boundary_push(const DeviceGraph& g, const uint32_t step, const uint32_t block) {
   const uint32_t k = block * GBP_LMK_PER_BLOCK + (threadIdx.x >> 2), q = threadIdx.x & 3;
   if (k < g.n_bnd_local && q < 3) {
     // one record per boundary landmark (k_boundary_records): the partial sum is two memory round trips deep --
@@ -1313,7 +1309,7 @@ __global__ void __launch_bounds__(GBP_TILE, GBP_UV_BLOCKS) k_update_vars(const D
   uint32_t b = blockIdx.x;
   GBP_TS_MIN(g, step, 0);  // first block of the launch
   if (b < n_push) {
-    if (!(lower_only & 16)) boundary_push(g, step, b, n_push);   // bits 4, 5: timing diagnostics (GBP_XCHG_DEBUG)
+    if (!(lower_only & 16)) boundary_push(g, step, b);   // bits 4, 5: timing diagnostics (GBP_XCHG_DEBUG)
   } else if ((b -= n_push) < nb_cam) {
     if (!(lower_only & 2)) update_cameras(g, reinterpret_cast<float*>(s_stage), s_bars, shift, b, lower_only & 1);   // bits 1, 2: timing diagnostics (GBP_UV_DEBUG)
     GBP_TS_MAX(g, step, 6);  // last camera block done

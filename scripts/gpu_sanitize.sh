@@ -9,6 +9,8 @@ for tool in memcheck racecheck synccheck; do
   echo "== $tool: rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/r2_sanitizer_$tool.log | tail -1)"
   grep -E "slam final|relin_mode|fast-math" gpurun_out/r2_sanitizer_$tool.log | head -4
 done
+timeout 600 compute-sanitizer --tool memcheck --print-limit 20 python scripts/sanitize_run.py fast > gpurun_out/r2_sanitizer_memcheck_fast_math.log 2>&1
+echo "== memcheck, fast-math build: rc=$? $(grep -E 'ERROR SUMMARY' gpurun_out/r2_sanitizer_memcheck_fast_math.log | tail -1)"; tail -4 gpurun_out/r2_sanitizer_memcheck_fast_math.log | cut -c1-200
 if [ "$(nvidia-smi -L | wc -l)" -ge 2 ]; then
   GBP_P2P_TIMEOUT_S=600 timeout 1500 compute-sanitizer --tool memcheck --target-processes all --print-limit 20 \
     python -m pytest tests/test_multigpu.py -q -x -m gpu -k "block_calls and 2" > gpurun_out/r2_sanitizer_memcheck_2gpu.log 2>&1

@@ -11,6 +11,15 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 import common  # noqa: E402
 from gbp_poplar_b200 import GBPEngine, MODE_SLAM, default_opts  # noqa: E402
 
+what = sys.argv[1] if len(sys.argv) > 1 else "main"
+if what == "fast":   # the opt-in contracted-FMA build of the sweep kernel, on its own
+    fast = GBPEngine(common.make_setup("fr2robot2").problem, default_opts(fast_math=1))
+    common.run_ba(fast, 12)
+    fast.iterate(5)
+    print("fast-math", fast.eval()["reproj_mean"], flush=True)
+    fast.close()
+    sys.exit(0)
+from gbp_poplar_b200 import _capi  # noqa: E402
 for relin_mode in (1, 2):
     st = common.make_setup("fr2robot2")
     eng = GBPEngine(st.problem, default_opts(relin_mode=relin_mode))
@@ -21,12 +30,9 @@ for relin_mode in (1, 2):
     eng.get_tensor("cam_messages_lambda")
     print("relin_mode", relin_mode, "reproj", stats[-1]["reproj_mean"], flush=True)
     eng.close()
+    _capi.load_library().gbp_cuda_release_cached_memory()   # the instrumented run is short of device memory
 st = common.make_setup("fr2robot2", mode=MODE_SLAM)
 eng = GBPEngine(st.problem)
 finals = common.slam_run(eng, st, 6, device_kf=True, stats_every_kf=False)
 print("slam final", finals[-1]["reproj_mean"], flush=True)
 eng.close()
-fast = GBPEngine(common.make_setup("fr2robot2").problem, default_opts(fast_math=1))
-fast.iterate(5)
-print("fast-math", fast.eval()["reproj_mean"], flush=True)
-fast.close()
