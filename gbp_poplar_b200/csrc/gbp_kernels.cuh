@@ -1293,19 +1293,27 @@ __global__ void __launch_bounds__(GBP_TILE, GBP_UV_BLOCKS) k_update_vars(const D
     g.relin_ring[GBP_RELIN_RING] = next;
   }
   // The exchange step lives on the device (the same sequence on every rank), so the launch has no per-sweep argument
-  // and can be replayed from a CUDA graph.  Thread 0 of every block reads it and THEN takes a ticket; the block that
-  // draws the last ticket knows every other block has read the step and advances it for the next launch.  The ticket's
-  // round trip overlaps the block's work (its result is only looked at when the block is done).
+  // and can be replayed from a CUDA graph.  Only the exchange blocks (push / finish) need it: thread 0 of each reads it
+  // and THEN takes a ticket; the block that draws the last of the 2 n_push tickets knows every other one has read the
+  // step and advances it for the next launch.  The ticket's round trip overlaps the block's work; camera and landmark
+  // blocks do not take part at all.
   __shared__ uint32_t s_step;
   uint32_t ticket = 0;
-  if (n_push) {
+  const uint32_t nb_cam_ = (g.C + GBP_CAM_PER_BLOCK - 1) / GBP_CAM_PER_BLOCK;
+  const bool xchg_block = n_push && (blockIdx.x < n_push || (lower_only & 8 ? blockIdx.x >= n_push + nb_cam_ + g.n_lmk_blocks
+                                                                            : (blockIdx.x >= n_push + nb_cam_ && blockIdx.x < 2 * n_push + nb_cam_)));
+  if (xchg_block) {
     if (threadIdx.x == 0) {
       s_step = *(volatile uint32_t*)g.p2p_step + 1u;
       ticket = atomicAdd(g.p2p_step + 1, 1u);
     }
     __syncthreads();
   }
-  const uint32_t step = n_push ? s_step : 0u;
+#ifdef GBP_DEBUG_TS   // the timeline build stamps every block: all of them read the step (diagnostics only)
+  const uint32_t step = xchg_block ? s_step : (n_push ? *(volatile uint32_t*)g.p2p_step + 1u : 0u);
+#else
+  const uint32_t step = xchg_block ? s_step : 0u;
+#endif
   uint32_t b = blockIdx.x;
   GBP_TS_MIN(g, step, 0);  // first block of the launch
   if (b < n_push) {
@@ -1326,7 +1334,7 @@ __global__ void __launch_bounds__(GBP_TILE, GBP_UV_BLOCKS) k_update_vars(const D
     if (!(lower_only & 4)) update_landmarks(g, s_stage, s_bars, shift, b);
     GBP_TS_MAX(g, step, 5);  // last landmark block done
   }
-  if (n_push && threadIdx.x == 0 && ticket == gridDim.x - 1) {
+  if (xchg_block && threadIdx.x == 0 && ticket == 2 * n_push - 1) {
     g.p2p_step[1] = 0u;
     g.p2p_step[0] = step;
   }

@@ -13,8 +13,13 @@ from gbp_poplar_b200 import GBPEngine, MODE_SLAM, default_opts  # noqa: E402
 
 what = sys.argv[1] if len(sys.argv) > 1 else "main"
 if what == "fast":   # the opt-in contracted-FMA build of the sweep kernel, on its own
-    fast = GBPEngine(common.make_setup("fr2robot2").problem, default_opts(fast_math=1))
+    import faulthandler
+    faulthandler.enable()
+    st = common.make_setup("fr2robot2")   # (kept alive: gbp_problem points into its arrays)
+    fast = GBPEngine(st.problem, default_opts(fast_math=1))
+    print("fast-math: handle built", flush=True)
     common.run_ba(fast, 12)
+    print("fast-math: schedule done", flush=True)
     fast.iterate(5)
     print("fast-math", fast.eval()["reproj_mean"], flush=True)
     fast.close()
