@@ -353,10 +353,15 @@ std::vector<CommEntry>& comm_cache() {
 int launch_update_vars(gbp_handle* h, bool lower_only_in = false, bool skip_cams = false) {
   static const int uv_debug = std::getenv("GBP_UV_DEBUG") ? std::atoi(std::getenv("GBP_UV_DEBUG")) : 0;  // timing diagnostics: 1 skips the cameras, 2 the landmarks (results are then WRONG)
   // bit 0: mirror the lower triangle of the camera beliefs; bit 1: the cameras are already done (fused into the sweep)
-  static const int finish_last = std::getenv("GBP_FINISH_LAST") ? std::atoi(std::getenv("GBP_FINISH_LAST")) : 0;
+  // where the finish blocks of the boundary exchange sit among the landmark blocks, in percent of the latter (see
+  // k_update_vars): 0 = before all of them, 100 = behind all of them
+  static const int finish_at = std::getenv("GBP_FINISH_AT") ? std::min(100, std::max(0, std::atoi(std::getenv("GBP_FINISH_AT")))) : GBP_FINISH_AT_DEFAULT;
   // timing diagnostics of the exchange (results are then WRONG): 1 = push blocks idle, 2 = finish blocks idle, 3 = both
+  // GBP_XCHG_PUSH=1: the partial sums are stored into the peers' buffers (round-2's first protocol, kept for A/B)
+  // instead of being read from the peers' buffers by the finish blocks (see boundary_push)
+  static const int xchg_push = std::getenv("GBP_XCHG_PUSH") ? std::atoi(std::getenv("GBP_XCHG_PUSH")) : 0;
   static const int xchg_debug = std::getenv("GBP_XCHG_DEBUG") ? std::atoi(std::getenv("GBP_XCHG_DEBUG")) : 0;
-  const int lower_only = (lower_only_in ? 1 : 0) | (skip_cams ? 2 : 0) | (uv_debug << 1) | (finish_last ? 8 : 0) | ((xchg_debug & 3) << 4);
+  const int lower_only = (lower_only_in ? 1 : 0) | (skip_cams ? 2 : 0) | (uv_debug << 1) | ((xchg_debug & 3) << 4) | (xchg_push ? 0 : 64);
   const int shift = h->pending_shift ? 1 : 0;
   const uint32_t grid = lmks_grid(h);
   const bool exchange = h->shard && h->g.n_bnd_global > 0;
@@ -365,7 +370,8 @@ int launch_update_vars(gbp_handle* h, bool lower_only_in = false, bool skip_cams
     // one launch: the first blocks form the partial sums and push them into every rank's receive buffer
     // over NVLink, the last blocks finish the boundary landmarks once every rank's flag has arrived
     const uint32_t n_x = std::max((h->g.n_bnd_local + GBP_LMK_PER_BLOCK - 1) / GBP_LMK_PER_BLOCK, 1u);
-    gbp::k_update_vars<<<n_x + cams_grid(h) + grid + n_x, GBP_TILE, 0, h->stream>>>(h->g, shift, n_x, lower_only);
+    const uint32_t finish_after = (uint32_t)((uint64_t)grid * finish_at / 100);
+    gbp::k_update_vars<<<n_x + cams_grid(h) + grid + n_x, GBP_TILE, 0, h->stream>>>(h->g, shift, n_x, lower_only, finish_after);
     h->kernels_launched++;
     h->exchanges++;
   } else {
@@ -382,7 +388,7 @@ int launch_update_vars(gbp_handle* h, bool lower_only_in = false, bool skip_cams
       h->exchanges++;
     }
     if (grid + cams_grid(h)) {
-      gbp::k_update_vars<<<grid + cams_grid(h), GBP_TILE, 0, h->stream>>>(h->g, shift, 0u, lower_only);
+      gbp::k_update_vars<<<grid + cams_grid(h), GBP_TILE, 0, h->stream>>>(h->g, shift, 0u, lower_only, 0u);
       h->kernels_launched++;
     }
     if (exchange) {
@@ -1141,16 +1147,12 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   A_(h->d_pprior_cam_eta, 6 * (size_t)C);
   A_(h->d_pprior_cam_lam, 36 * (size_t)C);
   A_(h->d_pprior_lmk, 3 * (size_t)L);
-  std::vector<uint32_t> lmk_bslot;
   if (h->shard) {
     const uint32_t nbl = gbp_shard_n_boundary_local(h->shard);
     g.n_bnd_local = nbl;
     g.n_bnd_global = gbp_shard_get_plan(h->shard)->n_boundary_points;
     g.world = h->world;
     g.rank = h->rank;
-    lmk_bslot.assign(L, 0xffffffffu);
-    for (uint32_t k = 0; k < nbl; ++k) lmk_bslot[gbp_shard_boundary_local(h->shard)[k]] = gbp_shard_boundary_slot(h->shard)[k];
-    A_(g.lmk_bslot, L);
     A_(g.bnd_local, nbl);
     A_(g.bnd_slot, nbl);
     A_(g.bnd_span, nbl);
@@ -1248,7 +1250,6 @@ int build(gbp_handle* h, const gbp_problem* p, const gbp_opts* o, const uint32_t
   U_(g.lmk_scaling, p->lmk_scaling, L);
   U_(g.lmk_wflag, p->lmk_weaken_flag, L);
   if (h->shard) {
-    U_(g.lmk_bslot, lmk_bslot.data(), L);
     U_(g.bnd_local, gbp_shard_boundary_local(h->shard), g.n_bnd_local);
     U_(g.bnd_slot, gbp_shard_boundary_slot(h->shard), g.n_bnd_local);
     U_(g.bnd_span, gbp_shard_boundary_ranks(h->shard), g.n_bnd_local);

@@ -60,11 +60,10 @@ struct DeviceGraph {
   float* lmk_scaling;     // [L]
   uint32_t* lmk_wflag;    // [L]
   uint32_t* lmk_ptr;      // [L+1] first message of every landmark in mlmk (messages in original edge order)
-  uint4* lmk_blk;         // [n_lmk_blocks] {first landmark, one past the last, first message, one past the last} of every belief-update block (<= 32 landmarks, <= GBP_LMK_CAP messages)
+  uint4* lmk_blk;         // [n_lmk_blocks] {first landmark, mask of its boundary landmarks (shards), first message, one past the last} of every belief-update block (32 landmarks; staged when <= GBP_LMK_CAP messages)
   uint32_t n_lmk_blocks;
   // multi-GPU shard (all null / 0 on a single-GPU handle): boundary landmarks = landmarks
   // that other ranks observe too; their beliefs are formed from all-gathered partials
-  uint32_t* lmk_bslot;    // [L] position in the global boundary list, 0xffffffff = interior
   uint32_t* bnd_local;    // [n_bnd_local] local landmark id
   uint32_t* bnd_slot;     // [n_bnd_local] position in the global boundary list
   uint32_t* bnd_span;     // [n_bnd_local] bit r: rank r observes the landmark -- the ranks its partials go to / come from
@@ -1090,7 +1089,7 @@ GBP_DEV void lmk_finish_quads(const DeviceGraph& g, const uint32_t l, const uint
 GBP_DEV void update_landmarks(const DeviceGraph& g, float4* s_msg, uint64_t* s_bars, const int shift, const uint32_t block) {
   uint64_t& s_bar = s_bars[0];
   const uint4 rec = __ldg(g.lmk_blk + block);
-  const uint32_t l0 = rec.x, l1 = rec.y, k0 = rec.z, k1 = rec.w;
+  const uint32_t l0 = rec.x, l1 = min(l0 + GBP_LMK_PER_BLOCK, g.L), k0 = rec.z, k1 = rec.w;
   const bool staged = k1 - k0 <= GBP_LMK_CAP && k1 > k0;
   if (staged && threadIdx.x == 0) {
     mbar_init(&s_bar, 1);
@@ -1102,10 +1101,9 @@ GBP_DEV void update_landmarks(const DeviceGraph& g, float4* s_msg, uint64_t* s_b
   }
   const uint32_t l = l0 + (threadIdx.x >> 2), q = threadIdx.x & 3;
   const bool here = l < l1;
-  // boundary landmarks of a multi-GPU shard are finished by the exchange blocks / kernels; whether this one is a
-  // boundary landmark is fetched alongside everything else (not ahead of it: one round trip less per block)
-  uint32_t bslot = 0xffffffffu;
-  if (here && g.lmk_bslot) bslot = g.lmk_bslot[l];
+  // boundary landmarks of a multi-GPU shard are finished by the exchange blocks / kernels: one bit per landmark in the
+  // block's record (a per-landmark word fetched beside the other inputs cost the launch 1.4 us, measured)
+  static_assert(GBP_LMK_PER_BLOCK == 32 && GBP_TILE == 4 * GBP_LMK_PER_BLOCK, "one mask bit per landmark of a block");
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), prev = make_float4(0.f, 0.f, 0.f, 0.f);
   uint32_t a0 = 0, a1 = 0;
   if (here && q < 3) {
@@ -1114,7 +1112,7 @@ GBP_DEV void update_landmarks(const DeviceGraph& g, float4* s_msg, uint64_t* s_b
     a1 = g.lmk_ptr[l + 1];
   }
   if (here && q == 0) prev = shift ? g.lmk_b[(size_t)l * GBP_LMKB_QUADS + 3] : g.lmk_mean_prev[l];
-  const bool mine = here && bslot == 0xffffffffu;
+  const bool mine = here && !((rec.y >> (threadIdx.x >> 2)) & 1u);
   if (staged) {
     __syncthreads();  // the barrier is initialised before anyone waits on it
     mbar_wait(&s_bar, 0);
@@ -1182,7 +1180,7 @@ GBP_DEV uint4 ld_pair_sys(const uint4* p) {
   return v;
 }
 
-GBP_DEV void boundary_push(const DeviceGraph& g, const uint32_t step, const uint32_t block) {
+GBP_DEV void boundary_push(const DeviceGraph& g, const uint32_t step, const uint32_t block, const bool pull) {
   const uint32_t k = block * GBP_LMK_PER_BLOCK + (threadIdx.x >> 2), q = threadIdx.x & 3;
   if (k < g.n_bnd_local && q < 3) {
     // one record per boundary landmark (k_boundary_records): the partial sum is two memory round trips deep --
@@ -1204,7 +1202,11 @@ GBP_DEV void boundary_push(const DeviceGraph& g, const uint32_t step, const uint
     // quad q of the landmark's slot in THIS rank's lane of the receive buffer = two 16-byte stores of tagged pairs,
     // to the ranks that observe this landmark (no other rank ever reads it)
     const size_t off = (((size_t)((step & 1u) * g.world + g.rank) * g.n_bnd_global + rec.w) * 3 + q) * 2;
-    for (uint32_t m = span; m; m &= m - 1) {
+    // pull (default): into this rank's own buffer only -- the peers' finish blocks read it from there over NVLink.  A
+    // kernel that has STORED into peer memory pays ~3.8 us at its end (measured, N=2: the system-scope flush of the
+    // remote writes), one that has only LOADED from a peer does not.  push (GBP_XCHG_PUSH=1, kept for A/B): into the
+    // buffer of every rank that observes the landmark.
+    for (uint32_t m = pull ? (span & (1u << g.rank)) : span; m; m &= m - 1) {
       uint4* dst = g.peer_recv[__ffs(m) - 1] + off;
       st_pair_sys(dst, acc.x, acc.y, step);
       st_pair_sys(dst + 1, acc.z, acc.w, step);
@@ -1213,7 +1215,7 @@ GBP_DEV void boundary_push(const DeviceGraph& g, const uint32_t step, const uint
   GBP_TS_MAX(g, step, 1);  // last push block has stored its partials
 }
 
-GBP_DEV void boundary_finish(const DeviceGraph& g, const int shift, const uint32_t step, const uint32_t block) {
+GBP_DEV void boundary_finish(const DeviceGraph& g, const int shift, const uint32_t step, const uint32_t block, const bool pull) {
   // everything that does not depend on the peers is fetched before the first poll: the record, the prior, the previous mean
   const uint32_t k = block * GBP_LMK_PER_BLOCK + (threadIdx.x >> 2), q = threadIdx.x & 3;
   const bool mine = k < g.n_bnd_local;
@@ -1230,11 +1232,12 @@ GBP_DEV void boundary_finish(const DeviceGraph& g, const int shift, const uint32
   if (mine && q < 3) {
     // rank order over the ranks that observe the landmark.  The others contribute +0 to the sum over ALL ranks that
     // defines the belief, and acc + (+0) == acc bit for bit (acc starts as 0 + prior, so it is never -0): skipped.
-    const uint4* base = g.p2p_recv + ((size_t)(step & 1u) * g.world * g.n_bnd_global + rec.w) * 6 + (size_t)q * 2;
+    const size_t base = ((size_t)(step & 1u) * g.world * g.n_bnd_global + rec.w) * 6 + (size_t)q * 2;
     const long long t0 = clock64();
     for (uint32_t m = span; m && ok; m &= m - 1) {  // ascending rank order
       const uint32_t r = __ffs(m) - 1;
-      const uint4* src = base + (size_t)r * g.n_bnd_global * 6;
+      // rank r's lane: in that rank's own buffer (pull; this rank's own lane is local) or in this rank's (push)
+      const uint4* src = (pull && r != g.rank ? (const uint4*)g.peer_recv[r] : g.p2p_recv) + base + (size_t)r * g.n_bnd_global * 6;
       uint4 a = ld_pair_sys(src), b = ld_pair_sys(src + 1);
       while (a.y != step || a.w != step || b.y != step || b.w != step) {  // that rank's partial has not landed yet
         if (clock64() - t0 > g.p2p_timeout) {  // a peer died or never made the matching call: do not hang the GPU
@@ -1259,12 +1262,13 @@ GBP_DEV void boundary_finish(const DeviceGraph& g, const int shift, const uint32
 }
 
 // {local landmark, first message, one past the last message, position in the global boundary list} of every boundary
-// landmark this rank touches (built once at init from the device-side lmk_ptr)
+// landmark this rank touches (built once at init from the device-side lmk_ptr), and its bit in the landmark-block record
 __global__ void k_boundary_records(const DeviceGraph g) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= g.n_bnd_local) return;
   const uint32_t l = g.bnd_local[k];
   g.bnd_rec[k] = make_uint4(l, g.lmk_ptr[l], g.lmk_ptr[l + 1], g.bnd_slot[k]);
+  atomicOr(&g.lmk_blk[l / GBP_LMK_PER_BLOCK].y, 1u << (l % GBP_LMK_PER_BLOCK));   // the landmark blocks skip it
 }
 
 // prog_ub in one launch.  Block roles, in dispatch order:
@@ -1276,11 +1280,14 @@ __global__ void k_boundary_records(const DeviceGraph g) {
 //                        they wait for on this rank was dispatched before them) while the landmark blocks stream, instead of
 //                        forming a serial tail after them
 // The register budget (10 blocks per SM) fits all paths.  n_push == 0: no fused exchange.
+#ifndef GBP_FINISH_AT_DEFAULT
+#define GBP_FINISH_AT_DEFAULT 0   // percent of the landmark blocks dispatched before the finish blocks of the exchange
+#endif
 #ifndef GBP_UV_BLOCKS
 #define GBP_UV_BLOCKS 9
 #endif
 __global__ void __launch_bounds__(GBP_TILE, GBP_UV_BLOCKS) k_update_vars(const DeviceGraph g, const int shift, const uint32_t n_push,
-                                                                         const int lower_only) {
+                                                                         const int lower_only, const uint32_t finish_after) {
   // one staging buffer per block, used by whichever role the block plays (landmark message run / camera partial runs)
   __shared__ __align__(128) float4 s_stage[GBP_LMK_CAP * GBP_MLMK_QUADS];
   __shared__ __align__(8) uint64_t s_bars[GBP_CAM_PER_BLOCK];
@@ -1292,6 +1299,11 @@ __global__ void __launch_bounds__(GBP_TILE, GBP_UV_BLOCKS) k_update_vars(const D
     g.relin_ring[next % GBP_RELIN_RING] = 0;
     g.relin_ring[GBP_RELIN_RING] = next;
   }
+  // Block roles in dispatch order: [push][cameras][landmarks 0 .. finish_after)[finish][landmarks finish_after ..).
+  // The finish blocks are the only ones that wait for a peer; placed behind the first `finish_after` landmark blocks
+  // they start a few microseconds into the launch, so a peer that arrives that much later costs this rank nothing,
+  // and the rest of the landmark blocks run beside them (no tail).
+  const uint32_t fin0 = n_push + nb_cam + min(finish_after, nb_lmk);   // first finish block
   // The exchange step lives on the device (the same sequence on every rank), so the launch has no per-sweep argument
   // and can be replayed from a CUDA graph.  Only the exchange blocks (push / finish) need it: thread 0 of each reads it
   // and THEN takes a ticket; the block that draws the last of the 2 n_push tickets knows every other one has read the
@@ -1299,9 +1311,7 @@ __global__ void __launch_bounds__(GBP_TILE, GBP_UV_BLOCKS) k_update_vars(const D
   // blocks do not take part at all.
   __shared__ uint32_t s_step;
   uint32_t ticket = 0;
-  const uint32_t nb_cam_ = (g.C + GBP_CAM_PER_BLOCK - 1) / GBP_CAM_PER_BLOCK;
-  const bool xchg_block = n_push && (blockIdx.x < n_push || (lower_only & 8 ? blockIdx.x >= n_push + nb_cam_ + g.n_lmk_blocks
-                                                                            : (blockIdx.x >= n_push + nb_cam_ && blockIdx.x < 2 * n_push + nb_cam_)));
+  const bool xchg_block = n_push && (blockIdx.x < n_push || (blockIdx.x >= fin0 && blockIdx.x < fin0 + n_push));
   if (xchg_block) {
     if (threadIdx.x == 0) {
       s_step = *(volatile uint32_t*)g.p2p_step + 1u;
@@ -1317,22 +1327,19 @@ __global__ void __launch_bounds__(GBP_TILE, GBP_UV_BLOCKS) k_update_vars(const D
   uint32_t b = blockIdx.x;
   GBP_TS_MIN(g, step, 0);  // first block of the launch
   if (b < n_push) {
-    if (!(lower_only & 16)) boundary_push(g, step, b);   // bits 4, 5: timing diagnostics (GBP_XCHG_DEBUG)
+    if (!(lower_only & 16)) boundary_push(g, step, b, lower_only & 64);   // bit 6: pull mode   // bits 4, 5: timing diagnostics (GBP_XCHG_DEBUG)
   } else if ((b -= n_push) < nb_cam) {
     if (!(lower_only & 2)) update_cameras(g, reinterpret_cast<float*>(s_stage), s_bars, shift, b, lower_only & 1);   // bits 1, 2: timing diagnostics (GBP_UV_DEBUG)
     GBP_TS_MAX(g, step, 6);  // last camera block done
-  } else if (lower_only & 8) {  // GBP_FINISH_LAST=1 (diagnostics): the finish blocks after the landmark blocks
-    if ((b -= nb_cam) < nb_lmk) {
+  } else if (xchg_block) {
+    if (!(lower_only & 32)) boundary_finish(g, shift, step, blockIdx.x - fin0, lower_only & 64);
+  } else {
+    b -= nb_cam;
+    if (blockIdx.x >= fin0) b -= n_push;   // landmark blocks behind the finish blocks
+    if (b < nb_lmk) {
       if (!(lower_only & 4)) update_landmarks(g, s_stage, s_bars, shift, b);
-      GBP_TS_MAX(g, step, 5);
-    } else {
-      boundary_finish(g, shift, step, b - nb_lmk);
+      GBP_TS_MAX(g, step, 5);  // last landmark block done
     }
-  } else if ((b -= nb_cam) < n_push) {
-    if (!(lower_only & 32)) boundary_finish(g, shift, step, b);
-  } else if ((b -= n_push) < nb_lmk) {
-    if (!(lower_only & 4)) update_landmarks(g, s_stage, s_bars, shift, b);
-    GBP_TS_MAX(g, step, 5);  // last landmark block done
   }
   if (xchg_block && threadIdx.x == 0 && ticket == 2 * n_push - 1) {
     g.p2p_step[1] = 0u;

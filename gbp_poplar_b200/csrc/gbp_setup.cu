@@ -135,7 +135,7 @@ __global__ void k_setup_lmks(const float* __restrict__ prior_eta, const float* _
   o[2] = make_float4(m[5], m[6], m[7], m[8]);
   if (l % per_block == 0) {
     const uint32_t l1 = min(L, l + per_block);
-    lmk_blk[l / per_block] = make_uint4(l, l1, lmk_ptr[l], lmk_ptr[l1]);
+    lmk_blk[l / per_block] = make_uint4(l, 0u, lmk_ptr[l], lmk_ptr[l1]);   // .y: mask of boundary landmarks, set by k_boundary_records on a shard
   }
 }
 
