@@ -112,6 +112,42 @@ def ba_preroll(engine):
         engine.iterate(1)
 
 
+def page_lock_problem(problem):
+    """Page-locks (cudaHostRegister) the caller-side arrays of a gbp_problem that gbp_cuda_init copies to the device, so
+    that the end-to-end job reads its inputs from pinned host memory as the benchmark contract asks (the library copies
+    straight from the caller's pointers).  Returns the registered pointers (for page_unlock) and a description."""
+    C_, L_, E_ = problem.n_keyframes, problem.n_points, problem.n_edges
+    sizes = {"cam_ids": 4 * E_, "lmk_ids": 4 * E_, "measurements": 8 * E_, "meas_variances": 4 * E_,
+             "cam_priors_eta": 24 * C_, "cam_priors_lambda": 144 * C_, "lmk_priors_eta": 12 * L_,
+             "lmk_priors_lambda": 36 * L_, "cam_scaling": 4 * C_, "lmk_scaling": 4 * L_, "cam_weaken_flag": 4 * C_,
+             "lmk_weaken_flag": 4 * L_, "active_flag": 4 * E_, "damping": 4 * E_, "damping_count": 4 * E_,
+             "mu": 36 * E_, "oldmu": 36 * E_}
+    done = []
+    try:
+        import ctypes
+        import torch
+        rt = torch.cuda.cudart()
+        for field, nbytes in sizes.items():
+            ptr = ctypes.cast(getattr(problem, field), ctypes.c_void_p).value
+            if ptr and nbytes:
+                err = rt.cudaHostRegister(ptr, nbytes, 0)
+                if int(err) != 0:
+                    raise RuntimeError(f"cudaHostRegister({field}) -> {err}")
+                done.append(ptr)
+        return done, "page-locked (cudaHostRegister on the caller's arrays)"
+    except Exception as e:  # noqa: BLE001 -- the job then runs from pageable memory, and says so
+        page_unlock(done)
+        return [], f"pageable ({e!r})"
+
+
+def page_unlock(ptrs):
+    if ptrs:
+        import torch
+        rt = torch.cuda.cudart()
+        for ptr in ptrs:
+            rt.cudaHostUnregister(ptr)
+
+
 def host_cores():
     try:
         return max(1, len(os.sched_getaffinity(0)))
@@ -297,7 +333,8 @@ def main():
     init_s = time.time() - t_init0
     E_loc, C_loc, L_loc = eng.n_edges, eng.n_keyframes, eng.n_points   # this rank's shard (== global at N=1)
     n_boundary = eng.shard.n_boundary_points if eng.shard else 0
-    exchange_mode = {"p2p": "peer-to-peer stores over NVLink (CUDA IPC) from the kernel that forms them",
+    exchange_mode = {"p2p": ("peer-to-peer stores" if os.environ.get("GBP_XCHG_PUSH", "0") not in ("", "0") else "peer-to-peer loads")
+                            + " over NVLink (CUDA IPC) inside the belief-update kernel, step-tagged words, no collective",
                      "nccl": "NCCL all-gather", "none": "nothing"}[eng.exchange_mode()]
     ba_preroll(eng)
 
@@ -450,6 +487,7 @@ def main():
     e2e = None
     eng.close()                                        # the e2e job below is a fresh one: nothing of the timed engine is kept
     if rank == 0 or world > 1:
+        locked, host_buffers = page_lock_problem(setup.problem)   # untimed: the job's inputs sit in pinned host memory
         barrier()
         t0 = time.time()
         eng2 = make_engine()                           # H2D of the (rank's part of the) problem + LINEARISE_PROG
@@ -477,8 +515,10 @@ def main():
         e2e = {"value": E * args.steps / wall, "unit": "factor-updates/s",
                "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
                "wall_s": wall, "init_s": t_init, "loop_s": t_loop, "read_s": wall - t_init - t_loop, "final_reproj_px": last["reproj_mean"] if last else None,
-               "what": "gbp_cuda_init + K x gbp_cuda_iterate(1, stats) + gbp_cuda_get_beliefs, host clock"}
+               "what": "gbp_cuda_init + K x gbp_cuda_iterate(1, stats) + gbp_cuda_get_beliefs, host clock",
+               "host_buffers": host_buffers}
         eng2.close()
+        page_unlock(locked)
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -497,7 +537,7 @@ def main():
                        "synthetic BAL 10k cameras / 1M landmarks / ~10M factors in total (configs[4]), partitioned by camera range",
                        "cameras": Cn, "landmarks": Ln, "factors": E, "per_gpu": False,
                        "parallelism": f"camera-range shards x{world}, boundary-landmark partials exchanged per sweep by "
-                                      f"{exchange_mode} ({n_boundary} boundary landmarks, {48 * n_boundary} B per rank and peer)"
+                                      f"{exchange_mode} ({n_boundary} boundary landmarks in the whole graph, 96 B each per observing peer)"
                        if world > 1 else "single",
                        "rank0_shard": {"cameras": C_loc, "landmarks": L_loc, "factors": E_loc},
                        "cache": "per-sweep working set ~0.65 GB per GPU >> 126 MB L2 (no flush needed)",

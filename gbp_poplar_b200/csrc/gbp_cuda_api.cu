@@ -367,8 +367,8 @@ int launch_update_vars(gbp_handle* h, bool lower_only_in = false, bool skip_cams
   const bool exchange = h->shard && h->g.n_bnd_global > 0;
   const uint32_t bgrid = (h->g.n_bnd_local + GBP_TILE - 1) / GBP_TILE;
   if (exchange && h->p2p) {
-    // one launch: the first blocks form the partial sums and push them into every rank's receive buffer
-    // over NVLink, the last blocks finish the boundary landmarks once every rank's flag has arrived
+    // one launch: the first blocks form the partial sums (tagged with the exchange step), later blocks finish the
+    // boundary landmarks once the tagged partials of every observing rank are there (see boundary_push / boundary_finish)
     const uint32_t n_x = std::max((h->g.n_bnd_local + GBP_LMK_PER_BLOCK - 1) / GBP_LMK_PER_BLOCK, 1u);
     const uint32_t finish_after = (uint32_t)((uint64_t)grid * finish_at / 100);
     gbp::k_update_vars<<<n_x + cams_grid(h) + grid + n_x, GBP_TILE, 0, h->stream>>>(h->g, shift, n_x, lower_only, finish_after);

@@ -1134,15 +1134,16 @@ GBP_DEV void update_landmarks(const DeviceGraph& g, float4* s_msg, uint64_t* s_b
 //     belief = (0 + prior) + partial[rank 0] + partial[rank 1] + ...
 // where partial[r] is rank r's sum of its own messages (slot order, from +0): the same
 // operations on every rank, so all replicas stay bit-identical.
-// boundary_push: the blocks that form this rank's partial sums store them straight into the
-// receive buffer of EVERY rank (its own included) through NVLink-mapped peer pointers (CUDA
-// IPC); the last of them to finish publishes `step` in every rank's arrival flag.  No
-// collective call, no communication stream, no host synchronisation: the transfer is in
-// flight while the rest of the grid updates the cameras and the interior landmarks.
-// boundary_finish: the LAST blocks of the same grid wait (bounded) for every rank's flag and
-// finish the boundary landmarks from the receive buffer (read past L1).
-// Buffers are double-buffered by step parity: a peer may already push step s+1 while this
-// rank still reads step s, never s+2 (it needs this rank's step-s+1 flag first).
+// boundary_push: the FIRST blocks of k_update_vars form this rank's partial sums and store them, every float tagged
+// with the exchange step, into this rank's exchange buffer (default) -- or straight into the buffer of every rank
+// that observes the landmark (GBP_XCHG_PUSH=1) -- through NVLink-mapped peer pointers (CUDA IPC between processes,
+// direct pointers inside one process).
+// boundary_finish: later blocks of the same grid poll the tagged words of every observing rank -- over NVLink in that
+// rank's buffer (default), or in their own buffer (push) -- until they carry the current step, add them in rank
+// order and finish the boundary landmarks.  No collective call, no communication stream, no host synchronisation,
+// no flag and no fence: the transfer overlaps the cameras and the interior landmarks of the same launch.
+// Buffers are double-buffered by step parity: a peer may already be at step s+1 while this rank still reads step s,
+// never at s+2 (it needs this rank's step-s+1 partials first).
 #ifdef GBP_DEBUG_TS
 GBP_DEV unsigned long long dbg_now() {
   unsigned long long t;
@@ -1272,14 +1273,14 @@ __global__ void k_boundary_records(const DeviceGraph g) {
 }
 
 // prog_ub in one launch.  Block roles, in dispatch order:
-//   [multi-GPU, peer-to-peer] boundary_push blocks  -- first, so the partials travel while the rest runs
+//   [multi-GPU, peer-to-peer] boundary_push blocks  -- first, so the partials are there when the peers look for them
 //   camera blocks     -- few, long-running (a serial 6x6 inverse + Rodrigues per camera, one warp each), nearly idle:
 //                        they overlap with the bandwidth-bound landmark blocks that fill the chip
-//   landmark blocks   -- up to GBP_LMK_PER_BLOCK landmarks each, their messages staged by one bulk copy
-//   [multi-GPU, peer-to-peer] boundary_finish blocks -- BEFORE the landmark blocks: they wait for the peers' flags (every block
-//                        they wait for on this rank was dispatched before them) while the landmark blocks stream, instead of
-//                        forming a serial tail after them
-// The register budget (10 blocks per SM) fits all paths.  n_push == 0: no fused exchange.
+//   [multi-GPU, peer-to-peer] boundary_finish blocks -- by default BEFORE the landmark blocks (finish_after = 0): they
+//                        poll for the peers' partials while the landmark blocks stream, instead of forming a serial
+//                        tail after them (measured at N=2: behind 80-100 % of the landmark blocks +0.5..2 us per sweep)
+//   landmark blocks   -- GBP_LMK_PER_BLOCK landmarks each, their messages staged by one bulk copy
+// The register budget (GBP_UV_BLOCKS blocks per SM) fits all paths.  n_push == 0: no fused exchange.
 #ifndef GBP_FINISH_AT_DEFAULT
 #define GBP_FINISH_AT_DEFAULT 0   // percent of the landmark blocks dispatched before the finish blocks of the exchange
 #endif

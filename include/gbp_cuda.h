@@ -86,8 +86,9 @@ typedef struct gbp_opts {
                                  1: the strict upper triangle is stored too (+64 B per factor and sweep),
                                  so that tensor is bit-identical to the reference's as well.  Beliefs,
                                  every other tensor and the trajectory are identical in both modes.     */
-  int exchange;               /* multi-GPU boundary exchange: 0 = auto (peer-to-peer stores over NVLink via
-                                 CUDA IPC when every rank can map every peer, else NCCL all-gather),
+  int exchange;               /* multi-GPU boundary exchange: 0 = auto (peer-to-peer over NVLink -- the
+                                 belief-update kernel reads the peers' step-tagged partial sums through
+                                 CUDA-IPC-mapped memory -- when every rank can map every peer, else NCCL all-gather),
                                  1 = NCCL all-gather, 2 = peer-to-peer or fail                          */
   int relin_mode;             /* how a sweep handles the in-loop relinearisation (results are bit-identical):
                                  1 = one fused kernel; 2 = state-machine pass + compacted relinearisation +
@@ -359,7 +360,7 @@ int gbp_cuda_release_cached_memory(void);
  * are NULL (the caller may free its arrays after init). */
 const gbp_shard* gbp_cuda_shard_info(gbp_handle* h);
 /* How this handle exchanges boundary partials: 0 = no exchange (single GPU or no boundary
- * landmarks), 1 = NCCL all-gather, 2 = peer-to-peer stores over NVLink. */
+ * landmarks), 1 = NCCL all-gather, 2 = peer-to-peer over NVLink (inside the belief-update kernel). */
 int gbp_cuda_exchange_mode(gbp_handle* h);
 
 #ifdef __cplusplus

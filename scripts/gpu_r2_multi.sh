@@ -3,7 +3,7 @@
 N=${1:-2}; TESTS=${2:-yes}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
-if [ "$TESTS" = yes ]; then timeout 1200 python -m pytest tests/test_multigpu.py tests/test_group_gpu.py -q -x -m gpu 2>&1 | tail -6 | tee gpurun_out/r2_multigpu_tests_n$N.log; fi
+if [ "$TESTS" = yes ]; then timeout 1200 python -m pytest tests/test_multigpu.py tests/test_group_gpu.py -q -x -m gpu 2>&1 | tail -60 | tee gpurun_out/r2_multigpu_tests_n$N.log | tail -6; fi
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 200 --warmup 10 > gpurun_out/r2_bench_n$N.json 2> gpurun_out/r2_bench_n$N.err
 python scripts/show_bench.py gpurun_out/r2_bench_n$N.json; grep -v "OMP_NUM_THREADS\|^\*\*\*\|^$" gpurun_out/r2_bench_n$N.err | tail -5
 python - <<PY
