@@ -164,6 +164,9 @@ struct gbp_handle {
   gbp::SweepMaps maps;
   int use_tma = 0;
   int fast_math = 0;  // gbp_opts.fast_math: the contracted-FMA build of the sweep kernel (gbp_fast.cu)
+  // GBP_XCHG_PUSH=1 (read when the handle is built): boundary partial sums are stored into the observers' buffers
+  // instead of read from the owners' (see boundary_push); every rank of a job must use the same setting
+  int xchg_push = std::getenv("GBP_XCHG_PUSH") ? (std::atoi(std::getenv("GBP_XCHG_PUSH")) != 0) : 0;
 };
 
 // A single-process group of shard handles: the exchange blocks of all ranks live (and die) together, so that
@@ -357,11 +360,8 @@ int launch_update_vars(gbp_handle* h, bool lower_only_in = false, bool skip_cams
   // k_update_vars): 0 = before all of them, 100 = behind all of them
   static const int finish_at = std::getenv("GBP_FINISH_AT") ? std::min(100, std::max(0, std::atoi(std::getenv("GBP_FINISH_AT")))) : GBP_FINISH_AT_DEFAULT;
   // timing diagnostics of the exchange (results are then WRONG): 1 = push blocks idle, 2 = finish blocks idle, 3 = both
-  // GBP_XCHG_PUSH=1: the partial sums are stored into the peers' buffers (round-2's first protocol, kept for A/B)
-  // instead of being read from the peers' buffers by the finish blocks (see boundary_push)
-  static const int xchg_push = std::getenv("GBP_XCHG_PUSH") ? std::atoi(std::getenv("GBP_XCHG_PUSH")) : 0;
   static const int xchg_debug = std::getenv("GBP_XCHG_DEBUG") ? std::atoi(std::getenv("GBP_XCHG_DEBUG")) : 0;
-  const int lower_only = (lower_only_in ? 1 : 0) | (skip_cams ? 2 : 0) | (uv_debug << 1) | ((xchg_debug & 3) << 4) | (xchg_push ? 0 : 64);
+  const int lower_only = (lower_only_in ? 1 : 0) | (skip_cams ? 2 : 0) | (uv_debug << 1) | ((xchg_debug & 3) << 4) | (h->xchg_push ? 0 : 64);
   const int shift = h->pending_shift ? 1 : 0;
   const uint32_t grid = lmks_grid(h);
   const bool exchange = h->shard && h->g.n_bnd_global > 0;

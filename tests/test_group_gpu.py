@@ -49,8 +49,12 @@ def make_group(st, world, devices, **opts):
     ("seq:fr1xyz", 3, (7, 1, 13, 30)),
     ("seq:fr2robot2", 4, (5, 2, 17)),
 ])
-def test_block_calls_without_stats_bit_identical_to_oracle(spec, world, blocks):
-    """The path bench.py --gpus N times: gbp_cuda_iterate(n) blocks with stats == NULL on sharded handles."""
+@pytest.mark.parametrize("protocol", ["pull", "push"])
+def test_block_calls_without_stats_bit_identical_to_oracle(spec, world, blocks, protocol, monkeypatch):
+    """The path bench.py --gpus N times: gbp_cuda_iterate(n) blocks with stats == NULL on sharded handles.  Both
+    directions of the boundary exchange: partial sums read from the peers' buffers (the default) and stored into
+    them (GBP_XCHG_PUSH=1, read when a handle is built)."""
+    monkeypatch.setenv("GBP_XCHG_PUSH", "1" if protocol == "push" else "0")
     st = shard_worker.make_problem(spec)
     for devices in device_layouts(world):
         grp = make_group(st, world, devices)
