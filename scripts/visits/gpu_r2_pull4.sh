@@ -1,4 +1,5 @@
 #!/bin/bash
+# N=4 (or $1): the same shards with the partial sums stored into the peers (push) and read from them (pull)
 N=${1:-4}
 mkdir -p gpurun_out
 run() {  # label, env...

@@ -1,5 +1,5 @@
 #!/bin/bash
-# bench several builds of the library: bash scripts/gpu_variants.sh lib1.so lib2.so ...
+# bench several builds of the library: bash scripts/visits/gpu_variants.sh lib1.so lib2.so ...
 mkdir -p gpurun_out
 for lib in "$@"; do
   echo "== $lib"
