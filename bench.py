@@ -403,7 +403,7 @@ def main():
     t_factor = ms_factor / args.steps / 1e3
     achieved = algo_bytes_factor_kernel / t_factor / 1e9
     roofline = {
-        "bound": "hbm", "kernel": "k_sweep<PREP=true,MSG=true,UPPER=false> (the last sweep of a call runs UPPER=true)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "bound": "hbm", "kernel": ("k_sweep" if os.environ.get("GBP_SWEEP", "tma") == "cpasync" else "k_sweep_tma") + "<PREP=true,MSG=true,UPPER=false> (the last sweep of a call runs UPPER=true)", "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
         "note": "achieved/frac use the contract figure (896 B per factor = every logical tensor element of the "
                 "reference, SURVEY 8d); the packed layout moves fewer bytes, see achieved_moved / frac_moved",
