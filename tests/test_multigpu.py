@@ -82,7 +82,12 @@ def test_world_of_one_sharded_handle_equals_plain_handle():
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "shard_world1_check.py")], capture_output=True,
-                       text=True, timeout=600, cwd=root)
+    cmd = [sys.executable, os.path.join(root, "scripts", "shard_world1_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    if r.returncode != 0 and "DIFFERENT" not in r.stdout:
+        # the process died before comparing anything (seen once on a 4-GPU box right after the 4-rank test, NCCL
+        # bootstrap of the one-rank group): show why, try once more; a comparison that ran and differed is never retried
+        print("first attempt failed:\n" + (r.stdout + r.stderr)[-3000:])
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
     assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
     assert "world-1 sharded vs plain: IDENTICAL" in r.stdout, r.stdout[-2000:]
